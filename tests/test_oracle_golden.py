@@ -1,0 +1,200 @@
+"""Pins the CPU oracle against every golden value in the reference's own tests
+(solver/src/lib.rs, cli/src/tests.rs — see tests/golden/reference_kats.json for file:line)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def f8(x):
+    s = f"{x:.8f}"
+    return "0.00000000" if s == "-0.00000000" else s
+
+
+def fmt3(v):
+    return [f8(float(c)) for c in v]
+
+
+def two_body(kats):
+    k = kats["two_body"]
+    return orc.State(k["pos"], k["vel"], k["mass"], k["box"]), orc.LennardJones(), k
+
+
+def test_lennard_jones(kats):  # solver/src/lib.rs:77-89
+    k = kats["lennard_jones"]
+    lj = orc.LennardJones(kats["argon"]["sigma"], kats["argon"]["eps"])
+    u, f = lj.get_potential_and_force(k["r"])
+    assert f8(u) == k["potential"]
+    assert f8(f) == k["force"]
+    assert lj.r_cut == 0.3418 * 2.5
+    assert lj.u_cut == pytest.approx(-0.027934517624831987, abs=0, rel=1e-15)
+    assert lj.get_potential_and_force(lj.r_cut + 1e-12) == (0.0, 0.0)
+    # inclusive cutoff, shifted potential is exactly zero at r_cut
+    assert lj.get_potential_and_force(lj.r_cut)[0] == 0.0
+
+
+def test_update_force_lennard_jones(kats):  # solver/src/lib.rs:91-107
+    k = kats["update_force_lennard_jones"]
+    st = orc.State(k["pos"], np.zeros((2, 3)), k["mass"], k["box"])
+    orc.update_force(orc.LennardJones(), st)
+    assert fmt3(st.force[0]) == k["force_p1"]
+
+
+def check_step(st, g):
+    for key, arr in (("pos1", st.pos[0]), ("pos2", st.pos[1]), ("vel1", st.vel[0]), ("vel2", st.vel[1]),
+                     ("force1", st.force[0]), ("force2", st.force[1])):
+        if key in g:
+            assert fmt3(arr) == g[key], (g["step"], key)
+
+
+@pytest.mark.parametrize("mode", ["n2", "cells"])
+def test_verlet_with_lennard_jones(kats, mode):  # solver/src/lib.rs:109-262, cli/src/tests.rs:35-98
+    st, lj, k = two_body(kats)
+    orc.update_force(lj, st, mode=mode)
+    check_step(st, k["steps"][0])
+    for g in k["steps"][1:]:
+        orc.step(lj, st, k["dt"], mode=mode)
+        check_step(st, g)
+
+
+def test_verlet_lj_1000_iterations(kats):  # solver/src/lib.rs:264-332
+    st, lj, k = two_body(kats)
+    g = kats["verlet_lj_1000_iterations"]
+    orc.update_force(lj, st)
+    orc.step(lj, st, k["dt"], n_steps=g["n_steps"])
+    check_step(st, dict(g, step=999))
+    m = orc.macro(st)
+    assert f8(m["kinetic"]) == g["kinetic"]
+    assert f8(m["thermal"]) == g["thermal"]
+    assert f8(m["potential"]) == g["potential"]
+    assert f8(m["thermal"] + m["potential"]) == g["internal"]
+    assert f8(m["kinetic"] + m["potential"]) == g["full"]
+    assert f8(m["temperature"] / 100.0) == g["temperature_over_100"]
+    assert f8(m["pressure"]) == g["pressure"]
+
+
+def test_energies_temperature_pressure(kats):  # solver/src/lib.rs:334-427
+    st, lj, _ = two_body(kats)
+    orc.update_force(lj, st)
+    m = orc.macro(st)
+    g = kats["energies"]
+    assert list(m["vcom"]) == g["vcom"]  # exact, as assert_eq!(mv, Vector3::new(0.0, 1.0, 0.0))
+    assert f8(m["kinetic"]) == g["kinetic"]
+    assert f8(m["thermal"]) == g["thermal"]
+    assert f8(m["potential"]) == g["potential"]
+    assert f8(m["thermal"] + m["potential"]) == g["internal"]
+    assert f8(m["kinetic"] + m["potential"]) == g["full"]
+    assert f8(m["temperature"]) == kats["temperature"]["value"]
+    assert f8(m["pressure"]) == kats["pressure"]["value"]
+
+
+def test_initialize_uniform_grid(kats):  # solver/src/lib.rs:17-47
+    g = kats["initialize_uniform_grid"]
+    pos = orc.init_positions("u", g["grid"], g["cell"])
+    assert list(pos[g["index"]]) == g["position"]  # z is the fastest index
+
+
+def test_initialization(kats):  # cli/src/tests.rs:9-33
+    g = kats["initialization"]
+    st = orc.argon_lattice(tuple(g["grid"]), g["cell"])
+    assert st.n == g["count"]
+    assert list(st.box) == [g["box"]] * 3
+
+
+def test_fcc_count_and_offsets():  # initializer/position.rs:53-101
+    pos = orc.init_positions("fcc", (2, 3, 4), 1.5)
+    assert pos.shape == (96, 3)
+    assert list(pos[1]) == [0.0, 0.75, 0.75]
+    assert list(pos[2]) == [0.75, 0.0, 0.75]
+    assert list(pos[3]) == [0.75, 0.75, 0.0]
+
+
+def test_momentum(kats):  # solver/src/lib.rs:49-75 (shortened horizon; the reference runs 100 000 steps)
+    g = kats["momentum"]
+    st = orc.argon_lattice(tuple(g["grid"]), g["cell"], g["temperature"])
+    lj = orc.LennardJones()
+    orc.update_force(lj, st)
+    for _ in range(2000):
+        orc.step(lj, st, g["dt"])
+        assert np.all(np.abs(st.vel.sum(axis=0)) < g["tolerance"])
+
+
+def test_velocity_initializer_structure():  # initializer/velocity.rs:6-29
+    vel = orc.init_velocities(1000, 273.15, orc.ARGON_MASS, seed=42)
+    assert np.array_equal(vel[500:], -vel[:500])
+    sigma = np.sqrt(orc.K_B * 2.7315 / orc.ARGON_MASS)
+    assert abs(vel[:500].std() / sigma - 1.0) < 0.05
+    assert np.array_equal(vel, orc.init_velocities(1000, 273.15, orc.ARGON_MASS, seed=42))
+
+
+def test_boundary_conditions():  # core/src/lib.rs:129-144, particle.rs:120-142
+    st = orc.State([[0.3, 1.1, 1.0], [-0.25, 0.5, 2.5]], np.zeros((2, 3)), 1.0, [1.0, 1.0, 1.0])
+    orc.apply_boundary_conditions(st)
+    assert np.allclose(st.pos[0], [0.3, 0.1, 0.0], atol=1e-15)
+    assert list(st.pos[1]) == [0.75, 0.5, 1.5]  # single shift only
+
+
+def liquid(n_side=8, seed=3, jitter=0.03):
+    cell = 0.36165
+    st = orc.argon_lattice(n_side, cell, 120.0, seed)
+    rng = np.random.default_rng(seed)
+    st.pos += rng.uniform(-jitter, jitter, st.pos.shape)
+    orc.apply_boundary_conditions(st)
+    return st
+
+
+@pytest.mark.parametrize("r_cut", [None, 1.1963])
+def test_cell_list_variant_is_bit_identical(r_cut):
+    """The Θ(N) oracle must reproduce the reference's Θ(N²) scan bit for bit (ascending-j sums)."""
+    lj = orc.LennardJones() if r_cut is None else orc.LennardJones(r_cut=r_cut, u_cut=-0.003723224030513348)
+    for st in (liquid(10), orc.State(orc.random_positions(3000, [9.0, 7.5, 8.1], 5), np.zeros((3000, 3)),
+                                      orc.ARGON_MASS, [9.0, 7.5, 8.1])):
+        a, b = st.copy(), st.copy()
+        orc.update_force(lj, a, mode="n2")
+        orc.update_force(lj, b, mode="cells")
+        assert np.array_equal(a.force, b.force)
+        assert np.array_equal(a.pot, b.pot)
+        assert np.array_equal(a.vir, b.vir)
+        assert np.abs(a.force).max() > 0
+
+
+def test_u_cut_for_long_cutoff():  # 3.5σ potentials.json entry
+    lj = orc.LennardJones(r_cut=1.1963)
+    assert lj.u_cut == pytest.approx(-0.003723224030513348, rel=1e-14)
+
+
+def test_neighbour_sets_match_bruteforce():
+    st = liquid(6)
+    r_list = 1.0
+    off, nbr = orc.neighbour_sets(st.pos, st.box, r_list)
+    n = st.n
+    for i in (0, 17, n - 1):
+        d = st.pos - st.pos[i]
+        for k in range(3):
+            L = st.box[k]
+            d[:, k] = np.where(d[:, k] < -L / 2.0, d[:, k] + L, np.where(d[:, k] > L / 2.0, d[:, k] - L, d[:, k]))
+        r = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+        want = [j for j in range(n) if j != i and r[j] <= r_list]
+        assert list(nbr[off[i]:off[i + 1]]) == want
+
+
+def test_thermostat_pulls_temperature():  # thermostat.rs:31-34 (the reference's own test is #[ignore]d)
+    st = orc.argon_lattice(2, orc.GAS_CELL, 273.15, seed=7)
+    lj = orc.LennardJones()
+    orc.update_force(lj, st)
+    th = orc.Thermostat(orc.Thermostat.BERENDSEN, 0.5, 300.0)
+    orc.step(lj, st, 0.002, thermostat=th, n_steps=5000)
+    assert abs(orc.macro(st)["temperature"] - 300.0) < 0.5
+
+
+def test_barostat_scales_box():  # barostat.rs:21-49
+    st = orc.argon_lattice(2, orc.GAS_CELL, 273.15, seed=7)
+    lj = orc.LennardJones()
+    orc.update_force(lj, st)
+    ba = orc.Barostat(1.0, 0.1, 0.101325)
+    p0 = orc.macro(st)["pressure"]
+    box0 = st.box.copy()
+    orc.step(lj, st, 0.002, barostat=ba)
+    mu = np.cbrt(1.0 + 0.002 * 1.0 / 0.1 * (p0 - 0.101325))
+    assert ba.myu == mu
+    assert np.array_equal(st.box, box0 * mu)
