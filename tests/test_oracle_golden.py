@@ -196,5 +196,5 @@ def test_barostat_scales_box():  # barostat.rs:21-49
     box0 = st.box.copy()
     orc.step(lj, st, 0.002, barostat=ba)
     mu = np.cbrt(1.0 + 0.002 * 1.0 / 0.1 * (p0 - 0.101325))
-    assert ba.myu == mu
-    assert np.array_equal(st.box, box0 * mu)
+    assert abs(ba.myu / mu - 1.0) < 4e-16  # numpy's cbrt and glibc's may differ in the last bit
+    assert np.array_equal(st.box, box0 * ba.myu)
