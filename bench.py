@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — atom-steps/s of the moldyn `solve` step loop on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+
+A "step" is one Integrator::calculate (velocity-Verlet + LJ forces + Berendsen thermostat) over the whole
+system.  `value` = atoms × K / device time of K consecutive steps with the state resident in HBM (CUDA events on
+the library's stream, list rebuilds included).  `e2e` = the same metric through the reference-facing per-call
+C-ABI (md_calculate_host: State in host memory in, State out, every step).  `--impl reference` times the CPU
+restatement of the reference's own Θ(N²) algorithm on the host cores (the reference is Rust; no toolchain here).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARGON_MASS = 66.335
+K_B = 1.380648528
+GAS_CELL = 3.338339
+LIQUID_CELL = 0.36165
+DT = 0.002
+ALGO_BYTES_STEP = 160       # r+w of x, v, F (144 B) + write U, W (16 B) per atom-step
+ALGO_BYTES_FORCE = 112      # k_force(+kick2): read x, v; write v, F, U, W
+ALGO_BYTES_KICK_DRIFT = 120  # k_kick_drift: read x, v, F; write x, v
+ALGO_FLOP_PAIR = 42         # flop per directed in-range pair
+ALGO_FLOP_ATOM = 30
+
+WORKLOADS = {
+    # name: side, lattice cell, T_init, (tau, T0), (beta, tau, P0) or None, (r_cut, u_cut) or None
+    "c1": dict(desc="argon 10x10x10 (1000 atoms) NPT Berendsen", side=10, cell=GAS_CELL, t_init=273.15,
+               thermostat=(10.0, 300.0), barostat=(1.0, 5.0, 1.01325), cut=None),
+    "c2": dict(desc="argon 32x32x32 (32768 atoms) NVT Berendsen", side=32, cell=GAS_CELL, t_init=273.15,
+               thermostat=(10.0, 300.0), barostat=None, cut=None),
+    "c3": dict(desc="argon 100x100x100 (1M atoms) NVT Berendsen", side=100, cell=GAS_CELL, t_init=273.15,
+               thermostat=(10.0, 300.0), barostat=None, cut=None),
+    "c4": dict(desc="argon 216^3 (10.08M atoms) NPT Berendsen", side=216, cell=GAS_CELL, t_init=273.15,
+               thermostat=(10.0, 300.0), barostat=(1.0, 5.0, 1.01325), cut=None),
+    "c5": dict(desc="liquid argon 64^3 (262144 atoms) NVT, r_cut 3.5 sigma", side=64, cell=LIQUID_CELL, t_init=120.0,
+               thermostat=(10.0, 120.0), barostat=None, cut=(1.1963, -0.003723224030513348)),
+    "big": dict(desc="argon 200^3 (8M atoms) NVT Berendsen (state > L2)", side=200, cell=GAS_CELL, t_init=273.15,
+                thermostat=(10.0, 300.0), barostat=None, cut=None),
+}
+
+
+def make_state(w, seed=42):
+    """`moldyn-cli initialize -t u -s side side side -l cell -T t_init` with a seeded RNG (synthetic input):
+    index = x*s*s + y*s + z, velocities N(0, K_B*T/100/m) with the second half the negated first half."""
+    s = w["side"]
+    g = np.arange(s, dtype=np.float64) * w["cell"]
+    pos = np.empty((s, s, s, 3))
+    pos[..., 0] = g[:, None, None]
+    pos[..., 1] = g[None, :, None]
+    pos[..., 2] = g[None, None, :]
+    pos = pos.reshape(-1, 3)
+    n = pos.shape[0]
+    sigma_v = np.sqrt(K_B * (w["t_init"] * 0.01) / ARGON_MASS)
+    half = np.random.default_rng(seed).standard_normal((n // 2, 3)) * sigma_v
+    vel = np.concatenate([half, -half])
+    if w["cell"] < 1.0:  # liquid: melt the perfect lattice faster
+        pos = pos + np.random.default_rng(seed + 1).uniform(-0.03, 0.03, pos.shape)
+        pos %= (w["cell"] * s)
+    box = np.array([w["cell"] * s] * 3)
+    return pos, vel, box
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.period, self.index = period, index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(w, sample_rows, threads=None):
+    """The reference's Θ(N²) update_force (potential.rs:158-216) on the host cores, rows [0, sample_rows) of the
+    workload's own positions against ALL N partners → atoms/s of force evaluation ≈ atom-steps/s of the CPU
+    solver (the Θ(N) parts of the step are negligible at these N)."""
+    from oracle import oracle as orc
+    if threads:
+        orc.set_num_threads(threads)
+    pos, vel, box = make_state(w)
+    st = orc.State(pos, vel, ARGON_MASS, box)
+    lj = orc.LennardJones() if w["cut"] is None else orc.LennardJones(r_cut=w["cut"][0], u_cut=w["cut"][1])
+    rows = min(sample_rows, st.n)
+    orc.update_force(lj, st, rows=(0, min(64, rows)))  # warm the threads
+    t0 = time.perf_counter()
+    orc.update_force(lj, st, rows=(0, rows))
+    dt = time.perf_counter() - t0
+    return rows / dt, dt, rows, st.n, orc.num_threads()
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_rows or max(256, int(2.0e9 / (w["side"] ** 3)))  # ≈ 2e9 pair tests per step
+    # warm-up + K bounded steps
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_reference_rate(w, 64)
+    rates, times = [], []
+    for _ in range(max(1, min(args.steps, 5))):
+        r, dt, rows, n, thr = cpu_reference_rate(w, sample)
+        rates.append(r)
+        times.append(dt)
+    value = float(np.mean(rates))
+    out = {
+        "impl": "reference", "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": args.gpus,
+        "steps": len(rates), "warmup": 1, "ms_per_step": float(np.mean(times)) * 1e3 * (n / rows),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "atoms": n, "dt": DT},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": thr, "kind": "port",
+                         "sample": f"update_force rows [0,{rows}) of {n} per step, each against all {n} partners "
+                                   f"(reference's Θ(N²) scan, potential.rs:158-216); ms_per_step extrapolated to N rows"},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ns_per_day": value / n * 0.1728,
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args, w):
+    import torch
+
+    import moldyn_b200 as md
+    from moldyn_b200 import _ffi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if world > 1:
+        raise SystemExit("multi-GPU spatial decomposition is not wired into bench.py yet")
+    torch.cuda.set_device(local)
+    pos, vel, box = make_state(w)
+    n = pos.shape[0]
+    th = lambda: (md.Thermostat.Berendsen(w["thermostat"][0]), w["thermostat"][1])  # noqa: E731
+    ba = (lambda: (md.Barostat.Berendsen(w["barostat"][0], w["barostat"][1]), w["barostat"][2])) if w["barostat"] \
+        else (lambda: None)
+
+    s = md.Solver(device=local, skin=args.skin)
+    if w["cut"]:
+        s.set_potential(md.Potential(0.3418, 1.712, *w["cut"]))
+    s.upload_arrays(pos, vel, ARGON_MASS, box)
+    s.update_force()
+    stream = torch.cuda.ExternalStream(s.stream(), device=local)
+    t_th, t_ba = th(), ba()
+    s.step(args.warmup, DT, thermostat=t_th, barostat=t_ba)
+    st0 = s.stats()
+
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sampler.start()
+    e0.record(stream)
+    s.step(args.steps, DT, thermostat=t_th, barostat=t_ba)
+    e1.record(stream)
+    s.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    st1 = s.stats()
+    value = n * args.steps / (ms * 1e-3)
+    macro = s.macro()
+
+    # --- per-kernel device times (CUDA events on the launching stream, host-stepped) ---------------------
+    kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
+    hbm, peak_src = peaks()
+    f_ms = kt["force"][0] / max(kt["force"][1], 1)
+    k_ms = kt["kick_drift"][0] / max(kt["kick_drift"][1], 1)
+    dominant = "k_force" if f_ms >= k_ms else "k_kick_drift"
+    dom_ms, dom_bytes = (f_ms, ALGO_BYTES_FORCE) if dominant == "k_force" else (k_ms, ALGO_BYTES_KICK_DRIFT)
+    achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+        "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_atom": dom_bytes, "avg_launch_ms": dom_ms,
+        "kernels_ms": {"k_force": f_ms, "k_kick_drift": k_ms,
+                       "rebuild": kt["rebuild"][0] / max(kt["rebuild"][1], 1) if kt["rebuild"][1] else None},
+        "step": {"algorithmic_bytes_per_atom_step": ALGO_BYTES_STEP,
+                 "achieved": ALGO_BYTES_STEP * value / 1e9, "frac": ALGO_BYTES_STEP * value / 1e9 / hbm},
+    }
+    if w["cut"] is not None or w["cell"] < 1.0:
+        pairs = s.stats()["nbr_mean"]
+        roofline["note"] = (f"dense system: force kernel is FP64/L1 bound; mean listed partners {pairs:.1f}; "
+                            f"algorithmic flop/atom-step ≈ {ALGO_FLOP_PAIR}*<in-range> + {ALGO_FLOP_ATOM}")
+
+    # --- e2e: reference-facing per-call API, State in pinned host memory in and out every step ------------
+    e2e = None
+    if args.e2e_steps > 0:
+        L = _ffi.lib()
+        hp = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * n, 3 * n, 3 * n, n, n)]
+        hbox = np.array(box)
+        s.download_arrays(*(t.data_ptr() for t in hp))
+        tc = t_th[0]._c(t_th[1])
+        bc = t_ba[0]._c(t_ba[1]) if t_ba else None
+
+        def call():
+            rc = L.md_calculate_host(s._ctx, n, hp[0].data_ptr(), hp[1].data_ptr(), hp[2].data_ptr(),
+                                     hp[3].data_ptr(), hp[4].data_ptr(), ARGON_MASS,
+                                     hbox.ctypes.data_as(C.c_void_p), DT, C.byref(tc), C.byref(bc) if bc else None)
+            _ffi.check(s._ctx, rc)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            call()
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": n * args.e2e_steps / t_e2e, "unit": "atom-steps/s",
+               "h2d_bytes_per_step": 88 * n, "d2h_bytes_per_step": 88 * n + 24,
+               "ms_per_step": t_e2e / args.e2e_steps * 1e3, "steps": args.e2e_steps,
+               "api": "md_calculate_host (≡ Integrator::calculate on a host State: upload x,v,F,U,W → 1 step → "
+                      "download x,v,F,U,W), pinned host buffers"}
+
+    cpu = None
+    if args.cpu_rows >= 0 and rank == 0:
+        rows = args.cpu_rows or max(256, int(6.0e9 / n))
+        r, dt_cpu, rows, _, thr = cpu_reference_rate(w, rows)
+        cpu = {"value": r, "unit": "atom-steps/s", "cores": thr, "kind": "port",
+               "sample": f"oracle update_force rows [0,{rows}) of {n}, each against all {n} partners "
+                         f"({dt_cpu:.1f} s; reference's Θ(N²) scan, potential.rs:158-216)"}
+
+    out = {
+        "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "atoms": n, "dt": DT, "thermostat": w["thermostat"],
+                   "barostat": w["barostat"], "r_cut": w["cut"][0] if w["cut"] else 0.8545,
+                   "skin": st1["skin"], "cells": st1["cells"],
+                   "l2": "one timed region of K consecutive, dependent MD steps of one trajectory (no input is "
+                         "re-run, so there is no L2 flush between steps); per-step state "
+                         f"{(88 * n + 4 * n) / 1e6:.0f} MB vs 126 MB L2 — see roofline for the HBM view"},
+        "ns_per_day": args.steps / (ms * 1e-3) * 0.1728,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
+        "rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
+        "graph_launches_in_timed_region": st1["graph_launches"] - st0["graph_launches"],
+        "state_check": {"temperature": macro["temperature"], "pressure": macro["pressure"],
+                        "momentum_abs_max": float(np.abs(macro["momentum"]).max())},
+    }
+    if rank == 0:
+        print(json.dumps(out))
+    s.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--skin", type=float, default=0.0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args, w)
+        return
+    n = w["side"] ** 3
+    if args.steps is None:
+        args.steps = 20000 if n <= 2_000_000 else 2000
+    if args.warmup is None:
+        args.warmup = 500 if n <= 2_000_000 else 100
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

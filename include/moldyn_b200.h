@@ -1,0 +1,183 @@
+/*
+ * moldyn_b200.h — C ABI of the B200-native replacement for moldyn's `solve` step loop.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every
+ * entry point names the reference interface it replaces (paths relative to the
+ * AndrewChe7/moldyn repository).  A Rust shim keeps the reference's
+ * enum/method signatures and forwards to these functions.
+ *
+ * Model: a context owns a device-resident copy of ONE particle type's State
+ * (core/src/particle.rs:6-32) in f64.  The reference's per-call semantics
+ * (`update_force(&db, &mut state)`, `Integrator::calculate(..)`) are available both as
+ * a device-resident session (upload once, step many times, download at frame
+ * boundaries) and as one-shot host-buffer calls (md_update_force_host, md_calculate_host).
+ *
+ * Conventions: every function returns an md_status (0 = ok) and never unwinds; the
+ * message of the last failure is md_last_error(ctx) (md_last_error(NULL) for
+ * md_create failures).  Host arrays are borrowed only for the duration of the call.
+ * Vectors are xyz-interleaved (pos[3*i+d]), like Vec<Vector3<f64>>.  A context is
+ * single-owner and not thread-safe (the reference solver is called from one thread).
+ * There is no CPU fallback: without a CUDA device md_create fails with MD_ERR_CUDA.
+ */
+#ifndef MOLDYN_B200_H
+#define MOLDYN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MD_API __attribute__((visibility("default")))
+
+typedef enum md_status {
+    MD_OK = 0,
+    MD_ERR_INVALID_ARGUMENT = 1,
+    MD_ERR_CUDA = 2,
+    MD_ERR_NCCL = 3,
+    MD_ERR_UNSUPPORTED = 4,        /* Custom variants (todo!() in the reference), multi-type states */
+    MD_ERR_NEIGHBOUR_OVERFLOW = 5, /* neighbour list could not be grown */
+    MD_ERR_NO_STATE = 6,           /* step/download before md_upload_state */
+    MD_ERR_NONFINITE = 7,          /* NaN/inf reached the step controls (e.g. Berendsen lambda at T = 0) */
+    MD_ERR_DECOMPOSITION = 8       /* box too small for the requested number of ranks */
+} md_status;
+
+/* force_mode */
+#define MD_FORCE_FAST 0  /* r^2-based LJ, FMA allowed, neighbour order = cell order (default) */
+#define MD_FORCE_EXACT 1 /* the reference's operation order (potential.rs:181-211) without FMA and with
+                            partners summed in ascending particle index: bit-identical to update_force */
+/* loop_mode */
+#define MD_LOOP_GRAPH 0 /* steady-state steps run inside one conditional (WHILE) CUDA graph (default) */
+#define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check) */
+
+typedef struct md_config {
+    int32_t device;         /* CUDA device ordinal */
+    int32_t force_mode;     /* MD_FORCE_* */
+    int32_t loop_mode;      /* MD_LOOP_* */
+    int32_t max_neighbours; /* initial neighbour-list capacity per atom; 0 = from density (grown on demand) */
+    int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = 1 */
+    int32_t reserved0;
+    double skin;            /* Verlet skin [nm]; <= 0 selects a default from r_cut and density */
+    double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 3 */
+} md_config;
+
+/* Thermostat (solver/src/initializer/thermostat.rs:4-22).  lambda/psi are written back after
+ * md_step, like the reference stores them in the enum (thermostat.rs:33,37-38). */
+#define MD_THERMOSTAT_NONE 0
+#define MD_THERMOSTAT_BERENDSEN 1
+#define MD_THERMOSTAT_NOSE_HOOVER 2 /* declared for surface parity; md_step returns MD_ERR_UNSUPPORTED */
+typedef struct md_thermostat {
+    int32_t kind;
+    int32_t reserved0;
+    double tau;
+    double target; /* target temperature [K] — the f64 paired with the thermostat in Integrator::calculate */
+    double lambda; /* out */
+    double psi;    /* in/out (Nose-Hoover) */
+} md_thermostat;
+
+/* Barostat (solver/src/initializer/barostat.rs:4-19). */
+#define MD_BAROSTAT_NONE 0
+#define MD_BAROSTAT_BERENDSEN 1
+typedef struct md_barostat {
+    int32_t kind;
+    int32_t reserved0;
+    double beta;
+    double tau;
+    double target; /* target pressure — the f64 paired with the barostat in Integrator::calculate */
+    double myu;    /* out */
+} md_barostat;
+
+/* macro_parameters::* of the resident state (solver/src/macro_parameters/{mod,energy,temperature,pressure}.rs) */
+typedef struct md_macro_out {
+    double kinetic_energy;   /* get_kinetic_energy   energy.rs:14-22 */
+    double thermal_energy;   /* get_thermal_energy   energy.rs:25-37 */
+    double potential_energy; /* get_potential_energy energy.rs:40-49 */
+    double temperature;      /* get_temperature [K]  temperature.rs:4-7 */
+    double pressure;         /* get_pressure         pressure.rs:5-20 (virial of the last force evaluation) */
+    double vcom[3];          /* get_center_of_mass_velocity mod.rs:12-25 */
+    double momentum[3];      /* get_momentum_of_system      mod.rs:28-34 */
+    double box[3];           /* State::boundary_box */
+    double lambda;           /* last Berendsen lambda (1 if none) */
+    double myu;              /* last Berendsen myu (1 if none) */
+    int64_t n;
+} md_macro_out;
+
+typedef struct md_stats {
+    int64_t steps;            /* MD steps executed since md_create */
+    int64_t rebuilds;         /* neighbour-list rebuilds */
+    int64_t kernel_launches;  /* kernels of this library launched (graph body launches included) */
+    int64_t graph_launches;   /* conditional-graph launches */
+    int32_t cells[3];         /* current cell grid */
+    int32_t nbr_capacity;     /* neighbour slots per atom */
+    int32_t nbr_max;          /* largest neighbour count seen at the last rebuild */
+    int32_t reserved0;
+    double skin;              /* skin in use */
+    double nbr_mean;          /* mean neighbour count at the last rebuild */
+} md_stats;
+
+typedef struct md_ctx md_ctx;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+MD_API int md_create(const md_config *cfg, md_ctx **out);
+MD_API void md_destroy(md_ctx *ctx);
+MD_API const char *md_last_error(const md_ctx *ctx);
+MD_API const char *md_version(void);
+
+/* ---- Potential (solver/src/solver/potential.rs:12-87) ------------------------------------- */
+/* Potential::new_lennard_jones (potential.rs:27-55): r_cut = 2.5 sigma, u_cut = U(r_cut). Host arithmetic. */
+MD_API int md_lj_new(double sigma, double eps, double *r_cut, double *u_cut);
+/* Potential::get_potential_and_force (potential.rs:57-70). Host arithmetic, scalar. */
+MD_API int md_lj_potential_and_force(double sigma, double eps, double r_cut, double u_cut, double r,
+                                     double *potential, double *force);
+/* PotentialsDatabase::set_potential(0,0,LennardJones{..}) (potential.rs:141-144) for the resident type.
+ * Default after md_create: PotentialsDatabase::new() → argon sigma=0.3418 eps=1.712 (potential.rs:95-101). */
+MD_API int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, double u_cut);
+
+/* ---- State transfer (core/src/particle.rs:6-32, core/src/save_data.rs:129-151) ------------ */
+/* pos, vel: 3n doubles.  force (3n), potential (n), virial (n = Particle.temp) may be NULL → zero, as after
+ * StateToSave → State (save_data.rs:86-98).  mass: ParticleDatabase mass of the type. box: boundary_box. */
+MD_API int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
+                           const double *potential, const double *virial, double mass, const double box[3]);
+/* Any output pointer may be NULL. Particles come back in the order they were uploaded. */
+MD_API int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, double *potential,
+                             double *virial, double box[3]);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/* update_force(&potentials_db, &mut state) (potential.rs:158-216) on the resident state. */
+MD_API int md_update_force(md_ctx *ctx);
+/* n_steps × Integrator::VerletMethod.calculate(&db, &mut state, dt, &mut barostat, &mut thermostat)
+ * (solver/src/solver/integrator.rs:14-59).  thermostat / barostat may be NULL (= None). */
+MD_API int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *thermostat, md_barostat *barostat);
+/* macro parameters of the resident state. */
+MD_API int md_macro(md_ctx *ctx, md_macro_out *out);
+
+/* One-shot host-buffer forms with the reference's per-call semantics (all arrays in/out, caller-owned):
+ * md_update_force_host ≡ update_force; md_calculate_host ≡ Integrator::calculate (one step). */
+MD_API int md_update_force_host(md_ctx *ctx, int64_t n, const double *pos, double mass, const double box[3],
+                                double *force, double *potential, double *virial);
+MD_API int md_calculate_host(md_ctx *ctx, int64_t n, double *pos, double *vel, double *force, double *potential,
+                             double *virial, double mass, double box[3], double dt, md_thermostat *thermostat,
+                             md_barostat *barostat);
+
+/* ---- introspection used by the parity tests and the bench ---------------------------------- */
+/* Cell index of every atom (upload order) at the last list build + grid dims.  cell = (cx*ny + cy)*nz + cz with
+ * c_d = min(nc_d-1, (int)(frac(x_d / L_d) * nc_d)). */
+MD_API int md_download_cells(md_ctx *ctx, int32_t *cell_of_atom, int32_t dims[3]);
+/* Verlet list of the last build in upload indices: counts[i], then partners (ascending) at offsets[i]. */
+MD_API int md_neighbour_counts(md_ctx *ctx, int64_t *counts);
+MD_API int md_neighbour_lists(md_ctx *ctx, const int64_t *offsets, int64_t *partners);
+MD_API int md_get_stats(md_ctx *ctx, md_stats *out);
+/* cudaStream_t the context launches on (for CUDA-event timing by the caller). */
+MD_API void *md_stream(md_ctx *ctx);
+MD_API int md_synchronize(md_ctx *ctx);
+/* md_step with one CUDA-event pair around every kernel (host-stepped): summed device milliseconds and launch
+ * counts of {k_kick_drift, k_force, list rebuild}.  Measurement aid for the roofline figures. */
+MD_API int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *thermostat,
+                           md_barostat *barostat, double ms[3], int64_t launches[3]);
+/* Forces a list rebuild before the next force evaluation (rebuild-stress tests). */
+MD_API int md_invalidate_lists(md_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLDYN_B200_H */

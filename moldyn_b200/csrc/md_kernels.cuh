@@ -1,0 +1,698 @@
+// md_kernels.cuh — sm_100a kernels of the moldyn `solve` step loop (f64 throughout).
+//
+//   K1  k_cell_count / k_scan_* / k_scatter / k_sort_cells / k_reorder   cell binning + counting sort
+//   K2  k_build_list                                                     Verlet-skin neighbour list
+//   K3  k_force  (+ fused second half-kick and K5 partial sums)          potential.rs:158-216, integrator.rs:47-53
+//   K4  k_kick_drift                                                     integrator.rs:28-45, barostat.rs:45-48
+//   K5  block→warp deterministic reductions + finalize                   macro_parameters/*.rs, thermostat.rs, barostat.rs
+//
+// No tensor cores: the pair force is an irregular gather, not a dense contraction.  The streaming kernels are
+// HBM-bound (coalesced SoA planes, 128-bit accesses), the force kernel is FP64-pipe / L1-gather bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace md {
+
+constexpr double K_B = 1.380648528;  // core/src/lib.rs:15
+
+// Structure-of-arrays planes of the resident State (core/src/particle.rs:6-23), in cell-sorted order.
+struct Arrays {
+    double *x, *y, *z;     // Particle.position
+    double *vx, *vy, *vz;  // Particle.velocity
+    double *fx, *fy, *fz;  // Particle.force
+    double *u;             // Particle.potential
+    double *w;             // Particle.temp (Σ F_ij·r_ij)
+    int *id;               // index of the particle in upload order
+};
+
+// Written by the host once per md_step / md_update_force call.
+struct Params {
+    double dt;         // delta_time
+    double half_dt_m;  // delta_time / (2.0 * mass)        integrator.rs:30
+    double mass;
+    double sigma, eps, r_cut, u_cut;  // Potential::LennardJones  potential.rs:13-18
+    double r_list;                    // r_cut + skin
+    double th_tau, th_target;         // Thermostat::Berendsen{tau} + target temperature
+    double ba_beta, ba_tau, ba_target;
+    long long n;
+    int th_kind, ba_kind;
+};
+
+// Device-resident step state: box, thermostat/barostat coefficients, reduction results, loop control.
+struct Scalars {
+    double box[3];      // State::boundary_box
+    double mu_pending;  // barostat.update's `position *= myu` not yet applied to x (1.0 = none)
+    double lambda;      // Berendsen lambda for the step about to run (1.0 without thermostat)
+    double mu;          // Berendsen myu for the step about to run (1.0 without barostat)
+    double inv_scale;   // Π 1/myu since the last list build
+    double disp_acc;    // upper bound of any atom's displacement since the list build (build-time units)
+    double disp_next;   // upper bound of the next drift's displacement
+    double shift[3];    // predicted COM velocity: shift of the one-pass thermal sum
+    // last reduction
+    double sum_mv[3], sum_th, sum_ke, sum_w, sum_u, max_w2;
+    double vcom[3], thermal, kinetic, potential, temperature, pressure;
+    double lambda_last, mu_last;  // coefficients used by the last executed step
+    long long steps_left, steps_done;
+    int need_rebuild;
+    int error;
+    unsigned int ticket;
+    int nbr_max;       // largest neighbour count of the last build
+    int nbr_overflow;  // some atom exceeded the capacity
+    int pad0;
+    unsigned long long nbr_total;
+};
+
+struct Grid {
+    int nc[3];
+    int nsub;   // stencil half-width in cells
+    int ncell;
+    int cap;    // neighbour slots per atom
+    int npad;   // row stride of the neighbour table
+};
+
+constexpr int NSUM = 8;  // Σ m vx, Σ m vy, Σ m vz, Σ m|v-c|², Σ m v·v, Σ W, Σ U, max |v + F c|²
+
+// ----------------------------------------------------------------------------------------------------
+// Pair geometry shared by list build and force kernels: r = p_j - p_i with the reference's single-shift
+// minimum image (potential.rs:181-200).  The comparisons are exact; only add/sub touch the FP64 pipe.
+__device__ __forceinline__ double min_image(double r, double L, double h)
+{
+    if (r < -h) r = __dadd_rn(r, L);
+    else if (r > h) r = __dsub_rn(r, L);
+    return r;
+}
+
+// nalgebra Vector3::norm(): sqrt((x*x + y*y) + z*z), no contraction.
+__device__ __forceinline__ double norm_exact(double rx, double ry, double rz)
+{
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)));
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K1: cell index.  c_d = min(nc_d - 1, (int)(frac(x_d / L_d) * nc_d)); positions outside the box are
+// binned by their periodic image (the force arithmetic itself never wraps them — the reference does not).
+__device__ __forceinline__ int cell_coord(double x, double L, int nc)
+{
+    double s = __ddiv_rn(x, L);
+    s = __dsub_rn(s, floor(s));
+    int c = (int)__dmul_rn(s, (double)nc);
+    return min(max(c, 0), nc - 1);
+}
+
+__global__ void k_cell_count(int n, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const Scalars *__restrict__ sc, Grid g,
+                             int *__restrict__ cell_of, int *__restrict__ cell_cnt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cx = cell_coord(x[i], sc->box[0], g.nc[0]);
+    int cy = cell_coord(y[i], sc->box[1], g.nc[1]);
+    int cz = cell_coord(z[i], sc->box[2], g.nc[2]);
+    int c = (cx * g.nc[1] + cy) * g.nc[2] + cz;
+    cell_of[i] = c;
+    atomicAdd(&cell_cnt[c], 1);
+}
+
+// Exclusive scan of cell counts: per-block scan (1024 items) → scan of block totals → add back.
+constexpr int SCAN_BLOCK = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total)
+{
+    __shared__ int warp_sums[32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int ws = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += t;
+        }
+        warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    int base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[31];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_block(int n, const int *__restrict__ in,
+                                                           int *__restrict__ out, int *__restrict__ block_sums)
+{
+    int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    int v = (i < n) ? in[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total);
+    if (i < n) out[i] = ex;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_sums(int nblocks, int *__restrict__ block_sums)
+{
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += SCAN_BLOCK) {
+        int i = base + threadIdx.x;
+        int v = (i < nblocks) ? block_sums[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        int carry = carry_s;
+        if (i < nblocks) block_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int n, int *__restrict__ out,
+                                                         const int *__restrict__ block_sums, int total_items)
+{
+    int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_sums[blockIdx.x];
+    if (i == 0) out[n] = total_items;
+}
+
+__global__ void k_scatter(int n, const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                          int *__restrict__ cell_fill, int *__restrict__ order)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of[i];
+    int slot = cell_start[c] + atomicAdd(&cell_fill[c], 1);
+    order[slot] = i;
+}
+
+// Makes the order inside every cell independent of atomic arrival order: ascending upload index.
+// The sorted order of the whole system is then the lexicographic (cell, upload index) order — deterministic.
+__global__ void k_sort_cells(int ncell, const int *__restrict__ cell_start, const int *__restrict__ id_old,
+                             int *__restrict__ order)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    int s = cell_start[c], e = cell_start[c + 1];
+    for (int a = s + 1; a < e; ++a) {
+        int item = order[a];
+        int key = id_old[item];
+        int b = a - 1;
+        while (b >= s && id_old[order[b]] > key) {
+            order[b + 1] = order[b];
+            --b;
+        }
+        order[b + 1] = item;
+    }
+}
+
+__global__ void k_reorder(int n, const int *__restrict__ order, const int *__restrict__ cell_of, Arrays src,
+                          Arrays dst, int *__restrict__ cell_sorted)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int s = order[p];
+    dst.x[p] = src.x[s];   dst.y[p] = src.y[s];   dst.z[p] = src.z[s];
+    dst.vx[p] = src.vx[s]; dst.vy[p] = src.vy[s]; dst.vz[p] = src.vz[s];
+    dst.fx[p] = src.fx[s]; dst.fy[p] = src.fy[s]; dst.fz[p] = src.fz[s];
+    dst.u[p] = src.u[s];   dst.w[p] = src.w[s];
+    dst.id[p] = src.id[s];
+    cell_sorted[p] = cell_of[s];
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K2: Verlet list.  One thread per atom walks the (deduplicated) cell stencil and keeps partners whose
+// reference min-image distance is <= r_list — the predicate of potential.rs:181-204 widened by the skin,
+// evaluated in the reference's exact arithmetic so the pair set is the reference's, bit for bit.
+// Table layout nbr[k * npad + p]: a warp reads one coalesced row per k.
+template <bool SORT_BY_ID>
+__global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *__restrict__ cell_sorted,
+                                                    const int *__restrict__ cell_start, Scalars *sc, Grid g,
+                                                    double r_list, int *__restrict__ nbr,
+                                                    int *__restrict__ nbr_cnt)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (p < n) {
+        const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+        const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
+        const double xi = a.x[p], yi = a.y[p], zi = a.z[p];
+        int c = cell_sorted[p];
+        int cz = c % g.nc[2];
+        int cy = (c / g.nc[2]) % g.nc[1];
+        int cx = c / (g.nc[2] * g.nc[1]);
+        int w = 2 * g.nsub + 1;
+        int lox, loy, loz, nx, ny, nz;
+        if (g.nc[0] >= w) { lox = cx - g.nsub; nx = w; } else { lox = 0; nx = g.nc[0]; }
+        if (g.nc[1] >= w) { loy = cy - g.nsub; ny = w; } else { loy = 0; ny = g.nc[1]; }
+        if (g.nc[2] >= w) { loz = cz - g.nsub; nz = w; } else { loz = 0; nz = g.nc[2]; }
+        for (int ia = 0; ia < nx; ++ia) {
+            int qx = lox + ia;
+            qx += (qx < 0) ? g.nc[0] : 0;
+            qx -= (qx >= g.nc[0]) ? g.nc[0] : 0;
+            for (int ib = 0; ib < ny; ++ib) {
+                int qy = loy + ib;
+                qy += (qy < 0) ? g.nc[1] : 0;
+                qy -= (qy >= g.nc[1]) ? g.nc[1] : 0;
+                for (int ic = 0; ic < nz; ++ic) {
+                    int qz = loz + ic;
+                    qz += (qz < 0) ? g.nc[2] : 0;
+                    qz -= (qz >= g.nc[2]) ? g.nc[2] : 0;
+                    int cell = (qx * g.nc[1] + qy) * g.nc[2] + qz;
+                    int s = cell_start[cell], e = cell_start[cell + 1];
+                    for (int q = s; q < e; ++q) {
+                        if (q == p) continue;
+                        double rx = min_image(__dsub_rn(a.x[q], xi), Lx, hx);
+                        double ry = min_image(__dsub_rn(a.y[q], yi), Ly, hy);
+                        double rz = min_image(__dsub_rn(a.z[q], zi), Lz, hz);
+                        double r = norm_exact(rx, ry, rz);
+                        if (r > r_list) continue;
+                        if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        nbr_cnt[p] = min(cnt, g.cap);
+        if (SORT_BY_ID && cnt <= g.cap) {
+            // ascending upload index == the reference's ascending j (potential.rs:177)
+            for (int s1 = 1; s1 < cnt; ++s1) {
+                int item = nbr[(size_t)s1 * g.npad + p];
+                int key = a.id[item];
+                int b = s1 - 1;
+                while (b >= 0 && a.id[nbr[(size_t)b * g.npad + p]] > key) {
+                    nbr[(size_t)(b + 1) * g.npad + p] = nbr[(size_t)b * g.npad + p];
+                    --b;
+                }
+                nbr[(size_t)(b + 1) * g.npad + p] = item;
+            }
+        }
+    }
+    // statistics: max / total / overflow (integer atomics — order-independent results)
+    int wmax = cnt;
+    unsigned int wsum = (unsigned int)cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && wsum) {
+        atomicMax(&sc->nbr_max, wmax);
+        atomicAdd(&sc->nbr_total, (unsigned long long)wsum);
+        if (wmax > g.cap) atomicExch(&sc->nbr_overflow, 1);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K5: deterministic reductions.  Lane tree (xor shuffles) → fixed-order sum over warps → one slot per block;
+// the last block to finish (atomic ticket) folds the per-block slots in a fixed order and finalizes.
+struct Sums {
+    double v[NSUM];
+};
+
+__device__ __forceinline__ void warp_reduce(Sums &s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < NSUM - 1; ++q) s.v[q] += __shfl_xor_sync(0xffffffffu, s.v[q], o);
+        s.v[NSUM - 1] = fmax(s.v[NSUM - 1], __shfl_xor_sync(0xffffffffu, s.v[NSUM - 1], o));
+    }
+}
+
+// All threads of the block must call. Result valid in thread 0.
+template <int BLOCK>
+__device__ __forceinline__ void block_reduce(Sums &s)
+{
+    __shared__ double sm[BLOCK / 32][NSUM];
+    warp_reduce(s);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; ++q) sm[wid][q] = s.v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < BLOCK / 32; ++w) {
+#pragma unroll
+            for (int q = 0; q < NSUM - 1; ++q) s.v[q] += sm[w][q];
+            s.v[NSUM - 1] = fmax(s.v[NSUM - 1], sm[w][NSUM - 1]);
+        }
+    }
+    __syncthreads();
+}
+
+// Step controls for the NEXT step from the current macro state (thermostat.rs:24-34, barostat.rs:21-31)
+// plus the displacement bookkeeping that triggers list rebuilds.
+__device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr)
+{
+    double lambda = 1.0, mu = 1.0;
+    if (pr->th_kind == 1) {
+        double lambda_squared = 1.0 + pr->dt / pr->th_tau * (pr->th_target / sc->temperature - 1.0);
+        lambda = sqrt(lambda_squared);
+    }
+    if (pr->ba_kind == 1) {
+        double myu_cubed = 1.0 + pr->dt * pr->ba_beta / pr->ba_tau * (sc->pressure - pr->ba_target);
+        mu = cbrt(myu_cubed);
+    }
+    sc->lambda = lambda;
+    sc->mu = mu;
+    // ΣF = 0, so the COM velocity after the next step's kicks is lambda * vcom: used as the shift that keeps
+    // the one-pass thermal sum Σ m|v-c|² free of cancellation.
+    sc->shift[0] = sc->vcom[0] * lambda;
+    sc->shift[1] = sc->vcom[1] * lambda;
+    sc->shift[2] = sc->vcom[2] * lambda;
+    // Next drift moves every atom by at most lambda*sqrt(max|v + F c|²)*dt; in build-time units that is
+    // multiplied by inv_scale (positions and box have been scaled by Π myu since the build).
+    double vmax = lambda * sqrt(sc->max_w2);
+    sc->disp_next = vmax * pr->dt * sc->inv_scale;
+    // Pair now within r_cut ⇒ at build time within r_cut*inv_scale + 2*disp ≤ r_list must hold.
+    double thr = 0.5 * (pr->r_list - pr->r_cut * sc->inv_scale) * (1.0 - 1e-9);
+    double d = sc->disp_acc + sc->disp_next;
+    sc->need_rebuild = (d > thr) ? 1 : 0;
+    if (!(d == d) || !(lambda == lambda) || !(mu == mu) || isinf(d) || isinf(lambda) || isinf(mu)) sc->error = 7;
+}
+
+// mode bits of finalize
+constexpr int FIN_STEP = 1;  // called at the end of an MD step: commit drift, apply barostat box scaling, count
+
+__device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Sums &t, int mode)
+{
+    const double n = (double)pr->n;
+    const double M = n * pr->mass;
+    for (int d = 0; d < 3; ++d) sc->sum_mv[d] = t.v[d];
+    sc->sum_th = t.v[3]; sc->sum_ke = t.v[4]; sc->sum_w = t.v[5]; sc->sum_u = t.v[6]; sc->max_w2 = t.v[7];
+    double vc[3], dd = 0.0;
+    for (int d = 0; d < 3; ++d) {
+        vc[d] = t.v[d] / M;  // get_center_of_mass_velocity  mod.rs:12-25
+        sc->vcom[d] = vc[d];
+        double e = vc[d] - sc->shift[d];
+        dd += e * e;
+    }
+    double th2 = t.v[3] - M * dd;       // Σ m |v - vcom|²
+    sc->thermal = th2 / 2.0;            // get_thermal_energy   energy.rs:25-37
+    sc->kinetic = t.v[4] / 2.0;         // get_kinetic_energy   energy.rs:14-22
+    sc->potential = t.v[6] / 2.0;       // get_potential_energy energy.rs:40-49
+    if (mode & FIN_STEP) {
+        sc->disp_acc += sc->disp_next;  // the drift that preceded this force evaluation
+        sc->lambda_last = sc->lambda;
+        sc->mu_last = sc->mu;
+        if (pr->ba_kind == 1) {         // barostat.update: boundary_box *= myu  (barostat.rs:45); x *= myu is deferred
+            double mu = sc->mu;
+            sc->box[0] *= mu; sc->box[1] *= mu; sc->box[2] *= mu;
+            sc->mu_pending = mu;
+            sc->inv_scale /= mu;
+        }
+    }
+    sc->temperature = (2.0 * sc->thermal) / (3.0 * n * K_B) * 100.0;  // temperature.rs:4-7
+    double volume = sc->box[0] * sc->box[1] * sc->box[2];
+    sc->pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;            // pressure.rs:5-20
+    compute_controls(sc, pr);
+    if (mode & FIN_STEP) {
+        sc->steps_left -= 1;
+        sc->steps_done += 1;
+    }
+}
+
+// Last-block epilogue shared by k_force and k_reduce_state.  `mine` is this block's reduced sums (thread 0).
+template <int BLOCK>
+__device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restrict__ partials, Scalars *sc,
+                                                     const Params *pr, int mode,
+                                                     unsigned long long cond_handle)
+{
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; ++q) __stcg(&partials[(size_t)blockIdx.x * NSUM + q], mine.v[q]);
+        __threadfence();
+        unsigned int t = atomicAdd(&sc->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Sums acc;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) acc.v[q] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {  // fixed assignment → fixed order
+#pragma unroll
+        for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += __ldcg(&partials[(size_t)b * NSUM + q]);
+        acc.v[NSUM - 1] = fmax(acc.v[NSUM - 1], __ldcg(&partials[(size_t)b * NSUM + NSUM - 1]));
+    }
+    block_reduce<BLOCK>(acc);
+    if (threadIdx.x == 0) {
+        finalize(sc, pr, acc, mode);
+        sc->ticket = 0;
+        if (cond_handle) {
+            unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
+            cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, go);
+        }
+    }
+}
+
+__device__ __forceinline__ void accumulate_sums(Sums &s, double m, double vx, double vy, double vz, double fx,
+                                                double fy, double fz, double w, double u, double c,
+                                                const double *shift)
+{
+    s.v[0] = m * vx; s.v[1] = m * vy; s.v[2] = m * vz;
+    double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
+    s.v[3] = m * (ax * ax + ay * ay + az * az);
+    s.v[4] = m * (vx * vx + vy * vy + vz * vz);
+    s.v[5] = w;
+    s.v[6] = u;
+    // velocity the next kick_drift will move this atom with (before lambda): v + F*c, same arithmetic
+    double wx = __dadd_rn(vx, __dmul_rn(fx, c)), wy = __dadd_rn(vy, __dmul_rn(fy, c)),
+           wz = __dadd_rn(vz, __dmul_rn(fz, c));
+    s.v[7] = wx * wx + wy * wy + wz * wz;
+}
+
+// Standalone K5 over the stored state (after upload, or when only the macro parameters are wanted).
+constexpr int RED_BLOCK = 256;
+__global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, double *__restrict__ partials,
+                                                            Scalars *sc, const Params *__restrict__ pr)
+{
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
+    int i = blockIdx.x * RED_BLOCK + threadIdx.x;
+    if (i < n) {
+        double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+        accumulate_sums(s, pr->mass, a.vx[i], a.vy[i], a.vz[i], a.fx[i], a.fy[i], a.fz[i], a.w[i], a.u[i],
+                        pr->half_dt_m, shift);
+    }
+    block_reduce<RED_BLOCK>(s);
+    grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, 0, 0ull);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K3: pair forces from the Verlet list, one thread per atom (each ordered pair evaluated from both sides,
+// like the reference — no Newton-3 sharing, no atomics, deterministic).
+//   EXACT: potential.rs:181-211 operation by operation, no FMA, partners in ascending upload index.
+//   FAST : r²-based Lennard-Jones (one division, no sqrt), FMA allowed.
+// KICK fuses the second half-kick v += F*dt/(2m) (integrator.rs:47-53) and the K5 sums of the new state.
+constexpr int FORCE_BLOCK = 128;
+
+template <bool EXACT, bool KICK>
+__global__ void __launch_bounds__(FORCE_BLOCK) k_force(int n, Arrays a, const int *__restrict__ nbr,
+                                                       const int *__restrict__ nbr_cnt, int npad,
+                                                       double *__restrict__ partials, Scalars *sc,
+                                                       const Params *__restrict__ pr,
+                                                       unsigned long long cond_handle)
+{
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
+    int i = blockIdx.x * FORCE_BLOCK + threadIdx.x;
+    if (i < n) {
+        const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+        const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
+        const double sigma = pr->sigma, eps = pr->eps, r_cut = pr->r_cut, u_cut = pr->u_cut;
+        const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+        double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0, w = 0.0;
+        const int cnt = nbr_cnt[i];
+        if (EXACT) {
+            const double eps4 = __dmul_rn(4.0, eps), eps24 = __dmul_rn(24.0, eps);
+            for (int k = 0; k < cnt; ++k) {
+                int j = nbr[(size_t)k * npad + i];
+                double rx = min_image(__dsub_rn(a.x[j], xi), Lx, hx);
+                double ry = min_image(__dsub_rn(a.y[j], yi), Ly, hy);
+                double rz = min_image(__dsub_rn(a.z[j], zi), Lz, hz);
+                double r = norm_exact(rx, ry, rz);
+                if (r > r_cut) continue;                       // potential.rs:202 (inclusive cutoff)
+                double sr = __ddiv_rn(sigma, r);                // potential.rs:63
+                double x2 = __dmul_rn(sr, sr), x4 = __dmul_rn(x2, x2);
+                double s6 = __dmul_rn(x2, x4);                  // powi(6) = x² · x⁴
+                double s12 = __dmul_rn(s6, s6);
+                double pu = __dsub_rn(__dmul_rn(eps4, __dsub_rn(s12, s6)), u_cut);
+                double pf = __dmul_rn(__ddiv_rn(eps24, r), __dsub_rn(s6, __dmul_rn(2.0, s12)));
+                double vx = __dmul_rn(__ddiv_rn(rx, r), pf);    // r / r_abs * force   potential.rs:207
+                double vy = __dmul_rn(__ddiv_rn(ry, r), pf);
+                double vz = __dmul_rn(__ddiv_rn(rz, r), pf);
+                double t = __dadd_rn(__dadd_rn(__dmul_rn(vx, rx), __dmul_rn(vy, ry)), __dmul_rn(vz, rz));
+                fx = __dadd_rn(fx, vx); fy = __dadd_rn(fy, vy); fz = __dadd_rn(fz, vz);
+                u = __dadd_rn(u, pu);
+                w = __dadd_rn(w, t);
+            }
+        } else {
+            const double rc2 = r_cut * r_cut, sigma2 = sigma * sigma, eps4 = 4.0 * eps, eps24 = 24.0 * eps;
+            for (int k = 0; k < cnt; ++k) {
+                int j = nbr[(size_t)k * npad + i];
+                double rx = min_image(a.x[j] - xi, Lx, hx);
+                double ry = min_image(a.y[j] - yi, Ly, hy);
+                double rz = min_image(a.z[j] - zi, Lz, hz);
+                double r2 = rx * rx + ry * ry + rz * rz;
+                if (r2 > rc2) continue;
+                double inv = 1.0 / r2;
+                double s2 = sigma2 * inv;
+                double s6 = s2 * s2 * s2;
+                double s12 = s6 * s6;
+                double fr = eps24 * inv * (s6 - 2.0 * s12);  // F / r
+                u += eps4 * (s12 - s6) - u_cut;
+                fx += fr * rx; fy += fr * ry; fz += fr * rz;
+                w += fr * r2;
+            }
+        }
+        a.fx[i] = fx; a.fy[i] = fy; a.fz[i] = fz;
+        a.u[i] = u; a.w[i] = w;
+        double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
+        const double c = pr->half_dt_m;
+        if (KICK) {  // particle.velocity += particle.force * temp   integrator.rs:49-52
+            vx = __dadd_rn(vx, __dmul_rn(fx, c));
+            vy = __dadd_rn(vy, __dmul_rn(fy, c));
+            vz = __dadd_rn(vz, __dmul_rn(fz, c));
+            a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz;
+        }
+        double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+        accumulate_sums(s, pr->mass, vx, vy, vz, fx, fy, fz, w, u, c, shift);
+    }
+    block_reduce<FORCE_BLOCK>(s);
+    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr, KICK ? FIN_STEP : 0, cond_handle);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K4: first half-kick, thermostat scale, pending barostat coordinate scale, drift, periodic wrap.
+//   integrator.rs:28-34  v = v + F*(dt/(2m))
+//   thermostat.rs:54-58  v *= lambda            (lambda == 1.0 without thermostat: bitwise no-op)
+//   barostat.rs:46-48    x *= myu of the previous step (mu_pending == 1.0 otherwise: bitwise no-op)
+//   integrator.rs:40-44  x += v*dt
+//   particle.rs:120-142  single-shift wrap into [0, L)
+// Element-wise and HBM-bound: two atoms per thread, 128-bit accesses; explicit _rn intrinsics keep the
+// reference's rounding (no FMA contraction).
+__device__ __forceinline__ void kd_one(double &x, double &v, double f, double c, double lambda, double mup,
+                                       double dt, double L)
+{
+    v = __dadd_rn(v, __dmul_rn(f, c));
+    v = __dmul_rn(v, lambda);
+    x = __dmul_rn(x, mup);
+    x = __dadd_rn(x, __dmul_rn(v, dt));
+    if (x < 0.0) x = __dadd_rn(x, L);
+    else if (x >= L) x = __dsub_rn(x, L);
+}
+
+__global__ void __launch_bounds__(256) k_kick_drift(int npairs, Arrays a, const Scalars *__restrict__ sc,
+                                                    const Params *__restrict__ pr)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) return;
+    const double c = pr->half_dt_m, dt = pr->dt;
+    const double lambda = sc->lambda, mup = sc->mu_pending;
+    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+    double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
+            z = reinterpret_cast<double2 *>(a.z)[t];
+    double2 vx = reinterpret_cast<double2 *>(a.vx)[t], vy = reinterpret_cast<double2 *>(a.vy)[t],
+            vz = reinterpret_cast<double2 *>(a.vz)[t];
+    const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
+                  fz = reinterpret_cast<const double2 *>(a.fz)[t];
+    kd_one(x.x, vx.x, fx.x, c, lambda, mup, dt, Lx); kd_one(x.y, vx.y, fx.y, c, lambda, mup, dt, Lx);
+    kd_one(y.x, vy.x, fy.x, c, lambda, mup, dt, Ly); kd_one(y.y, vy.y, fy.y, c, lambda, mup, dt, Ly);
+    kd_one(z.x, vz.x, fz.x, c, lambda, mup, dt, Lz); kd_one(z.y, vz.y, fz.y, c, lambda, mup, dt, Lz);
+    reinterpret_cast<double2 *>(a.x)[t] = x;   reinterpret_cast<double2 *>(a.y)[t] = y;
+    reinterpret_cast<double2 *>(a.z)[t] = z;   reinterpret_cast<double2 *>(a.vx)[t] = vx;
+    reinterpret_cast<double2 *>(a.vy)[t] = vy; reinterpret_cast<double2 *>(a.vz)[t] = vz;
+}
+
+// barostat.update's coordinate scaling when no kick_drift follows (end of an md_step batch).
+__global__ void k_scale_positions(int n, Arrays a, const Scalars *__restrict__ sc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mup = sc->mu_pending;
+    a.x[i] = __dmul_rn(a.x[i], mup);
+    a.y[i] = __dmul_rn(a.y[i], mup);
+    a.z[i] = __dmul_rn(a.z[i], mup);
+}
+
+// ---- one-thread control kernels ---------------------------------------------------------------------
+__global__ void k_clear_pending(Scalars *sc) { sc->mu_pending = 1.0; }
+
+__global__ void k_after_rebuild(Scalars *sc)
+{
+    sc->disp_acc = 0.0;
+    sc->disp_next = 0.0;
+    sc->inv_scale = 1.0;
+    sc->need_rebuild = 0;
+}
+
+__global__ void k_prepare(Scalars *sc, const Params *pr, long long n_steps)
+{
+    sc->steps_left = n_steps;
+    sc->steps_done = 0;
+    compute_controls(sc, pr);
+}
+
+__global__ void k_reset_list_stats(Scalars *sc)
+{
+    sc->nbr_max = 0;
+    sc->nbr_overflow = 0;
+    sc->nbr_total = 0ull;
+}
+
+__global__ void k_set_shift_to_vcom(Scalars *sc)
+{
+    sc->shift[0] = sc->vcom[0]; sc->shift[1] = sc->vcom[1]; sc->shift[2] = sc->vcom[2];
+}
+
+// ---- transfer helpers -------------------------------------------------------------------------------
+__global__ void k_deinterleave3(int n, const double *__restrict__ src, double *__restrict__ a,
+                                double *__restrict__ b, double *__restrict__ c)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = src[3 * (size_t)i]; b[i] = src[3 * (size_t)i + 1]; c[i] = src[3 * (size_t)i + 2];
+}
+
+__global__ void k_interleave3_unsort(int n, const double *__restrict__ a, const double *__restrict__ b,
+                                     const double *__restrict__ c, const int *__restrict__ id,
+                                     double *__restrict__ dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    size_t o = 3 * (size_t)id[p];
+    dst[o] = a[p]; dst[o + 1] = b[p]; dst[o + 2] = c[p];
+}
+
+__global__ void k_unsort1(int n, const double *__restrict__ a, const int *__restrict__ id, double *__restrict__ dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[id[p]] = a[p];
+}
+
+__global__ void k_unsort1i(int n, const int *__restrict__ a, const int *__restrict__ id, int *__restrict__ dst)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) dst[id[p]] = a[p];
+}
+
+__global__ void k_iota(int n, int *__restrict__ id)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) id[p] = p;
+}
+
+}  // namespace md

@@ -1,0 +1,899 @@
+// moldyn_b200.cu — C ABI (include/moldyn_b200.h) over the sm_100a kernels in md_kernels.cuh.
+//
+// Host side of the step loop: owns the device-resident State, orchestrates list rebuilds, and runs the
+// steady-state steps inside one conditional (WHILE) CUDA graph whose condition the force kernel's last
+// block sets on the device — the host is only involved when the neighbour list has to be rebuilt.
+#include "md_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/moldyn_b200.h"
+
+using namespace md;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct md_ctx {
+    md_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // potential (PotentialsDatabase default: potential.rs:95-101)
+    double sigma = 0.3418, eps = 1.712, r_cut = 0.0, u_cut = 0.0;
+    double skin = 0.0;
+
+    // state
+    int64_t n = 0;
+    int npad = 0;
+    double mass = 0.0;
+    bool has_state = false;
+    bool list_valid = false;
+    bool force_valid = false;
+    double sums_c = -1.0;  // half_dt_m the stored reduction was computed with
+
+    Arrays cur{}, alt{};
+    std::vector<DevBuf> owned;
+    double *stage = nullptr;  // 3*npad doubles, transfer staging
+    int *stage_i = nullptr;   // npad ints
+    Scalars *d_sc = nullptr;
+    Params *d_pr = nullptr;
+    Scalars *h_sc = nullptr;  // pinned
+    Params *h_pr = nullptr;   // pinned
+    Params prm{};
+    double *d_partials = nullptr;
+    int partial_blocks = 0;
+
+    // cells / lists
+    Grid grid{};
+    int *cell_of = nullptr, *cell_sorted = nullptr, *order = nullptr;
+    int *cell_cnt = nullptr, *cell_start = nullptr, *block_sums = nullptr;
+    int cell_alloc = 0;
+    int *nbr = nullptr, *nbr_cnt = nullptr;
+    size_t nbr_alloc = 0;
+
+    // graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphConditionalHandle cond = 0;
+    bool graph_ok = false;
+
+    md_stats stats{};
+
+    // per-kernel CUDA-event timing (md_time_kernels)
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double t_ms[3] = {0.0, 0.0, 0.0};   // kick_drift, force, rebuild
+    int64_t t_cnt[3] = {0, 0, 0};
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return ctx->fail(MD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                             __LINE__);                                                               \
+    } while (0)
+
+#define TRY(expr)              \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_ != MD_OK) return rc_; \
+    } while (0)
+
+namespace {
+
+inline int blocks_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// Host restatement of Potential::get_potential_and_force (potential.rs:57-70) for the scalar entry points.
+void lj_host(double sigma, double eps, double r_cut, double u_cut, double r, double *u, double *f)
+{
+    if (r > r_cut) {
+        *u = 0.0;
+        *f = 0.0;
+        return;
+    }
+    volatile double sigma_r = sigma / r;
+    volatile double x2 = sigma_r * sigma_r;
+    volatile double x4 = x2 * x2;
+    volatile double s6 = x2 * x4;
+    volatile double s12 = s6 * s6;
+    volatile double d = s12 - s6;
+    volatile double a = 4.0 * eps;
+    volatile double b = a * d;
+    *u = b - u_cut;
+    volatile double e = 24.0 * eps;
+    volatile double g = e / r;
+    volatile double h = 2.0 * s12;
+    volatile double k = s6 - h;
+    *f = g * k;
+}
+
+template <typename T>
+int dev_alloc(md_ctx *ctx, T **out, size_t count)
+{
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    ctx->owned.push_back({p, bytes});
+    *out = (T *)p;
+    return MD_OK;
+}
+
+void dev_free(md_ctx *ctx, void *p)
+{
+    if (!p) return;
+    for (auto &b : ctx->owned)
+        if (b.p == p) {
+            cudaFree(p);
+            b.p = nullptr;
+        }
+}
+
+int alloc_arrays(md_ctx *ctx, Arrays *a, int npad)
+{
+    TRY(dev_alloc(ctx, &a->x, npad)); TRY(dev_alloc(ctx, &a->y, npad)); TRY(dev_alloc(ctx, &a->z, npad));
+    TRY(dev_alloc(ctx, &a->vx, npad)); TRY(dev_alloc(ctx, &a->vy, npad)); TRY(dev_alloc(ctx, &a->vz, npad));
+    TRY(dev_alloc(ctx, &a->fx, npad)); TRY(dev_alloc(ctx, &a->fy, npad)); TRY(dev_alloc(ctx, &a->fz, npad));
+    TRY(dev_alloc(ctx, &a->u, npad)); TRY(dev_alloc(ctx, &a->w, npad));
+    TRY(dev_alloc(ctx, &a->id, npad));
+    return MD_OK;
+}
+
+void free_arrays(md_ctx *ctx, Arrays *a)
+{
+    dev_free(ctx, a->x); dev_free(ctx, a->y); dev_free(ctx, a->z);
+    dev_free(ctx, a->vx); dev_free(ctx, a->vy); dev_free(ctx, a->vz);
+    dev_free(ctx, a->fx); dev_free(ctx, a->fy); dev_free(ctx, a->fz);
+    dev_free(ctx, a->u); dev_free(ctx, a->w); dev_free(ctx, a->id);
+    *a = Arrays{};
+}
+
+void drop_graph(md_ctx *ctx)
+{
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
+    ctx->graph_exec = nullptr;
+    ctx->graph = nullptr;
+    ctx->cond = 0;
+    ctx->graph_ok = false;
+}
+
+int push_params(md_ctx *ctx)
+{
+    *ctx->h_pr = ctx->prm;
+    CK(cudaMemcpyAsync(ctx->d_pr, ctx->h_pr, sizeof(Params), cudaMemcpyHostToDevice, ctx->stream));
+    return MD_OK;
+}
+
+int pull_scalars(md_ctx *ctx)
+{
+    CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+void fill_potential_params(md_ctx *ctx)
+{
+    ctx->prm.sigma = ctx->sigma;
+    ctx->prm.eps = ctx->eps;
+    ctx->prm.r_cut = ctx->r_cut;
+    ctx->prm.u_cut = ctx->u_cut;
+    ctx->prm.r_list = ctx->r_cut + ctx->skin;
+    ctx->prm.mass = ctx->mass;
+    ctx->prm.n = ctx->n;
+}
+
+// Skin: user value, else 0.1·r_cut for dense systems and growing towards r_cut for dilute ones where extra
+// list entries are nearly free but every rebuild costs several steps of HBM traffic.
+double choose_skin(const md_ctx *ctx, const double box[3])
+{
+    if (ctx->cfg.skin > 0.0) return ctx->cfg.skin;
+    double volume = box[0] * box[1] * box[2];
+    double rho = (double)ctx->n / volume;
+    double in_cut = rho * 4.18879020478639 * ctx->r_cut * ctx->r_cut * ctx->r_cut;
+    double skin = in_cut > 8.0 ? 0.1 * ctx->r_cut : ctx->r_cut;
+    double min_box = std::min(box[0], std::min(box[1], box[2]));
+    // keep r_list below half the smallest box edge when that is possible (single-image list semantics)
+    if (ctx->r_cut + skin > 0.5 * min_box) skin = std::max(0.0, 0.5 * min_box - ctx->r_cut) * 0.5;
+    return skin;
+}
+
+int choose_grid(md_ctx *ctx, const double box[3])
+{
+    Grid g{};
+    int nsub = ctx->cfg.cell_subdiv >= 2 ? 2 : 1;
+    double r_list = ctx->r_cut + ctx->skin;
+    double volume = box[0] * box[1] * box[2];
+    double k = ctx->cfg.cell_atoms > 0.0 ? ctx->cfg.cell_atoms : 3.0;
+    double dilute_edge = std::cbrt(k * volume / (double)ctx->n);
+    double edge = std::max(r_list / nsub * 1.02, dilute_edge);
+    int64_t ncell = 1;
+    for (int d = 0; d < 3; ++d) {
+        int c = (int)std::floor(box[d] / edge);
+        if (c < 1) c = 1;
+        g.nc[d] = c;
+        ncell *= c;
+    }
+    if (ncell > (int64_t)1 << 30) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "cell grid too large");
+    g.nsub = nsub;
+    g.ncell = (int)ncell;
+    g.cap = ctx->grid.cap;
+    g.npad = ctx->npad;
+    ctx->grid = g;
+    if (g.ncell + 1 > ctx->cell_alloc) {
+        dev_free(ctx, ctx->cell_cnt); dev_free(ctx, ctx->cell_start); dev_free(ctx, ctx->block_sums);
+        ctx->cell_alloc = g.ncell + 1 + g.ncell / 8;
+        TRY(dev_alloc(ctx, &ctx->cell_cnt, ctx->cell_alloc));
+        TRY(dev_alloc(ctx, &ctx->cell_start, ctx->cell_alloc));
+        TRY(dev_alloc(ctx, &ctx->block_sums, blocks_for(ctx->cell_alloc, SCAN_BLOCK) + 1));
+    }
+    return MD_OK;
+}
+
+bool grid_still_valid(const md_ctx *ctx, const double box[3])
+{
+    double r_list = ctx->r_cut + ctx->skin;
+    for (int d = 0; d < 3; ++d) {
+        int w = 2 * ctx->grid.nsub + 1;
+        if (ctx->grid.nc[d] >= w && box[d] / ctx->grid.nc[d] * ctx->grid.nsub < r_list) return false;
+    }
+    return true;
+}
+
+int ensure_nbr_capacity(md_ctx *ctx, int cap)
+{
+    size_t need = (size_t)cap * (size_t)ctx->npad;
+    if (need > ctx->nbr_alloc) {
+        dev_free(ctx, ctx->nbr);
+        ctx->nbr = nullptr;
+        ctx->nbr_alloc = 0;
+        TRY(dev_alloc(ctx, &ctx->nbr, need));
+        ctx->nbr_alloc = need;
+    }
+    ctx->grid.cap = cap;
+    drop_graph(ctx);
+    return MD_OK;
+}
+
+// K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
+// (no pending barostat scaling).
+int rebuild_lists(md_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const int n = (int)ctx->n;
+    TRY(pull_scalars(ctx));
+    double box[3] = {ctx->h_sc->box[0], ctx->h_sc->box[1], ctx->h_sc->box[2]};
+    for (int d = 0; d < 3; ++d)
+        if (!(box[d] > 0.0) || !std::isfinite(box[d])) return ctx->fail(MD_ERR_NONFINITE, "boundary box is not finite/positive");
+    if (ctx->grid.ncell == 0 || !grid_still_valid(ctx, box) || !ctx->list_valid) TRY(choose_grid(ctx, box));
+    Grid &g = ctx->grid;
+
+    CK(cudaMemsetAsync(ctx->cell_cnt, 0, sizeof(int) * (g.ncell + 1), st));
+    k_cell_count<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->cur.x, ctx->cur.y, ctx->cur.z, ctx->d_sc, g,
+                                                      ctx->cell_of, ctx->cell_cnt);
+    int sb = blocks_for(g.ncell, SCAN_BLOCK);
+    k_scan_block<<<sb, SCAN_BLOCK, 0, st>>>(g.ncell, ctx->cell_cnt, ctx->cell_start, ctx->block_sums);
+    k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sb, ctx->block_sums);
+    k_scan_add<<<sb, SCAN_BLOCK, 0, st>>>(g.ncell, ctx->cell_start, ctx->block_sums, n);
+    CK(cudaMemsetAsync(ctx->cell_cnt, 0, sizeof(int) * (g.ncell + 1), st));
+    k_scatter<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->cell_of, ctx->cell_start, ctx->cell_cnt, ctx->order);
+    k_sort_cells<<<blocks_for(g.ncell, 128), 128, 0, st>>>(g.ncell, ctx->cell_start, ctx->cur.id, ctx->order);
+    k_reorder<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->order, ctx->cell_of, ctx->cur, ctx->alt,
+                                                   ctx->cell_sorted);
+    std::swap(ctx->cur, ctx->alt);
+    ctx->stats.kernel_launches += 7;
+    drop_graph(ctx);  // array pointers are baked into the captured kernels
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
+        if (ctx->cfg.force_mode == MD_FORCE_EXACT)
+            k_build_list<true><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
+                                                                   ctx->d_sc, g, ctx->prm.r_list, ctx->nbr,
+                                                                   ctx->nbr_cnt);
+        else
+            k_build_list<false><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
+                                                                    ctx->d_sc, g, ctx->prm.r_list, ctx->nbr,
+                                                                    ctx->nbr_cnt);
+        ctx->stats.kernel_launches += 2;
+        CK(cudaGetLastError());
+        TRY(pull_scalars(ctx));
+        if (!ctx->h_sc->nbr_overflow) break;
+        if (attempt == 3) return ctx->fail(MD_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow (max %d)", ctx->h_sc->nbr_max);
+        int cap = ((int)(ctx->h_sc->nbr_max * 1.25) + 8 + 7) / 8 * 8;
+        TRY(ensure_nbr_capacity(ctx, cap));
+    }
+    k_after_rebuild<<<1, 1, 0, st>>>(ctx->d_sc);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    ctx->stats.rebuilds += 1;
+    ctx->stats.nbr_max = ctx->h_sc->nbr_max;
+    ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
+    ctx->list_valid = true;
+    return MD_OK;
+}
+
+int launch_kick_drift(md_ctx *ctx)
+{
+    int npairs = (int)((ctx->n + 1) / 2);
+    k_kick_drift<<<blocks_for(npairs, 256), 256, 0, ctx->stream>>>(npairs, ctx->cur, ctx->d_sc, ctx->d_pr);
+    return MD_OK;
+}
+
+int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
+{
+    const int n = (int)ctx->n;
+    const int nb = blocks_for(n, FORCE_BLOCK);
+    const bool exact = ctx->cfg.force_mode == MD_FORCE_EXACT;
+#define LAUNCH_FORCE(E, K)                                                                                   \
+    k_force<E, K><<<nb, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,       \
+                                                        ctx->d_partials, ctx->d_sc, ctx->d_pr, cond)
+    if (exact && kick) LAUNCH_FORCE(true, true);
+    else if (exact) LAUNCH_FORCE(true, false);
+    else if (kick) LAUNCH_FORCE(false, true);
+    else LAUNCH_FORCE(false, false);
+#undef LAUNCH_FORCE
+    return MD_OK;
+}
+
+int launch_reduce(md_ctx *ctx)
+{
+    const int n = (int)ctx->n;
+    k_reduce_state<<<blocks_for(n, RED_BLOCK), RED_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->d_partials, ctx->d_sc,
+                                                                            ctx->d_pr);
+    ctx->stats.kernel_launches += 1;
+    return MD_OK;
+}
+
+// WHILE-graph: body = { k_kick_drift ; k_force<.., KICK> } ; the force kernel's last block sets the condition.
+int build_graph(md_ctx *ctx)
+{
+    drop_graph(ctx);
+    CK(cudaGraphCreate(&ctx->graph, 0));
+    CK(cudaGraphConditionalHandleCreate(&ctx->cond, ctx->graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = ctx->cond;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddNode(&node, ctx->graph, nullptr, 0, &np));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    launch_kick_drift(ctx);
+    launch_force(ctx, true, (unsigned long long)ctx->cond);
+    cudaGraph_t captured = nullptr;
+    CK(cudaStreamEndCapture(ctx->stream, &captured));
+    CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+    ctx->graph_ok = true;
+    return MD_OK;
+}
+
+int flush_pending_scale(md_ctx *ctx)
+{
+    const int n = (int)ctx->n;
+    k_scale_positions<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc);
+    k_clear_pending<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
+    ctx->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    return MD_OK;
+}
+
+int check_ctx(md_ctx *ctx, bool need_state)
+{
+    if (!ctx) return MD_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->fail(MD_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    if (need_state && !ctx->has_state) return ctx->fail(MD_ERR_NO_STATE, "no state uploaded");
+    return MD_OK;
+}
+
+int device_error(md_ctx *ctx)
+{
+    if (ctx->h_sc->error == MD_ERR_NONFINITE)
+        return ctx->fail(MD_ERR_NONFINITE, "non-finite thermostat/barostat coefficient or displacement "
+                                           "(temperature %.17g, pressure %.17g)", ctx->h_sc->temperature,
+                         ctx->h_sc->pressure);
+    if (ctx->h_sc->error) return ctx->fail(ctx->h_sc->error, "device-side error %d", ctx->h_sc->error);
+    return MD_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char *md_version(void) { return "moldyn_b200 0.1 (sm_100a)"; }
+
+const char *md_last_error(const md_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int md_lj_potential_and_force(double sigma, double eps, double r_cut, double u_cut, double r, double *potential,
+                              double *force)
+{
+    if (!potential || !force) return MD_ERR_INVALID_ARGUMENT;
+    lj_host(sigma, eps, r_cut, u_cut, r, potential, force);
+    return MD_OK;
+}
+
+int md_lj_new(double sigma, double eps, double *r_cut, double *u_cut)
+{
+    if (!r_cut || !u_cut) return MD_ERR_INVALID_ARGUMENT;
+    double rc = sigma * 2.5, u, f;  // potential.rs:28
+    lj_host(sigma, eps, rc, 0.0, rc, &u, &f);
+    *r_cut = rc;
+    *u_cut = u;
+    return MD_OK;
+}
+
+int md_create(const md_config *cfg, md_ctx **out)
+{
+    if (!out) return MD_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    md_ctx *ctx = new md_ctx();
+    if (cfg) ctx->cfg = *cfg;
+    ctx->device = ctx->cfg.device;
+    auto bail = [&](cudaError_t e, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e) +
+                         " (moldyn_b200 has no CPU fallback; a CUDA device is required)";
+        delete ctx;
+        return (int)MD_ERR_CUDA;
+    };
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return bail(e, "cudaGetDeviceCount");
+    if (count == 0) return bail(cudaErrorNoDevice, "cudaGetDeviceCount");
+    if (ctx->device < 0 || ctx->device >= count) {
+        g_create_error = "device ordinal out of range";
+        delete ctx;
+        return MD_ERR_INVALID_ARGUMENT;
+    }
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    if ((e = cudaMalloc((void **)&ctx->d_sc, sizeof(Scalars))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_pr, sizeof(Params))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMallocHost((void **)&ctx->h_sc, sizeof(Scalars))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    if ((e = cudaMallocHost((void **)&ctx->h_pr, sizeof(Params))) != cudaSuccess) return bail(e, "cudaMallocHost");
+    cudaMemset(ctx->d_sc, 0, sizeof(Scalars));
+    cudaMemset(ctx->d_pr, 0, sizeof(Params));
+    memset(ctx->h_sc, 0, sizeof(Scalars));
+    md_lj_new(ctx->sigma, ctx->eps, &ctx->r_cut, &ctx->u_cut);  // PotentialsDatabase::new()
+    *out = ctx;
+    return MD_OK;
+}
+
+void md_destroy(md_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drop_graph(ctx);
+    for (auto &e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &b : ctx->owned)
+        if (b.p) cudaFree(b.p);
+    if (ctx->d_sc) cudaFree(ctx->d_sc);
+    if (ctx->d_pr) cudaFree(ctx->d_pr);
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->h_pr) cudaFreeHost(ctx->h_pr);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, double u_cut)
+{
+    TRY(check_ctx(ctx, false));
+    if (!(sigma > 0.0) || !(r_cut > 0.0) || !std::isfinite(eps) || !std::isfinite(u_cut))
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "bad Lennard-Jones parameters");
+    ctx->sigma = sigma; ctx->eps = eps; ctx->r_cut = r_cut; ctx->u_cut = u_cut;
+    ctx->list_valid = false;
+    ctx->force_valid = false;
+    if (ctx->has_state) {
+        TRY(pull_scalars(ctx));
+        ctx->skin = choose_skin(ctx, ctx->h_sc->box);
+    }
+    fill_potential_params(ctx);
+    return MD_OK;
+}
+
+int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
+                    const double *potential, const double *virial, double mass, const double box[3])
+{
+    TRY(check_ctx(ctx, false));
+    if (n <= 0 || n > (int64_t)1 << 30 || !pos || !vel || !box)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: need n in [1, 2^30], pos, vel, box");
+    if (!(mass > 0.0) || !(box[0] > 0.0) || !(box[1] > 0.0) || !(box[2] > 0.0))
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: mass and box must be positive");
+    cudaStream_t st = ctx->stream;
+    if (n != ctx->n || !ctx->has_state) {
+        CK(cudaStreamSynchronize(st));
+        drop_graph(ctx);
+        free_arrays(ctx, &ctx->cur); free_arrays(ctx, &ctx->alt);
+        dev_free(ctx, ctx->stage); dev_free(ctx, ctx->stage_i); dev_free(ctx, ctx->d_partials);
+        dev_free(ctx, ctx->cell_of); dev_free(ctx, ctx->cell_sorted); dev_free(ctx, ctx->order);
+        dev_free(ctx, ctx->nbr_cnt); dev_free(ctx, ctx->nbr);
+        ctx->nbr = nullptr; ctx->nbr_alloc = 0;
+        ctx->owned.erase(std::remove_if(ctx->owned.begin(), ctx->owned.end(), [](const DevBuf &b) { return !b.p; }),
+                         ctx->owned.end());
+        ctx->n = n;
+        ctx->npad = (int)((n + 63) / 64 * 64);
+        TRY(alloc_arrays(ctx, &ctx->cur, ctx->npad));
+        TRY(alloc_arrays(ctx, &ctx->alt, ctx->npad));
+        TRY(dev_alloc(ctx, &ctx->stage, 3 * (size_t)ctx->npad));
+        TRY(dev_alloc(ctx, &ctx->stage_i, ctx->npad));
+        ctx->partial_blocks = std::max(blocks_for(n, FORCE_BLOCK), blocks_for(n, RED_BLOCK));
+        TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
+        TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
+        TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
+        TRY(dev_alloc(ctx, &ctx->order, ctx->npad));
+        TRY(dev_alloc(ctx, &ctx->nbr_cnt, ctx->npad));
+        ctx->grid = Grid{};
+    }
+    ctx->mass = mass;
+    ctx->has_state = true;
+    ctx->list_valid = false;
+    ctx->force_valid = force != nullptr;
+    const int ni = (int)n;
+    const int nb = blocks_for(n, 256);
+    const size_t b3 = 3 * (size_t)n * sizeof(double), b1 = (size_t)n * sizeof(double);
+    CK(cudaMemcpyAsync(ctx->stage, pos, b3, cudaMemcpyHostToDevice, st));
+    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.x, ctx->cur.y, ctx->cur.z);
+    CK(cudaMemcpyAsync(ctx->stage, vel, b3, cudaMemcpyHostToDevice, st));
+    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.vx, ctx->cur.vy, ctx->cur.vz);
+    if (force) {
+        CK(cudaMemcpyAsync(ctx->stage, force, b3, cudaMemcpyHostToDevice, st));
+        k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.fx, ctx->cur.fy, ctx->cur.fz);
+    } else {
+        CK(cudaMemsetAsync(ctx->cur.fx, 0, b1, st));
+        CK(cudaMemsetAsync(ctx->cur.fy, 0, b1, st));
+        CK(cudaMemsetAsync(ctx->cur.fz, 0, b1, st));
+    }
+    if (potential) CK(cudaMemcpyAsync(ctx->cur.u, potential, b1, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->cur.u, 0, b1, st));
+    if (virial) CK(cudaMemcpyAsync(ctx->cur.w, virial, b1, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->cur.w, 0, b1, st));
+    k_iota<<<nb, 256, 0, st>>>(ni, ctx->cur.id);
+    ctx->stats.kernel_launches += 3 + (force ? 1 : 0);
+
+    Scalars &h = *ctx->h_sc;
+    memset(&h, 0, sizeof h);
+    h.box[0] = box[0]; h.box[1] = box[1]; h.box[2] = box[2];
+    h.mu_pending = 1.0; h.lambda = 1.0; h.mu = 1.0; h.inv_scale = 1.0;
+    h.lambda_last = 1.0; h.mu_last = 1.0;
+    CK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    ctx->skin = choose_skin(ctx, box);
+    fill_potential_params(ctx);
+    // neighbour capacity from density
+    {
+        double volume = box[0] * box[1] * box[2];
+        double r_list = ctx->r_cut + ctx->skin;
+        double expect = (double)n / volume * 4.18879020478639 * r_list * r_list * r_list;
+        int cap = ctx->cfg.max_neighbours > 0 ? ctx->cfg.max_neighbours : (int)(expect * 1.5) + 16;
+        cap = std::min<int64_t>((cap + 7) / 8 * 8, std::max<int64_t>(8, (n - 1 + 7) / 8 * 8));
+        TRY(ensure_nbr_capacity(ctx, cap));
+    }
+    TRY(push_params(ctx));
+    // macro parameters of the uploaded state: two passes so the thermal sum is shifted by the true COM velocity
+    launch_reduce(ctx);
+    k_set_shift_to_vcom<<<1, 1, 0, st>>>(ctx->d_sc);
+    launch_reduce(ctx);
+    ctx->stats.kernel_launches += 1;
+    ctx->sums_c = ctx->prm.half_dt_m;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // host buffers are only borrowed for the duration of the call
+    return MD_OK;
+}
+
+int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, double *potential, double *virial,
+                      double box[3])
+{
+    TRY(check_ctx(ctx, true));
+    cudaStream_t st = ctx->stream;
+    const int n = (int)ctx->n;
+    const int nb = blocks_for(n, 256);
+    const size_t b3 = 3 * (size_t)n * sizeof(double), b1 = (size_t)n * sizeof(double);
+    const Arrays &a = ctx->cur;
+    if (pos) {
+        k_interleave3_unsort<<<nb, 256, 0, st>>>(n, a.x, a.y, a.z, a.id, ctx->stage);
+        CK(cudaMemcpyAsync(pos, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (vel) {
+        k_interleave3_unsort<<<nb, 256, 0, st>>>(n, a.vx, a.vy, a.vz, a.id, ctx->stage);
+        CK(cudaMemcpyAsync(vel, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (force) {
+        k_interleave3_unsort<<<nb, 256, 0, st>>>(n, a.fx, a.fy, a.fz, a.id, ctx->stage);
+        CK(cudaMemcpyAsync(force, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (potential) {
+        k_unsort1<<<nb, 256, 0, st>>>(n, a.u, a.id, ctx->stage);
+        CK(cudaMemcpyAsync(potential, ctx->stage, b1, cudaMemcpyDeviceToHost, st));
+    }
+    if (virial) {
+        k_unsort1<<<nb, 256, 0, st>>>(n, a.w, a.id, ctx->stage);
+        CK(cudaMemcpyAsync(virial, ctx->stage, b1, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->stats.kernel_launches += (pos != nullptr) + (vel != nullptr) + (force != nullptr) + (potential != nullptr) +
+                                  (virial != nullptr);
+    CK(cudaGetLastError());
+    TRY(pull_scalars(ctx));
+    if (box) {
+        box[0] = ctx->h_sc->box[0]; box[1] = ctx->h_sc->box[1]; box[2] = ctx->h_sc->box[2];
+    }
+    return MD_OK;
+}
+
+int md_update_force(md_ctx *ctx)
+{
+    TRY(check_ctx(ctx, true));
+    fill_potential_params(ctx);
+    TRY(push_params(ctx));
+    if (!ctx->list_valid) {
+        TRY(rebuild_lists(ctx));
+    } else {
+        TRY(pull_scalars(ctx));
+        if (ctx->h_sc->need_rebuild) TRY(rebuild_lists(ctx));
+    }
+    launch_force(ctx, false, 0ull);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    ctx->sums_c = ctx->prm.half_dt_m;
+    ctx->force_valid = true;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_barostat *ba)
+{
+    TRY(check_ctx(ctx, true));
+    if (n_steps < 0 || !std::isfinite(dt)) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_step: bad n_steps/dt");
+    if (th && th->kind == MD_THERMOSTAT_NOSE_HOOVER)
+        return ctx->fail(MD_ERR_UNSUPPORTED, "Nose-Hoover thermostat is not implemented on the device path yet");
+    if (th && th->kind != MD_THERMOSTAT_NONE && th->kind != MD_THERMOSTAT_BERENDSEN)
+        return ctx->fail(MD_ERR_UNSUPPORTED, "Thermostat::Custom is todo!() in the reference");
+    if (ba && ba->kind != MD_BAROSTAT_NONE && ba->kind != MD_BAROSTAT_BERENDSEN)
+        return ctx->fail(MD_ERR_UNSUPPORTED, "Barostat::Custom is todo!() in the reference");
+    if (n_steps == 0) return MD_OK;
+    cudaStream_t st = ctx->stream;
+
+    fill_potential_params(ctx);
+    Params &p = ctx->prm;
+    p.dt = dt;
+    p.half_dt_m = dt / (2.0 * ctx->mass);  // integrator.rs:30
+    p.th_kind = th ? th->kind : 0;
+    p.th_tau = th ? th->tau : 1.0;
+    p.th_target = th ? th->target : 0.0;
+    p.ba_kind = ba ? ba->kind : 0;
+    p.ba_beta = ba ? ba->beta : 0.0;
+    p.ba_tau = ba ? ba->tau : 1.0;
+    p.ba_target = ba ? ba->target : 0.0;
+    TRY(push_params(ctx));
+    // The displacement bound of the first drift needs max|v + F c|² for THIS c.
+    if (ctx->sums_c != p.half_dt_m) {
+        launch_reduce(ctx);
+        ctx->sums_c = p.half_dt_m;
+    }
+    k_prepare<<<1, 1, 0, st>>>(ctx->d_sc, ctx->d_pr, (long long)n_steps);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+
+    int64_t remaining = n_steps;
+    while (remaining > 0) {
+        TRY(pull_scalars(ctx));
+        TRY(device_error(ctx));
+        remaining = ctx->h_sc->steps_left;
+        if (remaining <= 0) break;
+        const bool rebuild = !ctx->list_valid || ctx->h_sc->need_rebuild;
+        if (rebuild || ctx->timing || ctx->cfg.loop_mode == MD_LOOP_HOST) {
+            // one step by hand: drift, (rebuild at the drifted positions,) forces
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], st));
+            launch_kick_drift(ctx);
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], st));
+            if (rebuild) TRY(rebuild_lists(ctx));
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st));
+            launch_force(ctx, true, 0ull);
+            if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], st));
+            ctx->stats.kernel_launches += 2;
+            ctx->stats.steps += 1;
+            CK(cudaGetLastError());
+            if (ctx->timing) {
+                CK(cudaEventSynchronize(ctx->ev[3]));
+                float a = 0.f, b = 0.f, c = 0.f;
+                CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+                CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+                CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
+                ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
+                ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
+                if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
+            }
+        } else {
+            if (!ctx->graph_ok) TRY(build_graph(ctx));
+            long long before = ctx->h_sc->steps_done;
+            CK(cudaGraphLaunch(ctx->graph_exec, st));
+            ctx->stats.graph_launches += 1;
+            TRY(pull_scalars(ctx));
+            long long ran = ctx->h_sc->steps_done - before;
+            ctx->stats.kernel_launches += 2 * ran;
+            ctx->stats.steps += ran;
+            TRY(device_error(ctx));
+            remaining = ctx->h_sc->steps_left;
+        }
+    }
+    if (p.ba_kind == MD_BAROSTAT_BERENDSEN) TRY(flush_pending_scale(ctx));
+    TRY(pull_scalars(ctx));
+    TRY(device_error(ctx));
+    if (th) th->lambda = ctx->h_sc->lambda_last;
+    if (ba) ba->myu = ctx->h_sc->mu_last;
+    ctx->force_valid = true;
+    return MD_OK;
+}
+
+int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_barostat *ba, double ms[3],
+                    int64_t launches[3])
+{
+    TRY(check_ctx(ctx, true));
+    if (!ms || !launches) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_time_kernels: NULL output");
+    for (auto &e : ctx->ev)
+        if (!e) CK(cudaEventCreate(&e));
+    for (int k = 0; k < 3; ++k) { ctx->t_ms[k] = 0.0; ctx->t_cnt[k] = 0; }
+    ctx->timing = true;
+    int rc = md_step(ctx, n_steps, dt, th, ba);
+    ctx->timing = false;
+    for (int k = 0; k < 3; ++k) { ms[k] = ctx->t_ms[k]; launches[k] = ctx->t_cnt[k]; }
+    return rc;
+}
+
+int md_macro(md_ctx *ctx, md_macro_out *out)
+{
+    TRY(check_ctx(ctx, true));
+    if (!out) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro: out is NULL");
+    TRY(pull_scalars(ctx));
+    const Scalars &h = *ctx->h_sc;
+    out->kinetic_energy = h.kinetic;
+    out->thermal_energy = h.thermal;
+    out->potential_energy = h.potential;
+    out->temperature = h.temperature;
+    out->pressure = h.pressure;
+    for (int d = 0; d < 3; ++d) {
+        out->vcom[d] = h.vcom[d];
+        out->momentum[d] = h.sum_mv[d];
+        out->box[d] = h.box[d];
+    }
+    out->lambda = h.lambda_last;
+    out->myu = h.mu_last;
+    out->n = ctx->n;
+    return MD_OK;
+}
+
+int md_update_force_host(md_ctx *ctx, int64_t n, const double *pos, double mass, const double box[3], double *force,
+                         double *potential, double *virial)
+{
+    TRY(check_ctx(ctx, false));
+    if (n <= 0 || !pos) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_update_force_host: bad arguments");
+    // velocities do not enter update_force; reuse pos as a stand-in so no extra host buffer is needed
+    TRY(md_upload_state(ctx, n, pos, pos, nullptr, nullptr, nullptr, mass, box));
+    TRY(md_update_force(ctx));
+    return md_download_state(ctx, nullptr, nullptr, force, potential, virial, nullptr);
+}
+
+int md_calculate_host(md_ctx *ctx, int64_t n, double *pos, double *vel, double *force, double *potential,
+                      double *virial, double mass, double box[3], double dt, md_thermostat *th, md_barostat *ba)
+{
+    TRY(check_ctx(ctx, false));
+    if (!force) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_calculate_host: force is required (the step starts "
+                                                          "with a half-kick from State.force)");
+    TRY(md_upload_state(ctx, n, pos, vel, force, potential, virial, mass, box));
+    TRY(md_step(ctx, 1, dt, th, ba));
+    return md_download_state(ctx, pos, vel, force, potential, virial, box);
+}
+
+int md_download_cells(md_ctx *ctx, int32_t *cell_of_atom, int32_t dims[3])
+{
+    TRY(check_ctx(ctx, true));
+    if (!ctx->list_valid) return ctx->fail(MD_ERR_NO_STATE, "no neighbour list built yet");
+    const int n = (int)ctx->n;
+    if (cell_of_atom) {
+        k_unsort1i<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cell_sorted, ctx->cur.id, ctx->stage_i);
+        CK(cudaMemcpyAsync(cell_of_atom, ctx->stage_i, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (dims) {
+        dims[0] = ctx->grid.nc[0]; dims[1] = ctx->grid.nc[1]; dims[2] = ctx->grid.nc[2];
+    }
+    return MD_OK;
+}
+
+static int fetch_lists(md_ctx *ctx, std::vector<int> &cnt, std::vector<int> &id, std::vector<int> *nbr)
+{
+    if (!ctx->list_valid) return ctx->fail(MD_ERR_NO_STATE, "no neighbour list built yet");
+    const size_t n = (size_t)ctx->n;
+    cnt.resize(n);
+    id.resize(n);
+    CK(cudaMemcpyAsync(cnt.data(), ctx->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(id.data(), ctx->cur.id, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nbr) {
+        nbr->resize((size_t)ctx->grid.cap * ctx->npad);
+        CK(cudaMemcpyAsync(nbr->data(), ctx->nbr, sizeof(int) * nbr->size(), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+int md_neighbour_counts(md_ctx *ctx, int64_t *counts)
+{
+    TRY(check_ctx(ctx, true));
+    if (!counts) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "counts is NULL");
+    std::vector<int> cnt, id;
+    TRY(fetch_lists(ctx, cnt, id, nullptr));
+    for (size_t p = 0; p < cnt.size(); ++p) counts[id[p]] = cnt[p];
+    return MD_OK;
+}
+
+int md_neighbour_lists(md_ctx *ctx, const int64_t *offsets, int64_t *partners)
+{
+    TRY(check_ctx(ctx, true));
+    if (!offsets || !partners) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "offsets/partners is NULL");
+    std::vector<int> cnt, id, nbr;
+    TRY(fetch_lists(ctx, cnt, id, &nbr));
+    for (size_t p = 0; p < cnt.size(); ++p) {
+        int64_t *dst = partners + offsets[id[p]];
+        for (int k = 0; k < cnt[p]; ++k) dst[k] = id[nbr[(size_t)k * ctx->npad + p]];
+        std::sort(dst, dst + cnt[p]);
+    }
+    return MD_OK;
+}
+
+int md_get_stats(md_ctx *ctx, md_stats *out)
+{
+    if (!ctx || !out) return MD_ERR_INVALID_ARGUMENT;
+    *out = ctx->stats;
+    out->cells[0] = ctx->grid.nc[0]; out->cells[1] = ctx->grid.nc[1]; out->cells[2] = ctx->grid.nc[2];
+    out->nbr_capacity = ctx->grid.cap;
+    out->skin = ctx->skin;
+    return MD_OK;
+}
+
+void *md_stream(md_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int md_synchronize(md_ctx *ctx)
+{
+    TRY(check_ctx(ctx, false));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+int md_invalidate_lists(md_ctx *ctx)
+{
+    TRY(check_ctx(ctx, false));
+    ctx->list_valid = false;
+    return MD_OK;
+}
+
+}  // extern "C"

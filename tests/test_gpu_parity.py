@@ -1,0 +1,412 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star / SURVEY §8d):
+  * cell assignments and neighbour sets: bit-exact;
+  * MD_FORCE_EXACT: per-atom force / potential / virial and NVE trajectories BIT-IDENTICAL to the oracle;
+  * MD_FORCE_FAST: |Δ| <= 1e-10 * max(Σ_j|f_ij|, global RMS) per atom; 100-step trajectories within 1e-8;
+  * thermostat / barostat runs: 1e-8 over 100 steps (the reductions are tree sums, not sequential sums);
+  * the reference's golden values to 8 decimals through the GPU path.
+"""
+import numpy as np
+import pytest
+
+import moldyn_b200 as md
+from oracle import oracle as orc
+
+from helpers import LONG_CUT, dense_gas, fmt3, f8, force_scale, gas, lj_pair, liquid, to_gpu_state
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.002
+
+
+@pytest.fixture(scope="module", params=["exact", "fast"])
+def mode(request):
+    return request.param
+
+
+def make_solver(mode, **kw):
+    return md.Solver(exact=(mode == "exact"), **kw)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own golden values, through the GPU path
+def two_body(kats):
+    k = kats["two_body"]
+    return md.State(k["pos"], k["vel"], k["mass"], k["box"]), k
+
+
+def check_golden_step(st, g):
+    for key, arr in (("pos1", st.position[0]), ("pos2", st.position[1]), ("vel1", st.velocity[0]),
+                     ("vel2", st.velocity[1]), ("force1", st.force[0]), ("force2", st.force[1])):
+        if key in g:
+            assert fmt3(arr) == g[key], (g.get("step"), key)
+
+
+@pytest.mark.parametrize("host_loop", [False, True])
+def test_golden_verlet_with_lennard_jones(kats, mode, host_loop):  # solver/src/lib.rs:109-262
+    st, k = two_body(kats)
+    with make_solver(mode, host_loop=host_loop) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.download(st)
+        check_golden_step(st, k["steps"][0])
+        for g in k["steps"][1:]:
+            s.step(1, k["dt"])
+            s.download(st)
+            check_golden_step(st, g)
+
+
+def test_golden_per_call_api(kats):  # cli/src/tests.rs:35-98 semantics: State in, State out, every call
+    st, k = two_body(kats)
+    db = md.PotentialsDatabase()
+    md.update_force(db, st)
+    check_golden_step(st, k["steps"][0])
+    for g in k["steps"][1:]:
+        md.Integrator.VerletMethod.calculate(db, st, k["dt"], None, None)
+        check_golden_step(st, g)
+
+
+def test_golden_1000_iterations_and_macro(kats, mode):  # solver/src/lib.rs:264-332
+    st, k = two_body(kats)
+    g = kats["verlet_lj_1000_iterations"]
+    with make_solver(mode) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(g["n_steps"], k["dt"])
+        s.download(st)
+        m = s.macro()
+    check_golden_step(st, g)
+    assert f8(m["kinetic"]) == g["kinetic"]
+    assert f8(m["thermal"]) == g["thermal"]
+    assert f8(m["potential"]) == g["potential"]
+    assert f8(m["thermal"] + m["potential"]) == g["internal"]
+    assert f8(m["kinetic"] + m["potential"]) == g["full"]
+    assert f8(m["temperature"] / 100.0) == g["temperature_over_100"]
+    assert f8(m["pressure"]) == g["pressure"]
+
+
+def test_golden_energies_temperature_pressure(kats, mode):  # solver/src/lib.rs:334-427
+    st, _ = two_body(kats)
+    with make_solver(mode) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        m = s.macro()
+    g = kats["energies"]
+    assert list(m["vcom"]) == g["vcom"]
+    assert f8(m["kinetic"]) == g["kinetic"]
+    assert f8(m["thermal"]) == g["thermal"]
+    assert f8(m["potential"]) == g["potential"]
+    assert f8(m["temperature"]) == kats["temperature"]["value"]
+    assert f8(m["pressure"]) == kats["pressure"]["value"]
+
+
+def test_golden_update_force(kats, mode):  # solver/src/lib.rs:91-107
+    k = kats["update_force_lennard_jones"]
+    st = md.State(k["pos"], np.zeros((2, 3)), k["mass"], k["box"])
+    with make_solver(mode) as s:
+        s.update_force_host(st)
+    assert fmt3(st.force[0]) == k["force_p1"]
+
+
+def test_momentum_invariant(kats, mode):  # solver/src/lib.rs:49-75
+    g = kats["momentum"]
+    o = orc.argon_lattice(tuple(g["grid"]), g["cell"], g["temperature"])
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        for _ in range(20):
+            s.step(500, g["dt"])
+            s.download(st)
+            assert np.all(np.abs(st.velocity.sum(axis=0)) < g["tolerance"])
+
+
+# ---------------------------------------------------------------------------------------------------
+SYSTEMS = {
+    "gas1000": lambda: (gas(10), None),
+    "dense_gas3000": lambda: (dense_gas(3000), None),
+    "liquid1000": lambda: (liquid(10), None),
+    "liquid4096_3.5sigma": lambda: (liquid(16), LONG_CUT),
+    "liquid_small_box": lambda: (liquid(5), None),   # box 1.81 nm: fewer than 3 cells per axis
+}
+
+
+@pytest.mark.parametrize("name", list(SYSTEMS))
+def test_forces_match_oracle(name, mode):
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    orc.update_force(olj, o, mode="n2")
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.download(st)
+    if mode == "exact":
+        assert np.array_equal(st.force, o.force)
+        assert np.array_equal(st.potential, o.pot)
+        assert np.array_equal(st.temp, o.vir)
+    else:
+        scale = force_scale(olj, o)
+        rms = np.sqrt((o.force ** 2).sum(axis=1).mean())
+        tol = 1e-10 * np.maximum(scale, rms)[:, None]
+        assert np.all(np.abs(st.force - o.force) <= tol + 1e-300)
+        assert np.all(np.abs(st.potential - o.pot) <= 1e-10 * (np.abs(o.pot) + 4 * olj.eps))
+        assert np.all(np.abs(st.temp - o.vir) <= 1e-10 * (scale * olj.r_cut + 1e-300) + 1e-300)
+
+
+@pytest.mark.parametrize("name", ["dense_gas3000", "liquid1000", "gas1000"])
+def test_cells_and_neighbour_sets_bit_exact(name, mode):
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        cell, dims = s.cells()
+        off, partners = s.neighbour_lists()
+        skin = s.stats()["skin"]
+    # cell assignment: c_d = min(nc_d-1, (int)(frac(x_d / L_d) * nc_d)), linear index (cx*ny + cy)*nz + cz
+    c = []
+    for d in range(3):
+        f = o.pos[:, d] / o.box[d]
+        f = f - np.floor(f)
+        c.append(np.minimum((f * float(dims[d])).astype(np.int64), dims[d] - 1))
+    want_cell = (c[0] * dims[1] + c[1]) * dims[2] + c[2]
+    assert np.array_equal(cell.astype(np.int64), want_cell)
+    # neighbour sets: the reference's pair predicate widened by the skin
+    woff, wpartners = orc.neighbour_sets(o.pos, o.box, olj.r_cut + skin)
+    assert np.array_equal(off, woff)
+    assert np.array_equal(partners, wpartners)
+
+
+def run_oracle(olj, o, n_steps, th=None, ba=None):
+    orc.update_force(olj, o, mode="cells")
+    orc.step(olj, o, DT, thermostat=th, barostat=ba, mode="cells", n_steps=n_steps)
+
+
+@pytest.mark.parametrize("name", ["liquid1000", "dense_gas3000", "gas1000"])
+def test_nve_trajectory_100_steps(name, mode):
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(100, DT)
+        s.download(st)
+        stats = s.stats()
+    run_oracle(olj, o, 100)
+    if mode == "exact":
+        assert np.array_equal(st.position, o.pos)
+        assert np.array_equal(st.velocity, o.vel)
+        assert np.array_equal(st.force, o.force)
+    else:
+        dx = np.abs(st.position - o.pos)
+        dx = np.minimum(dx, np.abs(dx - o.box))  # an atom may sit on either side of the wrap
+        assert dx.max() <= 1e-8
+        assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    assert stats["steps"] == 100
+
+
+@pytest.mark.parametrize("name", ["liquid1000", "gas1000"])
+@pytest.mark.parametrize("ensemble", ["nvt", "npt"])
+def test_thermostat_barostat_trajectory(name, ensemble, mode):
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    st = to_gpu_state(md, o)
+    t0 = 300.0 if name == "gas1000" else 120.0
+    oth, gth = orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, t0), (md.Thermostat.Berendsen(10.0), t0)
+    oba = gba = None
+    if ensemble == "npt":
+        oba, gba = orc.Barostat(1.0, 5.0, 1.01325), (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
+    with make_solver(mode) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(60, DT, thermostat=gth, barostat=gba)
+        s.step(40, DT, thermostat=gth, barostat=gba)  # batches must compose like single calls
+        s.download(st)
+        m = s.macro()
+    run_oracle(olj, o, 100, oth, oba)
+    om = orc.macro(o)
+    assert np.abs(st.boundary_box / o.box - 1.0).max() <= 1e-12
+    dx = np.abs(st.position - o.pos)
+    dx = np.minimum(dx, np.abs(dx - o.box))
+    assert dx.max() <= 1e-8
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    assert abs(gth[0].lambda_ / oth.lambda_ - 1.0) <= 1e-12
+    if oba is not None:
+        assert abs(gba[0].myu / oba.myu - 1.0) <= 1e-12
+    for key in ("kinetic", "thermal", "temperature", "pressure"):
+        assert abs(m[key] - om[key]) <= 1e-9 * max(1.0, abs(om[key])), key
+    assert abs(m["potential"] - om["potential"]) <= 1e-9 * max(1.0, abs(om["potential"]))
+
+
+def test_graph_loop_equals_host_loop(mode):
+    o = liquid(10)
+    out = []
+    for host_loop in (False, True):
+        st = to_gpu_state(md, o)
+        with make_solver(mode, host_loop=host_loop) as s:
+            s.upload(st, with_forces=False)
+            s.update_force()
+            s.step(150, DT, thermostat=(md.Thermostat.Berendsen(10.0), 120.0),
+                   barostat=(md.Barostat.Berendsen(1.0, 5.0), 1.01325))
+            s.download(st)
+            out.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.boundary_box.copy(), s.stats()))
+    for a, b in zip(out[0][:4], out[1][:4]):
+        assert np.array_equal(a, b)
+    assert out[0][4]["graph_launches"] > 0 and out[1][4]["graph_launches"] == 0
+    assert out[0][4]["rebuilds"] == out[1][4]["rebuilds"]
+
+
+def test_run_to_run_determinism():
+    o = liquid(12)
+    res = []
+    for _ in range(2):
+        st = to_gpu_state(md, o)
+        with md.Solver() as s:
+            s.upload(st, with_forces=False)
+            s.update_force()
+            s.step(200, DT, thermostat=(md.Thermostat.Berendsen(10.0), 120.0))
+            s.download(st)
+            res.append((st.position.copy(), st.velocity.copy(), st.force.copy(), s.macro()["pressure"]))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3]
+
+
+def test_rebuild_stress_small_skin(mode):
+    """Skin of 0.02 nm on the liquid forces a list rebuild every few steps; results must not change."""
+    o = liquid(10, temperature=300.0)
+    olj, _ = lj_pair(md)
+    st = to_gpu_state(md, o)
+    with make_solver(mode, skin=0.02) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(100, DT)
+        s.download(st)
+        stats = s.stats()
+    run_oracle(olj, o, 100)
+    assert stats["rebuilds"] >= 10
+    if mode == "exact":
+        assert np.array_equal(st.position, o.pos) and np.array_equal(st.velocity, o.vel)
+    else:
+        assert np.abs(st.velocity - o.vel).max() <= 1e-8
+
+
+def test_cell_subdivision_gives_same_pairs(mode):
+    o = liquid(12)
+    lists = []
+    for sub in (1, 2):
+        st = to_gpu_state(md, o)
+        with make_solver(mode, cell_subdiv=sub, skin=0.1) as s:
+            s.upload(st, with_forces=False)
+            s.update_force()
+            lists.append(s.neighbour_lists())
+            s.download(st)
+    assert np.array_equal(lists[0][0], lists[1][0]) and np.array_equal(lists[0][1], lists[1][1])
+
+
+def test_per_call_api_matches_session(mode):
+    o = liquid(8)
+    a, b = to_gpu_state(md, o), to_gpu_state(md, o)
+    th = lambda: (md.Thermostat.Berendsen(10.0), 120.0)  # noqa: E731
+    with make_solver(mode) as s:
+        s.upload(a, with_forces=False)
+        s.update_force()
+        s.step(5, DT, thermostat=th())
+        s.download(a)
+    with make_solver(mode) as s:
+        s.update_force_host(b)
+        t = th()
+        for _ in range(5):
+            s.calculate_host(b, DT, thermostat=t)
+    if mode == "exact":
+        # same pair sets and ascending-index sums → independent of when lists were built
+        assert np.array_equal(a.position, b.position) and np.array_equal(a.velocity, b.velocity)
+    else:
+        assert np.abs(a.velocity - b.velocity).max() <= 1e-12
+
+
+def test_macro_parameters_match_oracle(mode):
+    o = dense_gas(3000)
+    olj, plj = lj_pair(md)
+    orc.update_force(olj, o)
+    om = orc.macro(o)
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        m = s.macro()
+    for key in ("kinetic", "thermal", "potential", "temperature", "pressure"):
+        assert abs(m[key] - om[key]) <= 1e-12 * max(1.0, abs(om[key])), key
+    assert np.abs(m["vcom"] - om["vcom"]).max() <= 1e-15
+    # shifted one-pass thermal sum stays accurate with a large centre-of-mass drift
+    o.vel += np.array([50.0, -20.0, 10.0])
+    om = orc.macro(o)
+    st = to_gpu_state(md, o)
+    with make_solver(mode) as s:
+        s.upload(st)
+        m = s.macro()
+    assert abs(m["thermal"] / om["thermal"] - 1.0) <= 1e-12
+    assert abs(m["kinetic"] / om["kinetic"] - 1.0) <= 1e-12
+
+
+def test_errors():
+    st = md.State(np.zeros((2, 3)), np.zeros((2, 3)), 1.0, [2.0, 2.0, 2.0])
+    with md.Solver() as s:
+        with pytest.raises(md.MdError) as e:
+            s.step(1, DT)
+        assert e.value.code == 6  # MD_ERR_NO_STATE
+        s.upload(st)
+        with pytest.raises(md.MdError) as e:
+            s.step(1, DT, thermostat=(md.Thermostat.NoseHoover(1.0), 300.0))
+        assert e.value.code == 4  # MD_ERR_UNSUPPORTED
+        with pytest.raises(md.MdError) as e:  # T = 0 → Berendsen lambda is not finite (no guard in the reference)
+            s.step(1, DT, thermostat=(md.Thermostat.Berendsen(1.0), 300.0))
+        assert e.value.code == 7
+    with pytest.raises(md.MdError):
+        md.Integrator.Custom("x").calculate(md.PotentialsDatabase(), st, DT)
+    with pytest.raises(md.MdError):
+        md.State(np.zeros((0, 3)), np.zeros((0, 3)), 1.0, [1, 1, 1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs): size-independent checks + sampled rows against the oracle
+@pytest.mark.parametrize("n_side,cut", [(100, None), (64, LONG_CUT)])
+def test_full_size_sampled_rows_and_invariants(n_side, cut):
+    if cut is None:
+        o = gas(n_side)
+        # move the lattice off its zero-force symmetry point
+        rng = np.random.default_rng(1)
+        o.pos += rng.uniform(-1.45, 1.45, o.pos.shape)
+        orc.apply_boundary_conditions(o)
+    else:
+        o = liquid(n_side, jitter=0.03)
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    st = to_gpu_state(md, o)
+    with md.Solver(exact=True) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.download(st)
+        m0 = s.macro()
+        # sampled rows, bit-exact against the reference's Θ(N) row scan
+        for i0 in (0, o.n // 2 - 128, o.n - 256):
+            orc.update_force(olj, o, rows=(i0, i0 + 256))
+            assert np.array_equal(st.force[i0:i0 + 256], o.force[i0:i0 + 256])
+            assert np.array_equal(st.potential[i0:i0 + 256], o.pot[i0:i0 + 256])
+            assert np.array_equal(st.temp[i0:i0 + 256], o.vir[i0:i0 + 256])
+        # Newton's third law holds pairwise → net force is rounding noise
+        assert np.abs(st.force.sum(axis=0)).max() <= 1e-9 * np.abs(st.force).sum()
+        s.step(50, DT)
+        m1 = s.macro()
+    e0, e1 = m0["kinetic"] + m0["potential"], m1["kinetic"] + m1["potential"]
+    assert abs(e1 - e0) <= 1e-3 * abs(m0["kinetic"])       # NVE energy conservation at dt = 2 fs (oracle: 1.1e-4)
+    assert np.abs(m1["momentum"]).max() <= 1e-9 * o.n       # Σ m v stays ~0
