@@ -44,5 +44,23 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = [os.path.join(HERE, "host", "moldyn.cpp"), os.path.join(HERE, "host", "moldyn_cli.cpp")]
+HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", "moldyn.hpp"), os.path.join(ROOT, "include", "moldyn_b200.h")]
+CLI = os.path.join(HERE, "lib", "moldyn_cli")
+
+
+def build_cli(force: bool = False) -> str:
+    """C++ host mirror + the moldyn_cli-compatible driver, linked against libmoldyn_b200.so (rpath $ORIGIN)."""
+    build_library()
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(CLI) >= os.path.getmtime(d) for d in HOST_DEPS + [LIB]):
+        return CLI
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", CLI, *HOST_SRC, "-L", os.path.dirname(LIB),
+           "-lmoldyn_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return CLI
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cli(force="--force" in sys.argv))

@@ -59,7 +59,7 @@ struct Scalars {
     unsigned int ticket;
     int nbr_max;       // largest neighbour count of the last build
     int nbr_overflow;  // some atom exceeded the capacity
-    int pad0;
+    int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     unsigned long long nbr_total;
 };
 
@@ -417,6 +417,8 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
     if (mode & FIN_STEP) {
         sc->steps_left -= 1;
         sc->steps_done += 1;
+        // k_force stored u = v + F*c instead of v unless this was the last step of the batch
+        sc->vel_is_half = sc->steps_left > 0 ? 1 : 0;
     }
 }
 
@@ -440,6 +442,7 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
     Sums acc;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) acc.v[q] = 0.0;
+#pragma unroll 4
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {  // fixed assignment → fixed order
 #pragma unroll
         for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += __ldcg(&partials[(size_t)b * NSUM + q]);
@@ -456,20 +459,17 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
     }
 }
 
-__device__ __forceinline__ void accumulate_sums(Sums &s, double m, double vx, double vy, double vz, double fx,
-                                                double fy, double fz, double w, double u, double c,
-                                                const double *shift)
+// Adds one atom's terms. (wx,wy,wz) = v + F*c is the velocity the next kick_drift moves this atom with (before lambda).
+__device__ __forceinline__ void accumulate_sums(Sums &s, double m, double vx, double vy, double vz, double wx,
+                                                double wy, double wz, double w, double u, const double *shift)
 {
-    s.v[0] = m * vx; s.v[1] = m * vy; s.v[2] = m * vz;
+    s.v[0] += m * vx; s.v[1] += m * vy; s.v[2] += m * vz;
     double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
-    s.v[3] = m * (ax * ax + ay * ay + az * az);
-    s.v[4] = m * (vx * vx + vy * vy + vz * vz);
-    s.v[5] = w;
-    s.v[6] = u;
-    // velocity the next kick_drift will move this atom with (before lambda): v + F*c, same arithmetic
-    double wx = __dadd_rn(vx, __dmul_rn(fx, c)), wy = __dadd_rn(vy, __dmul_rn(fy, c)),
-           wz = __dadd_rn(vz, __dmul_rn(fz, c));
-    s.v[7] = wx * wx + wy * wy + wz * wz;
+    s.v[3] += m * (ax * ax + ay * ay + az * az);
+    s.v[4] += m * (vx * vx + vy * vy + vz * vz);
+    s.v[5] += w;
+    s.v[6] += u;
+    s.v[7] = fmax(s.v[7], wx * wx + wy * wy + wz * wz);
 }
 
 // Standalone K5 over the stored state (after upload, or when only the macro parameters are wanted).
@@ -480,39 +480,53 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
     Sums s;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
-    int i = blockIdx.x * RED_BLOCK + threadIdx.x;
-    if (i < n) {
-        double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
-        accumulate_sums(s, pr->mass, a.vx[i], a.vy[i], a.vz[i], a.fx[i], a.fy[i], a.fz[i], a.w[i], a.u[i],
-                        pr->half_dt_m, shift);
+    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    const double c = pr->half_dt_m, m = pr->mass;
+    for (int i = blockIdx.x * RED_BLOCK + threadIdx.x; i < n; i += gridDim.x * RED_BLOCK) {
+        double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
+        double wx = __dadd_rn(vx, __dmul_rn(a.fx[i], c)), wy = __dadd_rn(vy, __dmul_rn(a.fy[i], c)),
+               wz = __dadd_rn(vz, __dmul_rn(a.fz[i], c));
+        accumulate_sums(s, m, vx, vy, vz, wx, wy, wz, a.w[i], a.u[i], shift);
     }
     block_reduce<RED_BLOCK>(s);
     grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, 0, 0ull);
 }
 
 // ----------------------------------------------------------------------------------------------------
-// K3: pair forces from the Verlet list, one thread per atom (each ordered pair evaluated from both sides,
-// like the reference — no Newton-3 sharing, no atomics, deterministic).
+// K3: pair forces from the Verlet list (each ordered pair evaluated from both sides, like the reference — no
+// Newton-3 sharing, no atomics, deterministic), fused with both half-kicks that surround it and the K5 sums.
 //   EXACT: potential.rs:181-211 operation by operation, no FMA, partners in ascending upload index.
 //   FAST : r²-based Lennard-Jones (one division, no sqrt), FMA allowed.
-// KICK fuses the second half-kick v += F*dt/(2m) (integrator.rs:47-53) and the K5 sums of the new state.
+// Persistent grid (a fixed number of blocks, grid-stride over atoms): few per-block partials for the final
+// fixed-order reduction, and the atom→thread assignment (hence every sum) is fixed for a given grid.
+//
+// Velocity planes: on entry of a step they hold u = v + F_old*c (first half-kick done, thermostat scale not yet).
+//   v'  = lambda * u                       thermostat.rs:54-58 (the same product k_kick_drift drifted with)
+//   v'' = v' + F*c                         integrator.rs:47-53 — end-of-step velocity, enters the K5 sums
+//   u'  = v'' + F*c                        integrator.rs:28-34 of the NEXT step (same F, same c)
+// Steady state stores only u' (72 B/atom in, 24 B/atom out); the last step of a batch stores v'', F, U, W so the
+// resident State is complete whenever the host can observe it.
 constexpr int FORCE_BLOCK = 128;
 
-template <bool EXACT, bool KICK>
-__global__ void __launch_bounds__(FORCE_BLOCK) k_force(int n, Arrays a, const int *__restrict__ nbr,
-                                                       const int *__restrict__ nbr_cnt, int npad,
-                                                       double *__restrict__ partials, Scalars *sc,
-                                                       const Params *__restrict__ pr,
-                                                       unsigned long long cond_handle)
+template <bool EXACT>
+__global__ void __launch_bounds__(FORCE_BLOCK, EXACT ? 4 : 5) k_force(int n, Arrays a, const int *__restrict__ nbr,
+                                                                       const int *__restrict__ nbr_cnt, int npad,
+                                                                       double *__restrict__ partials, Scalars *sc,
+                                                                       const Params *__restrict__ pr, int do_step,
+                                                                       unsigned long long cond_handle)
 {
     Sums s;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
-    int i = blockIdx.x * FORCE_BLOCK + threadIdx.x;
-    if (i < n) {
-        const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-        const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
-        const double sigma = pr->sigma, eps = pr->eps, r_cut = pr->r_cut, u_cut = pr->u_cut;
+    // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
+    const bool store_state = !do_step || sc->steps_left <= 1;
+    const double lambda = sc->lambda;
+    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+    const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
+    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    const double sigma = pr->sigma, eps = pr->eps, r_cut = pr->r_cut, u_cut = pr->u_cut;
+    const double c = pr->half_dt_m, mass = pr->mass;
+    for (int i = blockIdx.x * FORCE_BLOCK + threadIdx.x; i < n; i += gridDim.x * FORCE_BLOCK) {
         const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
         double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0, w = 0.0;
         const int cnt = nbr_cnt[i];
@@ -558,37 +572,39 @@ __global__ void __launch_bounds__(FORCE_BLOCK) k_force(int n, Arrays a, const in
                 w += fr * r2;
             }
         }
-        a.fx[i] = fx; a.fy[i] = fy; a.fz[i] = fz;
-        a.u[i] = u; a.w[i] = w;
         double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
-        const double c = pr->half_dt_m;
-        if (KICK) {  // particle.velocity += particle.force * temp   integrator.rs:49-52
-            vx = __dadd_rn(vx, __dmul_rn(fx, c));
-            vy = __dadd_rn(vy, __dmul_rn(fy, c));
-            vz = __dadd_rn(vz, __dmul_rn(fz, c));
-            a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz;
+        if (do_step) {
+            vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(fx, c));  // v'' = lambda*u + F*c
+            vy = __dadd_rn(__dmul_rn(vy, lambda), __dmul_rn(fy, c));
+            vz = __dadd_rn(__dmul_rn(vz, lambda), __dmul_rn(fz, c));
         }
-        double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
-        accumulate_sums(s, pr->mass, vx, vy, vz, fx, fy, fz, w, u, c, shift);
+        const double wx = __dadd_rn(vx, __dmul_rn(fx, c)), wy = __dadd_rn(vy, __dmul_rn(fy, c)),
+                     wz = __dadd_rn(vz, __dmul_rn(fz, c));                // u' = v'' + F*c
+        accumulate_sums(s, mass, vx, vy, vz, wx, wy, wz, w, u, shift);
+        if (store_state) {
+            a.fx[i] = fx; a.fy[i] = fy; a.fz[i] = fz;
+            a.u[i] = u; a.w[i] = w;
+            if (do_step) { a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz; }
+        } else {
+            a.vx[i] = wx; a.vy[i] = wy; a.vz[i] = wz;
+        }
     }
     block_reduce<FORCE_BLOCK>(s);
-    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr, KICK ? FIN_STEP : 0, cond_handle);
+    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr, do_step ? FIN_STEP : 0, cond_handle);
 }
 
 // ----------------------------------------------------------------------------------------------------
-// K4: first half-kick, thermostat scale, pending barostat coordinate scale, drift, periodic wrap.
-//   integrator.rs:28-34  v = v + F*(dt/(2m))
-//   thermostat.rs:54-58  v *= lambda            (lambda == 1.0 without thermostat: bitwise no-op)
+// K4: (first half-kick,) thermostat scale, pending barostat coordinate scale, drift, periodic wrap.
+//   integrator.rs:28-34  u = v + F*(dt/(2m))    only on the first step of a batch; afterwards k_force left u
+//   thermostat.rs:54-58  v' = u*lambda          (lambda == 1.0 without thermostat: bitwise no-op)
 //   barostat.rs:46-48    x *= myu of the previous step (mu_pending == 1.0 otherwise: bitwise no-op)
-//   integrator.rs:40-44  x += v*dt
+//   integrator.rs:40-44  x += v'*dt
 //   particle.rs:120-142  single-shift wrap into [0, L)
 // Element-wise and HBM-bound: two atoms per thread, 128-bit accesses; explicit _rn intrinsics keep the
-// reference's rounding (no FMA contraction).
-__device__ __forceinline__ void kd_one(double &x, double &v, double f, double c, double lambda, double mup,
-                                       double dt, double L)
+// reference's rounding (no FMA contraction).  v' itself is not stored: k_force recomputes the same product.
+__device__ __forceinline__ void drift_one(double &x, double u, double lambda, double mup, double dt, double L)
 {
-    v = __dadd_rn(v, __dmul_rn(f, c));
-    v = __dmul_rn(v, lambda);
+    double v = __dmul_rn(u, lambda);
     x = __dmul_rn(x, mup);
     x = __dadd_rn(x, __dmul_rn(v, dt));
     if (x < 0.0) x = __dadd_rn(x, L);
@@ -603,18 +619,25 @@ __global__ void __launch_bounds__(256) k_kick_drift(int npairs, Arrays a, const 
     const double c = pr->half_dt_m, dt = pr->dt;
     const double lambda = sc->lambda, mup = sc->mu_pending;
     const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+    const bool half = sc->vel_is_half != 0;
     double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
             z = reinterpret_cast<double2 *>(a.z)[t];
-    double2 vx = reinterpret_cast<double2 *>(a.vx)[t], vy = reinterpret_cast<double2 *>(a.vy)[t],
-            vz = reinterpret_cast<double2 *>(a.vz)[t];
-    const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
-                  fz = reinterpret_cast<const double2 *>(a.fz)[t];
-    kd_one(x.x, vx.x, fx.x, c, lambda, mup, dt, Lx); kd_one(x.y, vx.y, fx.y, c, lambda, mup, dt, Lx);
-    kd_one(y.x, vy.x, fy.x, c, lambda, mup, dt, Ly); kd_one(y.y, vy.y, fy.y, c, lambda, mup, dt, Ly);
-    kd_one(z.x, vz.x, fz.x, c, lambda, mup, dt, Lz); kd_one(z.y, vz.y, fz.y, c, lambda, mup, dt, Lz);
-    reinterpret_cast<double2 *>(a.x)[t] = x;   reinterpret_cast<double2 *>(a.y)[t] = y;
-    reinterpret_cast<double2 *>(a.z)[t] = z;   reinterpret_cast<double2 *>(a.vx)[t] = vx;
-    reinterpret_cast<double2 *>(a.vy)[t] = vy; reinterpret_cast<double2 *>(a.vz)[t] = vz;
+    double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
+            uz = reinterpret_cast<double2 *>(a.vz)[t];
+    if (!half) {
+        const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
+                      fz = reinterpret_cast<const double2 *>(a.fz)[t];
+        ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
+        uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
+        uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));
+        reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
+        reinterpret_cast<double2 *>(a.vz)[t] = uz;
+    }
+    drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
+    drift_one(y.x, uy.x, lambda, mup, dt, Ly); drift_one(y.y, uy.y, lambda, mup, dt, Ly);
+    drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
+    reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
+    reinterpret_cast<double2 *>(a.z)[t] = z;
 }
 
 // barostat.update's coordinate scaling when no kick_drift follows (end of an md_step batch).

@@ -58,6 +58,7 @@ struct md_ctx {
     Params prm{};
     double *d_partials = nullptr;
     int partial_blocks = 0;
+    int force_grid = 1, reduce_grid = 1;
 
     // cells / lists
     Grid grid{};
@@ -350,25 +351,37 @@ int launch_kick_drift(md_ctx *ctx)
 int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
 {
     const int n = (int)ctx->n;
-    const int nb = blocks_for(n, FORCE_BLOCK);
-    const bool exact = ctx->cfg.force_mode == MD_FORCE_EXACT;
-#define LAUNCH_FORCE(E, K)                                                                                   \
-    k_force<E, K><<<nb, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,       \
-                                                        ctx->d_partials, ctx->d_sc, ctx->d_pr, cond)
-    if (exact && kick) LAUNCH_FORCE(true, true);
-    else if (exact) LAUNCH_FORCE(true, false);
-    else if (kick) LAUNCH_FORCE(false, true);
-    else LAUNCH_FORCE(false, false);
-#undef LAUNCH_FORCE
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
+        k_force<true><<<ctx->force_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,
+                                                                        ctx->d_partials, ctx->d_sc, ctx->d_pr,
+                                                                        kick ? 1 : 0, cond);
+    else
+        k_force<false><<<ctx->force_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,
+                                                                         ctx->d_partials, ctx->d_sc, ctx->d_pr,
+                                                                         kick ? 1 : 0, cond);
     return MD_OK;
 }
 
 int launch_reduce(md_ctx *ctx)
 {
     const int n = (int)ctx->n;
-    k_reduce_state<<<blocks_for(n, RED_BLOCK), RED_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->d_partials, ctx->d_sc,
-                                                                            ctx->d_pr);
+    k_reduce_state<<<ctx->reduce_grid, RED_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->d_partials, ctx->d_sc, ctx->d_pr);
     ctx->stats.kernel_launches += 1;
+    return MD_OK;
+}
+
+// Persistent grids: resident blocks per SM (occupancy API) × SM count, capped by the work available.
+int choose_grids(md_ctx *ctx)
+{
+    int sms = 0, occ_f = 0, occ_r = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_force<true>, FORCE_BLOCK, 0));
+    else
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_force<false>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
+    ctx->force_grid = std::max(1, std::min(blocks_for(ctx->n, FORCE_BLOCK), sms * std::max(occ_f, 1)));
+    ctx->reduce_grid = std::max(1, std::min(blocks_for(ctx->n, RED_BLOCK), sms * std::max(occ_r, 1)));
     return MD_OK;
 }
 
@@ -548,7 +561,8 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         TRY(alloc_arrays(ctx, &ctx->alt, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->stage, 3 * (size_t)ctx->npad));
         TRY(dev_alloc(ctx, &ctx->stage_i, ctx->npad));
-        ctx->partial_blocks = std::max(blocks_for(n, FORCE_BLOCK), blocks_for(n, RED_BLOCK));
+        TRY(choose_grids(ctx));
+        ctx->partial_blocks = std::max(ctx->force_grid, ctx->reduce_grid);
         TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
         TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
