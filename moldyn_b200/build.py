@@ -33,7 +33,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("MD_NVCC_EXTRA", "").split(), "-o", LIB, SRC]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), file=sys.stderr)

@@ -506,14 +506,99 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
 //   u'  = v'' + F*c                        integrator.rs:28-34 of the NEXT step (same F, same c)
 // Steady state stores only u' (72 B/atom in, 24 B/atom out); the last step of a batch stores v'', F, U, W so the
 // resident State is complete whenever the host can observe it.
+#ifndef MD_FORCE_MINB
+#define MD_FORCE_MINB 4
+#endif
 constexpr int FORCE_BLOCK = 128;
 
+struct LjConst {
+    double Lx, Ly, Lz, hx, hy, hz;
+    double sigma, sigma2, eps4, eps24, r_cut, rc2, u_cut;
+    int hxi, hyi, hzi;  // high words of hx, hy, hz: integer-pipe pre-test of the minimum-image condition
+};
+
+struct PairAcc {
+    double fx, fy, fz, u, w;
+};
+
+// |r| >= h can only hold if the high word of |r| is >= the high word of h: the common (no wrap) case costs one
+// integer compare instead of two FP64 compares; the exact single-shift rule runs only when the pre-test fires.
+__device__ __forceinline__ double min_image_fast(double r, double L, double h, int hhi)
+{
+    if ((__double2hiint(r) & 0x7fffffff) >= hhi) r = min_image(r, L, h);
+    return r;
+}
+
+// FAST pair term, branch-free: masked pairs (k beyond this atom's list, or outside the cutoff) contribute exact zeros.
+__device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, double yj, double zj, double xi,
+                                          double yi, double zi, const LjConst &c)
+{
+    double rx = min_image_fast(xj - xi, c.Lx, c.hx, c.hxi);
+    double ry = min_image_fast(yj - yi, c.Ly, c.hy, c.hyi);
+    double rz = min_image_fast(zj - zi, c.Lz, c.hz, c.hzi);
+    double r2 = rx * rx + ry * ry + rz * rz;
+    bool in = active && (r2 <= c.rc2);
+    double inv = 1.0 / (in ? r2 : 1.0);
+    double s2 = c.sigma2 * inv;
+    double s6 = s2 * s2 * s2;
+    double s12 = s6 * s6;
+    double fr = c.eps24 * inv * (s6 - 2.0 * s12);  // F / r
+    double pu = c.eps4 * (s12 - s6) - c.u_cut;
+    fr = in ? fr : 0.0;
+    pu = in ? pu : 0.0;
+    a.u += pu;
+    a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
+    a.w += fr * r2;
+}
+
+// EXACT pair term: potential.rs:181-211 operation by operation, no contraction, real branch on the cutoff.
+__device__ __forceinline__ void pair_exact(PairAcc &a, double xj, double yj, double zj, double xi, double yi,
+                                           double zi, const LjConst &c)
+{
+    double rx = min_image(__dsub_rn(xj, xi), c.Lx, c.hx);
+    double ry = min_image(__dsub_rn(yj, yi), c.Ly, c.hy);
+    double rz = min_image(__dsub_rn(zj, zi), c.Lz, c.hz);
+    double r = norm_exact(rx, ry, rz);
+    if (r > c.r_cut) return;                             // potential.rs:202 (inclusive cutoff)
+    double sr = __ddiv_rn(c.sigma, r);                    // potential.rs:63
+    double x2 = __dmul_rn(sr, sr), x4 = __dmul_rn(x2, x2);
+    double s6 = __dmul_rn(x2, x4);                        // powi(6) = x² · x⁴
+    double s12 = __dmul_rn(s6, s6);
+    double pu = __dsub_rn(__dmul_rn(c.eps4, __dsub_rn(s12, s6)), c.u_cut);
+    double pf = __dmul_rn(__ddiv_rn(c.eps24, r), __dsub_rn(s6, __dmul_rn(2.0, s12)));
+    double vx = __dmul_rn(__ddiv_rn(rx, r), pf);          // r / r_abs * force   potential.rs:207
+    double vy = __dmul_rn(__ddiv_rn(ry, r), pf);
+    double vz = __dmul_rn(__ddiv_rn(rz, r), pf);
+    double t = __dadd_rn(__dadd_rn(__dmul_rn(vx, rx), __dmul_rn(vy, ry)), __dmul_rn(vz, rz));
+    a.fx = __dadd_rn(a.fx, vx); a.fy = __dadd_rn(a.fy, vy); a.fz = __dadd_rn(a.fz, vz);
+    a.u = __dadd_rn(a.u, pu);
+    a.w = __dadd_rn(a.w, t);
+}
+
+// Both half-kicks around the force (see header comment above), the K5 terms, and the stores of one atom.
+__device__ __forceinline__ void finish_atom(Sums &s, const PairAcc &f, double &vx, double &vy, double &vz,
+                                            bool do_step, double lambda, double c, double mass, const double *shift,
+                                            double &wx, double &wy, double &wz)
+{
+    if (do_step) {
+        vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(f.fx, c));  // v'' = lambda*u + F*c
+        vy = __dadd_rn(__dmul_rn(vy, lambda), __dmul_rn(f.fy, c));
+        vz = __dadd_rn(__dmul_rn(vz, lambda), __dmul_rn(f.fz, c));
+    }
+    wx = __dadd_rn(vx, __dmul_rn(f.fx, c));                         // u' = v'' + F*c
+    wy = __dadd_rn(vy, __dmul_rn(f.fy, c));
+    wz = __dadd_rn(vz, __dmul_rn(f.fz, c));
+    accumulate_sums(s, mass, vx, vy, vz, wx, wy, wz, f.w, f.u, shift);
+}
+
+// Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
+// before the first use, and the neighbour loop advances both lists together (two independent gather chains).
 template <bool EXACT>
-__global__ void __launch_bounds__(FORCE_BLOCK, EXACT ? 4 : 5) k_force(int n, Arrays a, const int *__restrict__ nbr,
-                                                                       const int *__restrict__ nbr_cnt, int npad,
-                                                                       double *__restrict__ partials, Scalars *sc,
-                                                                       const Params *__restrict__ pr, int do_step,
-                                                                       unsigned long long cond_handle)
+__global__ void __launch_bounds__(FORCE_BLOCK, MD_FORCE_MINB) k_force(int n, Arrays a, const int *__restrict__ nbr,
+                                                          const int *__restrict__ nbr_cnt, int npad,
+                                                          double *__restrict__ partials, Scalars *sc,
+                                                          const Params *__restrict__ pr, int do_step,
+                                                          unsigned long long cond_handle)
 {
     Sums s;
 #pragma unroll
@@ -521,72 +606,86 @@ __global__ void __launch_bounds__(FORCE_BLOCK, EXACT ? 4 : 5) k_force(int n, Arr
     // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
     const bool store_state = !do_step || sc->steps_left <= 1;
     const double lambda = sc->lambda;
-    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-    const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
+    LjConst c;
+    c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
+    c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
+    c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
+    c.sigma = pr->sigma; c.r_cut = pr->r_cut; c.u_cut = pr->u_cut;
+    if (EXACT) {
+        c.eps4 = __dmul_rn(4.0, pr->eps); c.eps24 = __dmul_rn(24.0, pr->eps);
+        c.sigma2 = 0.0; c.rc2 = 0.0;
+    } else {
+        c.eps4 = 4.0 * pr->eps; c.eps24 = 24.0 * pr->eps;
+        c.sigma2 = c.sigma * c.sigma; c.rc2 = c.r_cut * c.r_cut;
+    }
     const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
-    const double sigma = pr->sigma, eps = pr->eps, r_cut = pr->r_cut, u_cut = pr->u_cut;
-    const double c = pr->half_dt_m, mass = pr->mass;
-    for (int i = blockIdx.x * FORCE_BLOCK + threadIdx.x; i < n; i += gridDim.x * FORCE_BLOCK) {
-        const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
-        double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0, w = 0.0;
-        const int cnt = nbr_cnt[i];
+    const double hc = pr->half_dt_m, mass = pr->mass;
+    const int npairs = (n + 1) >> 1;
+    const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
+    for (int t = blockIdx.x * FORCE_BLOCK + threadIdx.x; t < npairs; t += gridDim.x * FORCE_BLOCK) {
+        const int i0 = 2 * t;
+        const bool has1 = i0 + 1 < n;
+        const double2 X = reinterpret_cast<const double2 *>(px)[t], Y = reinterpret_cast<const double2 *>(py)[t],
+                      Z = reinterpret_cast<const double2 *>(pz)[t];
+        int2 C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
+        double2 VX = reinterpret_cast<double2 *>(a.vx)[t], VY = reinterpret_cast<double2 *>(a.vy)[t],
+                VZ = reinterpret_cast<double2 *>(a.vz)[t];
+        if (!has1) C.y = 0;
+        PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + t;
+        const size_t stride = (size_t)(npad >> 1);
         if (EXACT) {
-            const double eps4 = __dmul_rn(4.0, eps), eps24 = __dmul_rn(24.0, eps);
-            for (int k = 0; k < cnt; ++k) {
-                int j = nbr[(size_t)k * npad + i];
-                double rx = min_image(__dsub_rn(a.x[j], xi), Lx, hx);
-                double ry = min_image(__dsub_rn(a.y[j], yi), Ly, hy);
-                double rz = min_image(__dsub_rn(a.z[j], zi), Lz, hz);
-                double r = norm_exact(rx, ry, rz);
-                if (r > r_cut) continue;                       // potential.rs:202 (inclusive cutoff)
-                double sr = __ddiv_rn(sigma, r);                // potential.rs:63
-                double x2 = __dmul_rn(sr, sr), x4 = __dmul_rn(x2, x2);
-                double s6 = __dmul_rn(x2, x4);                  // powi(6) = x² · x⁴
-                double s12 = __dmul_rn(s6, s6);
-                double pu = __dsub_rn(__dmul_rn(eps4, __dsub_rn(s12, s6)), u_cut);
-                double pf = __dmul_rn(__ddiv_rn(eps24, r), __dsub_rn(s6, __dmul_rn(2.0, s12)));
-                double vx = __dmul_rn(__ddiv_rn(rx, r), pf);    // r / r_abs * force   potential.rs:207
-                double vy = __dmul_rn(__ddiv_rn(ry, r), pf);
-                double vz = __dmul_rn(__ddiv_rn(rz, r), pf);
-                double t = __dadd_rn(__dadd_rn(__dmul_rn(vx, rx), __dmul_rn(vy, ry)), __dmul_rn(vz, rz));
-                fx = __dadd_rn(fx, vx); fy = __dadd_rn(fy, vy); fz = __dadd_rn(fz, vz);
-                u = __dadd_rn(u, pu);
-                w = __dadd_rn(w, t);
+            for (int k = 0; k < C.x; ++k) {
+                int j = row[k * stride].x;
+                pair_exact(f0, px[j], py[j], pz[j], X.x, Y.x, Z.x, c);
+            }
+            for (int k = 0; k < C.y; ++k) {
+                int j = row[k * stride].y;
+                pair_exact(f1, px[j], py[j], pz[j], X.y, Y.y, Z.y, c);
             }
         } else {
-            const double rc2 = r_cut * r_cut, sigma2 = sigma * sigma, eps4 = 4.0 * eps, eps24 = 24.0 * eps;
-            for (int k = 0; k < cnt; ++k) {
-                int j = nbr[(size_t)k * npad + i];
-                double rx = min_image(a.x[j] - xi, Lx, hx);
-                double ry = min_image(a.y[j] - yi, Ly, hy);
-                double rz = min_image(a.z[j] - zi, Lz, hz);
-                double r2 = rx * rx + ry * ry + rz * rz;
-                if (r2 > rc2) continue;
-                double inv = 1.0 / r2;
-                double s2 = sigma2 * inv;
-                double s6 = s2 * s2 * s2;
-                double s12 = s6 * s6;
-                double fr = eps24 * inv * (s6 - 2.0 * s12);  // F / r
-                u += eps4 * (s12 - s6) - u_cut;
-                fx += fr * rx; fy += fr * ry; fz += fr * rz;
-                w += fr * r2;
+            const int kmax = max(C.x, C.y);
+            int k = 0;
+            for (; k + 1 < kmax; k += 2) {  // two rows per trip: 4 index loads, 12 gathers in flight
+                const int2 Ja = row[k * stride], Jb = row[(k + 1) * stride];
+                const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+                const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
+                const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
+                const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
+                const double xb0 = px[jb0], yb0 = py[jb0], zb0 = pz[jb0];
+                const double xb1 = px[jb1], yb1 = py[jb1], zb1 = pz[jb1];
+                pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
+                pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                pair_fast(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c);
+                pair_fast(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c);
+            }
+            if (k < kmax) {
+                const int2 Ja = row[k * stride];
+                const bool a0 = k < C.x, a1 = k < C.y;
+                const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
+                const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
+                const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
+                pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
+                pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
             }
         }
-        double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
-        if (do_step) {
-            vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(fx, c));  // v'' = lambda*u + F*c
-            vy = __dadd_rn(__dmul_rn(vy, lambda), __dmul_rn(fy, c));
-            vz = __dadd_rn(__dmul_rn(vz, lambda), __dmul_rn(fz, c));
-        }
-        const double wx = __dadd_rn(vx, __dmul_rn(fx, c)), wy = __dadd_rn(vy, __dmul_rn(fy, c)),
-                     wz = __dadd_rn(vz, __dmul_rn(fz, c));                // u' = v'' + F*c
-        accumulate_sums(s, mass, vx, vy, vz, wx, wy, wz, w, u, shift);
+        double2 WX, WY, WZ;
+        finish_atom(s, f0, VX.x, VY.x, VZ.x, do_step != 0, lambda, hc, mass, shift, WX.x, WY.x, WZ.x);
+        if (has1) finish_atom(s, f1, VX.y, VY.y, VZ.y, do_step != 0, lambda, hc, mass, shift, WX.y, WY.y, WZ.y);
+        else { WX.y = WY.y = WZ.y = 0.0; }
         if (store_state) {
-            a.fx[i] = fx; a.fy[i] = fy; a.fz[i] = fz;
-            a.u[i] = u; a.w[i] = w;
-            if (do_step) { a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz; }
+            reinterpret_cast<double2 *>(a.fx)[t] = make_double2(f0.fx, f1.fx);
+            reinterpret_cast<double2 *>(a.fy)[t] = make_double2(f0.fy, f1.fy);
+            reinterpret_cast<double2 *>(a.fz)[t] = make_double2(f0.fz, f1.fz);
+            reinterpret_cast<double2 *>(a.u)[t] = make_double2(f0.u, f1.u);
+            reinterpret_cast<double2 *>(a.w)[t] = make_double2(f0.w, f1.w);
+            if (do_step) {
+                reinterpret_cast<double2 *>(a.vx)[t] = VX; reinterpret_cast<double2 *>(a.vy)[t] = VY;
+                reinterpret_cast<double2 *>(a.vz)[t] = VZ;
+            }
         } else {
-            a.vx[i] = wx; a.vy[i] = wy; a.vz[i] = wz;
+            reinterpret_cast<double2 *>(a.vx)[t] = WX; reinterpret_cast<double2 *>(a.vy)[t] = WY;
+            reinterpret_cast<double2 *>(a.vz)[t] = WZ;
         }
     }
     block_reduce<FORCE_BLOCK>(s);

@@ -1,0 +1,5 @@
+#!/bin/bash
+# full ncu capture of k_force late in a c3 run (lists non-empty) and in c5
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_force' -s 12100 -c 2 -o gpurun_out/prof_c3_late -f python bench.py --workload c3 --steps 100 --warmup 12000 --e2e-steps 0 --cpu-rows -1 > gpurun_out/ncu_c3_late.log 2>&1; tail -2 gpurun_out/ncu_c3_late.log | cut -c1-200
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_force' -s 320 -c 1 -o gpurun_out/prof_c5_v3 -f python bench.py --workload c5 --steps 60 --warmup 300 --e2e-steps 0 --cpu-rows -1 > gpurun_out/ncu_c5_v3.log 2>&1; tail -2 gpurun_out/ncu_c5_v3.log | cut -c1-200
