@@ -197,7 +197,7 @@ def run_ours(args, w):
     ba = (lambda: (md.Barostat.Berendsen(w["barostat"][0], w["barostat"][1]), w["barostat"][2])) if w["barostat"] \
         else (lambda: None)
 
-    s = md.Solver(device=local, skin=args.skin)
+    s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv)
     if w["cut"]:
         s.set_potential(md.Potential(0.3418, 1.712, *w["cut"]))
     s.upload_arrays(pos, vel, ARGON_MASS, box)
@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--skin", type=float, default=0.0)
+    ap.add_argument("--cell-atoms", type=float, default=0.0)
+    ap.add_argument("--cell-subdiv", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
     args = ap.parse_args()

@@ -58,7 +58,7 @@ typedef struct md_config {
     int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = 1 */
     int32_t reserved0;
     double skin;            /* Verlet skin [nm]; <= 0 selects a default from r_cut and density */
-    double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 3 */
+    double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 1 */
 } md_config;
 
 /* Thermostat (solver/src/initializer/thermostat.rs:4-22).  lambda/psi are written back after

@@ -234,45 +234,56 @@ __global__ void k_reorder(int n, const int *__restrict__ order, const int *__res
 template <bool SORT_BY_ID>
 __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *__restrict__ cell_sorted,
                                                     const int *__restrict__ cell_start, Scalars *sc, Grid g,
-                                                    double r_list, int *__restrict__ nbr,
+                                                    double r_list, double r2_list, int *__restrict__ nbr,
                                                     int *__restrict__ nbr_cnt)
 {
+    // r2_list is the largest double whose correctly rounded square root is <= r_list (computed by the host), so
+    // `(rx*rx + ry*ry) + rz*rz <= r2_list` IS the predicate `norm(r) <= r_list` — without the square root.
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (p < n) {
         const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
         const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
         const double xi = a.x[p], yi = a.y[p], zi = a.z[p];
+        const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
         int c = cell_sorted[p];
-        int cz = c % g.nc[2];
-        int cy = (c / g.nc[2]) % g.nc[1];
-        int cx = c / (g.nc[2] * g.nc[1]);
+        int cz = c % ncz;
+        int cy = (c / ncz) % ncy;
+        int cx = c / (ncz * ncy);
         int w = 2 * g.nsub + 1;
-        int lox, loy, loz, nx, ny, nz;
-        if (g.nc[0] >= w) { lox = cx - g.nsub; nx = w; } else { lox = 0; nx = g.nc[0]; }
-        if (g.nc[1] >= w) { loy = cy - g.nsub; ny = w; } else { loy = 0; ny = g.nc[1]; }
-        if (g.nc[2] >= w) { loz = cz - g.nsub; nz = w; } else { loz = 0; nz = g.nc[2]; }
+        int lox, loy, nx, ny;
+        if (ncx >= w) { lox = cx - g.nsub; nx = w; } else { lox = 0; nx = ncx; }
+        if (ncy >= w) { loy = cy - g.nsub; ny = w; } else { loy = 0; ny = ncy; }
+        // z is the fastest cell index, so the z-stencil of one (x,y) column is at most two contiguous runs of cells
+        int z0a, z1a, z0b = 0, z1b = 0;  // half-open cell ranges [z0, z1)
+        if (ncz >= w) {
+            int lo = cz - g.nsub, hi = cz + g.nsub + 1;
+            if (lo < 0) { z0a = 0; z1a = hi; z0b = lo + ncz; z1b = ncz; }
+            else if (hi > ncz) { z0a = lo; z1a = ncz; z0b = 0; z1b = hi - ncz; }
+            else { z0a = lo; z1a = hi; }
+        } else { z0a = 0; z1a = ncz; }
         for (int ia = 0; ia < nx; ++ia) {
             int qx = lox + ia;
-            qx += (qx < 0) ? g.nc[0] : 0;
-            qx -= (qx >= g.nc[0]) ? g.nc[0] : 0;
+            qx += (qx < 0) ? ncx : 0;
+            qx -= (qx >= ncx) ? ncx : 0;
             for (int ib = 0; ib < ny; ++ib) {
                 int qy = loy + ib;
-                qy += (qy < 0) ? g.nc[1] : 0;
-                qy -= (qy >= g.nc[1]) ? g.nc[1] : 0;
-                for (int ic = 0; ic < nz; ++ic) {
-                    int qz = loz + ic;
-                    qz += (qz < 0) ? g.nc[2] : 0;
-                    qz -= (qz >= g.nc[2]) ? g.nc[2] : 0;
-                    int cell = (qx * g.nc[1] + qy) * g.nc[2] + qz;
-                    int s = cell_start[cell], e = cell_start[cell + 1];
+                qy += (qy < 0) ? ncy : 0;
+                qy -= (qy >= ncy) ? ncy : 0;
+                const int base = (qx * ncy + qy) * ncz;
+                // both runs' bounds are fetched before either is walked
+                const int sa = cell_start[base + z0a], ea = cell_start[base + z1a];
+                const int sb = (z1b > z0b) ? cell_start[base + z0b] : 0, eb = (z1b > z0b) ? cell_start[base + z1b] : 0;
+#pragma unroll 1
+                for (int run = 0; run < 2; ++run) {
+                    const int s = run ? sb : sa, e = run ? eb : ea;
                     for (int q = s; q < e; ++q) {
-                        if (q == p) continue;
                         double rx = min_image(__dsub_rn(a.x[q], xi), Lx, hx);
+                        if (fabs(rx) > r_list) continue;
                         double ry = min_image(__dsub_rn(a.y[q], yi), Ly, hy);
                         double rz = min_image(__dsub_rn(a.z[q], zi), Lz, hz);
-                        double r = norm_exact(rx, ry, rz);
-                        if (r > r_list) continue;
+                        double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                        if (r2 > r2_list || q == p) continue;
                         if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
                         ++cnt;
                     }
@@ -509,6 +520,9 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
 #ifndef MD_FORCE_MINB
 #define MD_FORCE_MINB 4
 #endif
+#ifndef MD_FORCE_MINB_DILUTE
+#define MD_FORCE_MINB_DILUTE 4
+#endif
 constexpr int FORCE_BLOCK = 128;
 
 struct LjConst {
@@ -592,13 +606,15 @@ __device__ __forceinline__ void finish_atom(Sums &s, const PairAcc &f, double &v
 }
 
 // Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
-// before the first use, and the neighbour loop advances both lists together (two independent gather chains).
-template <bool EXACT>
-__global__ void __launch_bounds__(FORCE_BLOCK, MD_FORCE_MINB) k_force(int n, Arrays a, const int *__restrict__ nbr,
-                                                          const int *__restrict__ nbr_cnt, int npad,
-                                                          double *__restrict__ partials, Scalars *sc,
-                                                          const Params *__restrict__ pr, int do_step,
-                                                          unsigned long long cond_handle)
+// before the first use, and the neighbour loop advances both lists together (independent gather chains) with the
+// next rows of partner indices prefetched while the current ones are in flight.
+//   ROWS = 2: two list rows per trip (dense systems; 12 gathers in flight, 128 registers)
+//   ROWS = 1: one row per trip (dilute systems: few partners, occupancy matters more than unrolling)
+template <bool EXACT, int ROWS>
+__global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
+    k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
+            double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
+            unsigned long long cond_handle)
 {
     Sums s;
 #pragma unroll
@@ -621,10 +637,13 @@ __global__ void __launch_bounds__(FORCE_BLOCK, MD_FORCE_MINB) k_force(int n, Arr
     const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
     const double hc = pr->half_dt_m, mass = pr->mass;
     const int npairs = (n + 1) >> 1;
+    const int last_row = cap - 1;
     const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
     for (int t = blockIdx.x * FORCE_BLOCK + threadIdx.x; t < npairs; t += gridDim.x * FORCE_BLOCK) {
         const int i0 = 2 * t;
         const bool has1 = i0 + 1 < n;
+        const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + t;
+        const size_t stride = (size_t)(npad >> 1);
         const double2 X = reinterpret_cast<const double2 *>(px)[t], Y = reinterpret_cast<const double2 *>(py)[t],
                       Z = reinterpret_cast<const double2 *>(pz)[t];
         int2 C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
@@ -632,8 +651,6 @@ __global__ void __launch_bounds__(FORCE_BLOCK, MD_FORCE_MINB) k_force(int n, Arr
                 VZ = reinterpret_cast<double2 *>(a.vz)[t];
         if (!has1) C.y = 0;
         PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
-        const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + t;
-        const size_t stride = (size_t)(npad >> 1);
         if (EXACT) {
             for (int k = 0; k < C.x; ++k) {
                 int j = row[k * stride].x;
@@ -646,27 +663,33 @@ __global__ void __launch_bounds__(FORCE_BLOCK, MD_FORCE_MINB) k_force(int n, Arr
         } else {
             const int kmax = max(C.x, C.y);
             int k = 0;
-            for (; k + 1 < kmax; k += 2) {  // two rows per trip: 4 index loads, 12 gathers in flight
-                const int2 Ja = row[k * stride], Jb = row[(k + 1) * stride];
-                const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
-                const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
-                const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
-                const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
-                const double xb0 = px[jb0], yb0 = py[jb0], zb0 = pz[jb0];
-                const double xb1 = px[jb1], yb1 = py[jb1], zb1 = pz[jb1];
-                pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
-                pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
-                pair_fast(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c);
-                pair_fast(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c);
+            int2 Ja = row[0];  // row 0 exists for every atom (cap >= 8): fetched together with the atom's own data
+            if (ROWS == 2) {
+                int2 Jb = row[min(1, last_row) * stride];
+                for (; k + 1 < kmax; k += 2) {
+                    const int2 Na = row[min(k + 2, last_row) * stride], Nb = row[min(k + 3, last_row) * stride];
+                    const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+                    const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
+                    const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
+                    const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
+                    const double xb0 = px[jb0], yb0 = py[jb0], zb0 = pz[jb0];
+                    const double xb1 = px[jb1], yb1 = py[jb1], zb1 = pz[jb1];
+                    pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
+                    pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                    pair_fast(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c);
+                    pair_fast(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c);
+                    Ja = Na; Jb = Nb;
+                }
             }
-            if (k < kmax) {
-                const int2 Ja = row[k * stride];
+            for (; k < kmax; ++k) {
+                const int2 Na = row[min(k + 1, last_row) * stride];
                 const bool a0 = k < C.x, a1 = k < C.y;
                 const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
                 const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
                 const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
                 pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
                 pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                Ja = Na;
             }
         }
         double2 WX, WY, WZ;

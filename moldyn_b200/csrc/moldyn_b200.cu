@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,7 +59,8 @@ struct md_ctx {
     Params prm{};
     double *d_partials = nullptr;
     int partial_blocks = 0;
-    int force_grid = 1, reduce_grid = 1;
+    int force_grid[3] = {1, 1, 1}, reduce_grid = 1;  // exact, fast dense, fast dilute
+    bool dense = false;                               // mean listed partners >= 8 at the last rebuild
 
     // cells / lists
     Grid grid{};
@@ -233,7 +235,7 @@ int choose_grid(md_ctx *ctx, const double box[3])
     int nsub = ctx->cfg.cell_subdiv >= 2 ? 2 : 1;
     double r_list = ctx->r_cut + ctx->skin;
     double volume = box[0] * box[1] * box[2];
-    double k = ctx->cfg.cell_atoms > 0.0 ? ctx->cfg.cell_atoms : 3.0;
+    double k = ctx->cfg.cell_atoms > 0.0 ? ctx->cfg.cell_atoms : 1.0;
     double dilute_edge = std::cbrt(k * volume / (double)ctx->n);
     double edge = std::max(r_list / nsub * 1.02, dilute_edge);
     int64_t ncell = 1;
@@ -284,6 +286,16 @@ int ensure_nbr_capacity(md_ctx *ctx, int cap)
     return MD_OK;
 }
 
+// Largest double t with sqrt(t) <= r (IEEE sqrt is correctly rounded and monotonic): turns the reference's
+// `norm(r) > r_cut` test into a comparison of squares with the identical outcome for every input.
+double sqrt_threshold(double r)
+{
+    double t = r * r;
+    while (std::sqrt(t) > r) t = std::nextafter(t, 0.0);
+    while (std::sqrt(std::nextafter(t, INFINITY)) <= r) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
 // (no pending barostat scaling).
 int rebuild_lists(md_ctx *ctx)
@@ -313,15 +325,16 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.kernel_launches += 7;
     drop_graph(ctx);  // array pointers are baked into the captured kernels
 
+    const double r2_list = sqrt_threshold(ctx->prm.r_list);
     for (int attempt = 0; attempt < 4; ++attempt) {
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         if (ctx->cfg.force_mode == MD_FORCE_EXACT)
             k_build_list<true><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
-                                                                   ctx->d_sc, g, ctx->prm.r_list, ctx->nbr,
+                                                                   ctx->d_sc, g, ctx->prm.r_list, r2_list, ctx->nbr,
                                                                    ctx->nbr_cnt);
         else
             k_build_list<false><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
-                                                                    ctx->d_sc, g, ctx->prm.r_list, ctx->nbr,
+                                                                    ctx->d_sc, g, ctx->prm.r_list, r2_list, ctx->nbr,
                                                                     ctx->nbr_cnt);
         ctx->stats.kernel_launches += 2;
         CK(cudaGetLastError());
@@ -337,6 +350,7 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.rebuilds += 1;
     ctx->stats.nbr_max = ctx->h_sc->nbr_max;
     ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
+    ctx->dense = ctx->stats.nbr_mean >= 8.0;
     ctx->list_valid = true;
     return MD_OK;
 }
@@ -351,14 +365,14 @@ int launch_kick_drift(md_ctx *ctx)
 int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
 {
     const int n = (int)ctx->n;
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
-        k_force<true><<<ctx->force_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,
-                                                                        ctx->d_partials, ctx->d_sc, ctx->d_pr,
-                                                                        kick ? 1 : 0, cond);
-    else
-        k_force<false><<<ctx->force_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,
-                                                                         ctx->d_partials, ctx->d_sc, ctx->d_pr,
-                                                                         kick ? 1 : 0, cond);
+#define LAUNCH_FORCE(E, R, GRID)                                                                                  \
+    k_force<E, R><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
+                                                         ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
+                                                         kick ? 1 : 0, cond)
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, ctx->force_grid[0]);
+    else if (ctx->dense) LAUNCH_FORCE(false, 2, ctx->force_grid[1]);
+    else LAUNCH_FORCE(false, 1, ctx->force_grid[2]);
+#undef LAUNCH_FORCE
     return MD_OK;
 }
 
@@ -373,14 +387,14 @@ int launch_reduce(md_ctx *ctx)
 // Persistent grids: resident blocks per SM (occupancy API) × SM count, capped by the work available.
 int choose_grids(md_ctx *ctx)
 {
-    int sms = 0, occ_f = 0, occ_r = 0;
+    int sms = 0, occ[3] = {0, 0, 0}, occ_r = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_force<true>, FORCE_BLOCK, 0));
-    else
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_force<false>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, 1>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, 2>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, 1>, FORCE_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
-    ctx->force_grid = std::max(1, std::min(blocks_for(ctx->n, FORCE_BLOCK), sms * std::max(occ_f, 1)));
+    const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
+    for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
     ctx->reduce_grid = std::max(1, std::min(blocks_for(ctx->n, RED_BLOCK), sms * std::max(occ_r, 1)));
     return MD_OK;
 }
@@ -471,6 +485,8 @@ int md_create(const md_config *cfg, md_ctx **out)
     *out = nullptr;
     md_ctx *ctx = new md_ctx();
     if (cfg) ctx->cfg = *cfg;
+    if (const char *e = std::getenv("MOLDYN_B200_LOOP"))  // profiling aid: ncu cannot see kernels of conditional graphs
+        if (!strcmp(e, "host")) ctx->cfg.loop_mode = MD_LOOP_HOST;
     ctx->device = ctx->cfg.device;
     auto bail = [&](cudaError_t e, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e) +
@@ -562,7 +578,8 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         TRY(dev_alloc(ctx, &ctx->stage, 3 * (size_t)ctx->npad));
         TRY(dev_alloc(ctx, &ctx->stage_i, ctx->npad));
         TRY(choose_grids(ctx));
-        ctx->partial_blocks = std::max(ctx->force_grid, ctx->reduce_grid);
+        ctx->partial_blocks = std::max(std::max(ctx->force_grid[0], ctx->force_grid[1]),
+                                       std::max(ctx->force_grid[2], ctx->reduce_grid));
         TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
         TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
