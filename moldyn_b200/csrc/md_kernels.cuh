@@ -565,6 +565,27 @@ __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, do
     a.w += fr * r2;
 }
 
+// FAST pair term for dilute systems: most listed partners are outside the cutoff (the skin is wide), so the
+// Lennard-Jones body sits behind a real branch and the FP64 pipe only sees the cheap distance test.
+__device__ __forceinline__ void pair_fast_branchy(PairAcc &a, bool active, double xj, double yj, double zj,
+                                                  double xi, double yi, double zi, const LjConst &c)
+{
+    double rx = min_image_fast(xj - xi, c.Lx, c.hx, c.hxi);
+    double ry = min_image_fast(yj - yi, c.Ly, c.hy, c.hyi);
+    double rz = min_image_fast(zj - zi, c.Lz, c.hz, c.hzi);
+    double r2 = rx * rx + ry * ry + rz * rz;
+    if (active && r2 <= c.rc2) {
+        double inv = 1.0 / r2;
+        double s2 = c.sigma2 * inv;
+        double s6 = s2 * s2 * s2;
+        double s12 = s6 * s6;
+        double fr = c.eps24 * inv * (s6 - 2.0 * s12);
+        a.u += c.eps4 * (s12 - s6) - c.u_cut;
+        a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
+        a.w += fr * r2;
+    }
+}
+
 // EXACT pair term: potential.rs:181-211 operation by operation, no contraction, real branch on the cutoff.
 __device__ __forceinline__ void pair_exact(PairAcc &a, double xj, double yj, double zj, double xi, double yi,
                                            double zi, const LjConst &c)
@@ -687,8 +708,13 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_M
                 const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
                 const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
                 const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
-                pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
-                pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                if (ROWS == 2) {
+                    pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
+                    pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                } else {
+                    pair_fast_branchy(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
+                    pair_fast_branchy(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
+                }
                 Ja = Na;
             }
         }

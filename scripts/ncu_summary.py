@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) into the handful of numbers DESIGN.md / profiles/ quote."""
+import csv, io, re, subprocess, sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__warps_eligible.avg.per_cycle_active", "smsp__warps_active.avg.per_cycle_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+]
+STALL = re.compile(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active.ratio")
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0]
+        print(f"## {name}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"  {k:75s} {r[i]:>16s} {units[i]}")
+        stalls = []
+        for i, h in enumerate(hdr):
+            m = STALL.match(h)
+            if m and r[i]:
+                stalls.append((float(r[i].replace(",", "")), m.group(1)))
+        stalls.sort(reverse=True)
+        print("  stalls (warps per issue):", ", ".join(f"{n}={v:.2f}" for v, n in stalls[:6]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
