@@ -188,9 +188,11 @@ def run_ours(args, w):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    if world > 1:
-        raise SystemExit("multi-GPU spatial decomposition is not wired into bench.py yet")
     torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pos, vel, box = make_state(w)
     n = pos.shape[0]
     th = lambda: (md.Thermostat.Berendsen(w["thermostat"][0]), w["thermostat"][1])  # noqa: E731
@@ -198,6 +200,9 @@ def run_ours(args, w):
         else (lambda: None)
 
     s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv)
+    if world > 1:
+        from moldyn_b200 import distributed as mdd
+        mdd.init_solver_comm(s)
     if w["cut"]:
         s.set_potential(md.Potential(0.3418, 1.712, *w["cut"]))
     s.upload_arrays(pos, vel, ARGON_MASS, box)
@@ -210,35 +215,49 @@ def run_ours(args, w):
     sampler = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
     sampler.start()
     e0.record(stream)
     s.step(args.steps, DT, thermostat=t_th, barostat=t_ba)
     e1.record(stream)
     s.synchronize()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop()
     st1 = s.stats()
     value = n * args.steps / (ms * 1e-3)
     macro = s.macro()
 
-    # --- per-kernel device times (CUDA events on the launching stream, host-stepped) ---------------------
-    kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
     hbm, peak_src = peaks()
-    f_ms = kt["force"][0] / max(kt["force"][1], 1)
-    k_ms = kt["kick_drift"][0] / max(kt["kick_drift"][1], 1)
-    dominant = "k_force" if f_ms >= k_ms else "k_kick_drift"
-    dom_ms, dom_bytes = (f_ms, ALGO_BYTES_FORCE) if dominant == "k_force" else (k_ms, ALGO_BYTES_KICK_DRIFT)
-    achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-        "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_atom": dom_bytes, "avg_launch_ms": dom_ms,
-        "kernels_ms": {"k_force": f_ms, "k_kick_drift": k_ms,
-                       "rebuild": kt["rebuild"][0] / max(kt["rebuild"][1], 1) if kt["rebuild"][1] else None},
-        "step": {"algorithmic_bytes_per_atom_step": ALGO_BYTES_STEP,
-                 "achieved": ALGO_BYTES_STEP * value / 1e9, "frac": ALGO_BYTES_STEP * value / 1e9 / hbm},
-    }
+    if world == 1:
+        # --- per-kernel device times (CUDA events on the launching stream, host-stepped) -----------------
+        kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
+        f_ms = kt["force"][0] / max(kt["force"][1], 1)
+        k_ms = kt["kick_drift"][0] / max(kt["kick_drift"][1], 1)
+        dominant = "k_force" if f_ms >= k_ms else "k_kick_drift"
+        dom_ms, dom_bytes = (f_ms, ALGO_BYTES_FORCE) if dominant == "k_force" else (k_ms, ALGO_BYTES_KICK_DRIFT)
+        achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_atom": dom_bytes, "avg_launch_ms": dom_ms,
+            "kernels_ms": {"k_force": f_ms, "k_kick_drift": k_ms,
+                           "rebuild": kt["rebuild"][0] / max(kt["rebuild"][1], 1) if kt["rebuild"][1] else None},
+        }
+    else:
+        roofline = {"bound": "hbm", "kernel": "step (per-kernel timing is single-GPU only)", "achieved": None,
+                    "peak": hbm * world, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                    "kernels_ms": {"k_force": None, "k_kick_drift": None, "rebuild": None}}
+    roofline["step"] = {"algorithmic_bytes_per_atom_step": ALGO_BYTES_STEP, "achieved": ALGO_BYTES_STEP * value / 1e9,
+                        "frac": ALGO_BYTES_STEP * value / 1e9 / (hbm * world)}
     if w["cut"] is not None or w["cell"] < 1.0:
         pairs = s.stats()["nbr_mean"]
         roofline["note"] = (f"dense system: force kernel is FP64/L1 bound; mean listed partners {pairs:.1f}; "
@@ -246,7 +265,7 @@ def run_ours(args, w):
 
     # --- e2e: reference-facing per-call API, State in pinned host memory in and out every step ------------
     e2e = None
-    if args.e2e_steps > 0:
+    if args.e2e_steps > 0 and world == 1:
         L = _ffi.lib()
         hp = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * n, 3 * n, 3 * n, n, n)]
         hbox = np.array(box)
@@ -272,6 +291,42 @@ def run_ours(args, w):
                "ms_per_step": t_e2e / args.e2e_steps * 1e3, "steps": args.e2e_steps,
                "api": "md_calculate_host (≡ Integrator::calculate on a host State: upload x,v,F,U,W → 1 step → "
                       "download x,v,F,U,W), pinned host buffers"}
+    elif args.e2e_steps > 0:
+        # decomposed form of the same call: every rank uploads the (pinned) host State, one collective step, every
+        # rank downloads its own slab
+        L = _ffi.lib()
+        hp = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * n, 3 * n)]
+        hp[0].copy_(torch.from_numpy(pos.reshape(-1)))
+        hp[1].copy_(torch.from_numpy(vel.reshape(-1)))
+        cap = int(1.6 * n / world) + 8192
+        out = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * cap, 3 * cap, 3 * cap, cap, cap)]
+        ids = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+        hbox = np.array(box)
+
+        def call():
+            s.upload_arrays(hp[0].data_ptr(), hp[1].data_ptr(), ARGON_MASS, box, n=n)
+            s.update_force()
+            s.step(1, DT, thermostat=t_th, barostat=t_ba)
+            _ffi.check(s._ctx, L.md_download_local(s._ctx, ids.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                                   out[2].data_ptr(), out[3].data_ptr(), out[4].data_ptr(),
+                                                   hbox.ctypes.data_as(C.c_void_p)))
+        call()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            call()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+        n_loc = s.local_count()[0]
+        e2e = {"value": n * args.e2e_steps / t_e2e, "unit": "atom-steps/s",
+               "h2d_bytes_per_step": 48 * n * world, "d2h_bytes_per_step": 96 * n_loc * world,
+               "ms_per_step": t_e2e / args.e2e_steps * 1e3, "steps": args.e2e_steps,
+               "api": "per step on every rank: md_upload_state(full host State) → md_update_force → md_step(1) → "
+                      "md_download_local(own slab), pinned host buffers"}
 
     cpu = None
     if args.cpu_rows >= 0 and rank == 0:
@@ -284,6 +339,7 @@ def run_ours(args, w):
     out = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (spatial decomposition), NCCL halo send/recv + all-gather of 8 sums per step",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "atoms": n, "dt": DT, "thermostat": w["thermostat"],
                    "barostat": w["barostat"], "r_cut": w["cut"][0] if w["cut"] else 0.8545,
@@ -299,9 +355,15 @@ def run_ours(args, w):
         "state_check": {"temperature": macro["temperature"], "pressure": macro["pressure"],
                         "momentum_abs_max": float(np.abs(macro["momentum"]).max())},
     }
+    if world > 1:
+        alls = [None] * world if rank == 0 else None
+        dist.gather_object({k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds")}, alls, dst=0)
+        out["per_rank"] = alls
     if rank == 0:
         print(json.dumps(out))
     s.close()
+    if dist:
+        dist.destroy_process_group()
 
 
 def main():

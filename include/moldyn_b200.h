@@ -113,6 +113,9 @@ typedef struct md_stats {
     int32_t reserved0;
     double skin;              /* skin in use */
     double nbr_mean;          /* mean neighbour count at the last rebuild */
+    int64_t n_owned;          /* atoms this rank owns (== n on one GPU) */
+    int64_t n_ghost;          /* halo atoms held for the neighbours' partners */
+    int64_t migrated;         /* atoms handed to a neighbouring rank so far */
 } md_stats;
 
 typedef struct md_ctx md_ctx;
@@ -158,6 +161,25 @@ MD_API int md_update_force_host(md_ctx *ctx, int64_t n, const double *pos, doubl
 MD_API int md_calculate_host(md_ctx *ctx, int64_t n, double *pos, double *vel, double *force, double *potential,
                              double *virial, double mass, double box[3], double dt, md_thermostat *thermostat,
                              md_barostat *barostat);
+
+/* ---- multi-GPU: one process per GPU, 1-D slab decomposition along x ----------------------
+ * The reference has no distributed mode (rayon threads only); these entry points have no reference counterpart.
+ * Rank 0 creates an id (ncclGetUniqueId), the host layer broadcasts it (torch.distributed / MPI / a file), every
+ * rank calls md_comm_init BEFORE md_upload_state.  md_upload_state then takes the FULL state on every rank and
+ * keeps the atoms whose fractional x lies in this rank's slab; md_update_force / md_step / md_macro are collective
+ * (every rank calls them with the same arguments; md_macro returns the same global values everywhere);
+ * md_download_local returns this rank's owned atoms with their upload indices. */
+#define MD_UNIQUE_ID_BYTES 128
+MD_API int md_comm_unique_id(uint8_t id[MD_UNIQUE_ID_BYTES]);
+MD_API int md_comm_init(md_ctx *ctx, int rank, int nranks, const uint8_t id[MD_UNIQUE_ID_BYTES]);
+MD_API int md_local_count(md_ctx *ctx, int64_t *n_owned, int64_t *n_ghost);
+/* ids[n_owned], pos/vel/force[3 n_owned], potential/virial[n_owned]; any pointer may be NULL */
+MD_API int md_download_local(md_ctx *ctx, int64_t *ids, double *pos, double *vel, double *force, double *potential,
+                             double *virial, double box[3]);
+/* Host-only (no GPU): the slab [x_lo, x_hi) rank owns, its ring neighbours and a per-rank atom capacity hint.
+ * MD_ERR_DECOMPOSITION if a slab would be narrower than 2.1 x r_list. */
+MD_API int md_plan_decomposition(int64_t n, const double box[3], double r_list, int nranks, int rank, double *x_lo,
+                                 double *x_hi, int *left, int *right, int64_t *capacity_hint);
 
 /* ---- introspection used by the parity tests and the bench ---------------------------------- */
 /* Cell index of every atom (upload order) at the last list build + grid dims.  cell = (cx*ny + cy)*nz + cz with

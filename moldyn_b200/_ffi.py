@@ -12,6 +12,7 @@ ERR_NAMES = {
     1: "MD_ERR_INVALID_ARGUMENT", 2: "MD_ERR_CUDA", 3: "MD_ERR_NCCL", 4: "MD_ERR_UNSUPPORTED",
     5: "MD_ERR_NEIGHBOUR_OVERFLOW", 6: "MD_ERR_NO_STATE", 7: "MD_ERR_NONFINITE", 8: "MD_ERR_DECOMPOSITION",
 }
+UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT = 0, 1
 LOOP_GRAPH, LOOP_HOST = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
@@ -50,7 +51,8 @@ class MacroOut(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("graph_launches", C.c_int64), ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32),
-                ("nbr_max", C.c_int32), ("reserved0", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double)]
+                ("nbr_max", C.c_int32), ("reserved0", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64)]
 
 
 # every symbol include/moldyn_b200.h declares (tests check the library exports all of them)
@@ -59,6 +61,7 @@ SYMBOLS = [
     "md_set_potential_lj", "md_upload_state", "md_download_state", "md_update_force", "md_step", "md_macro",
     "md_update_force_host", "md_calculate_host", "md_download_cells", "md_neighbour_counts",
     "md_neighbour_lists", "md_get_stats", "md_stream", "md_synchronize", "md_invalidate_lists", "md_time_kernels",
+    "md_comm_unique_id", "md_comm_init", "md_local_count", "md_download_local", "md_plan_decomposition",
 ]
 
 _lib = None
@@ -102,6 +105,12 @@ def lib():
             "md_synchronize": (C.c_int, [vp]),
             "md_invalidate_lists": (C.c_int, [vp]),
             "md_time_kernels": (C.c_int, [vp, i64, f64, C.POINTER(ThermostatC), C.POINTER(BarostatC), pd, pd]),
+            "md_comm_unique_id": (C.c_int, [pd]),
+            "md_comm_init": (C.c_int, [vp, C.c_int, C.c_int, pd]),
+            "md_local_count": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+            "md_download_local": (C.c_int, [vp, pd, pd, pd, pd, pd, pd, pd]),
+            "md_plan_decomposition": (C.c_int, [i64, pd, f64, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64),
+                                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
         }
         assert set(sig) == set(SYMBOLS)
         for name, (res, args) in sig.items():

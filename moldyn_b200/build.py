@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "moldyn_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "md_kernels.cuh"), os.path.join(ROOT, "include", "moldyn_b200.h")]
+DEPS = [SRC, os.path.join(HERE, "csrc", "md_kernels.cuh"), os.path.join(HERE, "csrc", "md_dist.inc"), os.path.join(ROOT, "include", "moldyn_b200.h")]
 LIB = os.path.join(HERE, "lib", "libmoldyn_b200.so")
 
 NVCC_FLAGS = [
@@ -33,7 +33,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("MD_NVCC_EXTRA", "").split(), "-o", LIB, SRC]
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("MD_NVCC_EXTRA", "").split(), "-o", LIB, SRC, "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), file=sys.stderr)

@@ -5,9 +5,13 @@
 // block sets on the device — the host is only involved when the neighbour list has to be rebuilt.
 #include "md_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed on first multi-GPU use (see nccl_api below)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +21,43 @@
 #include "../../include/moldyn_b200.h"
 
 using namespace md;
+
+// NCCL is bound at run time, not link time: single-GPU users never load it, and inside a process that has already
+// imported PyTorch the dlopen() resolves to the libnccl.so.2 that is already mapped (two different NCCL builds in one
+// process do not mix).
+namespace nccl_api {
+#define MD_NCCL_SYMBOLS(X)                                                                                   \
+    X(ncclGetUniqueId) X(ncclCommInitRank) X(ncclCommDestroy) X(ncclSend) X(ncclRecv) X(ncclGroupStart)       \
+    X(ncclGroupEnd) X(ncclAllGather) X(ncclGetErrorString)
+#define X(name) decltype(&::name) name = nullptr;
+MD_NCCL_SYMBOLS(X)
+#undef X
+const char *load()
+{
+    static const char *err = nullptr;
+    static bool done = false;
+    if (done) return err;
+    done = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return err = "libnccl.so.2 not found (needed only for multi-GPU runs)";
+#define X(name)                                         \
+    name = (decltype(name))dlsym(h, #name);             \
+    if (!name) return err = "libnccl lacks " #name;
+    MD_NCCL_SYMBOLS(X)
+#undef X
+    return nullptr;
+}
+}  // namespace nccl_api
+#define ncclGetUniqueId nccl_api::ncclGetUniqueId
+#define ncclCommInitRank nccl_api::ncclCommInitRank
+#define ncclCommDestroy nccl_api::ncclCommDestroy
+#define ncclSend nccl_api::ncclSend
+#define ncclRecv nccl_api::ncclRecv
+#define ncclGroupStart nccl_api::ncclGroupStart
+#define ncclGroupEnd nccl_api::ncclGroupEnd
+#define ncclAllGather nccl_api::ncclAllGather
+#define ncclGetErrorString nccl_api::ncclGetErrorString
 
 namespace {
 
@@ -39,8 +80,8 @@ struct md_ctx {
     double sigma = 0.3418, eps = 1.712, r_cut = 0.0, u_cut = 0.0;
     double skin = 0.0;
 
-    // state
-    int64_t n = 0;
+    // state (n = global atom count; n_own/n_ghost = this rank's owned and halo atoms, n_own == n on one GPU)
+    int64_t n = 0, n_own = 0, n_ghost = 0;
     int npad = 0;
     double mass = 0.0;
     bool has_state = false;
@@ -77,6 +118,24 @@ struct md_ctx {
     bool graph_ok = false;
 
     md_stats stats{};
+
+    // multi-GPU slab decomposition (md_dist.inc)
+    struct Dist {
+        bool on = false;
+        int rank = 0, nranks = 1, left = 0, right = 0;
+        ncclComm_t comm = nullptr;
+        double *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};  // [0] left, [1] right neighbour
+        int *send_ids[2] = {nullptr, nullptr}, *recv_ids[2] = {nullptr, nullptr};
+        size_t buf_cap = 0;
+        int *flag = nullptr, *scan = nullptr, *scan_sums = nullptr, *idx_stay = nullptr;
+        int *idx_send[2] = {nullptr, nullptr};
+        int *ghost_idx[2] = {nullptr, nullptr};  // owned atoms (sorted indices) whose positions go to each neighbour
+        int ghost_send[2] = {0, 0}, ghost_recv[2] = {0, 0};
+        int *ghost_cell_of = nullptr, *ghost_order = nullptr, *ghost_start = nullptr;
+        int *d_cnt = nullptr, *h_cnt = nullptr;
+        double *all_sums = nullptr;
+        int64_t migrated = 0;
+    } dist;
 
     // per-kernel CUDA-event timing (md_time_kernels)
     bool timing = false;
@@ -357,8 +416,8 @@ int rebuild_lists(md_ctx *ctx)
 
 int launch_kick_drift(md_ctx *ctx)
 {
-    int npairs = (int)((ctx->n + 1) / 2);
-    k_kick_drift<<<blocks_for(npairs, 256), 256, 0, ctx->stream>>>(npairs, ctx->cur, ctx->d_sc, ctx->d_pr);
+    const int n = (int)ctx->n_own;
+    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr);
     return MD_OK;
 }
 
@@ -379,7 +438,7 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
 int launch_reduce(md_ctx *ctx)
 {
     const int n = (int)ctx->n;
-    k_reduce_state<<<ctx->reduce_grid, RED_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->d_partials, ctx->d_sc, ctx->d_pr);
+    k_reduce_state<<<ctx->reduce_grid, RED_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->d_partials, ctx->d_sc, ctx->d_pr, 0);
     ctx->stats.kernel_launches += 1;
     return MD_OK;
 }
@@ -425,7 +484,7 @@ int build_graph(md_ctx *ctx)
 
 int flush_pending_scale(md_ctx *ctx)
 {
-    const int n = (int)ctx->n;
+    const int n = (int)ctx->n_own;
     k_scale_positions<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc);
     k_clear_pending<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
     ctx->stats.kernel_launches += 2;
@@ -451,6 +510,8 @@ int device_error(md_ctx *ctx)
     if (ctx->h_sc->error) return ctx->fail(ctx->h_sc->error, "device-side error %d", ctx->h_sc->error);
     return MD_OK;
 }
+
+#include "md_dist.inc"
 
 }  // namespace
 
@@ -524,6 +585,8 @@ void md_destroy(md_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drop_graph(ctx);
+    if (ctx->dist.comm) ncclCommDestroy(ctx->dist.comm);
+    if (ctx->dist.h_cnt) cudaFreeHost(ctx->dist.h_cnt);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto &b : ctx->owned)
@@ -560,6 +623,7 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: need n in [1, 2^30], pos, vel, box");
     if (!(mass > 0.0) || !(box[0] > 0.0) || !(box[1] > 0.0) || !(box[2] > 0.0))
         return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: mass and box must be positive");
+    if (ctx->dist.on) return dist_upload(ctx, n, pos, vel, force, potential, virial, mass, box);
     cudaStream_t st = ctx->stream;
     if (n != ctx->n || !ctx->has_state) {
         CK(cudaStreamSynchronize(st));
@@ -572,6 +636,8 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         ctx->owned.erase(std::remove_if(ctx->owned.begin(), ctx->owned.end(), [](const DevBuf &b) { return !b.p; }),
                          ctx->owned.end());
         ctx->n = n;
+        ctx->n_own = n;
+        ctx->n_ghost = 0;
         ctx->npad = (int)((n + 63) / 64 * 64);
         TRY(alloc_arrays(ctx, &ctx->cur, ctx->npad));
         TRY(alloc_arrays(ctx, &ctx->alt, ctx->npad));
@@ -646,6 +712,8 @@ int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, doub
                       double box[3])
 {
     TRY(check_ctx(ctx, true));
+    if (ctx->dist.on)
+        return ctx->fail(MD_ERR_UNSUPPORTED, "md_download_state on a decomposed state: use md_download_local per rank");
     cudaStream_t st = ctx->stream;
     const int n = (int)ctx->n;
     const int nb = blocks_for(n, 256);
@@ -686,6 +754,20 @@ int md_update_force(md_ctx *ctx)
     TRY(check_ctx(ctx, true));
     fill_potential_params(ctx);
     TRY(push_params(ctx));
+    if (ctx->dist.on) {
+        if (!ctx->list_valid) {
+            TRY(dist_rebuild(ctx));
+        } else {
+            TRY(pull_scalars(ctx));
+            if (ctx->h_sc->need_rebuild) TRY(dist_rebuild(ctx));
+            else TRY(dist_halo_exchange(ctx));
+        }
+        TRY(dist_launch_force(ctx, false));
+        ctx->sums_c = ctx->prm.half_dt_m;
+        ctx->force_valid = true;
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MD_OK;
+    }
     if (!ctx->list_valid) {
         TRY(rebuild_lists(ctx));
     } else {
@@ -728,7 +810,8 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     TRY(push_params(ctx));
     // The displacement bound of the first drift needs max|v + F c|² for THIS c.
     if (ctx->sums_c != p.half_dt_m) {
-        launch_reduce(ctx);
+        if (ctx->dist.on) TRY(dist_launch_reduce(ctx));
+        else launch_reduce(ctx);
         ctx->sums_c = p.half_dt_m;
     }
     k_prepare<<<1, 1, 0, st>>>(ctx->d_sc, ctx->d_pr, (long long)n_steps);
@@ -736,6 +819,10 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     CK(cudaGetLastError());
 
     int64_t remaining = n_steps;
+    if (ctx->dist.on) {
+        TRY(dist_run_steps(ctx));
+        remaining = 0;
+    }
     while (remaining > 0) {
         TRY(pull_scalars(ctx));
         TRY(device_error(ctx));
@@ -799,6 +886,108 @@ int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, 
     ctx->timing = false;
     for (int k = 0; k < 3; ++k) { ms[k] = ctx->t_ms[k]; launches[k] = ctx->t_cnt[k]; }
     return rc;
+}
+
+int md_comm_unique_id(uint8_t id[MD_UNIQUE_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == MD_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    if (!id) return MD_ERR_INVALID_ARGUMENT;
+    if (const char *e = nccl_api::load()) {
+        g_create_error = e;
+        return MD_ERR_NCCL;
+    }
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) {
+        g_create_error = "ncclGetUniqueId failed";
+        return MD_ERR_NCCL;
+    }
+    memcpy(id, &u, sizeof u);
+    return MD_OK;
+}
+
+int md_comm_init(md_ctx *ctx, int rank, int nranks, const uint8_t id[MD_UNIQUE_ID_BYTES])
+{
+    TRY(check_ctx(ctx, false));
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_comm_init: bad rank/nranks/id");
+    if (ctx->has_state) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_comm_init must precede md_upload_state");
+    if (nranks == 1) return MD_OK;  // a single slab is the single-GPU path
+    if (const char *e = nccl_api::load()) return ctx->fail(MD_ERR_NCCL, "%s", e);
+    auto &d = ctx->dist;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NCK(ncclCommInitRank(&d.comm, nranks, u, rank));
+    d.on = true;
+    d.rank = rank;
+    d.nranks = nranks;
+    d.left = (rank + nranks - 1) % nranks;
+    d.right = (rank + 1) % nranks;
+    TRY(dev_alloc(ctx, &d.d_cnt, 8));
+    CK(cudaMallocHost((void **)&d.h_cnt, 8 * sizeof(int)));
+    ctx->cfg.loop_mode = MD_LOOP_HOST;
+    return MD_OK;
+}
+
+int md_local_count(md_ctx *ctx, int64_t *n_owned, int64_t *n_ghost)
+{
+    TRY(check_ctx(ctx, true));
+    if (n_owned) *n_owned = ctx->n_own;
+    if (n_ghost) *n_ghost = ctx->n_ghost;
+    return MD_OK;
+}
+
+int md_download_local(md_ctx *ctx, int64_t *ids, double *pos, double *vel, double *force, double *potential,
+                      double *virial, double box[3])
+{
+    TRY(check_ctx(ctx, true));
+    cudaStream_t st = ctx->stream;
+    const int n = (int)ctx->n_own;
+    const int nb = std::max(1, blocks_for(n, 256));
+    const size_t b3 = 3 * (size_t)n * sizeof(double), b1 = (size_t)n * sizeof(double);
+    const Arrays &a = ctx->cur;
+    if (ctx->h_sc->mu_pending != 1.0) { /* pending scaling is flushed at the end of md_step */ }
+    if (pos && n) {
+        k_interleave3<<<nb, 256, 0, st>>>(n, a.x, a.y, a.z, ctx->stage);
+        CK(cudaMemcpyAsync(pos, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (vel && n) {
+        k_interleave3<<<nb, 256, 0, st>>>(n, a.vx, a.vy, a.vz, ctx->stage);
+        CK(cudaMemcpyAsync(vel, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (force && n) {
+        k_interleave3<<<nb, 256, 0, st>>>(n, a.fx, a.fy, a.fz, ctx->stage);
+        CK(cudaMemcpyAsync(force, ctx->stage, b3, cudaMemcpyDeviceToHost, st));
+    }
+    if (potential && n) CK(cudaMemcpyAsync(potential, a.u, b1, cudaMemcpyDeviceToHost, st));
+    if (virial && n) CK(cudaMemcpyAsync(virial, a.w, b1, cudaMemcpyDeviceToHost, st));
+    if (ids && n) {
+        std::vector<int> tmp((size_t)n);
+        CK(cudaMemcpyAsync(tmp.data(), a.id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n; ++i) ids[i] = tmp[(size_t)i];
+    }
+    CK(cudaGetLastError());
+    TRY(pull_scalars(ctx));
+    if (box) {
+        box[0] = ctx->h_sc->box[0]; box[1] = ctx->h_sc->box[1]; box[2] = ctx->h_sc->box[2];
+    }
+    return MD_OK;
+}
+
+// Host-only description of the slab a rank owns (fractional cut along x) and a capacity hint; no GPU involved.
+int md_plan_decomposition(int64_t n, const double box[3], double r_list, int nranks, int rank, double *x_lo,
+                          double *x_hi, int *left, int *right, int64_t *capacity_hint)
+{
+    if (n <= 0 || !box || nranks < 1 || rank < 0 || rank >= nranks || !(r_list > 0.0)) return MD_ERR_INVALID_ARGUMENT;
+    if (nranks > 1 && box[0] / nranks < 2.1 * r_list) return MD_ERR_DECOMPOSITION;
+    if (x_lo) *x_lo = box[0] * ((double)rank / (double)nranks);
+    if (x_hi) *x_hi = box[0] * ((double)(rank + 1) / (double)nranks);
+    if (left) *left = (rank + nranks - 1) % nranks;
+    if (right) *right = (rank + 1) % nranks;
+    if (capacity_hint) {
+        double own = (double)n / nranks, ghosts = nranks > 1 ? 2.0 * (double)n * r_list / box[0] : 0.0;
+        *capacity_hint = (int64_t)(1.5 * own + 3.0 * ghosts) + 4096;
+    }
+    return MD_OK;
 }
 
 int md_macro(md_ctx *ctx, md_macro_out *out)
@@ -908,6 +1097,9 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->cells[0] = ctx->grid.nc[0]; out->cells[1] = ctx->grid.nc[1]; out->cells[2] = ctx->grid.nc[2];
     out->nbr_capacity = ctx->grid.cap;
     out->skin = ctx->skin;
+    out->n_owned = ctx->n_own;
+    out->n_ghost = ctx->n_ghost;
+    out->migrated = ctx->dist.migrated;
     return MD_OK;
 }
 

@@ -273,7 +273,8 @@ class Solver:
         self._ck(_ffi.lib().md_get_stats(self._ctx, C.byref(s)))
         return {"steps": s.steps, "rebuilds": s.rebuilds, "kernel_launches": s.kernel_launches,
                 "graph_launches": s.graph_launches, "cells": list(s.cells), "nbr_capacity": s.nbr_capacity,
-                "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean}
+                "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean, "n_owned": s.n_owned,
+                "n_ghost": s.n_ghost, "migrated": s.migrated}
 
     def stream(self):
         return _ffi.lib().md_stream(self._ctx)
@@ -283,6 +284,34 @@ class Solver:
 
     def invalidate_lists(self):
         self._ck(_ffi.lib().md_invalidate_lists(self._ctx))
+
+    # -- multi-GPU (one process per GPU; see moldyn_b200/distributed.py for the torch.distributed plumbing) --------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * _ffi.UNIQUE_ID_BYTES)()
+        _ffi.check(None, _ffi.lib().md_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, unique_id: bytes):
+        buf = (C.c_uint8 * _ffi.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        self._ck(_ffi.lib().md_comm_init(self._ctx, int(rank), int(nranks), C.cast(buf, C.c_void_p)))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def local_count(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(_ffi.lib().md_local_count(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download_local(self):
+        """This rank's owned atoms: dict(ids, position, velocity, force, potential, temp, box)."""
+        n, _ = self.local_count()
+        ids = np.zeros(n, dtype=np.int64)
+        pos, vel, force = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        pot, vir, box = np.zeros(n), np.zeros(n), np.zeros(3)
+        self._ck(_ffi.lib().md_download_local(self._ctx, _ptr(ids), _ptr(pos), _ptr(vel), _ptr(force), _ptr(pot),
+                                              _ptr(vir), _ptr(box)))
+        return {"ids": ids, "position": pos, "velocity": vel, "force": force, "potential": pot, "temp": vir,
+                "box": box}
 
     # -- one-shot host-buffer forms ----------------------------------------------------------------
     def update_force_host(self, state: State):

@@ -1,0 +1,99 @@
+"""Multi-GPU parity worker — run under torchrun (one process per GPU), see tests/test_multi_gpu.py.
+
+Every rank builds the same seeded state, the library decomposes it into x-slabs, and rank 0 compares the gathered
+result with the CPU oracle: exact-mode forces and NVE trajectories bit-identical (pair sets and ascending-index sums
+do not depend on the decomposition), thermostat/barostat runs within 1e-8."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import moldyn_b200 as md  # noqa: E402
+from moldyn_b200 import distributed as mdd  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from helpers import dense_gas, gas, liquid  # noqa: E402
+
+DT = 0.002
+
+
+def run_case(name, o, exact, n_steps, thermostat=None, barostat=None, rank=0):
+    lj = orc.LennardJones()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    with md.Solver(device=local, exact=exact) as s:
+        mdd.init_solver_comm(s)
+        s.upload_arrays(o.pos, o.vel, o.mass, o.box)
+        s.update_force()
+        got0 = mdd.gather_by_id(s.download_local(), o.n)
+        gth = (md.Thermostat.Berendsen(thermostat[0]), thermostat[1]) if thermostat else None
+        gba = (md.Barostat.Berendsen(barostat[0], barostat[1]), barostat[2]) if barostat else None
+        s.step(n_steps // 2, DT, thermostat=gth, barostat=gba)
+        s.step(n_steps - n_steps // 2, DT, thermostat=gth, barostat=gba)
+        got1 = mdd.gather_by_id(s.download_local(), o.n)
+        m = s.macro()
+        stats = s.stats()
+    all_stats = [None] * dist.get_world_size() if rank == 0 else None
+    dist.gather_object(stats, all_stats, dst=0)
+    if rank != 0:
+        return
+    ref = o.copy()
+    orc.update_force(lj, ref, mode="cells")
+    if exact:
+        assert np.array_equal(got0["force"], ref.force), name
+        assert np.array_equal(got0["potential"], ref.pot) and np.array_equal(got0["temp"], ref.vir), name
+    else:
+        scale = max(np.abs(ref.force).max(), 1.0)
+        assert np.abs(got0["force"] - ref.force).max() <= 1e-10 * scale * 100, name
+    oth = orc.Thermostat(orc.Thermostat.BERENDSEN, *thermostat) if thermostat else None
+    oba = orc.Barostat(*barostat) if barostat else None
+    orc.step(lj, ref, DT, thermostat=oth, barostat=oba, mode="cells", n_steps=n_steps)
+    if exact and not thermostat and not barostat:
+        assert np.array_equal(got1["position"], ref.pos), name
+        assert np.array_equal(got1["velocity"], ref.vel), name
+        assert np.array_equal(got1["force"], ref.force), name
+    else:
+        dx = np.abs(got1["position"] - ref.pos)
+        dx = np.minimum(dx, np.abs(dx - ref.box))
+        assert dx.max() <= 1e-8 and np.abs(got1["velocity"] - ref.vel).max() <= 1e-8, name
+        assert np.abs(got1["box"] / ref.box - 1.0).max() <= 1e-12, name
+    om = orc.macro(ref)
+    for key in ("kinetic", "thermal", "potential", "temperature", "pressure"):
+        assert abs(m[key] - om[key]) <= 1e-9 * max(1.0, abs(om[key])), (name, key, m[key], om[key])
+    migrated = sum(st["migrated"] for st in all_stats)
+    print(f"  {name}: ok  owned={got1['owned_per_rank']} ghosts={[st['n_ghost'] for st in all_stats]} "
+          f"migrated={migrated} rebuilds={all_stats[0]['rebuilds']}", flush=True)
+    return migrated
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank = dist.get_rank()
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    hot = gas(10, temperature=3000.0)   # fast atoms: plenty of slab crossings in 200 steps
+    cases = [
+        ("liquid4096 exact NVE", liquid(16), True, 100, None, None),
+        ("liquid4096 fast NVT", liquid(16), False, 100, (10.0, 120.0), None),
+        ("liquid4096 exact NPT", liquid(16), True, 100, (10.0, 120.0), (1.0, 5.0, 1.01325)),
+        ("dense_gas3000 exact NVE", dense_gas(3000), True, 100, None, None),
+        ("hot gas1000 exact NVE", hot, True, 200, None, None),
+        ("gas1000 fast NPT", gas(10), False, 100, (10.0, 300.0), (1.0, 5.0, 1.01325)),
+    ]
+    total_migrated = 0
+    for name, o, exact, n_steps, th, ba in cases:
+        mig = run_case(name, o, exact, n_steps, th, ba, rank)
+        if rank == 0:
+            total_migrated += mig
+        dist.barrier()
+    if rank == 0:
+        assert total_migrated > 0, "no atom ever changed rank: migration path untested"
+        print("DIST_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
