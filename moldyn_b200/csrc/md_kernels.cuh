@@ -69,6 +69,13 @@ struct Scalars {
     int g_left, g_right, pad1, pad2;
 };
 
+// Speculatively enqueued steps (multi-GPU chunks) turn into no-ops once the loop has to stop: every kernel of such a
+// step checks this before touching anything.
+__device__ __forceinline__ bool halted(const Scalars *sc)
+{
+    return sc->need_rebuild != 0 || sc->error != 0 || sc->steps_left <= 0;
+}
+
 struct Grid {
     int nc[3];
     int nsub;   // stencil half-width in cells
@@ -655,6 +662,7 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_M
             double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
             unsigned long long cond_handle)
 {
+    if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
     Sums s;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
@@ -803,10 +811,11 @@ __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *
 }
 
 __global__ void __launch_bounds__(256) k_kick_drift(int n, Arrays a, const Scalars *__restrict__ sc,
-                                                    const Params *__restrict__ pr)
+                                                    const Params *__restrict__ pr, int guarded)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (2 * t >= n) return;
+    if (guarded && halted(sc)) return;
     if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
         kick_drift_tail(2 * t, a, sc, pr);
         return;
@@ -927,8 +936,10 @@ __device__ __forceinline__ int owner_of(double x, double Lx, int nranks) { retur
 
 // Finalize after the all-gather of per-rank sums: every rank folds the ranks in the same order → identical
 // lambda / myu / rebuild decision everywhere, deterministic for a fixed rank count.
-__global__ void k_finalize_dist(const double *__restrict__ all_sums, int nranks, Scalars *sc, const Params *pr, int mode)
+__global__ void k_finalize_dist(const double *__restrict__ all_sums, int nranks, Scalars *sc, const Params *pr, int mode,
+                                int guarded)
 {
+    if (guarded && halted(sc)) return;
     Sums t;
     for (int q = 0; q < NSUM; ++q) t.v[q] = 0.0;
     for (int r = 0; r < nranks; ++r) {
@@ -1045,19 +1056,22 @@ __global__ void k_take_owned(int n, const int *__restrict__ flag, const int *__r
 
 // per-step halo: positions of the atoms in idx → buf [x | y | z] (3*m doubles); and the inverse on the receiver
 __global__ void k_pack_halo(int m, const int *__restrict__ idx, const double *__restrict__ x, const double *__restrict__ y,
-                            const double *__restrict__ z, double *__restrict__ buf)
+                            const double *__restrict__ z, double *__restrict__ buf, const Scalars *__restrict__ sc,
+                            int guarded)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
+    if (guarded && halted(sc)) return;
     int i = idx[k];
     buf[k] = x[i]; buf[m + k] = y[i]; buf[2 * (size_t)m + k] = z[i];
 }
 
 __global__ void k_unpack_halo(int m, const double *__restrict__ buf, double *__restrict__ x, double *__restrict__ y,
-                              double *__restrict__ z, int at)
+                              double *__restrict__ z, int at, const Scalars *__restrict__ sc, int guarded)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
+    if (guarded && halted(sc)) return;
     x[at + k] = buf[k]; y[at + k] = buf[m + k]; z[at + k] = buf[2 * (size_t)m + k];
 }
 

@@ -111,7 +111,9 @@ struct md_ctx {
     int *nbr = nullptr, *nbr_cnt = nullptr;
     size_t nbr_alloc = 0;
 
-    // graph
+    // graph (single GPU: WHILE graph; multi-GPU: a chunk of guarded steps incl. the NCCL calls)
+    cudaGraph_t dist_graph = nullptr;
+    cudaGraphExec_t dist_graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraphConditionalHandle cond = 0;
@@ -242,6 +244,10 @@ void drop_graph(md_ctx *ctx)
 {
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->graph) cudaGraphDestroy(ctx->graph);
+    if (ctx->dist_graph_exec) cudaGraphExecDestroy(ctx->dist_graph_exec);
+    if (ctx->dist_graph) cudaGraphDestroy(ctx->dist_graph);
+    ctx->dist_graph_exec = nullptr;
+    ctx->dist_graph = nullptr;
     ctx->graph_exec = nullptr;
     ctx->graph = nullptr;
     ctx->cond = 0;
@@ -414,10 +420,10 @@ int rebuild_lists(md_ctx *ctx)
     return MD_OK;
 }
 
-int launch_kick_drift(md_ctx *ctx)
+int launch_kick_drift(md_ctx *ctx, int guarded = 0)
 {
     const int n = (int)ctx->n_own;
-    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr);
+    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded);
     return MD_OK;
 }
 
