@@ -24,6 +24,7 @@ struct Arrays {
     double *u;             // Particle.potential
     double *w;             // Particle.temp (Σ F_ij·r_ij)
     int *id;               // index of the particle in upload order
+    double4 *q4;           // (x, y, z, -) packed copy for gathers in dense systems: one 32 B sector per partner
 };
 
 // Written by the host once per md_step / md_update_force call.
@@ -63,6 +64,7 @@ struct Scalars {
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     unsigned long long nbr_total;
+    unsigned long long probe[8];  // MD_TIMING_PROBES: %globaltimer stamps of k_force phases
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
     // multi-GPU rebuild bookkeeping
     int n_stay, n_left, n_right, n_lost;
@@ -75,6 +77,22 @@ __device__ __forceinline__ bool halted(const Scalars *sc)
 {
     return sc->need_rebuild != 0 || sc->error != 0 || sc->steps_left <= 0;
 }
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#ifdef MD_TIMING_PROBES
+#define PROBE(k) sc->probe[k] = gtime()
+#define PROBE_MIN(k) atomicMin(&sc->probe[k], gtime())
+#define PROBE_MAX(k) atomicMax(&sc->probe[k], gtime())
+#else
+#define PROBE(k)
+#define PROBE_MIN(k)
+#define PROBE_MAX(k)
+#endif
 
 struct Grid {
     int nc[3];
@@ -414,42 +432,74 @@ constexpr int FIN_DIST = 2;  // multi-GPU: publish this rank's sums only; k_fina
 
 __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Sums &t, int mode)
 {
-    const double n = (double)pr->n;
-    const double M = n * pr->mass;
-    for (int d = 0; d < 3; ++d) sc->sum_mv[d] = t.v[d];
-    sc->sum_th = t.v[3]; sc->sum_ke = t.v[4]; sc->sum_w = t.v[5]; sc->sum_u = t.v[6]; sc->max_w2 = t.v[7];
-    double vc[3], dd = 0.0;
-    for (int d = 0; d < 3; ++d) {
-        vc[d] = t.v[d] / M;  // get_center_of_mass_velocity  mod.rs:12-25
-        sc->vcom[d] = vc[d];
-        double e = vc[d] - sc->shift[d];
-        dd += e * e;
-    }
-    double th2 = t.v[3] - M * dd;       // Σ m |v - vcom|²
-    sc->thermal = th2 / 2.0;            // get_thermal_energy   energy.rs:25-37
-    sc->kinetic = t.v[4] / 2.0;         // get_kinetic_energy   energy.rs:14-22
-    sc->potential = t.v[6] / 2.0;       // get_potential_energy energy.rs:40-49
+    // all inputs first (independent loads → one round trip), then arithmetic, then stores
+    const double n = (double)pr->n, mass = pr->mass, dt = pr->dt, r_list = pr->r_list, r_cut = pr->r_cut;
+    const int th_kind = pr->th_kind, ba_kind = pr->ba_kind;
+    const double th_tau = pr->th_tau, th_target = pr->th_target;
+    const double ba_beta = pr->ba_beta, ba_tau = pr->ba_tau, ba_target = pr->ba_target;
+    double box0 = sc->box[0], box1 = sc->box[1], box2 = sc->box[2];
+    const double shift0 = sc->shift[0], shift1 = sc->shift[1], shift2 = sc->shift[2];
+    const double lambda_used = sc->lambda, mu_used = sc->mu;
+    double disp_acc = sc->disp_acc, inv_scale = sc->inv_scale;
+    const double disp_next_old = sc->disp_next;
+    const long long steps_left = sc->steps_left, steps_done = sc->steps_done;
+
+    const double M = n * mass;
+    const double vc0 = t.v[0] / M, vc1 = t.v[1] / M, vc2 = t.v[2] / M;  // get_center_of_mass_velocity  mod.rs:12-25
+    const double e0 = vc0 - shift0, e1 = vc1 - shift1, e2 = vc2 - shift2;
+    const double th2 = t.v[3] - M * (e0 * e0 + e1 * e1 + e2 * e2);       // Σ m |v - vcom|²
+    const double thermal = th2 / 2.0;                                    // get_thermal_energy   energy.rs:25-37
     if (mode & FIN_STEP) {
-        sc->disp_acc += sc->disp_next;  // the drift that preceded this force evaluation
-        sc->lambda_last = sc->lambda;
-        sc->mu_last = sc->mu;
-        if (pr->ba_kind == 1) {         // barostat.update: boundary_box *= myu  (barostat.rs:45); x *= myu is deferred
-            double mu = sc->mu;
-            sc->box[0] *= mu; sc->box[1] *= mu; sc->box[2] *= mu;
-            sc->mu_pending = mu;
-            sc->inv_scale /= mu;
+        disp_acc += disp_next_old;  // the drift that preceded this force evaluation
+        if (ba_kind == 1) {         // barostat.update: boundary_box *= myu  (barostat.rs:45); x *= myu is deferred
+            box0 *= mu_used; box1 *= mu_used; box2 *= mu_used;
+            inv_scale /= mu_used;
         }
     }
-    sc->temperature = (2.0 * sc->thermal) / (3.0 * n * K_B) * 100.0;  // temperature.rs:4-7
-    double volume = sc->box[0] * sc->box[1] * sc->box[2];
-    sc->pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;            // pressure.rs:5-20
-    compute_controls(sc, pr);
+    const double temperature = (2.0 * thermal) / (3.0 * n * K_B) * 100.0;  // temperature.rs:4-7
+    const double volume = box0 * box1 * box2;
+    const double pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;         // pressure.rs:5-20
+    // controls of the NEXT step (thermostat.rs:24-34, barostat.rs:21-31)
+    double lambda = 1.0, mu = 1.0;
+    if (th_kind == 1) lambda = sqrt(1.0 + dt / th_tau * (th_target / temperature - 1.0));
+    if (ba_kind == 1) mu = cbrt(1.0 + dt * ba_beta / ba_tau * (pressure - ba_target));
+    const double vmax = lambda * sqrt(t.v[7]);
+    const double disp_next = vmax * dt * inv_scale;
+    const double thr = 0.5 * (r_list - r_cut * inv_scale) * (1.0 - 1e-9);
+    const double d = disp_acc + disp_next;
+
+    for (int k = 0; k < 3; ++k) sc->sum_mv[k] = t.v[k];
+    sc->sum_th = t.v[3]; sc->sum_ke = t.v[4]; sc->sum_w = t.v[5]; sc->sum_u = t.v[6]; sc->max_w2 = t.v[7];
+    sc->vcom[0] = vc0; sc->vcom[1] = vc1; sc->vcom[2] = vc2;
+    sc->thermal = thermal;
+    sc->kinetic = t.v[4] / 2.0;    // get_kinetic_energy   energy.rs:14-22
+    sc->potential = t.v[6] / 2.0;  // get_potential_energy energy.rs:40-49
+    sc->temperature = temperature;
+    sc->pressure = pressure;
     if (mode & FIN_STEP) {
-        sc->steps_left -= 1;
-        sc->steps_done += 1;
+        sc->lambda_last = lambda_used;
+        sc->mu_last = mu_used;
+        if (ba_kind == 1) {
+            sc->box[0] = box0; sc->box[1] = box1; sc->box[2] = box2;
+            sc->mu_pending = mu_used;
+        }
+        sc->steps_left = steps_left - 1;
+        sc->steps_done = steps_done + 1;
         // k_force stored u = v + F*c instead of v unless this was the last step of the batch
-        sc->vel_is_half = sc->steps_left > 0 ? 1 : 0;
+        sc->vel_is_half = steps_left - 1 > 0 ? 1 : 0;
     }
+    sc->disp_acc = disp_acc;
+    sc->inv_scale = inv_scale;
+    sc->lambda = lambda;
+    sc->mu = mu;
+    // ΣF = 0, so the COM velocity after the next step's kicks is lambda * vcom: the shift that keeps the one-pass
+    // thermal sum Σ m|v-c|² free of cancellation.
+    sc->shift[0] = vc0 * lambda; sc->shift[1] = vc1 * lambda; sc->shift[2] = vc2 * lambda;
+    // Next drift moves every atom by at most lambda*sqrt(max|v + F c|²)*dt (in build-time units: x inv_scale).
+    // A pair now within r_cut must have been within r_cut*inv_scale + 2*disp <= r_list at build time.
+    sc->disp_next = disp_next;
+    sc->need_rebuild = (d > thr) ? 1 : 0;
+    if (!(d == d) || !(lambda == lambda) || !(mu == mu) || isinf(d) || isinf(lambda) || isinf(mu)) sc->error = 7;
 }
 
 // Last-block epilogue shared by k_force and k_reduce_state.  `mine` is this block's reduced sums (thread 0).
@@ -468,18 +518,31 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
     }
     __syncthreads();
     if (!is_last) return;
+    if (threadIdx.x == 0) { PROBE(2); }
     __threadfence();
     Sums acc;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) acc.v[q] = 0.0;
-#pragma unroll 4
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {  // fixed assignment → fixed order
+    // fixed assignment (block b → thread b % BLOCK, ascending b) → fixed order; 8 slots are fetched per trip so all of
+    // a thread's loads are in flight together (one L2 round trip for grids up to 8*BLOCK blocks)
+    for (unsigned int base = threadIdx.x; base < gridDim.x; base += 8 * BLOCK) {
+        double v[8][NSUM];
 #pragma unroll
-        for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += __ldcg(&partials[(size_t)b * NSUM + q]);
-        acc.v[NSUM - 1] = fmax(acc.v[NSUM - 1], __ldcg(&partials[(size_t)b * NSUM + NSUM - 1]));
+        for (int u = 0; u < 8; ++u) {
+            const unsigned int b = base + u * BLOCK;
+#pragma unroll
+            for (int q = 0; q < NSUM; ++q) v[u][q] = b < gridDim.x ? __ldcg(&partials[(size_t)b * NSUM + q]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += v[u][q];
+            acc.v[NSUM - 1] = fmax(acc.v[NSUM - 1], v[u][NSUM - 1]);
+        }
     }
     block_reduce<BLOCK>(acc);
     if (threadIdx.x == 0) {
+        PROBE(3);
         if (mode & FIN_DIST) {
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) sc->rank_sums[q] = acc.v[q];
@@ -488,6 +551,7 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
         }
         finalize(sc, pr, acc, mode);
         sc->ticket = 0;
+        PROBE(4);
         if (cond_handle) {
             unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
             cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, go);
@@ -548,11 +612,21 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
 #ifndef MD_FORCE_MINB_DILUTE
 #define MD_FORCE_MINB_DILUTE 4
 #endif
+#ifndef MD_DILUTE_ROWS
+#define MD_DILUTE_ROWS 1
+#endif
 constexpr int FORCE_BLOCK = 128;
+
+// Launch constants of the force kernel: passed BY VALUE so they live in the constant bank and feed FP64 instructions
+// as c[bank][offset] operands instead of occupying ~20 registers per thread.
+struct ForceConsts {
+    double sigma, sigma2, eps4, eps24, r_cut, rc2, u_cut;
+    double hc;    // dt / (2 m)
+    double mass;
+};
 
 struct LjConst {
     double Lx, Ly, Lz, hx, hy, hz;
-    double sigma, sigma2, eps4, eps24, r_cut, rc2, u_cut;
     int hxi, hyi, hzi;  // high words of hx, hy, hz: integer-pipe pre-test of the minimum-image condition
 };
 
@@ -568,21 +642,45 @@ __device__ __forceinline__ double min_image_fast(double r, double L, double h, i
     return r;
 }
 
-// FAST pair term, branch-free: masked pairs (k beyond this atom's list, or outside the cutoff) contribute exact zeros.
-__device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, double yj, double zj, double xi,
-                                          double yi, double zi, const LjConst &c)
+// 1/x without the IEEE division's slow-path branch: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (~1 ulp).
+__device__ __forceinline__ double rcp_nr(double x)
 {
-    double rx = min_image_fast(xj - xi, c.Lx, c.hx, c.hxi);
-    double ry = min_image_fast(yj - yi, c.Ly, c.hy, c.hyi);
-    double rz = min_image_fast(zj - zi, c.Lz, c.hz, c.hzi);
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// branch-free single-shift minimum image (same rule as min_image): two compares, a select, one add
+__device__ __forceinline__ double min_image_sel(double r, double L, double h)
+{
+    const double s = r > h ? -L : (r < -h ? L : 0.0);
+    return r + s;
+}
+
+// FAST pair term for dense systems, branch-free: masked pairs (k beyond this atom's list, or outside the cutoff)
+// contribute exact zeros.  WRAP = false is used by warps whose atoms all sit further than r_list + skin from every box
+// face: none of their partners can be a periodic image, so the minimum-image step is skipped altogether.
+template <bool WRAP>
+__device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, double yj, double zj, double xi,
+                                          double yi, double zi, const LjConst &c, const ForceConsts &fc)
+{
+    double rx = xj - xi, ry = yj - yi, rz = zj - zi;
+    if (WRAP) {
+        rx = min_image_sel(rx, c.Lx, c.hx);
+        ry = min_image_sel(ry, c.Ly, c.hy);
+        rz = min_image_sel(rz, c.Lz, c.hz);
+    }
     double r2 = rx * rx + ry * ry + rz * rz;
-    bool in = active && (r2 <= c.rc2);
-    double inv = 1.0 / (in ? r2 : 1.0);
-    double s2 = c.sigma2 * inv;
+    bool in = active && (r2 <= fc.rc2);
+    double inv = rcp_nr(in ? r2 : 1.0);
+    double s2 = fc.sigma2 * inv;
     double s6 = s2 * s2 * s2;
     double s12 = s6 * s6;
-    double fr = c.eps24 * inv * (s6 - 2.0 * s12);  // F / r
-    double pu = c.eps4 * (s12 - s6) - c.u_cut;
+    double fr = fc.eps24 * inv * (s6 - 2.0 * s12);  // F / r
+    double pu = fc.eps4 * (s12 - s6) - fc.u_cut;
     fr = in ? fr : 0.0;
     pu = in ? pu : 0.0;
     a.u += pu;
@@ -593,19 +691,20 @@ __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, do
 // FAST pair term for dilute systems: most listed partners are outside the cutoff (the skin is wide), so the
 // Lennard-Jones body sits behind a real branch and the FP64 pipe only sees the cheap distance test.
 __device__ __forceinline__ void pair_fast_branchy(PairAcc &a, bool active, double xj, double yj, double zj,
-                                                  double xi, double yi, double zi, const LjConst &c)
+                                                  double xi, double yi, double zi, const LjConst &c,
+                                                  const ForceConsts &fc)
 {
     double rx = min_image_fast(xj - xi, c.Lx, c.hx, c.hxi);
     double ry = min_image_fast(yj - yi, c.Ly, c.hy, c.hyi);
     double rz = min_image_fast(zj - zi, c.Lz, c.hz, c.hzi);
     double r2 = rx * rx + ry * ry + rz * rz;
-    if (active && r2 <= c.rc2) {
+    if (active && r2 <= fc.rc2) {
         double inv = 1.0 / r2;
-        double s2 = c.sigma2 * inv;
+        double s2 = fc.sigma2 * inv;
         double s6 = s2 * s2 * s2;
         double s12 = s6 * s6;
-        double fr = c.eps24 * inv * (s6 - 2.0 * s12);
-        a.u += c.eps4 * (s12 - s6) - c.u_cut;
+        double fr = fc.eps24 * inv * (s6 - 2.0 * s12);
+        a.u += fc.eps4 * (s12 - s6) - fc.u_cut;
         a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
         a.w += fr * r2;
     }
@@ -613,19 +712,19 @@ __device__ __forceinline__ void pair_fast_branchy(PairAcc &a, bool active, doubl
 
 // EXACT pair term: potential.rs:181-211 operation by operation, no contraction, real branch on the cutoff.
 __device__ __forceinline__ void pair_exact(PairAcc &a, double xj, double yj, double zj, double xi, double yi,
-                                           double zi, const LjConst &c)
+                                           double zi, const LjConst &c, const ForceConsts &fc)
 {
     double rx = min_image(__dsub_rn(xj, xi), c.Lx, c.hx);
     double ry = min_image(__dsub_rn(yj, yi), c.Ly, c.hy);
     double rz = min_image(__dsub_rn(zj, zi), c.Lz, c.hz);
     double r = norm_exact(rx, ry, rz);
-    if (r > c.r_cut) return;                             // potential.rs:202 (inclusive cutoff)
-    double sr = __ddiv_rn(c.sigma, r);                    // potential.rs:63
+    if (r > fc.r_cut) return;                            // potential.rs:202 (inclusive cutoff)
+    double sr = __ddiv_rn(fc.sigma, r);                   // potential.rs:63
     double x2 = __dmul_rn(sr, sr), x4 = __dmul_rn(x2, x2);
     double s6 = __dmul_rn(x2, x4);                        // powi(6) = x² · x⁴
     double s12 = __dmul_rn(s6, s6);
-    double pu = __dsub_rn(__dmul_rn(c.eps4, __dsub_rn(s12, s6)), c.u_cut);
-    double pf = __dmul_rn(__ddiv_rn(c.eps24, r), __dsub_rn(s6, __dmul_rn(2.0, s12)));
+    double pu = __dsub_rn(__dmul_rn(fc.eps4, __dsub_rn(s12, s6)), fc.u_cut);
+    double pf = __dmul_rn(__ddiv_rn(fc.eps24, r), __dsub_rn(s6, __dmul_rn(2.0, s12)));
     double vx = __dmul_rn(__ddiv_rn(rx, r), pf);          // r / r_abs * force   potential.rs:207
     double vy = __dmul_rn(__ddiv_rn(ry, r), pf);
     double vz = __dmul_rn(__ddiv_rn(rz, r), pf);
@@ -636,7 +735,12 @@ __device__ __forceinline__ void pair_exact(PairAcc &a, double xj, double yj, dou
 }
 
 // Both half-kicks around the force (see header comment above), the K5 terms, and the stores of one atom.
-__device__ __forceinline__ void finish_atom(Sums &s, const PairAcc &f, double &vx, double &vy, double &vz,
+// per-thread running sums kept in shared memory (column per thread → conflict-free), not in 16 registers
+struct SumsSmem {
+    double v[NSUM][FORCE_BLOCK];
+};
+
+__device__ __forceinline__ void finish_atom(SumsSmem &ss, const PairAcc &f, double &vx, double &vy, double &vz,
                                             bool do_step, double lambda, double c, double mass, const double *shift,
                                             double &wx, double &wy, double &wz)
 {
@@ -648,7 +752,69 @@ __device__ __forceinline__ void finish_atom(Sums &s, const PairAcc &f, double &v
     wx = __dadd_rn(vx, __dmul_rn(f.fx, c));                         // u' = v'' + F*c
     wy = __dadd_rn(vy, __dmul_rn(f.fy, c));
     wz = __dadd_rn(vz, __dmul_rn(f.fz, c));
-    accumulate_sums(s, mass, vx, vy, vz, wx, wy, wz, f.w, f.u, shift);
+    const int l = threadIdx.x;
+    ss.v[0][l] += mass * vx; ss.v[1][l] += mass * vy; ss.v[2][l] += mass * vz;
+    const double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
+    ss.v[3][l] += mass * (ax * ax + ay * ay + az * az);
+    ss.v[4][l] += mass * (vx * vx + vy * vy + vz * vz);
+    ss.v[5][l] += f.w;
+    ss.v[6][l] += f.u;
+    ss.v[7][l] = fmax(ss.v[7][l], wx * wx + wy * wy + wz * wz);
+}
+
+// Neighbour loop of one atom pair (FAST modes).  The next rows of partner indices are prefetched while the current
+// ones are in flight; MASKED = branch-free pair term + packed gathers (dense), else branchy pair term + plane gathers.
+template <int ROWS, bool MASKED, bool WRAP>
+__device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const Arrays &a, const int2 *__restrict__ row,
+                                               size_t stride, int last_row, int2 C, int i0, double2 X, double2 Y,
+                                               double2 Z, const LjConst &c, const ForceConsts &fc)
+{
+    const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
+    const int kmax = max(C.x, C.y);
+    int k = 0;
+    int2 Ja = row[0];  // row 0 exists for every atom (cap >= 8): fetched together with the atom's own data
+    if (ROWS == 2) {
+        int2 Jb = row[min(1, last_row) * stride];
+        for (; k + 1 < kmax; k += 2) {
+            const int2 Na = row[min(k + 2, last_row) * stride], Nb = row[min(k + 3, last_row) * stride];
+            const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+            const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
+            double xa0, ya0, za0, xa1, ya1, za1, xb0, yb0, zb0, xb1, yb1, zb1;
+            if (MASKED) {  // dense: one 32 B sector per partner from the packed copy
+                const double4 qa0 = a.q4[ja0], qa1 = a.q4[ja1], qb0 = a.q4[jb0], qb1 = a.q4[jb1];
+                xa0 = qa0.x; ya0 = qa0.y; za0 = qa0.z; xa1 = qa1.x; ya1 = qa1.y; za1 = qa1.z;
+                xb0 = qb0.x; yb0 = qb0.y; zb0 = qb0.z; xb1 = qb1.x; yb1 = qb1.y; zb1 = qb1.z;
+                pair_fast<WRAP>(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c, fc);
+                pair_fast<WRAP>(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c, fc);
+                pair_fast<WRAP>(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c, fc);
+                pair_fast<WRAP>(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c, fc);
+            } else {
+                xa0 = px[ja0]; ya0 = py[ja0]; za0 = pz[ja0]; xa1 = px[ja1]; ya1 = py[ja1]; za1 = pz[ja1];
+                xb0 = px[jb0]; yb0 = py[jb0]; zb0 = pz[jb0]; xb1 = px[jb1]; yb1 = py[jb1]; zb1 = pz[jb1];
+                pair_fast_branchy(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c, fc);
+                pair_fast_branchy(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c, fc);
+                pair_fast_branchy(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c, fc);
+                pair_fast_branchy(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c, fc);
+            }
+            Ja = Na; Jb = Nb;
+        }
+    }
+    for (; k < kmax; ++k) {
+        const int2 Na = row[min(k + 1, last_row) * stride];
+        const bool a0 = k < C.x, a1 = k < C.y;
+        const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
+        if (MASKED) {
+            const double4 qa0 = a.q4[ja0], qa1 = a.q4[ja1];
+            pair_fast<WRAP>(f0, a0, qa0.x, qa0.y, qa0.z, X.x, Y.x, Z.x, c, fc);
+            pair_fast<WRAP>(f1, a1, qa1.x, qa1.y, qa1.z, X.y, Y.y, Z.y, c, fc);
+        } else {
+            const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
+            const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
+            pair_fast_branchy(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c, fc);
+            pair_fast_branchy(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c, fc);
+        }
+        Ja = Na;
+    }
 }
 
 // Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
@@ -656,16 +822,17 @@ __device__ __forceinline__ void finish_atom(Sums &s, const PairAcc &f, double &v
 // next rows of partner indices prefetched while the current ones are in flight.
 //   ROWS = 2: two list rows per trip (dense systems; 12 gathers in flight, 128 registers)
 //   ROWS = 1: one row per trip (dilute systems: few partners, occupancy matters more than unrolling)
-template <bool EXACT, int ROWS>
-__global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
+template <bool EXACT, int ROWS, bool MASKED>
+__global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
     k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
             double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
-            unsigned long long cond_handle)
+            unsigned long long cond_handle, const ForceConsts fc)
 {
     if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
-    Sums s;
+    if (threadIdx.x == 0) { PROBE_MIN(0); }
+    __shared__ SumsSmem ss;
 #pragma unroll
-    for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
+    for (int q = 0; q < NSUM; ++q) ss.v[q][threadIdx.x] = 0.0;
     // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
     const bool store_state = !(do_step & 1) || sc->steps_left <= 1;
     const double lambda = sc->lambda;
@@ -673,16 +840,9 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_M
     c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
     c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
     c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
-    c.sigma = pr->sigma; c.r_cut = pr->r_cut; c.u_cut = pr->u_cut;
-    if (EXACT) {
-        c.eps4 = __dmul_rn(4.0, pr->eps); c.eps24 = __dmul_rn(24.0, pr->eps);
-        c.sigma2 = 0.0; c.rc2 = 0.0;
-    } else {
-        c.eps4 = 4.0 * pr->eps; c.eps24 = 24.0 * pr->eps;
-        c.sigma2 = c.sigma * c.sigma; c.rc2 = c.r_cut * c.r_cut;
-    }
     const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
-    const double hc = pr->half_dt_m, mass = pr->mass;
+    // partners listed at the last build are now at most r_list + skin away (each atom moved < skin/2)
+    const double wrap_margin = (2.0 * pr->r_list - pr->r_cut) * 1.02;
     const int npairs = (n + 1) >> 1;
     const int last_row = cap - 1;
     const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
@@ -701,52 +861,29 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_M
         if (EXACT) {
             for (int k = 0; k < C.x; ++k) {
                 int j = row[k * stride].x;
-                pair_exact(f0, px[j], py[j], pz[j], X.x, Y.x, Z.x, c);
+                pair_exact(f0, px[j], py[j], pz[j], X.x, Y.x, Z.x, c, fc);
             }
             for (int k = 0; k < C.y; ++k) {
                 int j = row[k * stride].y;
-                pair_exact(f1, px[j], py[j], pz[j], X.y, Y.y, Z.y, c);
+                pair_exact(f1, px[j], py[j], pz[j], X.y, Y.y, Z.y, c, fc);
             }
         } else {
-            const int kmax = max(C.x, C.y);
-            int k = 0;
-            int2 Ja = row[0];  // row 0 exists for every atom (cap >= 8): fetched together with the atom's own data
-            if (ROWS == 2) {
-                int2 Jb = row[min(1, last_row) * stride];
-                for (; k + 1 < kmax; k += 2) {
-                    const int2 Na = row[min(k + 2, last_row) * stride], Nb = row[min(k + 3, last_row) * stride];
-                    const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
-                    const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
-                    const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
-                    const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
-                    const double xb0 = px[jb0], yb0 = py[jb0], zb0 = pz[jb0];
-                    const double xb1 = px[jb1], yb1 = py[jb1], zb1 = pz[jb1];
-                    pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
-                    pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
-                    pair_fast(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c);
-                    pair_fast(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c);
-                    Ja = Na; Jb = Nb;
-                }
-            }
-            for (; k < kmax; ++k) {
-                const int2 Na = row[min(k + 1, last_row) * stride];
-                const bool a0 = k < C.x, a1 = k < C.y;
-                const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
-                const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
-                const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
-                if (ROWS == 2) {
-                    pair_fast(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
-                    pair_fast(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
-                } else {
-                    pair_fast_branchy(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c);
-                    pair_fast_branchy(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c);
-                }
-                Ja = Na;
+            if (MASKED) {
+                // warp-uniform choice: is any atom of this warp within r_list + skin of a box face?
+                const double m = wrap_margin;
+                const bool near = X.x < m || X.x > c.Lx - m || Y.x < m || Y.x > c.Ly - m || Z.x < m || Z.x > c.Lz - m ||
+                                  X.y < m || X.y > c.Lx - m || Y.y < m || Y.y > c.Ly - m || Z.y < m || Z.y > c.Lz - m;
+                if (__any_sync(__activemask(), near))
+                    neighbour_loop<ROWS, true, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
+                else
+                    neighbour_loop<ROWS, true, false>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
+            } else {
+                neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
             }
         }
         double2 WX, WY, WZ;
-        finish_atom(s, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, hc, mass, shift, WX.x, WY.x, WZ.x);
-        if (has1) finish_atom(s, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lambda, hc, mass, shift, WX.y, WY.y, WZ.y);
+        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y);
         else { WX.y = WY.y = WZ.y = 0.0; }
         if (!has1) {  // odd tail: scalar stores only (slot i0+1 may hold a ghost atom in the distributed layout)
             if (store_state) {
@@ -770,6 +907,10 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || ROWS == 2) ? MD_FORCE_M
             reinterpret_cast<double2 *>(a.vz)[t] = WZ;
         }
     }
+    if (threadIdx.x == 0) { PROBE_MAX(1); }
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][threadIdx.x];
     block_reduce<FORCE_BLOCK>(s);
     grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr, (do_step & 1 ? FIN_STEP : 0) | (do_step & 2 ? FIN_DIST : 0),
                                       cond_handle);
@@ -794,7 +935,7 @@ __device__ __forceinline__ void drift_one(double &x, double u, double lambda, do
 }
 
 __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *__restrict__ sc,
-                                                const Params *__restrict__ pr)
+                                                const Params *__restrict__ pr, bool write_q4)
 {
     const double c = pr->half_dt_m, dt = pr->dt, lambda = sc->lambda, mup = sc->mu_pending;
     double ux = a.vx[i], uy = a.vy[i], uz = a.vz[i];
@@ -808,16 +949,17 @@ __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *
     drift_one(y, uy, lambda, mup, dt, sc->box[1]);
     drift_one(z, uz, lambda, mup, dt, sc->box[2]);
     a.x[i] = x; a.y[i] = y; a.z[i] = z;
+    if (write_q4) a.q4[i] = make_double4(x, y, z, 0.0);
 }
 
-__global__ void __launch_bounds__(256) k_kick_drift(int n, Arrays a, const Scalars *__restrict__ sc,
-                                                    const Params *__restrict__ pr, int guarded)
+__global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, const Scalars *__restrict__ sc,
+                                                    const Params *__restrict__ pr, int guarded, int write_q4)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (2 * t >= n) return;
     if (guarded && halted(sc)) return;
     if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
-        kick_drift_tail(2 * t, a, sc, pr);
+        kick_drift_tail(2 * t, a, sc, pr, write_q4 != 0);
         return;
     }
     const double c = pr->half_dt_m, dt = pr->dt;
@@ -842,6 +984,17 @@ __global__ void __launch_bounds__(256) k_kick_drift(int n, Arrays a, const Scala
     drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
     reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
     reinterpret_cast<double2 *>(a.z)[t] = z;
+    if (write_q4) {
+        a.q4[2 * t] = make_double4(x.x, y.x, z.x, 0.0);
+        a.q4[2 * t + 1] = make_double4(x.y, y.y, z.y, 0.0);
+    }
+}
+
+// (re)builds the packed gather copy from the planes: after a reorder, a ghost exchange or a coordinate rescale
+__global__ void k_pack_q4(int n, Arrays a)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a.q4[i] = make_double4(a.x[i], a.y[i], a.z[i], 0.0);
 }
 
 // barostat.update's coordinate scaling when no kick_drift follows (end of an md_step batch).
@@ -1067,12 +1220,15 @@ __global__ void k_pack_halo(int m, const int *__restrict__ idx, const double *__
 }
 
 __global__ void k_unpack_halo(int m, const double *__restrict__ buf, double *__restrict__ x, double *__restrict__ y,
-                              double *__restrict__ z, int at, const Scalars *__restrict__ sc, int guarded)
+                              double *__restrict__ z, int at, const Scalars *__restrict__ sc, int guarded,
+                              double4 *__restrict__ q4)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     if (guarded && halted(sc)) return;
-    x[at + k] = buf[k]; y[at + k] = buf[m + k]; z[at + k] = buf[2 * (size_t)m + k];
+    const double px = buf[k], py = buf[m + k], pz = buf[2 * (size_t)m + k];
+    x[at + k] = px; y[at + k] = py; z[at + k] = pz;
+    if (q4) q4[at + k] = make_double4(px, py, pz, 0.0);
 }
 
 // local cell index: x is measured from (slab lower face - halo), unwrapped periodically; y, z as in the global grid

@@ -102,6 +102,8 @@ struct md_ctx {
     int partial_blocks = 0;
     int force_grid[3] = {1, 1, 1}, reduce_grid = 1;  // exact, fast dense, fast dilute
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
+    bool use_q4 = false;                              // packed gather copy maintained (dense systems)
+    double graph_hc = -1.0;                           // dt/(2m) baked into the captured force kernel
 
     // cells / lists
     Grid grid{};
@@ -228,6 +230,7 @@ int alloc_arrays(md_ctx *ctx, Arrays *a, int npad)
     TRY(dev_alloc(ctx, &a->fx, npad)); TRY(dev_alloc(ctx, &a->fy, npad)); TRY(dev_alloc(ctx, &a->fz, npad));
     TRY(dev_alloc(ctx, &a->u, npad)); TRY(dev_alloc(ctx, &a->w, npad));
     TRY(dev_alloc(ctx, &a->id, npad));
+    TRY(dev_alloc(ctx, &a->q4, npad));
     return MD_OK;
 }
 
@@ -236,7 +239,7 @@ void free_arrays(md_ctx *ctx, Arrays *a)
     dev_free(ctx, a->x); dev_free(ctx, a->y); dev_free(ctx, a->z);
     dev_free(ctx, a->vx); dev_free(ctx, a->vy); dev_free(ctx, a->vz);
     dev_free(ctx, a->fx); dev_free(ctx, a->fy); dev_free(ctx, a->fz);
-    dev_free(ctx, a->u); dev_free(ctx, a->w); dev_free(ctx, a->id);
+    dev_free(ctx, a->u); dev_free(ctx, a->w); dev_free(ctx, a->id); dev_free(ctx, a->q4);
     *a = Arrays{};
 }
 
@@ -361,6 +364,30 @@ double sqrt_threshold(double r)
     return t;
 }
 
+ForceConsts force_consts(const md_ctx *ctx)
+{
+    ForceConsts fc;
+    fc.sigma = ctx->sigma;
+    fc.sigma2 = ctx->sigma * ctx->sigma;
+    fc.eps4 = 4.0 * ctx->eps;    // == __dmul_rn(4.0, eps): the product the reference forms (potential.rs:67)
+    fc.eps24 = 24.0 * ctx->eps;  // potential.rs:68
+    fc.r_cut = ctx->r_cut;
+    fc.rc2 = ctx->r_cut * ctx->r_cut;
+    fc.u_cut = ctx->u_cut;
+    fc.hc = ctx->prm.half_dt_m;
+    fc.mass = ctx->mass;
+    return fc;
+}
+
+int refresh_q4(md_ctx *ctx)
+{
+    if (!ctx->use_q4) return MD_OK;
+    const int n = (int)(ctx->n_own + ctx->n_ghost);
+    k_pack_q4<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur);
+    ctx->stats.kernel_launches += 1;
+    return MD_OK;
+}
+
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
 // (no pending barostat scaling).
 int rebuild_lists(md_ctx *ctx)
@@ -416,6 +443,8 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.nbr_max = ctx->h_sc->nbr_max;
     ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
     ctx->dense = ctx->stats.nbr_mean >= 8.0;
+    ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT;
+    TRY(refresh_q4(ctx));
     ctx->list_valid = true;
     return MD_OK;
 }
@@ -423,20 +452,22 @@ int rebuild_lists(md_ctx *ctx)
 int launch_kick_drift(md_ctx *ctx, int guarded = 0)
 {
     const int n = (int)ctx->n_own;
-    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded);
+    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded,
+                                                                        ctx->use_q4 ? 1 : 0);
     return MD_OK;
 }
 
 int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
 {
     const int n = (int)ctx->n;
-#define LAUNCH_FORCE(E, R, GRID)                                                                                  \
-    k_force<E, R><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
+    const ForceConsts fc = force_consts(ctx);
+#define LAUNCH_FORCE(E, R, M, GRID)                                                                                  \
+    k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
                                                          ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
-                                                         kick ? 1 : 0, cond)
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, ctx->force_grid[0]);
-    else if (ctx->dense) LAUNCH_FORCE(false, 2, ctx->force_grid[1]);
-    else LAUNCH_FORCE(false, 1, ctx->force_grid[2]);
+                                                         kick ? 1 : 0, cond, fc)
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
+    else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
+    else LAUNCH_FORCE(false, MD_DILUTE_ROWS, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
     return MD_OK;
 }
@@ -454,9 +485,9 @@ int choose_grids(md_ctx *ctx)
 {
     int sms = 0, occ[3] = {0, 0, 0}, occ_r = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, 1>, FORCE_BLOCK, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, 2>, FORCE_BLOCK, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, 1>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, 1, false>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, 2, true>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, MD_DILUTE_ROWS, false>, FORCE_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
     const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
     for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
@@ -494,6 +525,7 @@ int flush_pending_scale(md_ctx *ctx)
     k_scale_positions<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc);
     k_clear_pending<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
     ctx->stats.kernel_launches += 2;
+    TRY(refresh_q4(ctx));
     CK(cudaGetLastError());
     return MD_OK;
 }
@@ -814,6 +846,10 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     p.ba_tau = ba ? ba->tau : 1.0;
     p.ba_target = ba ? ba->target : 0.0;
     TRY(push_params(ctx));
+    if (ctx->graph_hc != p.half_dt_m) {  // dt/(2m) is a launch constant of the captured force kernel
+        drop_graph(ctx);
+        ctx->graph_hc = p.half_dt_m;
+    }
     // The displacement bound of the first drift needs max|v + F c|² for THIS c.
     if (ctx->sums_c != p.half_dt_m) {
         if (ctx->dist.on) TRY(dist_launch_reduce(ctx));
@@ -1110,6 +1146,27 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
 }
 
 void *md_stream(md_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// MD_TIMING_PROBES builds only: %globaltimer stamps (ns) of the last k_force launch:
+// [0] first block start, [1] last block leaves the atom loop, [2] last-block reduction starts, [3] reduction done,
+// [4] finalize done.  probe[0]/[1] must be reset by the caller (md_probe_reset) before the launch.
+__attribute__((visibility("default"))) int md_probe_read(md_ctx *ctx, unsigned long long out[8])
+{
+    TRY(check_ctx(ctx, false));
+    TRY(pull_scalars(ctx));
+    for (int k = 0; k < 8; ++k) out[k] = ctx->h_sc->probe[k];
+    return MD_OK;
+}
+
+__attribute__((visibility("default"))) int md_probe_reset(md_ctx *ctx)
+{
+    TRY(check_ctx(ctx, false));
+    unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->d_sc) + offsetof(Scalars, probe), init, sizeof init,
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
 
 int md_synchronize(md_ctx *ctx)
 {
