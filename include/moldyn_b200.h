@@ -55,7 +55,7 @@ typedef struct md_config {
     int32_t force_mode;     /* MD_FORCE_* */
     int32_t loop_mode;      /* MD_LOOP_* */
     int32_t max_neighbours; /* initial neighbour-list capacity per atom; 0 = from density (grown on demand) */
-    int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = 1 */
+    int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = by density */
     int32_t reserved0;
     double skin;            /* Verlet skin [nm]; <= 0 selects a default from r_cut and density */
     double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 1 */
@@ -65,7 +65,7 @@ typedef struct md_config {
  * md_step, like the reference stores them in the enum (thermostat.rs:33,37-38). */
 #define MD_THERMOSTAT_NONE 0
 #define MD_THERMOSTAT_BERENDSEN 1
-#define MD_THERMOSTAT_NOSE_HOOVER 2 /* declared for surface parity; md_step returns MD_ERR_UNSUPPORTED */
+#define MD_THERMOSTAT_NOSE_HOOVER 2 /* thermostat.rs:35-39,59-65: psi is carried by the caller, like the enum field */
 typedef struct md_thermostat {
     int32_t kind;
     int32_t reserved0;

@@ -40,7 +40,11 @@ struct Params {
     int th_kind, ba_kind;
 };
 
-constexpr int NSUM = 8;  // Σ m vx, Σ m vy, Σ m vz, Σ m|v-c|², Σ m v·v, Σ W, Σ U, max |v + F c|²
+// K5 slots: Σ m v (3), Σ m|v-c|², Σ m v·v, Σ W, Σ U, then the same COM/thermal sums for u = v + F c (the velocity
+// right after the NEXT step's first half-kick: Nose-Hoover's second psi update needs its temperature,
+// thermostat.rs:47-65), and last max |u|² (the displacement bound).  The max slot must stay last.
+constexpr int NSUM = 12;
+constexpr int S_MV = 0, S_TH = 3, S_KE = 4, S_W = 5, S_U = 6, S_MU = 7, S_THU = 10, S_MAX = NSUM - 1;
 
 // Device-resident step state: box, thermostat/barostat coefficients, reduction results, loop control.
 struct Scalars {
@@ -56,6 +60,8 @@ struct Scalars {
     double sum_mv[3], sum_th, sum_ke, sum_w, sum_u, max_w2;
     double vcom[3], thermal, kinetic, potential, temperature, pressure;
     double lambda_last, mu_last;  // coefficients used by the last executed step
+    double psi;                   // Nose-Hoover friction after the last executed step (thermostat.rs:10-14)
+    double temperature_mid;       // temperature of u = v + F c (after the next first half-kick, before scaling)
     long long steps_left, steps_done;
     int need_rebuild;
     int error;
@@ -395,21 +401,38 @@ __device__ __forceinline__ void block_reduce(Sums &s)
     __syncthreads();
 }
 
-// Step controls for the NEXT step from the current macro state (thermostat.rs:24-34, barostat.rs:21-31)
-// plus the displacement bookkeeping that triggers list rebuilds.
-__device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr)
+// Thermostat coefficient of the NEXT step.  Berendsen (thermostat.rs:31-34): lambda from the temperature at the step
+// start.  Nose-Hoover (thermostat.rs:35-39, 59-65): psi advances by half a step with the start temperature, lambda =
+// exp(-psi dt/2), then psi advances again with the temperature after the first half-kick (before scaling).
+__device__ __forceinline__ double thermostat_lambda(int kind, double dt, double tau, double target, double t_start,
+                                                    double t_mid, double &psi)
 {
-    double lambda = 1.0, mu = 1.0;
-    if (pr->th_kind == 1) {
-        double lambda_squared = 1.0 + pr->dt / pr->th_tau * (pr->th_target / sc->temperature - 1.0);
-        lambda = sqrt(lambda_squared);
+    if (kind == 1) return sqrt(1.0 + dt / tau * (target / t_start - 1.0));
+    if (kind == 2) {
+        double psi_dot = -((target / t_start) - 1.0) / tau;
+        psi += psi_dot * (dt / 2.0);
+        const double lambda = exp(-psi * dt / 2.0);
+        psi_dot = -((target / t_mid) - 1.0) / tau;
+        psi += psi_dot * (dt / 2.0);
+        return lambda;
     }
+    return 1.0;
+}
+
+// Step controls for the first step of a batch from the stored macro state (thermostat.rs:24-44, barostat.rs:21-31)
+// plus the displacement bookkeeping that triggers list rebuilds.  psi_in: the caller's Nose-Hoover state.
+__device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr, double psi_in)
+{
+    double mu = 1.0, psi = psi_in;
+    const double lambda = thermostat_lambda(pr->th_kind, pr->dt, pr->th_tau, pr->th_target, sc->temperature,
+                                            sc->temperature_mid, psi);
     if (pr->ba_kind == 1) {
         double myu_cubed = 1.0 + pr->dt * pr->ba_beta / pr->ba_tau * (sc->pressure - pr->ba_target);
         mu = cbrt(myu_cubed);
     }
     sc->lambda = lambda;
     sc->mu = mu;
+    sc->psi = psi;
     // ΣF = 0, so the COM velocity after the next step's kicks is lambda * vcom: used as the shift that keeps
     // the one-pass thermal sum Σ m|v-c|² free of cancellation.
     sc->shift[0] = sc->vcom[0] * lambda;
@@ -443,6 +466,7 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
     double disp_acc = sc->disp_acc, inv_scale = sc->inv_scale;
     const double disp_next_old = sc->disp_next;
     const long long steps_left = sc->steps_left, steps_done = sc->steps_done;
+    double psi = sc->psi;
 
     const double M = n * mass;
     const double vc0 = t.v[0] / M, vc1 = t.v[1] / M, vc2 = t.v[2] / M;  // get_center_of_mass_velocity  mod.rs:12-25
@@ -457,25 +481,35 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
         }
     }
     const double temperature = (2.0 * thermal) / (3.0 * n * K_B) * 100.0;  // temperature.rs:4-7
+    // same for u = v + F c (the state thermostat.update sees after the next first half-kick)
+    const double uc0 = t.v[S_MU] / M - shift0, uc1 = t.v[S_MU + 1] / M - shift1, uc2 = t.v[S_MU + 2] / M - shift2;
+    const double thu2 = t.v[S_THU] - M * (uc0 * uc0 + uc1 * uc1 + uc2 * uc2);
+    const double temperature_mid = (2.0 * (thu2 / 2.0)) / (3.0 * n * K_B) * 100.0;
     const double volume = box0 * box1 * box2;
     const double pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;         // pressure.rs:5-20
     // controls of the NEXT step (thermostat.rs:24-34, barostat.rs:21-31)
+    // (Nose-Hoover's psi is only advanced when this batch has a next step: the first step of the next batch is
+    // prepared by k_prepare from the caller's psi.)
     double lambda = 1.0, mu = 1.0;
-    if (th_kind == 1) lambda = sqrt(1.0 + dt / th_tau * (th_target / temperature - 1.0));
+    const bool more = !(mode & FIN_STEP) || steps_left - 1 > 0;
+    if (th_kind == 1 || (th_kind == 2 && more))
+        lambda = thermostat_lambda(th_kind, dt, th_tau, th_target, temperature, temperature_mid, psi);
     if (ba_kind == 1) mu = cbrt(1.0 + dt * ba_beta / ba_tau * (pressure - ba_target));
-    const double vmax = lambda * sqrt(t.v[7]);
+    const double vmax = lambda * sqrt(t.v[S_MAX]);
     const double disp_next = vmax * dt * inv_scale;
     const double thr = 0.5 * (r_list - r_cut * inv_scale) * (1.0 - 1e-9);
     const double d = disp_acc + disp_next;
 
     for (int k = 0; k < 3; ++k) sc->sum_mv[k] = t.v[k];
-    sc->sum_th = t.v[3]; sc->sum_ke = t.v[4]; sc->sum_w = t.v[5]; sc->sum_u = t.v[6]; sc->max_w2 = t.v[7];
+    sc->sum_th = t.v[3]; sc->sum_ke = t.v[4]; sc->sum_w = t.v[5]; sc->sum_u = t.v[6]; sc->max_w2 = t.v[S_MAX];
     sc->vcom[0] = vc0; sc->vcom[1] = vc1; sc->vcom[2] = vc2;
     sc->thermal = thermal;
     sc->kinetic = t.v[4] / 2.0;    // get_kinetic_energy   energy.rs:14-22
     sc->potential = t.v[6] / 2.0;  // get_potential_energy energy.rs:40-49
     sc->temperature = temperature;
+    sc->temperature_mid = temperature_mid;
     sc->pressure = pressure;
+    if (mode & FIN_STEP) sc->psi = psi;
     if (mode & FIN_STEP) {
         sc->lambda_last = lambda_used;
         sc->mu_last = mu_used;
@@ -523,18 +557,18 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
     Sums acc;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) acc.v[q] = 0.0;
-    // fixed assignment (block b → thread b % BLOCK, ascending b) → fixed order; 8 slots are fetched per trip so all of
-    // a thread's loads are in flight together (one L2 round trip for grids up to 8*BLOCK blocks)
-    for (unsigned int base = threadIdx.x; base < gridDim.x; base += 8 * BLOCK) {
-        double v[8][NSUM];
+    // fixed assignment (block b → thread b % BLOCK, ascending b) → fixed order; several slots are fetched per trip so
+    // a thread's loads are in flight together (4 slots per trip)
+    for (unsigned int base = threadIdx.x; base < gridDim.x; base += 4 * BLOCK) {
+        double v[4][NSUM];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const unsigned int b = base + u * BLOCK;
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) v[u][q] = b < gridDim.x ? __ldcg(&partials[(size_t)b * NSUM + q]) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
             for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += v[u][q];
             acc.v[NSUM - 1] = fmax(acc.v[NSUM - 1], v[u][NSUM - 1]);
@@ -565,11 +599,14 @@ __device__ __forceinline__ void accumulate_sums(Sums &s, double m, double vx, do
 {
     s.v[0] += m * vx; s.v[1] += m * vy; s.v[2] += m * vz;
     double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
-    s.v[3] += m * (ax * ax + ay * ay + az * az);
-    s.v[4] += m * (vx * vx + vy * vy + vz * vz);
-    s.v[5] += w;
-    s.v[6] += u;
-    s.v[7] = fmax(s.v[7], wx * wx + wy * wy + wz * wz);
+    s.v[S_TH] += m * (ax * ax + ay * ay + az * az);
+    s.v[S_KE] += m * (vx * vx + vy * vy + vz * vz);
+    s.v[S_W] += w;
+    s.v[S_U] += u;
+    s.v[S_MU] += m * wx; s.v[S_MU + 1] += m * wy; s.v[S_MU + 2] += m * wz;
+    double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
+    s.v[S_THU] += m * (bx * bx + by * by + bz * bz);
+    s.v[S_MAX] = fmax(s.v[S_MAX], wx * wx + wy * wy + wz * wz);
 }
 
 // Standalone K5 over the stored state (after upload, or when only the macro parameters are wanted).
@@ -757,9 +794,12 @@ __device__ __forceinline__ void finish_atom(SumsSmem &ss, const PairAcc &f, doub
     const double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
     ss.v[3][l] += mass * (ax * ax + ay * ay + az * az);
     ss.v[4][l] += mass * (vx * vx + vy * vy + vz * vz);
-    ss.v[5][l] += f.w;
-    ss.v[6][l] += f.u;
-    ss.v[7][l] = fmax(ss.v[7][l], wx * wx + wy * wy + wz * wz);
+    ss.v[S_W][l] += f.w;
+    ss.v[S_U][l] += f.u;
+    ss.v[S_MU][l] += mass * wx; ss.v[S_MU + 1][l] += mass * wy; ss.v[S_MU + 2][l] += mass * wz;
+    const double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
+    ss.v[S_THU][l] += mass * (bx * bx + by * by + bz * bz);
+    ss.v[S_MAX][l] = fmax(ss.v[S_MAX][l], wx * wx + wy * wy + wz * wz);
 }
 
 // Neighbour loop of one atom pair (FAST modes).  The next rows of partner indices are prefetched while the current
@@ -1019,11 +1059,11 @@ __global__ void k_after_rebuild(Scalars *sc)
     sc->need_rebuild = 0;
 }
 
-__global__ void k_prepare(Scalars *sc, const Params *pr, long long n_steps)
+__global__ void k_prepare(Scalars *sc, const Params *pr, long long n_steps, double psi)
 {
     sc->steps_left = n_steps;
     sc->steps_done = 0;
-    compute_controls(sc, pr);
+    compute_controls(sc, pr, psi);
 }
 
 __global__ void k_reset_list_stats(Scalars *sc)

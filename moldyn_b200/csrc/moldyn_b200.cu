@@ -300,9 +300,11 @@ double choose_skin(const md_ctx *ctx, const double box[3])
 int choose_grid(md_ctx *ctx, const double box[3])
 {
     Grid g{};
-    int nsub = ctx->cfg.cell_subdiv >= 2 ? 2 : 1;
     double r_list = ctx->r_cut + ctx->skin;
     double volume = box[0] * box[1] * box[2];
+    // dense systems: half-size cells and a 5x5x5 stencil (fewer candidates per list build, tighter sorted order)
+    const double in_list = (double)ctx->n / volume * 4.18879020478639 * r_list * r_list * r_list;
+    int nsub = ctx->cfg.cell_subdiv >= 2 ? 2 : (ctx->cfg.cell_subdiv == 1 ? 1 : (in_list > 40.0 ? 2 : 1));
     double k = ctx->cfg.cell_atoms > 0.0 ? ctx->cfg.cell_atoms : 1.0;
     double dilute_edge = std::cbrt(k * volume / (double)ctx->n);
     double edge = std::max(r_list / nsub * 1.02, dilute_edge);
@@ -825,9 +827,8 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
 {
     TRY(check_ctx(ctx, true));
     if (n_steps < 0 || !std::isfinite(dt)) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_step: bad n_steps/dt");
-    if (th && th->kind == MD_THERMOSTAT_NOSE_HOOVER)
-        return ctx->fail(MD_ERR_UNSUPPORTED, "Nose-Hoover thermostat is not implemented on the device path yet");
-    if (th && th->kind != MD_THERMOSTAT_NONE && th->kind != MD_THERMOSTAT_BERENDSEN)
+    if (th && th->kind != MD_THERMOSTAT_NONE && th->kind != MD_THERMOSTAT_BERENDSEN &&
+        th->kind != MD_THERMOSTAT_NOSE_HOOVER)
         return ctx->fail(MD_ERR_UNSUPPORTED, "Thermostat::Custom is todo!() in the reference");
     if (ba && ba->kind != MD_BAROSTAT_NONE && ba->kind != MD_BAROSTAT_BERENDSEN)
         return ctx->fail(MD_ERR_UNSUPPORTED, "Barostat::Custom is todo!() in the reference");
@@ -856,7 +857,7 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
         else launch_reduce(ctx);
         ctx->sums_c = p.half_dt_m;
     }
-    k_prepare<<<1, 1, 0, st>>>(ctx->d_sc, ctx->d_pr, (long long)n_steps);
+    k_prepare<<<1, 1, 0, st>>>(ctx->d_sc, ctx->d_pr, (long long)n_steps, th ? th->psi : 0.0);
     ctx->stats.kernel_launches += 1;
     CK(cudaGetLastError());
 
@@ -909,7 +910,10 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     if (p.ba_kind == MD_BAROSTAT_BERENDSEN) TRY(flush_pending_scale(ctx));
     TRY(pull_scalars(ctx));
     TRY(device_error(ctx));
-    if (th) th->lambda = ctx->h_sc->lambda_last;
+    if (th) {
+        th->lambda = ctx->h_sc->lambda_last;
+        if (th->kind == MD_THERMOSTAT_NOSE_HOOVER) th->psi = ctx->h_sc->psi;
+    }
     if (ba) ba->myu = ctx->h_sc->mu_last;
     ctx->force_valid = true;
     return MD_OK;

@@ -246,6 +246,29 @@ def test_thermostat_barostat_trajectory(name, ensemble, mode):
     assert abs(m["potential"] - om["potential"]) <= 1e-9 * max(1.0, abs(om["potential"]))
 
 
+@pytest.mark.parametrize("name", ["liquid1000", "gas1000"])
+def test_nose_hoover_trajectory(name, mode):  # thermostat.rs:35-39, 59-65
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    st = to_gpu_state(md, o)
+    t0 = 300.0 if name == "gas1000" else 120.0
+    oth, gth = orc.Thermostat(orc.Thermostat.NOSE_HOOVER, 0.5, t0), (md.Thermostat.NoseHoover(0.5), t0)
+    with make_solver(mode) as s:
+        s.set_potential(plj)
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(1, DT, thermostat=gth)     # psi is carried by the caller between calls, like the enum field
+        s.step(59, DT, thermostat=gth)
+        s.step(40, DT, thermostat=gth)
+        s.download(st)
+    run_oracle(olj, o, 100, oth)
+    assert abs(gth[0].psi - oth.psi) <= 1e-10 * max(1.0, abs(oth.psi))
+    assert abs(gth[0].lambda_ / oth.lambda_ - 1.0) <= 1e-12
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    dx = np.abs(st.position - o.pos)
+    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
+
+
 def test_graph_loop_equals_host_loop(mode):
     o = liquid(10)
     out = []
@@ -365,8 +388,10 @@ def test_errors():
             s.step(1, DT)
         assert e.value.code == 6  # MD_ERR_NO_STATE
         s.upload(st)
+        bad = md.Thermostat.Berendsen(1.0)
+        bad.kind = 99  # Thermostat::Custom is todo!() in the reference
         with pytest.raises(md.MdError) as e:
-            s.step(1, DT, thermostat=(md.Thermostat.NoseHoover(1.0), 300.0))
+            s.step(1, DT, thermostat=(bad, 300.0))
         assert e.value.code == 4  # MD_ERR_UNSUPPORTED
         with pytest.raises(md.MdError) as e:  # T = 0 → Berendsen lambda is not finite (no guard in the reference)
             s.step(1, DT, thermostat=(md.Thermostat.Berendsen(1.0), 300.0))
