@@ -33,6 +33,7 @@ DT = 0.002
 ALGO_BYTES_STEP = 160       # r+w of x, v, F (144 B) + write U, W (16 B) per atom-step
 ALGO_BYTES_FORCE = 112      # k_force(+kick2): read x, v; write v, F, U, W
 ALGO_BYTES_KICK_DRIFT = 120  # k_kick_drift: read x, v, F; write x, v
+ALGO_BYTES_FUSED_STEP = 104  # k_step_dilute: read x, u (48) + list count and first row (8); write x', u' (48)
 ALGO_FLOP_PAIR = 42         # flop per directed in-range pair
 ALGO_FLOP_ATOM = 30
 
@@ -199,7 +200,8 @@ def run_ours(args, w):
     ba = (lambda: (md.Barostat.Berendsen(w["barostat"][0], w["barostat"][1]), w["barostat"][2])) if w["barostat"] \
         else (lambda: None)
 
-    s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv)
+    s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv,
+                  split_step=args.split_step)
     if world > 1:
         from moldyn_b200 import distributed as mdd
         mdd.init_solver_comm(s)
@@ -240,22 +242,26 @@ def run_ours(args, w):
     if world == 1:
         # --- per-kernel device times (CUDA events on the launching stream, host-stepped) -----------------
         kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
-        f_ms = kt["force"][0] / max(kt["force"][1], 1)
-        k_ms = kt["kick_drift"][0] / max(kt["kick_drift"][1], 1)
-        dominant = "k_force" if f_ms >= k_ms else "k_kick_drift"
-        dom_ms, dom_bytes = (f_ms, ALGO_BYTES_FORCE) if dominant == "k_force" else (k_ms, ALGO_BYTES_KICK_DRIFT)
+        per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt}
+        f_ms, k_ms, s_ms = per["force"], per["kick_drift"], per["fused_step"]
+        if s_ms is not None and kt["fused_step"][1] >= kt["force"][1]:
+            dominant, dom_ms, dom_bytes = "k_step_dilute", s_ms, ALGO_BYTES_FUSED_STEP
+        elif f_ms >= k_ms:
+            dominant, dom_ms, dom_bytes = "k_force", f_ms, ALGO_BYTES_FORCE
+        else:
+            dominant, dom_ms, dom_bytes = "k_kick_drift", k_ms, ALGO_BYTES_KICK_DRIFT
         achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
             "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_atom": dom_bytes, "avg_launch_ms": dom_ms,
-            "kernels_ms": {"k_force": f_ms, "k_kick_drift": k_ms,
-                           "rebuild": kt["rebuild"][0] / max(kt["rebuild"][1], 1) if kt["rebuild"][1] else None},
+            "kernels_ms": {"k_step_dilute": s_ms, "k_force": f_ms, "k_kick_drift": k_ms, "rebuild": per["rebuild"]},
+            "launches_timed": {k: kt[k][1] for k in kt},
         }
     else:
         roofline = {"bound": "hbm", "kernel": "step (per-kernel timing is single-GPU only)", "achieved": None,
                     "peak": hbm * world, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                    "kernels_ms": {"k_force": None, "k_kick_drift": None, "rebuild": None}}
+                    "kernels_ms": {"k_step_dilute": None, "k_force": None, "k_kick_drift": None, "rebuild": None}}
     roofline["step"] = {"algorithmic_bytes_per_atom_step": ALGO_BYTES_STEP, "achieved": ALGO_BYTES_STEP * value / 1e9,
                         "frac": ALGO_BYTES_STEP * value / 1e9 / (hbm * world)}
     if w["cut"] is not None or w["cell"] < 1.0:
@@ -352,6 +358,7 @@ def run_ours(args, w):
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
         "graph_launches_in_timed_region": st1["graph_launches"] - st0["graph_launches"],
+        "fused_steps_in_timed_region": st1["fused_steps"] - st0["fused_steps"],
         "state_check": {"temperature": macro["temperature"], "pressure": macro["pressure"],
                         "momentum_abs_max": float(np.abs(macro["momentum"]).max())},
     }
@@ -376,6 +383,7 @@ def main():
     ap.add_argument("--skin", type=float, default=0.0)
     ap.add_argument("--cell-atoms", type=float, default=0.0)
     ap.add_argument("--cell-subdiv", type=int, default=0)
+    ap.add_argument("--split-step", action="store_true", help="k_kick_drift + k_force even for dilute systems")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
     args = ap.parse_args()

@@ -50,13 +50,18 @@ typedef enum md_status {
 #define MD_LOOP_GRAPH 0 /* steady-state steps run inside one conditional (WHILE) CUDA graph (default) */
 #define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check) */
 
+/* step_mode */
+#define MD_STEP_AUTO 0  /* dilute systems on one GPU: one fused kernel per step (drift + forces + both half-kicks +
+                           reductions); dense systems: k_kick_drift + k_force */
+#define MD_STEP_SPLIT 1 /* always k_kick_drift + k_force (cross-check) */
+
 typedef struct md_config {
     int32_t device;         /* CUDA device ordinal */
     int32_t force_mode;     /* MD_FORCE_* */
     int32_t loop_mode;      /* MD_LOOP_* */
     int32_t max_neighbours; /* initial neighbour-list capacity per atom; 0 = from density (grown on demand) */
     int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = by density */
-    int32_t reserved0;
+    int32_t step_mode;      /* MD_STEP_* */
     double skin;            /* Verlet skin [nm]; <= 0 selects a default from r_cut and density */
     double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 1 */
 } md_config;
@@ -116,6 +121,7 @@ typedef struct md_stats {
     int64_t n_owned;          /* atoms this rank owns (== n on one GPU) */
     int64_t n_ghost;          /* halo atoms held for the neighbours' partners */
     int64_t migrated;         /* atoms handed to a neighbouring rank so far */
+    int64_t fused_steps;      /* of `steps`: executed by the fused one-kernel step (k_step_dilute) */
 } md_stats;
 
 typedef struct md_ctx md_ctx;
@@ -193,9 +199,9 @@ MD_API int md_get_stats(md_ctx *ctx, md_stats *out);
 MD_API void *md_stream(md_ctx *ctx);
 MD_API int md_synchronize(md_ctx *ctx);
 /* md_step with one CUDA-event pair around every kernel (host-stepped): summed device milliseconds and launch
- * counts of {k_kick_drift, k_force, list rebuild}.  Measurement aid for the roofline figures. */
+ * counts of {k_kick_drift, k_force, list rebuild, k_step_dilute}.  Measurement aid for the roofline figures. */
 MD_API int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *thermostat,
-                           md_barostat *barostat, double ms[3], int64_t launches[3]);
+                           md_barostat *barostat, double ms[4], int64_t launches[4]);
 /* Forces a list rebuild before the next force evaluation (rebuild-stress tests). */
 MD_API int md_invalidate_lists(md_ctx *ctx);
 

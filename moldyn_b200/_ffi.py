@@ -15,6 +15,7 @@ ERR_NAMES = {
 UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT = 0, 1
 LOOP_GRAPH, LOOP_HOST = 0, 1
+STEP_AUTO, STEP_SPLIT = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
 BAROSTAT_NONE, BAROSTAT_BERENDSEN = 0, 1
 
@@ -27,7 +28,7 @@ class MdError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("force_mode", C.c_int32), ("loop_mode", C.c_int32),
-                ("max_neighbours", C.c_int32), ("cell_subdiv", C.c_int32), ("reserved0", C.c_int32),
+                ("max_neighbours", C.c_int32), ("cell_subdiv", C.c_int32), ("step_mode", C.c_int32),
                 ("skin", C.c_double), ("cell_atoms", C.c_double)]
 
 
@@ -52,7 +53,7 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("graph_launches", C.c_int64), ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32),
                 ("nbr_max", C.c_int32), ("reserved0", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
-                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64)]
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64), ("fused_steps", C.c_int64)]
 
 
 # every symbol include/moldyn_b200.h declares (tests check the library exports all of them)

@@ -69,6 +69,7 @@ struct Scalars {
     int nbr_max;       // largest neighbour count of the last build
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
+    int parity;        // fused one-kernel steps ping-pong x and v between two plane sets: which set is current
     unsigned long long nbr_total;
     unsigned long long probe[8];  // MD_TIMING_PROBES: %globaltimer stamps of k_force phases
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
@@ -452,6 +453,7 @@ __device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr, 
 // mode bits of finalize
 constexpr int FIN_STEP = 1;  // called at the end of an MD step: commit drift, apply barostat box scaling, count
 constexpr int FIN_DIST = 2;  // multi-GPU: publish this rank's sums only; k_finalize_dist finalizes after the all-gather
+constexpr int FIN_FLIP = 4;  // fused one-kernel step: the step wrote the other plane set, flip sc->parity
 
 __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Sums &t, int mode)
 {
@@ -521,6 +523,7 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
         sc->steps_done = steps_done + 1;
         // k_force stored u = v + F*c instead of v unless this was the last step of the batch
         sc->vel_is_half = steps_left - 1 > 0 ? 1 : 0;
+        if (mode & FIN_FLIP) sc->parity ^= 1;
     }
     sc->disp_acc = disp_acc;
     sc->inv_scale = inv_scale;
@@ -1029,6 +1032,224 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, const Sc
         a.q4[2 * t + 1] = make_double4(x.y, y.y, z.y, 0.0);
     }
 }
+
+// ----------------------------------------------------------------------------------------------------
+// K3+K4 fused — ONE kernel per step for dilute systems (few listed partners per atom).
+//
+// k_kick_drift exists as a separate kernel only because the forces need every partner's drifted position.  A thread
+// can just as well drift its partners itself: x_j' = wrap(x_j*mu + (u_j*lambda)*dt) is the same instruction sequence
+// the owner of j runs, hence the same bits.  With ~0.5 partners per atom that costs a few extra gathers and saves a
+// full pass over the state: the step reads x,u (48 B/atom) + list count and first row (8 B) and writes x',u' (48 B).
+// In-place updates would race with those partner reads, so x and v ping-pong between two plane sets (sc->parity
+// names the current one; the last block flips it).
+//
+// Streaming side: each block walks its tiles of STEP_TILE atoms; the tile's eight plane segments are fetched by TMA
+// bulk copies (cp.async.bulk → shared memory, mbarrier completion) into a two-stage ring, so the next tile's HBM
+// requests are in flight while the block is busy with gathers and arithmetic of the current tile.
+constexpr int STEP_TILE = 2 * FORCE_BLOCK;
+
+struct StepStage {
+    double x[STEP_TILE], y[STEP_TILE], z[STEP_TILE], ux[STEP_TILE], uy[STEP_TILE], uz[STEP_TILE];
+    int cnt[STEP_TILE], row0[STEP_TILE];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 1-D TMA bulk copy global → shared; bytes and both addresses are multiples of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// drifted position of an atom from its stored (x, u): thermostat.rs:54-58, barostat.rs:46-48, integrator.rs:40-45
+__device__ __forceinline__ void drift3(double &x, double &y, double &z, double ux, double uy, double uz, double lambda,
+                                       double mup, double dt, const LjConst &c)
+{
+    drift_one(x, ux, lambda, mup, dt, c.Lx);
+    drift_one(y, uy, lambda, mup, dt, c.Ly);
+    drift_one(z, uz, lambda, mup, dt, c.Lz);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(FORCE_BLOCK, 4)
+    k_step_dilute(int n, Arrays P0, Arrays P1, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad,
+                  int cap, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int flags,
+                  unsigned long long cond_handle, const ForceConsts fc)
+{
+    if ((flags & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
+    __shared__ __align__(128) StepStage stg[2];
+    __shared__ SumsSmem ss;
+    __shared__ __align__(8) unsigned long long full[2];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) ss.v[q][tid] = 0.0;
+    // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
+    const bool par = sc->parity != 0;
+    const bool store_state = sc->steps_left <= 1;
+    const double lambda = sc->lambda, mup = sc->mu_pending, dt = pr->dt;
+    LjConst c;
+    c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
+    c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
+    c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
+    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    const double *__restrict__ ix = par ? P1.x : P0.x, *__restrict__ iy = par ? P1.y : P0.y,
+                 *__restrict__ iz = par ? P1.z : P0.z, *__restrict__ iux = par ? P1.vx : P0.vx,
+                 *__restrict__ iuy = par ? P1.vy : P0.vy, *__restrict__ iuz = par ? P1.vz : P0.vz;
+    double *__restrict__ ox = par ? P0.x : P1.x, *__restrict__ oy = par ? P0.y : P1.y, *__restrict__ oz = par ? P0.z : P1.z,
+           *__restrict__ ovx = par ? P0.vx : P1.vx, *__restrict__ ovy = par ? P0.vy : P1.vy,
+           *__restrict__ ovz = par ? P0.vz : P1.vz;
+    const int ntiles = (n + STEP_TILE - 1) / STEP_TILE;
+    const size_t stride = (size_t)(npad >> 1);
+
+    auto issue = [&](int tile, int s) {  // one thread: arm the barrier, launch the eight segment copies
+        const int base = tile * STEP_TILE;
+        const unsigned na = (unsigned)min(STEP_TILE, npad - base);  // npad is a multiple of 64 atoms
+        mbar_expect_tx(&full[s], na * 56u);
+        tma_load_1d(stg[s].x, ix + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].y, iy + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].z, iz + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].ux, iux + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].uy, iuy + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].uz, iuz + base, na * 8u, &full[s]);
+        tma_load_1d(stg[s].cnt, nbr_cnt + base, na * 4u, &full[s]);
+        tma_load_1d(stg[s].row0, nbr + base, na * 4u, &full[s]);
+    };
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < ntiles) issue(blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+
+    for (int it = 0;; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        if (tile >= ntiles) break;
+        const int s = it & 1;
+        mbar_wait(&full[s], (unsigned)(it >> 1) & 1u);
+        double2 X = reinterpret_cast<const double2 *>(stg[s].x)[tid], Y = reinterpret_cast<const double2 *>(stg[s].y)[tid],
+                Z = reinterpret_cast<const double2 *>(stg[s].z)[tid];
+        double2 VX = reinterpret_cast<const double2 *>(stg[s].ux)[tid], VY = reinterpret_cast<const double2 *>(stg[s].uy)[tid],
+                VZ = reinterpret_cast<const double2 *>(stg[s].uz)[tid];
+        int2 C = reinterpret_cast<const int2 *>(stg[s].cnt)[tid];
+        int2 J = reinterpret_cast<const int2 *>(stg[s].row0)[tid];
+        const int i0 = tile * STEP_TILE + 2 * tid;
+        const bool has0 = i0 < n, has1 = i0 + 1 < n;
+        if (!has0) C.x = 0;
+        if (!has1) C.y = 0;
+        // own atoms: thermostat scale, pending barostat scale, drift, wrap
+        drift3(X.x, Y.x, Z.x, VX.x, VY.x, VZ.x, lambda, mup, dt, c);
+        drift3(X.y, Y.y, Z.y, VX.y, VY.y, VZ.y, lambda, mup, dt, c);
+        PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const int kmax = max(C.x, C.y);
+        const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + (size_t)(i0 >> 1);
+        for (int k = 0; k < kmax; ++k) {
+            const bool a0 = k < C.x, a1 = k < C.y;
+            const int j0 = a0 ? J.x : 0, j1 = a1 ? J.y : 0;
+            if (k + 1 < kmax) J = row[(size_t)(k + 1) * stride];
+            // all twelve gathers of this trip are issued before the first use
+            double xa = __ldg(ix + j0), ya = __ldg(iy + j0), za = __ldg(iz + j0);
+            const double uxa = __ldg(iux + j0), uya = __ldg(iuy + j0), uza = __ldg(iuz + j0);
+            double xb = __ldg(ix + j1), yb = __ldg(iy + j1), zb = __ldg(iz + j1);
+            const double uxb = __ldg(iux + j1), uyb = __ldg(iuy + j1), uzb = __ldg(iuz + j1);
+            if (a0) {
+                drift3(xa, ya, za, uxa, uya, uza, lambda, mup, dt, c);
+                if (EXACT) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+                else pair_fast_branchy(f0, true, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+            }
+            if (a1) {
+                drift3(xb, yb, zb, uxb, uyb, uzb, lambda, mup, dt, c);
+                if (EXACT) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                else pair_fast_branchy(f1, true, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+            }
+        }
+        double2 WX, WY, WZ;
+        WX.x = WY.x = WZ.x = WX.y = WY.y = WZ.y = 0.0;
+        if (has0) finish_atom(ss, f0, VX.x, VY.x, VZ.x, true, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, true, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y);
+        if (has1) {
+            const int t = i0 >> 1;
+            reinterpret_cast<double2 *>(ox)[t] = X; reinterpret_cast<double2 *>(oy)[t] = Y;
+            reinterpret_cast<double2 *>(oz)[t] = Z;
+            if (store_state) {
+                reinterpret_cast<double2 *>(ovx)[t] = VX; reinterpret_cast<double2 *>(ovy)[t] = VY;
+                reinterpret_cast<double2 *>(ovz)[t] = VZ;
+                reinterpret_cast<double2 *>(P0.fx)[t] = make_double2(f0.fx, f1.fx);
+                reinterpret_cast<double2 *>(P0.fy)[t] = make_double2(f0.fy, f1.fy);
+                reinterpret_cast<double2 *>(P0.fz)[t] = make_double2(f0.fz, f1.fz);
+                reinterpret_cast<double2 *>(P0.u)[t] = make_double2(f0.u, f1.u);
+                reinterpret_cast<double2 *>(P0.w)[t] = make_double2(f0.w, f1.w);
+            } else {
+                reinterpret_cast<double2 *>(ovx)[t] = WX; reinterpret_cast<double2 *>(ovy)[t] = WY;
+                reinterpret_cast<double2 *>(ovz)[t] = WZ;
+            }
+        } else if (has0) {  // odd tail: scalar stores only
+            ox[i0] = X.x; oy[i0] = Y.x; oz[i0] = Z.x;
+            if (store_state) {
+                ovx[i0] = VX.x; ovy[i0] = VY.x; ovz[i0] = VZ.x;
+                P0.fx[i0] = f0.fx; P0.fy[i0] = f0.fy; P0.fz[i0] = f0.fz; P0.u[i0] = f0.u; P0.w[i0] = f0.w;
+            } else {
+                ovx[i0] = WX.x; ovy[i0] = WY.x; ovz[i0] = WZ.x;
+            }
+        }
+        // Refill stage s for the tile after next.  The TMA engine writes shared memory through the async proxy, which
+        // is not ordered against shared-memory loads that are merely *issued*: the barrier therefore sits at the END of
+        // the iteration, where every thread has consumed (stored results computed from) what it loaded from the stage.
+        // (With the barrier right after the loads, a backed-up LSU queue let the refill overtake a warp's LDS.)
+        __syncthreads();
+        if (tid == 0) {
+            const int next = tile + 2 * gridDim.x;
+            if (next < ntiles) issue(next, s);
+        }
+    }
+    Sums sum;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) sum.v[q] = ss.v[q][tid];
+    block_reduce<FORCE_BLOCK>(sum);
+    grid_reduce_finalize<FORCE_BLOCK>(sum, partials, sc, pr, FIN_STEP | FIN_FLIP | (flags & 2 ? FIN_DIST : 0), cond_handle);
+}
+
+// First step of a batch for the fused path: the velocity planes hold v (not u = v + F c) after an upload or after the
+// last step of the previous batch (integrator.rs:28-34).
+__global__ void k_first_half_kick(int n, Arrays a, Scalars *sc, const Params *__restrict__ pr)
+{
+    if (sc->vel_is_half) return;  // rewritten only by k_mark_half, a separate launch
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double c = pr->half_dt_m;
+    a.vx[i] = __dadd_rn(a.vx[i], __dmul_rn(a.fx[i], c));
+    a.vy[i] = __dadd_rn(a.vy[i], __dmul_rn(a.fy[i], c));
+    a.vz[i] = __dadd_rn(a.vz[i], __dmul_rn(a.fz[i], c));
+}
+
+__global__ void k_mark_half(Scalars *sc) { sc->vel_is_half = 1; }
 
 // (re)builds the packed gather copy from the planes: after a reorder, a ghost exchange or a coordinate rescale
 __global__ void k_pack_q4(int n, Arrays a)

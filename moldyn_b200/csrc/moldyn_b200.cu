@@ -101,6 +101,8 @@ struct md_ctx {
     double *d_partials = nullptr;
     int partial_blocks = 0;
     int force_grid[3] = {1, 1, 1}, reduce_grid = 1;  // exact, fast dense, fast dilute
+    int step_grid[2] = {1, 1};                        // fused one-kernel step: exact, fast
+    int parity_host = 0;                              // which plane set ctx->cur's x/v pointers name (see sync_parity)
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
     bool use_q4 = false;                              // packed gather copy maintained (dense systems)
     double graph_hc = -1.0;                           // dt/(2m) baked into the captured force kernel
@@ -120,6 +122,7 @@ struct md_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     cudaGraphConditionalHandle cond = 0;
     bool graph_ok = false;
+    bool graph_fused = false;  // the captured body is the fused one-kernel step
 
     md_stats stats{};
 
@@ -144,8 +147,8 @@ struct md_ctx {
     // per-kernel CUDA-event timing (md_time_kernels)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double t_ms[3] = {0.0, 0.0, 0.0};   // kick_drift, force, rebuild
-    int64_t t_cnt[3] = {0, 0, 0};
+    double t_ms[4] = {0.0, 0.0, 0.0, 0.0};   // kick_drift, force, rebuild, fused step
+    int64_t t_cnt[4] = {0, 0, 0, 0};
 
     int fail(int code, const char *fmt, ...)
     {
@@ -264,10 +267,21 @@ int push_params(md_ctx *ctx)
     return MD_OK;
 }
 
+// Fused one-kernel steps ping-pong x and v between the plane sets of cur and alt; the device counts the flips
+// (sc->parity).  Whenever the host looks at the device state it rebinds cur's six pointers to the current set.
+void sync_parity(md_ctx *ctx)
+{
+    if ((ctx->h_sc->parity & 1) == ctx->parity_host) return;
+    std::swap(ctx->cur.x, ctx->alt.x); std::swap(ctx->cur.y, ctx->alt.y); std::swap(ctx->cur.z, ctx->alt.z);
+    std::swap(ctx->cur.vx, ctx->alt.vx); std::swap(ctx->cur.vy, ctx->alt.vy); std::swap(ctx->cur.vz, ctx->alt.vz);
+    ctx->parity_host ^= 1;
+}
+
 int pull_scalars(md_ctx *ctx)
 {
     CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    sync_parity(ctx);
     return MD_OK;
 }
 
@@ -416,6 +430,7 @@ int rebuild_lists(md_ctx *ctx)
     k_reorder<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->order, ctx->cell_of, ctx->cur, ctx->alt,
                                                    ctx->cell_sorted);
     std::swap(ctx->cur, ctx->alt);
+    // (sc->parity and parity_host stay as they are: cur keeps naming the plane set the device calls current)
     ctx->stats.kernel_launches += 7;
     drop_graph(ctx);  // array pointers are baked into the captured kernels
 
@@ -474,6 +489,50 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
     return MD_OK;
 }
 
+// The fused one-kernel step is used for dilute systems on one GPU (see k_step_dilute).
+bool use_fused(const md_ctx *ctx)
+{
+    return ctx->cfg.step_mode != MD_STEP_SPLIT && !ctx->dense && !ctx->dist.on && ctx->list_valid;
+}
+
+// plane set 0 / 1 as the device parity names them; F, U, W, id are shared
+void fused_views(const md_ctx *ctx, Arrays *p0, Arrays *p1)
+{
+    Arrays other = ctx->cur;
+    other.x = ctx->alt.x; other.y = ctx->alt.y; other.z = ctx->alt.z;
+    other.vx = ctx->alt.vx; other.vy = ctx->alt.vy; other.vz = ctx->alt.vz;
+    *p0 = ctx->parity_host ? other : ctx->cur;
+    *p1 = ctx->parity_host ? ctx->cur : other;
+}
+
+int launch_fused_step(md_ctx *ctx, unsigned long long cond)
+{
+    const int n = (int)ctx->n;
+    const ForceConsts fc = force_consts(ctx);
+    Arrays p0, p1;
+    fused_views(ctx, &p0, &p1);
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
+        k_step_dilute<true><<<ctx->step_grid[0], FORCE_BLOCK, 0, ctx->stream>>>(
+            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, 0, cond, fc);
+    else
+        k_step_dilute<false><<<ctx->step_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
+            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, 0, cond, fc);
+    return MD_OK;
+}
+
+// the fused step expects u = v + F c in the velocity planes
+int ensure_half_kick(md_ctx *ctx)
+{
+    if (ctx->h_sc->vel_is_half) return MD_OK;
+    const int n = (int)ctx->n;
+    k_first_half_kick<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr);
+    k_mark_half<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
+    ctx->h_sc->vel_is_half = 1;
+    ctx->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    return MD_OK;
+}
+
 int launch_reduce(md_ctx *ctx)
 {
     const int n = (int)ctx->n;
@@ -493,6 +552,10 @@ int choose_grids(md_ctx *ctx)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
     const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
     for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
+    int occ_s[2] = {0, 0};
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[0], k_step_dilute<true>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[1], k_step_dilute<false>, FORCE_BLOCK, 0));
+    for (int k = 0; k < 2; ++k) ctx->step_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ_s[k], 1)));
     ctx->reduce_grid = std::max(1, std::min(blocks_for(ctx->n, RED_BLOCK), sms * std::max(occ_r, 1)));
     return MD_OK;
 }
@@ -512,8 +575,13 @@ int build_graph(md_ctx *ctx)
     CK(cudaGraphAddNode(&node, ctx->graph, nullptr, 0, &np));
     cudaGraph_t body = np.conditional.phGraph_out[0];
     CK(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    launch_kick_drift(ctx);
-    launch_force(ctx, true, (unsigned long long)ctx->cond);
+    ctx->graph_fused = use_fused(ctx);
+    if (ctx->graph_fused) {
+        launch_fused_step(ctx, (unsigned long long)ctx->cond);
+    } else {
+        launch_kick_drift(ctx);
+        launch_force(ctx, true, (unsigned long long)ctx->cond);
+    }
     cudaGraph_t captured = nullptr;
     CK(cudaStreamEndCapture(ctx->stream, &captured));
     CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
@@ -686,6 +754,7 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         TRY(choose_grids(ctx));
         ctx->partial_blocks = std::max(std::max(ctx->force_grid[0], ctx->force_grid[1]),
                                        std::max(ctx->force_grid[2], ctx->reduce_grid));
+        ctx->partial_blocks = std::max(ctx->partial_blocks, std::max(ctx->step_grid[0], ctx->step_grid[1]));
         TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
         TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
@@ -725,6 +794,8 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
     h.mu_pending = 1.0; h.lambda = 1.0; h.mu = 1.0; h.inv_scale = 1.0;
     h.lambda_last = 1.0; h.mu_last = 1.0;
     CK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    ctx->parity_host = 0;
+    drop_graph(ctx);
     ctx->skin = choose_skin(ctx, box);
     fill_potential_params(ctx);
     // neighbour capacity from density
@@ -872,17 +943,21 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
         remaining = ctx->h_sc->steps_left;
         if (remaining <= 0) break;
         const bool rebuild = !ctx->list_valid || ctx->h_sc->need_rebuild;
+        const bool fused = !rebuild && use_fused(ctx);
+        if (fused) TRY(ensure_half_kick(ctx));
         if (rebuild || ctx->timing || ctx->cfg.loop_mode == MD_LOOP_HOST) {
-            // one step by hand: drift, (rebuild at the drifted positions,) forces
+            // one step by hand: drift, (rebuild at the drifted positions,) forces — or the fused one-kernel step
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], st));
-            launch_kick_drift(ctx);
+            if (!fused) launch_kick_drift(ctx);
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], st));
             if (rebuild) TRY(rebuild_lists(ctx));
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st));
-            launch_force(ctx, true, 0ull);
+            if (fused) launch_fused_step(ctx, 0ull);
+            else launch_force(ctx, true, 0ull);
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], st));
-            ctx->stats.kernel_launches += 2;
+            ctx->stats.kernel_launches += fused ? 1 : 2;
             ctx->stats.steps += 1;
+            ctx->stats.fused_steps += fused ? 1 : 0;
             CK(cudaGetLastError());
             if (ctx->timing) {
                 CK(cudaEventSynchronize(ctx->ev[3]));
@@ -890,19 +965,24 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
                 CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
                 CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
                 CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
-                ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
-                ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
+                if (fused) { ctx->t_ms[3] += c; ctx->t_cnt[3] += 1; }
+                else {
+                    ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
+                    ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
+                }
                 if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
             }
         } else {
+            if (ctx->graph_ok && ctx->graph_fused != fused) drop_graph(ctx);
             if (!ctx->graph_ok) TRY(build_graph(ctx));
             long long before = ctx->h_sc->steps_done;
             CK(cudaGraphLaunch(ctx->graph_exec, st));
             ctx->stats.graph_launches += 1;
             TRY(pull_scalars(ctx));
             long long ran = ctx->h_sc->steps_done - before;
-            ctx->stats.kernel_launches += 2 * ran;
+            ctx->stats.kernel_launches += (fused ? 1 : 2) * ran;
             ctx->stats.steps += ran;
+            ctx->stats.fused_steps += fused ? ran : 0;
             TRY(device_error(ctx));
             remaining = ctx->h_sc->steps_left;
         }
@@ -919,18 +999,18 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     return MD_OK;
 }
 
-int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_barostat *ba, double ms[3],
-                    int64_t launches[3])
+int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_barostat *ba, double ms[4],
+                    int64_t launches[4])
 {
     TRY(check_ctx(ctx, true));
     if (!ms || !launches) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_time_kernels: NULL output");
     for (auto &e : ctx->ev)
         if (!e) CK(cudaEventCreate(&e));
-    for (int k = 0; k < 3; ++k) { ctx->t_ms[k] = 0.0; ctx->t_cnt[k] = 0; }
+    for (int k = 0; k < 4; ++k) { ctx->t_ms[k] = 0.0; ctx->t_cnt[k] = 0; }
     ctx->timing = true;
     int rc = md_step(ctx, n_steps, dt, th, ba);
     ctx->timing = false;
-    for (int k = 0; k < 3; ++k) { ms[k] = ctx->t_ms[k]; launches[k] = ctx->t_cnt[k]; }
+    for (int k = 0; k < 4; ++k) { ms[k] = ctx->t_ms[k]; launches[k] = ctx->t_cnt[k]; }
     return rc;
 }
 

@@ -154,11 +154,11 @@ class Solver:
     """Device-resident session: owns an md_ctx. `exact=True` selects MD_FORCE_EXACT (bit-identical forces)."""
 
     def __init__(self, device=0, exact=False, host_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
-                 cell_atoms=0.0):
+                 cell_atoms=0.0, split_step=False):
         self._ctx = C.c_void_p()
         cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else _ffi.FORCE_FAST,
-                          _ffi.LOOP_HOST if host_loop else _ffi.LOOP_GRAPH, max_neighbours, cell_subdiv, 0,
-                          skin, cell_atoms)
+                          _ffi.LOOP_HOST if host_loop else _ffi.LOOP_GRAPH, max_neighbours, cell_subdiv,
+                          _ffi.STEP_SPLIT if split_step else _ffi.STEP_AUTO, skin, cell_atoms)
         L = _ffi.lib()
         rc = L.md_create(C.byref(cfg), C.byref(self._ctx))
         if rc != _ffi.MD_OK:
@@ -238,11 +238,11 @@ class Solver:
         """Same as step(), host-stepped with CUDA events around each kernel → {name: (ms_total, launches)}."""
         th = thermostat[0]._c(thermostat[1]) if thermostat else None
         ba = barostat[0]._c(barostat[1]) if barostat else None
-        ms = np.zeros(3)
-        cnt = np.zeros(3, dtype=np.int64)
+        ms = np.zeros(4)
+        cnt = np.zeros(4, dtype=np.int64)
         self._ck(_ffi.lib().md_time_kernels(self._ctx, int(n_steps), float(dt), C.byref(th) if th else None,
                                             C.byref(ba) if ba else None, _ptr(ms), _ptr(cnt)))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("kick_drift", "force", "rebuild"))}
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("kick_drift", "force", "rebuild", "fused_step"))}
 
     def macro(self):
         m = _ffi.MacroOut()
@@ -274,7 +274,7 @@ class Solver:
         return {"steps": s.steps, "rebuilds": s.rebuilds, "kernel_launches": s.kernel_launches,
                 "graph_launches": s.graph_launches, "cells": list(s.cells), "nbr_capacity": s.nbr_capacity,
                 "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean, "n_owned": s.n_owned,
-                "n_ghost": s.n_ghost, "migrated": s.migrated}
+                "n_ghost": s.n_ghost, "migrated": s.migrated, "fused_steps": s.fused_steps}
 
     def stream(self):
         return _ffi.lib().md_stream(self._ctx)

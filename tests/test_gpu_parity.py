@@ -287,6 +287,33 @@ def test_graph_loop_equals_host_loop(mode):
     assert out[0][4]["rebuilds"] == out[1][4]["rebuilds"]
 
 
+@pytest.mark.parametrize("host_loop", [False, True])
+def test_fused_step_equals_split_step(mode, host_loop):
+    """Dilute systems step with ONE fused kernel (k_step_dilute: partners are drifted on the fly, x/v ping-pong between
+    two plane sets); it must reproduce the k_kick_drift + k_force path bit for bit, for any batch length/parity."""
+    o = orc.argon_lattice(12, 1.0, 900.0, 7)   # 1728 atoms, ~6 listed partners each, hot: collisions and list rebuilds
+    out = []
+    for split in (True, False):
+        st = to_gpu_state(md, o)
+        th = (md.Thermostat.Berendsen(10.0), 300.0)
+        ba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
+        with make_solver(mode, host_loop=host_loop, split_step=split, skin=0.3) as s:
+            s.upload(st, with_forces=False)
+            s.update_force()
+            for k in (7, 1, 30, 63, 200):
+                s.step(k, DT, thermostat=th, barostat=ba)
+            s.download(st)
+            m = s.macro()
+            out.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.potential.copy(), st.temp.copy(),
+                        st.boundary_box.copy(), np.array([m["temperature"], m["pressure"], th[0].lambda_, ba[0].myu]),
+                        s.stats()))
+    for a, b in zip(out[0][:7], out[1][:7]):
+        assert np.array_equal(a, b)
+    assert out[0][7]["fused_steps"] == 0 and out[1][7]["fused_steps"] > 250
+    assert out[0][7]["rebuilds"] == out[1][7]["rebuilds"] > 1
+    assert np.abs(out[1][2]).max() > 0.0   # pair terms were exercised
+
+
 def test_run_to_run_determinism():
     o = liquid(12)
     res = []
