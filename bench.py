@@ -201,7 +201,7 @@ def run_ours(args, w):
         else (lambda: None)
 
     s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv,
-                  split_step=args.split_step)
+                  step_mode=args.step_mode)
     if world > 1:
         from moldyn_b200 import distributed as mdd
         mdd.init_solver_comm(s)
@@ -383,7 +383,8 @@ def main():
     ap.add_argument("--skin", type=float, default=0.0)
     ap.add_argument("--cell-atoms", type=float, default=0.0)
     ap.add_argument("--cell-subdiv", type=int, default=0)
-    ap.add_argument("--split-step", action="store_true", help="k_kick_drift + k_force even for dilute systems")
+    ap.add_argument("--step-mode", default="auto", choices=["auto", "split", "fused"],
+                    help="split: k_kick_drift + k_force; fused: k_step_dilute (dilute systems, one GPU)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
     args = ap.parse_args()

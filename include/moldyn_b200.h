@@ -51,9 +51,10 @@ typedef enum md_status {
 #define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check) */
 
 /* step_mode */
-#define MD_STEP_AUTO 0  /* dilute systems on one GPU: one fused kernel per step (drift + forces + both half-kicks +
-                           reductions); dense systems: k_kick_drift + k_force */
-#define MD_STEP_SPLIT 1 /* always k_kick_drift + k_force (cross-check) */
+#define MD_STEP_AUTO 0  /* the faster of the two below as measured on B200: currently MD_STEP_SPLIT everywhere */
+#define MD_STEP_SPLIT 1 /* k_kick_drift + k_force */
+#define MD_STEP_FUSED 2 /* dilute systems on one GPU: ONE kernel per step (k_step_dilute: partners drifted on the fly,
+                           TMA-staged tiles, x/v ping-pong between two plane sets); otherwise as MD_STEP_SPLIT */
 
 typedef struct md_config {
     int32_t device;         /* CUDA device ordinal */

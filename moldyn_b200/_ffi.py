@@ -15,7 +15,7 @@ ERR_NAMES = {
 UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT = 0, 1
 LOOP_GRAPH, LOOP_HOST = 0, 1
-STEP_AUTO, STEP_SPLIT = 0, 1
+STEP_AUTO, STEP_SPLIT, STEP_FUSED = 0, 1, 2
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
 BAROSTAT_NONE, BAROSTAT_BERENDSEN = 0, 1
 

@@ -486,7 +486,9 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
     // same for u = v + F c (the state thermostat.update sees after the next first half-kick)
     const double uc0 = t.v[S_MU] / M - shift0, uc1 = t.v[S_MU + 1] / M - shift1, uc2 = t.v[S_MU + 2] / M - shift2;
     const double thu2 = t.v[S_THU] - M * (uc0 * uc0 + uc1 * uc1 + uc2 * uc2);
-    const double temperature_mid = (2.0 * (thu2 / 2.0)) / (3.0 * n * K_B) * 100.0;
+    // (the u sums are only accumulated when something reads them: Nose-Hoover, or a plain force evaluation)
+    const double temperature_mid = (th_kind == 2 || !(mode & FIN_STEP)) ? (2.0 * (thu2 / 2.0)) / (3.0 * n * K_B) * 100.0
+                                                                         : temperature;
     const double volume = box0 * box1 * box2;
     const double pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;         // pressure.rs:5-20
     // controls of the NEXT step (thermostat.rs:24-34, barostat.rs:21-31)
@@ -780,9 +782,10 @@ struct SumsSmem {
     double v[NSUM][FORCE_BLOCK];
 };
 
+// nh (uniform): also accumulate the COM/thermal sums of u', which only Nose-Hoover's second psi update reads.
 __device__ __forceinline__ void finish_atom(SumsSmem &ss, const PairAcc &f, double &vx, double &vy, double &vz,
                                             bool do_step, double lambda, double c, double mass, const double *shift,
-                                            double &wx, double &wy, double &wz)
+                                            double &wx, double &wy, double &wz, bool nh)
 {
     if (do_step) {
         vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(f.fx, c));  // v'' = lambda*u + F*c
@@ -799,9 +802,11 @@ __device__ __forceinline__ void finish_atom(SumsSmem &ss, const PairAcc &f, doub
     ss.v[4][l] += mass * (vx * vx + vy * vy + vz * vz);
     ss.v[S_W][l] += f.w;
     ss.v[S_U][l] += f.u;
-    ss.v[S_MU][l] += mass * wx; ss.v[S_MU + 1][l] += mass * wy; ss.v[S_MU + 2][l] += mass * wz;
-    const double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
-    ss.v[S_THU][l] += mass * (bx * bx + by * by + bz * bz);
+    if (nh) {
+        ss.v[S_MU][l] += mass * wx; ss.v[S_MU + 1][l] += mass * wy; ss.v[S_MU + 2][l] += mass * wz;
+        const double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
+        ss.v[S_THU][l] += mass * (bx * bx + by * by + bz * bz);
+    }
     ss.v[S_MAX][l] = fmax(ss.v[S_MAX][l], wx * wx + wy * wy + wz * wz);
 }
 
@@ -878,6 +883,7 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
     for (int q = 0; q < NSUM; ++q) ss.v[q][threadIdx.x] = 0.0;
     // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
     const bool store_state = !(do_step & 1) || sc->steps_left <= 1;
+    const bool nh = pr->th_kind == 2 || !(do_step & 1);  // a plain force evaluation keeps every stored sum valid
     const double lambda = sc->lambda;
     LjConst c;
     c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
@@ -925,8 +931,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
             }
         }
         double2 WX, WY, WZ;
-        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x);
-        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y);
+        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y, nh);
         else { WX.y = WY.y = WZ.y = 0.0; }
         if (!has1) {  // odd tail: scalar stores only (slot i0+1 may hold a ghost atom in the distributed layout)
             if (store_state) {
@@ -1095,8 +1101,11 @@ __device__ __forceinline__ void drift3(double &x, double &y, double &z, double u
     drift_one(z, uz, lambda, mup, dt, c.Lz);
 }
 
+#ifndef MD_STEP_MINB
+#define MD_STEP_MINB 4
+#endif
 template <bool EXACT>
-__global__ void __launch_bounds__(FORCE_BLOCK, 4)
+__global__ void __launch_bounds__(FORCE_BLOCK, MD_STEP_MINB)
     k_step_dilute(int n, Arrays P0, Arrays P1, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad,
                   int cap, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int flags,
                   unsigned long long cond_handle, const ForceConsts fc)
@@ -1111,6 +1120,7 @@ __global__ void __launch_bounds__(FORCE_BLOCK, 4)
     // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
     const bool par = sc->parity != 0;
     const bool store_state = sc->steps_left <= 1;
+    const bool nh = pr->th_kind == 2;
     const double lambda = sc->lambda, mup = sc->mu_pending, dt = pr->dt;
     LjConst c;
     c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
@@ -1192,8 +1202,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, 4)
         }
         double2 WX, WY, WZ;
         WX.x = WY.x = WZ.x = WX.y = WY.y = WZ.y = 0.0;
-        if (has0) finish_atom(ss, f0, VX.x, VY.x, VZ.x, true, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x);
-        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, true, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y);
+        if (has0) finish_atom(ss, f0, VX.x, VY.x, VZ.x, true, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, true, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y, nh);
         if (has1) {
             const int t = i0 >> 1;
             reinterpret_cast<double2 *>(ox)[t] = X; reinterpret_cast<double2 *>(oy)[t] = Y;

@@ -88,6 +88,7 @@ struct md_ctx {
     bool list_valid = false;
     bool force_valid = false;
     double sums_c = -1.0;  // half_dt_m the stored reduction was computed with
+    bool sums_nh = false;  // the stored reduction includes the sums of u = v + F c (Nose-Hoover's second psi update)
 
     Arrays cur{}, alt{};
     std::vector<DevBuf> owned;
@@ -489,10 +490,11 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
     return MD_OK;
 }
 
-// The fused one-kernel step is used for dilute systems on one GPU (see k_step_dilute).
+// The fused one-kernel step (k_step_dilute) is opt-in: on B200 it ties with k_kick_drift + k_force at 8M atoms and
+// loses at 1M (both are bound by gather latency at 16 warps/SM, and the fused kernel's per-tile chain is longer).
 bool use_fused(const md_ctx *ctx)
 {
-    return ctx->cfg.step_mode != MD_STEP_SPLIT && !ctx->dense && !ctx->dist.on && ctx->list_valid;
+    return ctx->cfg.step_mode == MD_STEP_FUSED && !ctx->dense && !ctx->dist.on && ctx->list_valid;
 }
 
 // plane set 0 / 1 as the device parity names them; F, U, W, id are shared
@@ -814,6 +816,7 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
     launch_reduce(ctx);
     ctx->stats.kernel_launches += 1;
     ctx->sums_c = ctx->prm.half_dt_m;
+    ctx->sums_nh = true;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));  // host buffers are only borrowed for the duration of the call
     return MD_OK;
@@ -875,6 +878,7 @@ int md_update_force(md_ctx *ctx)
         }
         TRY(dist_launch_force(ctx, false));
         ctx->sums_c = ctx->prm.half_dt_m;
+        ctx->sums_nh = true;
         ctx->force_valid = true;
         CK(cudaStreamSynchronize(ctx->stream));
         return MD_OK;
@@ -889,6 +893,7 @@ int md_update_force(md_ctx *ctx)
     ctx->stats.kernel_launches += 1;
     CK(cudaGetLastError());
     ctx->sums_c = ctx->prm.half_dt_m;
+    ctx->sums_nh = true;
     ctx->force_valid = true;
     CK(cudaStreamSynchronize(ctx->stream));
     return MD_OK;
@@ -923,11 +928,13 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
         ctx->graph_hc = p.half_dt_m;
     }
     // The displacement bound of the first drift needs max|v + F c|² for THIS c.
-    if (ctx->sums_c != p.half_dt_m) {
+    if (ctx->sums_c != p.half_dt_m || (p.th_kind == MD_THERMOSTAT_NOSE_HOOVER && !ctx->sums_nh)) {
         if (ctx->dist.on) TRY(dist_launch_reduce(ctx));
         else launch_reduce(ctx);
         ctx->sums_c = p.half_dt_m;
+        ctx->sums_nh = true;
     }
+    ctx->sums_nh = p.th_kind == MD_THERMOSTAT_NOSE_HOOVER;  // what the step kernels of this batch will leave behind
     k_prepare<<<1, 1, 0, st>>>(ctx->d_sc, ctx->d_pr, (long long)n_steps, th ? th->psi : 0.0);
     ctx->stats.kernel_launches += 1;
     CK(cudaGetLastError());

@@ -154,11 +154,12 @@ class Solver:
     """Device-resident session: owns an md_ctx. `exact=True` selects MD_FORCE_EXACT (bit-identical forces)."""
 
     def __init__(self, device=0, exact=False, host_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
-                 cell_atoms=0.0, split_step=False):
+                 cell_atoms=0.0, step_mode="auto"):
         self._ctx = C.c_void_p()
         cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else _ffi.FORCE_FAST,
                           _ffi.LOOP_HOST if host_loop else _ffi.LOOP_GRAPH, max_neighbours, cell_subdiv,
-                          _ffi.STEP_SPLIT if split_step else _ffi.STEP_AUTO, skin, cell_atoms)
+                          {"auto": _ffi.STEP_AUTO, "split": _ffi.STEP_SPLIT, "fused": _ffi.STEP_FUSED}[step_mode], skin,
+                          cell_atoms)
         L = _ffi.lib()
         rc = L.md_create(C.byref(cfg), C.byref(self._ctx))
         if rc != _ffi.MD_OK:

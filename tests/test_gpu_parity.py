@@ -293,11 +293,11 @@ def test_fused_step_equals_split_step(mode, host_loop):
     two plane sets); it must reproduce the k_kick_drift + k_force path bit for bit, for any batch length/parity."""
     o = orc.argon_lattice(12, 1.0, 900.0, 7)   # 1728 atoms, ~6 listed partners each, hot: collisions and list rebuilds
     out = []
-    for split in (True, False):
+    for step_mode in ("split", "fused"):
         st = to_gpu_state(md, o)
         th = (md.Thermostat.Berendsen(10.0), 300.0)
         ba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
-        with make_solver(mode, host_loop=host_loop, split_step=split, skin=0.3) as s:
+        with make_solver(mode, host_loop=host_loop, step_mode=step_mode, skin=0.3) as s:
             s.upload(st, with_forces=False)
             s.update_force()
             for k in (7, 1, 30, 63, 200):
