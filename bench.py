@@ -345,7 +345,10 @@ def run_ours(args, w):
     out = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (spatial decomposition), NCCL halo send/recv + all-gather of 8 sums per step",
+        "parallelism": "single GPU" if world == 1 else (f"{world} x-slabs (spatial decomposition); per step: ghost positions stored into the neighbours' HBM by "
+                                                                "the drift kernel, rank sums exchanged through peer-memory mailboxes inside the force kernel"
+                                                                if st1["peer_memory"] else
+                                                                f"{world} x-slabs (spatial decomposition), NCCL halo send/recv + all-gather of 12 sums per step"),
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "atoms": n, "dt": DT, "thermostat": w["thermostat"],
                    "barostat": w["barostat"], "r_cut": w["cut"][0] if w["cut"] else 0.8545,
@@ -364,7 +367,12 @@ def run_ours(args, w):
     }
     if world > 1:
         alls = [None] * world if rank == 0 else None
-        dist.gather_object({k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds")}, alls, dst=0)
+        mine = {k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds", "peer_memory")}
+        mine["wait_halo_us_per_step"] = (st1["wait_halo_ms"] - st0["wait_halo_ms"]) * 1e3 / args.steps
+        mine["wait_sums_us_per_step"] = (st1["wait_sums_ms"] - st0["wait_sums_ms"]) * 1e3 / args.steps
+        for k in ("force_atoms", "force_tail", "drift_push"):
+            mine[k + "_us_per_step"] = (st1[k + "_ms"] - st0[k + "_ms"]) * 1e3 / args.steps
+        dist.gather_object(mine, alls, dst=0)
         out["per_rank"] = alls
     if rank == 0:
         print(json.dumps(out))

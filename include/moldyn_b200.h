@@ -123,6 +123,13 @@ typedef struct md_stats {
     int64_t n_ghost;          /* halo atoms held for the neighbours' partners */
     int64_t migrated;         /* atoms handed to a neighbouring rank so far */
     int64_t fused_steps;      /* of `steps`: executed by the fused one-kernel step (k_step_dilute) */
+    double wait_halo_ms;      /* multi-GPU peer-memory path: time block 0 of k_force polled for the neighbours' ghosts, */
+    double wait_sums_ms;      /* and the last block polled for the other ranks' reduction sums (since the last upload)   */
+    int32_t peer_memory;      /* 1: halo and reduction go through peer memory (NVLink stores), 0: NCCL send/recv path     */
+    int32_t reserved1;
+    double force_atoms_ms;    /* peer-memory path diagnostics: k_force first block start -> all atoms done,               */
+    double force_tail_ms;     /*   -> mailbox exchange + finalize done,                                                  */
+    double drift_push_ms;     /*   k_kick_drift start -> neighbours' flags raised (last pushing block)                   */
 } md_stats;
 
 typedef struct md_ctx md_ctx;

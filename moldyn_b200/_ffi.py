@@ -53,7 +53,9 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("graph_launches", C.c_int64), ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32),
                 ("nbr_max", C.c_int32), ("reserved0", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
-                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64), ("fused_steps", C.c_int64)]
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64), ("fused_steps", C.c_int64), ("wait_halo_ms", C.c_double),
+                ("wait_sums_ms", C.c_double), ("peer_memory", C.c_int32), ("reserved1", C.c_int32),
+                ("force_atoms_ms", C.c_double), ("force_tail_ms", C.c_double), ("drift_push_ms", C.c_double)]
 
 
 # every symbol include/moldyn_b200.h declares (tests check the library exports all of them)

@@ -70,6 +70,10 @@ struct Scalars {
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     int parity;        // fused one-kernel steps ping-pong x and v between two plane sets: which set is current
+    unsigned long long epoch;  // multi-GPU peer-memory path: sequence number of the last finalized collective reduction
+    unsigned long long wait_halo_ns, wait_sums_ns;  // time spent polling the mailboxes (block 0 / last block), accumulated
+    unsigned long long t_start;                     // %globaltimer when the first block of the running k_force started
+    unsigned long long force_atoms_ns, force_tail_ns, drift_push_ns;  // accumulated phase times (multi-GPU diagnostics)
     unsigned long long nbr_total;
     unsigned long long probe[8];  // MD_TIMING_PROBES: %globaltimer stamps of k_force phases
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
@@ -91,6 +95,21 @@ __device__ __forceinline__ unsigned long long gtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Per-thread asynchronous copies global → shared (LDGSTS): a thread parks the NEXT tile's operands in shared memory while
+// it works on the current one, and reads back only what it copied itself — no barrier, no cross-thread hazard.
+__device__ __forceinline__ void cp_async16(void *smem, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 #ifdef MD_TIMING_PROBES
 #define PROBE(k) sc->probe[k] = gtime()
 #define PROBE_MIN(k) atomicMin(&sc->probe[k], gtime())
@@ -100,6 +119,45 @@ __device__ __forceinline__ unsigned long long gtime()
 #define PROBE_MIN(k)
 #define PROBE_MAX(k)
 #endif
+
+// ---- multi-GPU peer-memory mailboxes (NVLink/NVSwitch, one process per GPU, buffers shared through CUDA IPC) ----------
+// Every rank owns one Mail in its own HBM; the OTHER ranks write into it with plain stores over NVLink and the owner polls
+// it locally.  Sequence numbers only grow, so nothing is ever reset; the sums are double-buffered by sequence parity because
+// a rank may publish reduction s+1 while a non-neighbour is still folding reduction s.
+constexpr int MAX_PEERS = 8;
+struct Mail {
+    double sums[2][MAX_PEERS][12];          // [seq & 1][source rank][K5 slot]
+    unsigned long long sums_seq[MAX_PEERS];  // sums_seq[r] = s: rank r's sums of reduction s have landed
+    unsigned long long halo_seq[2];          // [0] left neighbour's, [1] right neighbour's ghost positions of step s landed
+};
+static_assert(NSUM == 12, "Mail::sums holds NSUM slots per rank");
+struct Peers {      // lives in device memory; kernels get a pointer (NULL on one GPU)
+    Mail *mail[MAX_PEERS];  // rank r's Mail as mapped into this process (mail[rank] is the local one)
+    int rank, nranks;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polls a local flag a peer writes.  Gives up after ~20 s (a peer died or the ranks diverged) so a broken run ends with an
+// error instead of hanging the GPU.
+__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq)
+{
+    if (ld_acquire_sys(flag) >= seq) return true;
+    const unsigned long long t0 = gtime();
+    for (;;) {
+        for (int spin = 0; spin < 64; ++spin)
+            if (ld_acquire_sys(flag) >= seq) return true;
+        if (gtime() - t0 > 20000000000ull) return false;
+    }
+}
 
 struct Grid {
     int nc[3];
@@ -454,21 +512,24 @@ __device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr, 
 constexpr int FIN_STEP = 1;  // called at the end of an MD step: commit drift, apply barostat box scaling, count
 constexpr int FIN_DIST = 2;  // multi-GPU: publish this rank's sums only; k_finalize_dist finalizes after the all-gather
 constexpr int FIN_FLIP = 4;  // fused one-kernel step: the step wrote the other plane set, flip sc->parity
+constexpr int FIN_P2P = 8;   // multi-GPU: exchange the rank sums through the peer mailboxes and finalize right here
 
-__device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Sums &t, int mode)
+// `in` / `pr`: the control words and parameters as they were when the kernel started (the last block copies them into
+// shared memory while it waits for the partial sums, so finalize starts without a trip to global memory); `sc`: where the
+// results go.  The two may alias (k_finalize_dist).
+__device__ __forceinline__ void finalize(Scalars *sc, const Scalars *in, const Params *pr, const Sums &t, int mode)
 {
-    // all inputs first (independent loads → one round trip), then arithmetic, then stores
     const double n = (double)pr->n, mass = pr->mass, dt = pr->dt, r_list = pr->r_list, r_cut = pr->r_cut;
     const int th_kind = pr->th_kind, ba_kind = pr->ba_kind;
     const double th_tau = pr->th_tau, th_target = pr->th_target;
     const double ba_beta = pr->ba_beta, ba_tau = pr->ba_tau, ba_target = pr->ba_target;
-    double box0 = sc->box[0], box1 = sc->box[1], box2 = sc->box[2];
-    const double shift0 = sc->shift[0], shift1 = sc->shift[1], shift2 = sc->shift[2];
-    const double lambda_used = sc->lambda, mu_used = sc->mu;
-    double disp_acc = sc->disp_acc, inv_scale = sc->inv_scale;
-    const double disp_next_old = sc->disp_next;
-    const long long steps_left = sc->steps_left, steps_done = sc->steps_done;
-    double psi = sc->psi;
+    double box0 = in->box[0], box1 = in->box[1], box2 = in->box[2];
+    const double shift0 = in->shift[0], shift1 = in->shift[1], shift2 = in->shift[2];
+    const double lambda_used = in->lambda, mu_used = in->mu;
+    double disp_acc = in->disp_acc, inv_scale = in->inv_scale;
+    const double disp_next_old = in->disp_next;
+    const long long steps_left = in->steps_left, steps_done = in->steps_done;
+    double psi = in->psi;
 
     const double M = n * mass;
     const double vc0 = t.v[0] / M, vc1 = t.v[1] / M, vc2 = t.v[2] / M;  // get_center_of_mass_velocity  mod.rs:12-25
@@ -484,11 +545,13 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
     }
     const double temperature = (2.0 * thermal) / (3.0 * n * K_B) * 100.0;  // temperature.rs:4-7
     // same for u = v + F c (the state thermostat.update sees after the next first half-kick)
-    const double uc0 = t.v[S_MU] / M - shift0, uc1 = t.v[S_MU + 1] / M - shift1, uc2 = t.v[S_MU + 2] / M - shift2;
-    const double thu2 = t.v[S_THU] - M * (uc0 * uc0 + uc1 * uc1 + uc2 * uc2);
     // (the u sums are only accumulated when something reads them: Nose-Hoover, or a plain force evaluation)
-    const double temperature_mid = (th_kind == 2 || !(mode & FIN_STEP)) ? (2.0 * (thu2 / 2.0)) / (3.0 * n * K_B) * 100.0
-                                                                         : temperature;
+    double temperature_mid = temperature;
+    if (th_kind == 2 || !(mode & FIN_STEP)) {
+        const double uc0 = t.v[S_MU] / M - shift0, uc1 = t.v[S_MU + 1] / M - shift1, uc2 = t.v[S_MU + 2] / M - shift2;
+        const double thu2 = t.v[S_THU] - M * (uc0 * uc0 + uc1 * uc1 + uc2 * uc2);
+        temperature_mid = (2.0 * (thu2 / 2.0)) / (3.0 * n * K_B) * 100.0;
+    }
     const double volume = box0 * box1 * box2;
     const double pressure = (th2 + (-t.v[5]) * 0.5) / volume / 3.0;         // pressure.rs:5-20
     // controls of the NEXT step (thermostat.rs:24-34, barostat.rs:21-31)
@@ -545,7 +608,7 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Params *pr, const Su
 template <int BLOCK>
 __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restrict__ partials, Scalars *sc,
                                                      const Params *pr, int mode,
-                                                     unsigned long long cond_handle)
+                                                     unsigned long long cond_handle, const Peers *peers_p)
 {
     __shared__ bool is_last;
     if (threadIdx.x == 0) {
@@ -559,27 +622,128 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
     if (!is_last) return;
     if (threadIdx.x == 0) { PROBE(2); }
     __threadfence();
-    Sums acc;
-#pragma unroll
-    for (int q = 0; q < NSUM; ++q) acc.v[q] = 0.0;
-    // fixed assignment (block b → thread b % BLOCK, ascending b) → fixed order; several slots are fetched per trip so
-    // a thread's loads are in flight together (4 slots per trip)
-    for (unsigned int base = threadIdx.x; base < gridDim.x; base += 4 * BLOCK) {
-        double v[4][NSUM];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned int b = base + u * BLOCK;
-#pragma unroll
-            for (int q = 0; q < NSUM; ++q) v[u][q] = b < gridDim.x ? __ldcg(&partials[(size_t)b * NSUM + q]) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int q = 0; q < NSUM - 1; ++q) acc.v[q] += v[u][q];
-            acc.v[NSUM - 1] = fmax(acc.v[NSUM - 1], v[u][NSUM - 1]);
+    // Last block.  (1) A copy of the control words and parameters finalize reads goes to shared memory — those loads are in
+    // flight together with (2) the fold of the per-block partials: thread (g, q) adds slot q of blocks g, g+G, g+2G, … in
+    // ascending order (independent loads, one L2 round trip), then the G group sums of a slot are added in group order.
+    // Fixed assignment, fixed order: the result depends on the grid size only.
+    constexpr int H = NSUM / 2;   // slot pairs: 128-bit loads
+    constexpr int G = BLOCK / H;  // groups of blocks
+    static_assert(NSUM % 2 == 0, "slots are folded in pairs");
+    __shared__ double fold[G][NSUM];
+    __shared__ double folded[NSUM];
+    __shared__ Scalars sc_in;
+    __shared__ Params pr_in;
+    {
+        constexpr int WS = (int)(sizeof(Scalars) / 8), WP = (int)(sizeof(Params) / 8);
+        static_assert(sizeof(Scalars) % 8 == 0 && sizeof(Params) % 8 == 0, "copied as 64-bit words");
+        const unsigned long long *gs = reinterpret_cast<const unsigned long long *>(sc);
+        const unsigned long long *gp = reinterpret_cast<const unsigned long long *>(pr);
+        unsigned long long *ss_ = reinterpret_cast<unsigned long long *>(&sc_in), *sp_ = reinterpret_cast<unsigned long long *>(&pr_in);
+        for (int w = threadIdx.x; w < WS + WP; w += BLOCK) {
+            if (w < WS) ss_[w] = __ldcg(gs + w);
+            else sp_[w - WS] = __ldcg(gp + (w - WS));
         }
     }
-    block_reduce<BLOCK>(acc);
+    {
+        const int h = threadIdx.x % H, g = threadIdx.x / H;
+        if (g < G) {
+            const bool has_max = (h == H - 1);  // the last slot of the last pair is the running maximum
+            double ax = 0.0, ay = 0.0;
+            const double2 *src = reinterpret_cast<const double2 *>(partials) + h;
+            constexpr int U = 16;               // loads in flight per thread
+            unsigned int b = g;
+            for (; b + (U - 1) * G < gridDim.x; b += U * G) {
+                double2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = __ldcg(src + (size_t)(b + u * G) * H);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ax += v[u].x;
+                    ay = has_max ? fmax(ay, v[u].y) : ay + v[u].y;
+                }
+            }
+            {
+                double2 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned int bb = b + u * G;
+                    v[u] = bb < gridDim.x ? __ldcg(src + (size_t)bb * H) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ax += v[u].x;
+                    ay = has_max ? fmax(ay, v[u].y) : ay + v[u].y;
+                }
+            }
+            fold[g][2 * h] = ax;
+            fold[g][2 * h + 1] = ay;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NSUM) {
+        const int q = threadIdx.x;
+        double a = fold[0][q];
+        for (int g = 1; g < G; ++g) a = (q == NSUM - 1) ? fmax(a, fold[g][q]) : a + fold[g][q];
+        folded[q] = a;
+    }
+    __syncthreads();
+    Sums acc;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; ++q) acc.v[q] = folded[q];
+    }
+    const unsigned long long t_last = gtime();  // every block has finished its atoms
+    if (mode & FIN_P2P) {
+        // All-gather of the rank sums through peer memory, fused into this kernel: every rank stores its 12 sums into every
+        // rank's mailbox (NVLink stores), raises its sequence flag there, waits for the flags of all ranks in its own
+        // mailbox and folds the ranks in rank order — identical lambda / myu / rebuild decision everywhere.
+        __shared__ double my_sums[NSUM];
+        __shared__ int timed_out;
+        const Peers &peers = *peers_p;
+        const unsigned long long seq = sc->epoch + 1;
+        const int buf = (int)(seq & 1ull);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < NSUM; ++q) my_sums[q] = acc.v[q];
+            timed_out = 0;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < peers.nranks * NSUM; t += BLOCK) {
+            const int r = t / NSUM, q = t - r * NSUM;
+            *reinterpret_cast<volatile double *>(&peers.mail[r]->sums[buf][peers.rank][q]) = my_sums[q];
+        }
+        __syncthreads();  // the stores above happen-before the release stores below (cumulative over the barrier)
+        const unsigned long long t_wait = gtime();
+        if ((int)threadIdx.x < peers.nranks) {
+            st_release_sys(&peers.mail[threadIdx.x]->sums_seq[peers.rank], seq);
+            if (!wait_seq(&peers.mail[peers.rank]->sums_seq[threadIdx.x], seq)) timed_out = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) sc->wait_sums_ns += gtime() - t_wait;
+        if (threadIdx.x == 0) {
+            Sums t;
+#pragma unroll
+            for (int q = 0; q < NSUM; ++q) t.v[q] = 0.0;
+            const Mail *own = peers.mail[peers.rank];
+            for (int r = 0; r < peers.nranks; ++r) {
+#pragma unroll
+                for (int q = 0; q < NSUM - 1; ++q) t.v[q] += __ldcg(&own->sums[buf][r][q]);
+                t.v[NSUM - 1] = fmax(t.v[NSUM - 1], __ldcg(&own->sums[buf][r][NSUM - 1]));
+            }
+            finalize(sc, &sc_in, &pr_in, t, mode);
+            if (timed_out) sc->error = 3;  // MD_ERR_NCCL: a peer never delivered
+            sc->force_atoms_ns += t_last - sc->t_start;
+            sc->force_tail_ns += gtime() - t_last;
+            sc->t_start = ~0ull;
+            sc->epoch = seq;
+            sc->ticket = 0;
+            if (cond_handle) {
+                unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
+                cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, go);
+            }
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         PROBE(3);
         if (mode & FIN_DIST) {
@@ -588,7 +752,7 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
             sc->ticket = 0;
             return;
         }
-        finalize(sc, pr, acc, mode);
+        finalize(sc, &sc_in, &pr_in, acc, mode);
         sc->ticket = 0;
         PROBE(4);
         if (cond_handle) {
@@ -631,7 +795,7 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
         accumulate_sums(s, m, vx, vy, vz, wx, wy, wz, a.w[i], a.u[i], shift);
     }
     block_reduce<RED_BLOCK>(s);
-    grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, mode, 0ull);
+    grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, mode, 0ull, nullptr);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -815,12 +979,12 @@ __device__ __forceinline__ void finish_atom(SumsSmem &ss, const PairAcc &f, doub
 template <int ROWS, bool MASKED, bool WRAP>
 __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const Arrays &a, const int2 *__restrict__ row,
                                                size_t stride, int last_row, int2 C, int i0, double2 X, double2 Y,
-                                               double2 Z, const LjConst &c, const ForceConsts &fc)
+                                               double2 Z, const LjConst &c, const ForceConsts &fc, int2 Ja)
 {
+    // Ja = row[0]: it exists for every atom (cap >= 8) and the caller fetched it together with the atom's own data
     const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
     const int kmax = max(C.x, C.y);
     int k = 0;
-    int2 Ja = row[0];  // row 0 exists for every atom (cap >= 8): fetched together with the atom's own data
     if (ROWS == 2) {
         int2 Jb = row[min(1, last_row) * stride];
         for (; k + 1 < kmax; k += 2) {
@@ -874,9 +1038,25 @@ template <bool EXACT, int ROWS, bool MASKED>
 __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
     k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
             double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
-            unsigned long long cond_handle, const ForceConsts fc)
+            unsigned long long cond_handle, const ForceConsts fc, const Peers *peers)
 {
+    // do_step bits: 1 = MD step (both half-kicks fused in), 2 = multi-GPU (publish rank sums only), 4 = guarded,
+    //               8 = multi-GPU over peer memory (sums exchanged and finalized here), 16 = wait for the neighbours' ghosts
     if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
+    if ((do_step & 8) && threadIdx.x == 0) atomicMin(&sc->t_start, gtime());
+    if (do_step & 16) {
+        // ghost positions of this step are pushed into our planes by the neighbours' k_halo_push
+        __shared__ int halo_late;
+        if (threadIdx.x == 0) {
+            const unsigned long long seq = sc->epoch + 1;
+            const Mail *own = peers->mail[peers->rank];
+            const unsigned long long t0 = gtime();
+            halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
+            if (blockIdx.x == 0) sc->wait_halo_ns += gtime() - t0;
+        }
+        __syncthreads();
+        if (halo_late && threadIdx.x == 0) atomicExch(&sc->error, 3);
+    }
     if (threadIdx.x == 0) { PROBE_MIN(0); }
     __shared__ SumsSmem ss;
 #pragma unroll
@@ -895,25 +1075,60 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
     const int npairs = (n + 1) >> 1;
     const int last_row = cap - 1;
     const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
-    for (int t = blockIdx.x * FORCE_BLOCK + threadIdx.x; t < npairs; t += gridDim.x * FORCE_BLOCK) {
+    // Dilute / exact variants: the next pair's operands (x, y, z, u, list count, first list row: 112 B per thread) are
+    // copied into shared memory by cp.async while the current pair's gathers and arithmetic run, so the streaming loads
+    // overlap the latency-bound neighbour phase instead of alternating with it.  (The dense variant is bound by its
+    // neighbour loop and keeps its L1 for gathers.)
+    constexpr bool PREFETCH = !MASKED;
+    __shared__ __align__(16) double2 pf[PREFETCH ? 2 : 1][PREFETCH ? 6 : 1][PREFETCH ? FORCE_BLOCK : 1];
+    __shared__ __align__(8) int2 pfi[PREFETCH ? 2 : 1][PREFETCH ? 2 : 1][PREFETCH ? FORCE_BLOCK : 1];
+    const int tstride = gridDim.x * FORCE_BLOCK;
+#define MD_PREFETCH_PAIR(S, TT)                                                                  \
+    do {                                                                                         \
+        const int l_ = threadIdx.x;                                                              \
+        cp_async16(&pf[S][0][l_], reinterpret_cast<const double2 *>(px) + (TT));                 \
+        cp_async16(&pf[S][1][l_], reinterpret_cast<const double2 *>(py) + (TT));                 \
+        cp_async16(&pf[S][2][l_], reinterpret_cast<const double2 *>(pz) + (TT));                 \
+        cp_async16(&pf[S][3][l_], reinterpret_cast<const double2 *>(a.vx) + (TT));               \
+        cp_async16(&pf[S][4][l_], reinterpret_cast<const double2 *>(a.vy) + (TT));               \
+        cp_async16(&pf[S][5][l_], reinterpret_cast<const double2 *>(a.vz) + (TT));               \
+        cp_async8(&pfi[S][0][l_], reinterpret_cast<const int2 *>(nbr_cnt) + (TT));               \
+        cp_async8(&pfi[S][1][l_], reinterpret_cast<const int2 *>(nbr) + (TT));                   \
+        cp_async_commit();                                                                       \
+    } while (0)
+    int t = blockIdx.x * FORCE_BLOCK + threadIdx.x;
+    if (PREFETCH && t < npairs) MD_PREFETCH_PAIR(0, t);
+    for (int it = 0; t < npairs; t += tstride, ++it) {
         const int i0 = 2 * t;
         const bool has1 = i0 + 1 < n;
         const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + t;
         const size_t stride = (size_t)(npad >> 1);
-        const double2 X = reinterpret_cast<const double2 *>(px)[t], Y = reinterpret_cast<const double2 *>(py)[t],
-                      Z = reinterpret_cast<const double2 *>(pz)[t];
-        int2 C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
-        double2 VX = reinterpret_cast<double2 *>(a.vx)[t], VY = reinterpret_cast<double2 *>(a.vy)[t],
-                VZ = reinterpret_cast<double2 *>(a.vz)[t];
+        double2 X, Y, Z, VX, VY, VZ;
+        int2 C, J0;
+        if (PREFETCH) {
+            const int s = it & 1, l = threadIdx.x;
+            cp_async_wait_all();
+            X = pf[s][0][l]; Y = pf[s][1][l]; Z = pf[s][2][l];
+            VX = pf[s][3][l]; VY = pf[s][4][l]; VZ = pf[s][5][l];
+            C = pfi[s][0][l]; J0 = pfi[s][1][l];
+            if (t + tstride < npairs) MD_PREFETCH_PAIR(s ^ 1, t + tstride);
+        } else {
+            X = reinterpret_cast<const double2 *>(px)[t]; Y = reinterpret_cast<const double2 *>(py)[t];
+            Z = reinterpret_cast<const double2 *>(pz)[t];
+            C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
+            J0 = row[0];
+            VX = reinterpret_cast<double2 *>(a.vx)[t]; VY = reinterpret_cast<double2 *>(a.vy)[t];
+            VZ = reinterpret_cast<double2 *>(a.vz)[t];
+        }
         if (!has1) C.y = 0;
         PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
         if (EXACT) {
             for (int k = 0; k < C.x; ++k) {
-                int j = row[k * stride].x;
+                int j = k ? row[k * stride].x : J0.x;
                 pair_exact(f0, px[j], py[j], pz[j], X.x, Y.x, Z.x, c, fc);
             }
             for (int k = 0; k < C.y; ++k) {
-                int j = row[k * stride].y;
+                int j = k ? row[k * stride].y : J0.y;
                 pair_exact(f1, px[j], py[j], pz[j], X.y, Y.y, Z.y, c, fc);
             }
         } else {
@@ -923,11 +1138,11 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
                 const bool near = X.x < m || X.x > c.Lx - m || Y.x < m || Y.x > c.Ly - m || Z.x < m || Z.x > c.Lz - m ||
                                   X.y < m || X.y > c.Lx - m || Y.y < m || Y.y > c.Ly - m || Z.y < m || Z.y > c.Lz - m;
                 if (__any_sync(__activemask(), near))
-                    neighbour_loop<ROWS, true, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
+                    neighbour_loop<ROWS, true, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
                 else
-                    neighbour_loop<ROWS, true, false>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
+                    neighbour_loop<ROWS, true, false>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             } else {
-                neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc);
+                neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             }
         }
         double2 WX, WY, WZ;
@@ -961,8 +1176,9 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][threadIdx.x];
     block_reduce<FORCE_BLOCK>(s);
-    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr, (do_step & 1 ? FIN_STEP : 0) | (do_step & 2 ? FIN_DIST : 0),
-                                      cond_handle);
+    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr,
+                                      (do_step & 1 ? FIN_STEP : 0) | (do_step & 2 ? FIN_DIST : 0) | (do_step & 8 ? FIN_P2P : 0),
+                                      cond_handle, peers);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -1001,41 +1217,97 @@ __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *
     if (write_q4) a.q4[i] = make_double4(x, y, z, 0.0);
 }
 
-__global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, const Scalars *__restrict__ sc,
-                                                    const Params *__restrict__ pr, int guarded, int write_q4)
+// Multi-GPU over peer memory: the face atoms of a slab are a prefix [0, m_left) and a suffix [n - m_right, n) of its
+// cell-sorted order (ghosts are selected by x cell layer), so the drift kernel itself stores their new positions into the
+// neighbours' ghost slots — NVLink stores into the neighbour's HBM — and the last of the pushing blocks raises the step's
+// sequence flag in both neighbours' mailboxes.  k_force on the other side polls that flag before it touches a ghost.
+struct HaloPush {
+    int m[2];                    // face atoms for the left / right neighbour (0, 0 and expected == 0: single GPU)
+    double *x[2], *y[2], *z[2];  // the neighbour's planes (mapped), already offset to the first ghost slot we own there
+    double4 *q4[2];
+    unsigned long long *flag[2];  // the neighbour's Mail::halo_seq entry for data coming from our side
+    unsigned int *ticket;
+    unsigned int expected;       // blocks that hold face atoms (block 0 always counts)
+    int fence_all;               // experiment: every pushing thread fences at system scope (instead of one per block)
+};
+
+__device__ __forceinline__ void push_atom(const HaloPush &h, int i, int n, double x, double y, double z)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (2 * t >= n) return;
+    if (i < h.m[0]) {
+        h.x[0][i] = x; h.y[0][i] = y; h.z[0][i] = z;
+        if (h.q4[0]) h.q4[0][i] = make_double4(x, y, z, 0.0);
+    }
+    const int k = i - (n - h.m[1]);
+    if (k >= 0) {
+        h.x[1][k] = x; h.y[1][k] = y; h.z[1][k] = z;
+        if (h.q4[1]) h.q4[1][k] = make_double4(x, y, z, 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars *sc,
+                                                    const Params *__restrict__ pr, int guarded, int write_q4,
+                                                    const HaloPush h)
+{
     if (guarded && halted(sc)) return;
-    if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
-        kick_drift_tail(2 * t, a, sc, pr, write_q4 != 0);
-        return;
+    const unsigned long long t_begin = gtime();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // block-uniform: does this block hold face atoms?  (512 atoms per block)
+    const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
+    const bool pushes = h.expected != 0 && (blockIdx.x == 0 || b_lo < h.m[0] || b_hi > n - h.m[1]);
+    if (2 * t < n) {
+        if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
+            kick_drift_tail(2 * t, a, sc, pr, write_q4 != 0);
+            if (pushes) push_atom(h, 2 * t, n, a.x[2 * t], a.y[2 * t], a.z[2 * t]);
+        } else {
+            const double c = pr->half_dt_m, dt = pr->dt;
+            const double lambda = sc->lambda, mup = sc->mu_pending;
+            const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+            const bool half = sc->vel_is_half != 0;
+            double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
+                    z = reinterpret_cast<double2 *>(a.z)[t];
+            double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
+                    uz = reinterpret_cast<double2 *>(a.vz)[t];
+            if (!half) {
+                const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
+                              fz = reinterpret_cast<const double2 *>(a.fz)[t];
+                ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
+                uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
+                uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));
+                reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
+                reinterpret_cast<double2 *>(a.vz)[t] = uz;
+            }
+            drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
+            drift_one(y.x, uy.x, lambda, mup, dt, Ly); drift_one(y.y, uy.y, lambda, mup, dt, Ly);
+            drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
+            reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
+            reinterpret_cast<double2 *>(a.z)[t] = z;
+            if (write_q4) {
+                a.q4[2 * t] = make_double4(x.x, y.x, z.x, 0.0);
+                a.q4[2 * t + 1] = make_double4(x.y, y.y, z.y, 0.0);
+            }
+            if (pushes) {
+                push_atom(h, 2 * t, n, x.x, y.x, z.x);
+                push_atom(h, 2 * t + 1, n, x.y, y.y, z.y);
+            }
+        }
     }
-    const double c = pr->half_dt_m, dt = pr->dt;
-    const double lambda = sc->lambda, mup = sc->mu_pending;
-    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-    const bool half = sc->vel_is_half != 0;
-    double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
-            z = reinterpret_cast<double2 *>(a.z)[t];
-    double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
-            uz = reinterpret_cast<double2 *>(a.vz)[t];
-    if (!half) {
-        const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
-                      fz = reinterpret_cast<const double2 *>(a.fz)[t];
-        ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
-        uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
-        uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));
-        reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
-        reinterpret_cast<double2 *>(a.vz)[t] = uz;
-    }
-    drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
-    drift_one(y.x, uy.x, lambda, mup, dt, Ly); drift_one(y.y, uy.y, lambda, mup, dt, Ly);
-    drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
-    reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
-    reinterpret_cast<double2 *>(a.z)[t] = z;
-    if (write_q4) {
-        a.q4[2 * t] = make_double4(x.x, y.x, z.x, 0.0);
-        a.q4[2 * t + 1] = make_double4(x.y, y.y, z.y, 0.0);
+    if (pushes) {
+        // the block's stores happen-before the barrier, thread 0's fence is cumulative over them, the ticket chains the
+        // blocks, and the last one releases the flags at system scope
+        if (h.fence_all) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int k = atomicAdd(h.ticket, 1u);
+            if (k == h.expected - 1) {
+                __threadfence_system();
+                const unsigned long long seq = sc->epoch + 1;
+                st_release_sys(h.flag[0], seq);
+                st_release_sys(h.flag[1], seq);
+                *h.ticket = 0;
+                sc->drift_push_ns += gtime() - t_begin;
+            }
+        }
     }
 }
 
@@ -1058,8 +1330,6 @@ struct StepStage {
     double x[STEP_TILE], y[STEP_TILE], z[STEP_TILE], ux[STEP_TILE], uy[STEP_TILE], uz[STEP_TILE];
     int cnt[STEP_TILE], row0[STEP_TILE];
 };
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
@@ -1243,7 +1513,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, MD_STEP_MINB)
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) sum.v[q] = ss.v[q][tid];
     block_reduce<FORCE_BLOCK>(sum);
-    grid_reduce_finalize<FORCE_BLOCK>(sum, partials, sc, pr, FIN_STEP | FIN_FLIP | (flags & 2 ? FIN_DIST : 0), cond_handle);
+    grid_reduce_finalize<FORCE_BLOCK>(sum, partials, sc, pr, FIN_STEP | FIN_FLIP | (flags & 2 ? FIN_DIST : 0), cond_handle,
+                                      nullptr);
 }
 
 // First step of a batch for the fused path: the velocity planes hold v (not u = v + F c) after an upload or after the
@@ -1370,7 +1641,7 @@ __global__ void k_finalize_dist(const double *__restrict__ all_sums, int nranks,
         for (int q = 0; q < NSUM - 1; ++q) t.v[q] += all_sums[r * NSUM + q];
         t.v[NSUM - 1] = fmax(t.v[NSUM - 1], all_sums[r * NSUM + NSUM - 1]);
     }
-    finalize(sc, pr, t, mode);
+    finalize(sc, sc, pr, t, mode);
 }
 
 // flags for stable (scan-based) compaction: flag[i] = 1 if atom i belongs to class `want`
@@ -1398,17 +1669,15 @@ __global__ void k_flag_owned(int n, const double *__restrict__ x_interleaved, do
     if (i < n) flag[i] = owner_of(x_interleaved[3 * (size_t)i], Lx, sl.nranks) == sl.rank ? 1 : 0;
 }
 
-// ghost candidates among the (sorted) owned atoms: side 0 = within halo of the left face, 1 = right face
-__global__ void k_flag_ghost(int n, const double *__restrict__ x, const Scalars *__restrict__ sc, Slab sl, int side,
-                             int *__restrict__ flag)
+// ghost candidates among the (sorted) owned atoms, selected by x CELL LAYER: side 0 = layers that reach into the halo of the
+// left face, side 1 = of the right face.  A superset of the atoms within `halo` of the face (by at most one layer), and —
+// because x is the slowest index of the cell sort — a prefix (side 0) / suffix (side 1) of the sorted order.
+__global__ void k_flag_ghost(int n, const int *__restrict__ cell_sorted, Grid g, int layer, int side, int *__restrict__ flag)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double Lx = sc->box[0];
-    const double xlo = Lx * ((double)sl.rank / (double)sl.nranks);
-    const double xhi = Lx * ((double)(sl.rank + 1) / (double)sl.nranks);
-    double d = side == 0 ? x[i] - xlo : xhi - x[i];
-    flag[i] = d <= sl.halo ? 1 : 0;
+    const int cx = cell_sorted[i] / (g.nc[1] * g.nc[2]);
+    flag[i] = (side == 0 ? cx <= layer : cx >= layer) ? 1 : 0;
 }
 
 // idx[pos[i]] = i for flagged i (pos = exclusive scan of flag) → ascending, deterministic

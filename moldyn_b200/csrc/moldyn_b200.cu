@@ -143,6 +143,22 @@ struct md_ctx {
         int *d_cnt = nullptr, *h_cnt = nullptr;
         double *all_sums = nullptr;
         int64_t migrated = 0;
+        // peer-memory path (NVLink stores into the neighbours' HBM; buffers shared through CUDA IPC)
+        bool p2p = false;
+        double *slab = nullptr;       // x, y, z of both plane sets + both q4 copies in ONE allocation (one IPC handle)
+        int64_t slab_npad = 0;
+        Mail *mail = nullptr;         // this rank's mailbox
+        Peers peers{};                // every rank's mailbox as mapped here
+        Peers *peers_dev = nullptr;   // the same, in device memory (kernel argument)
+        double *peer_slab[2] = {nullptr, nullptr};  // left / right neighbour's slab as mapped here
+        int64_t peer_npad[2] = {0, 0};
+        int peer_base[2] = {0, 0}, peer_half[2] = {0, 0};  // where our face atoms land in the neighbour's planes
+        unsigned int *push_ticket = nullptr;
+        char *gather_buf = nullptr;   // small persistent device buffer for host-level all-gathers
+        char *up_buf = nullptr;       // upload staging arena (kept between uploads)
+        size_t up_bytes = 0;
+        void *ipc_opened[2 * MAX_PEERS] = {};
+        int n_ipc_opened = 0;
     } dist;
 
     // per-kernel CUDA-event timing (md_time_kernels)
@@ -467,11 +483,11 @@ int rebuild_lists(md_ctx *ctx)
     return MD_OK;
 }
 
-int launch_kick_drift(md_ctx *ctx, int guarded = 0)
+int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr)
 {
     const int n = (int)ctx->n_own;
-    k_kick_drift<<<blocks_for((n + 1) / 2, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded,
-                                                                        ctx->use_q4 ? 1 : 0);
+    k_kick_drift<<<std::max(1, blocks_for((n + 1) / 2, 256)), 256, 0, ctx->stream>>>(
+        n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded, ctx->use_q4 ? 1 : 0, push ? *push : HaloPush{});
     return MD_OK;
 }
 
@@ -482,7 +498,7 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
 #define LAUNCH_FORCE(E, R, M, GRID)                                                                                  \
     k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
                                                          ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
-                                                         kick ? 1 : 0, cond, fc)
+                                                         kick ? 1 : 0, cond, fc, nullptr)
     if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
     else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
     else LAUNCH_FORCE(false, MD_DILUTE_ROWS, false, ctx->force_grid[2]);
@@ -695,6 +711,7 @@ void md_destroy(md_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drop_graph(ctx);
+    for (int k = 0; k < ctx->dist.n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->dist.ipc_opened[k]);
     if (ctx->dist.comm) ncclCommDestroy(ctx->dist.comm);
     if (ctx->dist.h_cnt) cudaFreeHost(ctx->dist.h_cnt);
     for (auto &e : ctx->ev)
@@ -1233,6 +1250,12 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->n_owned = ctx->n_own;
     out->n_ghost = ctx->n_ghost;
     out->migrated = ctx->dist.migrated;
+    out->wait_halo_ms = (double)ctx->h_sc->wait_halo_ns * 1e-6;  // as of the last time the host looked at the device
+    out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
+    out->peer_memory = ctx->dist.p2p ? 1 : 0;
+    out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
+    out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;
+    out->drift_push_ms = (double)ctx->h_sc->drift_push_ns * 1e-6;
     return MD_OK;
 }
 

@@ -275,7 +275,9 @@ class Solver:
         return {"steps": s.steps, "rebuilds": s.rebuilds, "kernel_launches": s.kernel_launches,
                 "graph_launches": s.graph_launches, "cells": list(s.cells), "nbr_capacity": s.nbr_capacity,
                 "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean, "n_owned": s.n_owned,
-                "n_ghost": s.n_ghost, "migrated": s.migrated, "fused_steps": s.fused_steps}
+                "n_ghost": s.n_ghost, "migrated": s.migrated, "fused_steps": s.fused_steps, "wait_halo_ms": s.wait_halo_ms,
+                "wait_sums_ms": s.wait_sums_ms, "peer_memory": s.peer_memory, "force_atoms_ms": s.force_atoms_ms,
+                "force_tail_ms": s.force_tail_ms, "drift_push_ms": s.drift_push_ms}
 
     def stream(self):
         return _ffi.lib().md_stream(self._ctx)
