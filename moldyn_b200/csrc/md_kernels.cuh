@@ -134,6 +134,7 @@ static_assert(NSUM == 12, "Mail::sums holds NSUM slots per rank");
 struct Peers {      // lives in device memory; kernels get a pointer (NULL on one GPU)
     Mail *mail[MAX_PEERS];  // rank r's Mail as mapped into this process (mail[rank] is the local one)
     int rank, nranks;
+    int left, right;        // ring neighbours (slab decomposition along x)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
@@ -1049,6 +1050,12 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
         __shared__ int halo_late;
         if (threadIdx.x == 0) {
             const unsigned long long seq = sc->epoch + 1;
+            // Our own face atoms were stored into the neighbours' planes by the preceding k_kick_drift; a kernel boundary
+            // orders those stores system-wide, so the flags can go up right away — no fence inside the drift kernel.
+            if (blockIdx.x == 0) {
+                st_release_sys(&peers->mail[peers->left]->halo_seq[1], seq);   // we are the left neighbour's right side
+                st_release_sys(&peers->mail[peers->right]->halo_seq[0], seq);
+            }
             const Mail *own = peers->mail[peers->rank];
             const unsigned long long t0 = gtime();
             halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
@@ -1219,16 +1226,12 @@ __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *
 
 // Multi-GPU over peer memory: the face atoms of a slab are a prefix [0, m_left) and a suffix [n - m_right, n) of its
 // cell-sorted order (ghosts are selected by x cell layer), so the drift kernel itself stores their new positions into the
-// neighbours' ghost slots — NVLink stores into the neighbour's HBM — and the last of the pushing blocks raises the step's
-// sequence flag in both neighbours' mailboxes.  k_force on the other side polls that flag before it touches a ghost.
+// neighbours' ghost slots — plain NVLink stores into the neighbour's HBM, no fence here.  The kernel boundary orders them;
+// the first thing k_force does is raise the step's sequence flag in both neighbours' mailboxes and poll its own.
 struct HaloPush {
-    int m[2];                    // face atoms for the left / right neighbour (0, 0 and expected == 0: single GPU)
+    int m[2];                    // face atoms for the left / right neighbour (0, 0: nothing to push, e.g. single GPU)
     double *x[2], *y[2], *z[2];  // the neighbour's planes (mapped), already offset to the first ghost slot we own there
     double4 *q4[2];
-    unsigned long long *flag[2];  // the neighbour's Mail::halo_seq entry for data coming from our side
-    unsigned int *ticket;
-    unsigned int expected;       // blocks that hold face atoms (block 0 always counts)
-    int fence_all;               // experiment: every pushing thread fences at system scope (instead of one per block)
 };
 
 __device__ __forceinline__ void push_atom(const HaloPush &h, int i, int n, double x, double y, double z)
@@ -1249,11 +1252,10 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
                                                     const HaloPush h)
 {
     if (guarded && halted(sc)) return;
-    const unsigned long long t_begin = gtime();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     // block-uniform: does this block hold face atoms?  (512 atoms per block)
     const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
-    const bool pushes = h.expected != 0 && (blockIdx.x == 0 || b_lo < h.m[0] || b_hi > n - h.m[1]);
+    const bool pushes = (h.m[0] | h.m[1]) != 0 && (b_lo < h.m[0] || b_hi > n - h.m[1]);
     if (2 * t < n) {
         if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
             kick_drift_tail(2 * t, a, sc, pr, write_q4 != 0);
@@ -1288,24 +1290,6 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
             if (pushes) {
                 push_atom(h, 2 * t, n, x.x, y.x, z.x);
                 push_atom(h, 2 * t + 1, n, x.y, y.y, z.y);
-            }
-        }
-    }
-    if (pushes) {
-        // the block's stores happen-before the barrier, thread 0's fence is cumulative over them, the ticket chains the
-        // blocks, and the last one releases the flags at system scope
-        if (h.fence_all) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            const unsigned int k = atomicAdd(h.ticket, 1u);
-            if (k == h.expected - 1) {
-                __threadfence_system();
-                const unsigned long long seq = sc->epoch + 1;
-                st_release_sys(h.flag[0], seq);
-                st_release_sys(h.flag[1], seq);
-                *h.ticket = 0;
-                sc->drift_push_ns += gtime() - t_begin;
             }
         }
     }

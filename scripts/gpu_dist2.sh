@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 run() { # tag, env...
   tag=$1; shift
-  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --workload ${W:-c3} --steps ${STEPS:-2000} --warmup 200 --e2e-steps 0 --cpu-rows -1 > gpurun_out/ab_${tag}_$N.json 2> gpurun_out/ab_${tag}_$N.err
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --workload ${W:-c3} --steps ${STEPS:-2000} --warmup ${WARM:-200} --e2e-steps 0 --cpu-rows -1 > gpurun_out/ab_${tag}_$N.json 2> gpurun_out/ab_${tag}_$N.err
   python - <<PY
 import json
 try:
@@ -15,6 +15,6 @@ PY
 }
 timeout 1200 python -m pytest tests/test_multi_gpu.py -m gpu -q --timeout 1100 -x 2>&1 | tail -3
 run default X=1
-run fenceall MOLDYN_B200_P2P_FENCE_ALL=1
-run chunk MOLDYN_B200_DIST_WHILE=0
+run while MOLDYN_B200_DIST_WHILE=1
 W=big STEPS=300 run big_default X=1
+W=c3 STEPS=2000 WARM=6000 run late X=1
