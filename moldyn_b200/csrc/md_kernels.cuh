@@ -849,14 +849,13 @@ __device__ __forceinline__ double min_image_fast(double r, double L, double h, i
     return r;
 }
 
-// 1/x without the IEEE division's slow-path branch: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (~1 ulp).
+// 1/x without the IEEE division's slow-path branch: MUFU.RCP64H seed (relative error <= 2^-23) + one Newton step →
+// <= 2^-46 (1.4e-14), three orders below the 1e-10 parity bar of the FAST mode.
 __device__ __forceinline__ double rcp_nr(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
+    const double e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
 
@@ -872,7 +871,8 @@ __device__ __forceinline__ double min_image_sel(double r, double L, double h)
 // face: none of their partners can be a periodic image, so the minimum-image step is skipped altogether.
 template <bool WRAP>
 __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, double yj, double zj, double xi,
-                                          double yi, double zi, const LjConst &c, const ForceConsts &fc)
+                                          double yi, double zi, const LjConst &c, const ForceConsts &fc, bool need_u,
+                                          bool need_w)
 {
     double rx = xj - xi, ry = yj - yi, rz = zj - zi;
     if (WRAP) {
@@ -887,12 +887,14 @@ __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, do
     double s6 = s2 * s2 * s2;
     double s12 = s6 * s6;
     double fr = fc.eps24 * inv * (s6 - 2.0 * s12);  // F / r
-    double pu = fc.eps4 * (s12 - s6) - fc.u_cut;
     fr = in ? fr : 0.0;
-    pu = in ? pu : 0.0;
-    a.u += pu;
     a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
-    a.w += fr * r2;
+    // per-atom potential / virial: uniform flags — steady-state steps of a batch only need what feeds the controls
+    if (need_u) {
+        double pu = fc.eps4 * (s12 - s6) - fc.u_cut;
+        a.u += in ? pu : 0.0;
+    }
+    if (need_w) a.w += fr * r2;
 }
 
 // FAST pair term for dilute systems: most listed partners are outside the cutoff (the skin is wide), so the
@@ -997,10 +999,10 @@ __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const A
                 const double4 qa0 = a.q4[ja0], qa1 = a.q4[ja1], qb0 = a.q4[jb0], qb1 = a.q4[jb1];
                 xa0 = qa0.x; ya0 = qa0.y; za0 = qa0.z; xa1 = qa1.x; ya1 = qa1.y; za1 = qa1.z;
                 xb0 = qb0.x; yb0 = qb0.y; zb0 = qb0.z; xb1 = qb1.x; yb1 = qb1.y; zb1 = qb1.z;
-                pair_fast<WRAP>(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c, fc);
-                pair_fast<WRAP>(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c, fc);
-                pair_fast<WRAP>(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c, fc);
-                pair_fast<WRAP>(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c, fc);
+                pair_fast<WRAP>(f0, a0, xa0, ya0, za0, X.x, Y.x, Z.x, c, fc, true, true);
+                pair_fast<WRAP>(f1, a1, xa1, ya1, za1, X.y, Y.y, Z.y, c, fc, true, true);
+                pair_fast<WRAP>(f0, b0, xb0, yb0, zb0, X.x, Y.x, Z.x, c, fc, true, true);
+                pair_fast<WRAP>(f1, b1, xb1, yb1, zb1, X.y, Y.y, Z.y, c, fc, true, true);
             } else {
                 xa0 = px[ja0]; ya0 = py[ja0]; za0 = pz[ja0]; xa1 = px[ja1]; ya1 = py[ja1]; za1 = pz[ja1];
                 xb0 = px[jb0]; yb0 = py[jb0]; zb0 = pz[jb0]; xb1 = px[jb1]; yb1 = py[jb1]; zb1 = pz[jb1];
@@ -1018,8 +1020,8 @@ __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const A
         const int ja0 = a0 ? Ja.x : i0, ja1 = a1 ? Ja.y : i0;
         if (MASKED) {
             const double4 qa0 = a.q4[ja0], qa1 = a.q4[ja1];
-            pair_fast<WRAP>(f0, a0, qa0.x, qa0.y, qa0.z, X.x, Y.x, Z.x, c, fc);
-            pair_fast<WRAP>(f1, a1, qa1.x, qa1.y, qa1.z, X.y, Y.y, Z.y, c, fc);
+            pair_fast<WRAP>(f0, a0, qa0.x, qa0.y, qa0.z, X.x, Y.x, Z.x, c, fc, true, true);
+            pair_fast<WRAP>(f1, a1, qa1.x, qa1.y, qa1.z, X.y, Y.y, Z.y, c, fc, true, true);
         } else {
             const double xa0 = px[ja0], ya0 = py[ja0], za0 = pz[ja0];
             const double xa1 = px[ja1], ya1 = py[ja1], za1 = pz[ja1];
@@ -1028,6 +1030,91 @@ __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const A
         }
         Ja = Na;
     }
+}
+
+// Dense systems (hundreds of listed partners per atom): the neighbour table is far larger than L2 and streams from HBM, so a
+// one-trip-ahead index prefetch leaves the warp waiting on DRAM every trip.  Each thread therefore keeps a ring of the next
+// RING_D trips' index rows (two rows per trip) in shared memory, filled by cp.async — no registers, no barrier (a thread only
+// reads what it copied), ~RING_D trips of DRAM latency hidden.
+constexpr int RING_D = 8;
+struct IndexRing {
+    int2 r[RING_D][2][FORCE_BLOCK];
+};
+
+template <bool WRAP>
+__device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, const double4 *__restrict__ q4,
+                                                     const int2 *__restrict__ row, size_t stride, int2 C, int i0,
+                                                     double2 X, double2 Y, double2 Z, const LjConst &c,
+                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w)
+{
+    const int l = threadIdx.x;
+    const int kmax = max(C.x, C.y);
+    const int ntrips = (kmax + 1) >> 1;
+    // rows beyond this pair's lists are never read (the copies are skipped, the lanes masked)
+#pragma unroll
+    for (int d = 0; d < RING_D; ++d) {
+        if (d < ntrips) {
+            cp_async8(&ring.r[d][0][l], row + (size_t)(2 * d) * stride);
+            if (2 * d + 1 < kmax) cp_async8(&ring.r[d][1][l], row + (size_t)(2 * d + 1) * stride);
+        }
+        cp_async_commit();
+    }
+    // software pipeline: the gathers of trip t+1 are in flight while the pair terms of trip t are computed.
+#define MD_FETCH_ROWS(T, JA, JB)                                                                           \
+    do {                                                                                                   \
+        const int slot_ = (T) % RING_D;                                                                    \
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING_D - 1) : "memory");                              \
+        JA = ring.r[slot_][0][l];                                                                          \
+        JB = ring.r[slot_][1][l];                                                                          \
+        const int tn_ = (T) + RING_D; /* refill the slot with the rows of trip T + RING_D */               \
+        if (tn_ < ntrips) {                                                                                \
+            cp_async8(&ring.r[slot_][0][l], row + (size_t)(2 * tn_) * stride);                             \
+            if (2 * tn_ + 1 < kmax) cp_async8(&ring.r[slot_][1][l], row + (size_t)(2 * tn_ + 1) * stride); \
+        }                                                                                                  \
+        cp_async_commit();                                                                                 \
+    } while (0)
+    // one 256-bit load per partner (LDG.E.256, new with sm_100): a divergent gather costs the L1 one pass per lane and
+    // instruction, and this loop is co-limited by exactly that — half the passes of an (x, y) + z pair of loads
+#define MD_GATHER(J, XY, ZZ)                                                                              \
+    do {                                                                                                  \
+        double w_;                                                                                        \
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"                                                    \
+            : "=d"(XY.x), "=d"(XY.y), "=d"(ZZ), "=d"(w_)                                                  \
+            : "l"(q4 + (J)));                                                                             \
+    } while (0)
+    // masked lanes (list shorter than the warp's longest) all gather the same address: one L1 pass instead of 32
+    i0 &= ~63;
+    double2 pa0, pa1, pb0, pb1;
+    double za0, za1, zb0, zb1;
+    pa0 = pa1 = pb0 = pb1 = make_double2(0.0, 0.0);
+    za0 = za1 = zb0 = zb1 = 0.0;
+    if (ntrips > 0) {
+        int2 Ja, Jb;
+        MD_FETCH_ROWS(0, Ja, Jb);
+        MD_GATHER(0 < C.x ? Ja.x : i0, pa0, za0); MD_GATHER(0 < C.y ? Ja.y : i0, pa1, za1);
+        MD_GATHER(1 < C.x ? Jb.x : i0, pb0, zb0); MD_GATHER(1 < C.y ? Jb.y : i0, pb1, zb1);
+    }
+    for (int t = 0; t < ntrips; ++t) {
+        const int k = 2 * t;
+        double2 na0 = pa0, na1 = pa1, nb0 = pb0, nb1 = pb1;
+        double ya0 = za0, ya1 = za1, yb0 = zb0, yb1 = zb1;
+        if (t + 1 < ntrips) {
+            int2 Ja, Jb;
+            MD_FETCH_ROWS(t + 1, Ja, Jb);
+            MD_GATHER(k + 2 < C.x ? Ja.x : i0, na0, ya0); MD_GATHER(k + 2 < C.y ? Ja.y : i0, na1, ya1);
+            MD_GATHER(k + 3 < C.x ? Jb.x : i0, nb0, yb0); MD_GATHER(k + 3 < C.y ? Jb.y : i0, nb1, yb1);
+        }
+        const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+        pair_fast<WRAP>(f0, a0, pa0.x, pa0.y, za0, X.x, Y.x, Z.x, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f1, a1, pa1.x, pa1.y, za1, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f0, b0, pb0.x, pb0.y, zb0, X.x, Y.x, Z.x, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f1, b1, pb1.x, pb1.y, zb1, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pa0 = na0; pa1 = na1; pb0 = nb0; pb1 = nb1;
+        za0 = ya0; za1 = ya1; zb0 = yb0; zb1 = yb1;
+    }
+#undef MD_FETCH_ROWS
+#undef MD_GATHER
+    cp_async_wait_all();
 }
 
 // Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
@@ -1087,6 +1174,11 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
     // overlap the latency-bound neighbour phase instead of alternating with it.  (The dense variant is bound by its
     // neighbour loop and keeps its L1 for gathers.)
     constexpr bool PREFETCH = !MASKED;
+    __shared__ __align__(8) int2 ring_store[MASKED ? RING_D * 2 * FORCE_BLOCK : 1];
+    IndexRing &ring = *reinterpret_cast<IndexRing *>(ring_store);
+    // per-atom potential and virial enter nothing but the stored State and the S_U / S_W sums: the potential sum is only
+    // reported, the virial sum feeds the barostat — steady-state steps of a batch skip what nobody reads
+    const bool need_u = store_state, need_w = store_state || pr->ba_kind != 0;
     __shared__ __align__(16) double2 pf[PREFETCH ? 2 : 1][PREFETCH ? 6 : 1][PREFETCH ? FORCE_BLOCK : 1];
     __shared__ __align__(8) int2 pfi[PREFETCH ? 2 : 1][PREFETCH ? 2 : 1][PREFETCH ? FORCE_BLOCK : 1];
     const int tstride = gridDim.x * FORCE_BLOCK;
@@ -1124,8 +1216,10 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
             Z = reinterpret_cast<const double2 *>(pz)[t];
             C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
             J0 = row[0];
-            VX = reinterpret_cast<double2 *>(a.vx)[t]; VY = reinterpret_cast<double2 *>(a.vy)[t];
-            VZ = reinterpret_cast<double2 *>(a.vz)[t];
+            if (!MASKED) {  // dense: the velocities are fetched after the (long) neighbour loop — 12 registers less in it
+                VX = reinterpret_cast<double2 *>(a.vx)[t]; VY = reinterpret_cast<double2 *>(a.vy)[t];
+                VZ = reinterpret_cast<double2 *>(a.vz)[t];
+            }
         }
         if (!has1) C.y = 0;
         PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1145,12 +1239,16 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
                 const bool near = X.x < m || X.x > c.Lx - m || Y.x < m || Y.x > c.Ly - m || Z.x < m || Z.x > c.Lz - m ||
                                   X.y < m || X.y > c.Lx - m || Y.y < m || Y.y > c.Ly - m || Z.y < m || Z.y > c.Lz - m;
                 if (__any_sync(__activemask(), near))
-                    neighbour_loop<ROWS, true, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
+                    neighbour_loop_dense<true>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w);
                 else
-                    neighbour_loop<ROWS, true, false>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
+                    neighbour_loop_dense<false>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w);
             } else {
                 neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             }
+        }
+        if (MASKED) {
+            VX = reinterpret_cast<double2 *>(a.vx)[t]; VY = reinterpret_cast<double2 *>(a.vy)[t];
+            VZ = reinterpret_cast<double2 *>(a.vz)[t];
         }
         double2 WX, WY, WZ;
         finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
