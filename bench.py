@@ -34,6 +34,14 @@ ALGO_BYTES_STEP = 160       # r+w of x, v, F (144 B) + write U, W (
 ALGO_BYTES_FORCE = 112      # k_force(+kick2): read x, v; write v, F, U, W
 ALGO_BYTES_KICK_DRIFT = 120  # k_kick_drift: read x, v, F; write x, v
 ALGO_BYTES_FUSED_STEP = 104  # k_step_dilute: read x, u (48) + list count and first row (8); write x', u' (48)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/):
+# (workload, kernel) -> (bytes, capture)
+NCU_TRAFFIC = {
+    ("c3", "k_force"): (66.44e6, "profiles/r01_ncu_c3_v6_k_force_k_kick_drift.txt"),
+    ("c3", "k_kick_drift"): (48.01e6, "profiles/r01_ncu_c3_v6_k_force_k_kick_drift.txt"),
+    ("c3", "k_step_dilute"): (73.33e6, "profiles/r01_ncu_c3_v1_k_step_dilute.txt"),
+    ("c5", "k_force"): (250.85e6, "profiles/r01_ncu_c5_v8_k_force.txt"),
+}
 ALGO_FLOP_PAIR = 42         # flop per directed in-range pair
 ALGO_FLOP_ATOM = 30
 
@@ -253,8 +261,10 @@ def run_ours(args, w):
         achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-            "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_atom": dom_bytes, "avg_launch_ms": dom_ms,
+            "frac": achieved / hbm, "traffic": NCU_TRAFFIC.get((args.workload, dominant), (None, None))[0],
+            "traffic_source": NCU_TRAFFIC.get((args.workload, dominant), (None, None))[1], "peak_source": peak_src,
+            "algorithmic_bytes_per_atom": dom_bytes, "algorithmic_bytes_per_launch": dom_bytes * n,
+            "avg_launch_ms": dom_ms,
             "kernels_ms": {"k_step_dilute": s_ms, "k_force": f_ms, "k_kick_drift": k_ms, "rebuild": per["rebuild"]},
             "launches_timed": {k: kt[k][1] for k in kt},
         }
@@ -293,10 +303,10 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         e2e = {"value": n * args.e2e_steps / t_e2e, "unit": "atom-steps/s",
-               "h2d_bytes_per_step": 88 * n, "d2h_bytes_per_step": 88 * n + 24,
+               "h2d_bytes_per_step": (80 if t_ba else 72) * n + 24, "d2h_bytes_per_step": 88 * n + 24,
                "ms_per_step": t_e2e / args.e2e_steps * 1e3, "steps": args.e2e_steps,
-               "api": "md_calculate_host (≡ Integrator::calculate on a host State: upload x,v,F,U,W → 1 step → "
-                      "download x,v,F,U,W), pinned host buffers"}
+               "api": "md_calculate_host (≡ Integrator::calculate on a host State: upload x,v,F → 1 step → "
+                      "download x,v,F,U,W; the incoming U — and W without a barostat — are dead and not uploaded), pinned host buffers"}
     elif args.e2e_steps > 0:
         # decomposed form of the same call: every rank uploads the (pinned) host State, one collective step, every
         # rank downloads its own slab

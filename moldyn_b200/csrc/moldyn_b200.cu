@@ -1179,7 +1179,11 @@ int md_calculate_host(md_ctx *ctx, int64_t n, double *pos, double *vel, double *
     TRY(check_ctx(ctx, false));
     if (!force) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_calculate_host: force is required (the step starts "
                                                           "with a half-kick from State.force)");
-    TRY(md_upload_state(ctx, n, pos, vel, force, potential, virial, mass, box));
+    // Particle.potential of the incoming State does not enter the step (update_force zeroes it, potential.rs:160-166) and
+    // Particle.temp (the virial) only through barostat.calculate_myu's get_pressure (barostat.rs:23-29): what nothing
+    // reads is not uploaded, only written back
+    const bool need_virial = ba && ba->kind != MD_BAROSTAT_NONE;
+    TRY(md_upload_state(ctx, n, pos, vel, force, nullptr, need_virial ? virial : nullptr, mass, box));
     TRY(md_step(ctx, 1, dt, th, ba));
     return md_download_state(ctx, pos, vel, force, potential, virial, box);
 }

@@ -67,6 +67,29 @@ def test_golden_per_call_api(kats):  # cli/src/tests.rs:35-98 semantics: State i
         check_golden_step(st, g)
 
 
+def test_per_call_api_npt_matches_oracle():
+    """Integrator::calculate on a HOST State, every step, with thermostat + barostat: the incoming virial feeds
+    calculate_myu (barostat.rs:23-29), the incoming potential is dead — 25 calls must track the oracle."""
+    o = liquid(8)
+    olj = orc.LennardJones()
+    orc.update_force(olj, o, mode="cells")
+    st = to_gpu_state(md, o)
+    db = md.PotentialsDatabase()
+    oth, gth = orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, 120.0), (md.Thermostat.Berendsen(10.0), 120.0)
+    oba, gba = orc.Barostat(1.0, 5.0, 1.01325), (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
+    for _ in range(25):
+        st.potential[:] = 123.0  # dead on entry
+        md.Integrator.VerletMethod.calculate(db, st, DT, gba, gth)
+    orc.step(olj, o, DT, thermostat=oth, barostat=oba, mode="cells", n_steps=25)
+    assert np.abs(st.boundary_box / o.box - 1.0).max() <= 1e-12
+    assert abs(gba[0].myu / oba.myu - 1.0) <= 1e-12 and abs(gth[0].lambda_ / oth.lambda_ - 1.0) <= 1e-12
+    dx = np.abs(st.position - o.pos)
+    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    assert np.abs(st.potential - o.pot).max() <= 1e-9 * max(1.0, np.abs(o.pot).max())
+    assert np.abs(st.temp - o.vir).max() <= 1e-9 * max(1.0, np.abs(o.vir).max())
+
+
 def test_golden_1000_iterations_and_macro(kats, mode):  # solver/src/lib.rs:264-332
     st, k = two_body(kats)
     g = kats["verlet_lj_1000_iterations"]
