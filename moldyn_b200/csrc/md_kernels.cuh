@@ -1117,23 +1117,29 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
     cp_async_wait_all();
 }
 
-// Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
-// before the first use, and the neighbour loop advances both lists together (independent gather chains) with the
-// next rows of partner indices prefetched while the current ones are in flight.
-//   ROWS = 2: two list rows per trip (dense systems; 12 gathers in flight, 128 registers)
-//   ROWS = 1: one row per trip (dilute systems: few partners, occupancy matters more than unrolling)
-template <bool EXACT, int ROWS, bool MASKED>
-__global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
-    k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
-            double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
-            unsigned long long cond_handle, const ForceConsts fc, const Peers *peers)
+// ----------------------------------------------------------------------------------------------------
+// K3 for dilute systems, FAST mode: k_force_sparse (opt-in experiment, MOLDYN_B200_SPARSE=1 — slower than k_force on B200).
+// In a 300 K argon gas ~78 % of the atoms have NO listed partner (even with skin = r_cut), but with two atoms per thread
+// and 32 threads per warp every warp of k_force still walks the whole gather path with most lanes idle.  Here the work
+// is split by atom class, inside one launch and with the same persistent grid:
+//   phase S  every atom WITHOUT partners: F = 0, so neither its position nor the list is read — 28 B in (u, count),
+//            24 B out per atom, two independent pairs of atoms in flight per thread;
+//   phase A  the atoms WITH partners, through the compacted index list built at the last rebuild (k_flag_active + scan):
+//            one atom per thread, every lane has real gather work.
+// The arithmetic of an atom is the same finish_atom() as everywhere else (with F = 0 for phase S), the atom → thread map is
+// fixed by the grid, so results stay run-to-run reproducible.
+__global__ void k_flag_active(int n, const int *__restrict__ nbr_cnt, int *__restrict__ flag)
 {
-    // do_step bits: 1 = MD step (both half-kicks fused in), 2 = multi-GPU (publish rank sums only), 4 = guarded,
-    //               8 = multi-GPU over peer memory (sums exchanged and finalized here), 16 = wait for the neighbours' ghosts
-    if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = nbr_cnt[i] > 0 ? 1 : 0;
+}
+
+// shared by the force kernels: guarded early-out, phase clock, wait for the neighbours' ghosts (peer-memory path)
+__device__ __forceinline__ bool force_prologue(int do_step, Scalars *sc, const Peers *peers)
+{
+    if ((do_step & 4) && halted(sc)) return false;  // uniform over the grid: nobody takes a ticket
     if ((do_step & 8) && threadIdx.x == 0) atomicMin(&sc->t_start, gtime());
     if (do_step & 16) {
-        // ghost positions of this step are pushed into our planes by the neighbours' k_halo_push
         __shared__ int halo_late;
         if (threadIdx.x == 0) {
             const unsigned long long seq = sc->epoch + 1;
@@ -1151,6 +1157,139 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
         __syncthreads();
         if (halo_late && threadIdx.x == 0) atomicExch(&sc->error, 3);
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(FORCE_BLOCK, 5)
+    k_force_sparse(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad,
+                   const int *__restrict__ active_idx, const int *__restrict__ n_active_p, double *__restrict__ partials,
+                   Scalars *sc, const Params *__restrict__ pr, int do_step, unsigned long long cond_handle,
+                   const ForceConsts fc, const Peers *peers)
+{
+    if (!force_prologue(do_step, sc, peers)) return;
+    __shared__ SumsSmem ss;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) ss.v[q][threadIdx.x] = 0.0;
+    const bool step = (do_step & 1) != 0;
+    const bool store_state = !step || sc->steps_left <= 1;
+    const bool nh = pr->th_kind == 2 || !step;
+    const double lambda = sc->lambda;
+    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    const PairAcc zero = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int tstride = gridDim.x * FORCE_BLOCK;
+
+    // ---- phase S: atoms without partners ---------------------------------------------------------------------------
+    const int npairs = (n + 1) >> 1;
+    for (int t0 = blockIdx.x * FORCE_BLOCK + threadIdx.x; t0 < npairs; t0 += 2 * tstride) {
+        // two pairs of atoms per trip: all loads first
+        const int t1 = t0 + tstride;
+        const bool two = t1 < npairs;
+        int2 C[2];
+        double2 VX[2], VY[2], VZ[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = u ? t1 : t0;
+            if (u == 0 || two) {
+                C[u] = reinterpret_cast<const int2 *>(nbr_cnt)[t];
+                VX[u] = reinterpret_cast<const double2 *>(a.vx)[t]; VY[u] = reinterpret_cast<const double2 *>(a.vy)[t];
+                VZ[u] = reinterpret_cast<const double2 *>(a.vz)[t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = u ? t1 : t0;
+            if (u == 1 && !two) break;
+            const int i0 = 2 * t;
+            const bool has1 = i0 + 1 < n;
+            const bool s0 = C[u].x == 0, s1 = has1 && C[u].y == 0;  // this phase's atoms
+            double2 WX, WY, WZ;
+            WX.x = WY.x = WZ.x = WX.y = WY.y = WZ.y = 0.0;
+            if (s0) finish_atom(ss, zero, VX[u].x, VY[u].x, VZ[u].x, step, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
+            if (s1) finish_atom(ss, zero, VX[u].y, VY[u].y, VZ[u].y, step, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y, nh);
+            if (s0 && s1) {
+                if (store_state) {
+                    const double2 z2 = make_double2(0.0, 0.0);
+                    reinterpret_cast<double2 *>(a.fx)[t] = z2; reinterpret_cast<double2 *>(a.fy)[t] = z2;
+                    reinterpret_cast<double2 *>(a.fz)[t] = z2; reinterpret_cast<double2 *>(a.u)[t] = z2;
+                    reinterpret_cast<double2 *>(a.w)[t] = z2;
+                    if (step) {
+                        reinterpret_cast<double2 *>(a.vx)[t] = VX[u]; reinterpret_cast<double2 *>(a.vy)[t] = VY[u];
+                        reinterpret_cast<double2 *>(a.vz)[t] = VZ[u];
+                    }
+                } else {
+                    reinterpret_cast<double2 *>(a.vx)[t] = WX; reinterpret_cast<double2 *>(a.vy)[t] = WY;
+                    reinterpret_cast<double2 *>(a.vz)[t] = WZ;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!(h ? s1 : s0)) continue;
+                    const int i = i0 + h;
+                    const double vx = h ? VX[u].y : VX[u].x, vy = h ? VY[u].y : VY[u].x, vz = h ? VZ[u].y : VZ[u].x;
+                    const double wx = h ? WX.y : WX.x, wy = h ? WY.y : WY.x, wz = h ? WZ.y : WZ.x;
+                    if (store_state) {
+                        a.fx[i] = 0.0; a.fy[i] = 0.0; a.fz[i] = 0.0; a.u[i] = 0.0; a.w[i] = 0.0;
+                        if (step) { a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz; }
+                    } else {
+                        a.vx[i] = wx; a.vy[i] = wy; a.vz[i] = wz;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- phase A: atoms with partners, one per thread ---------------------------------------------------------------
+    LjConst c;
+    c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
+    c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
+    c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
+    const double *__restrict__ px = a.x, *__restrict__ py = a.y, *__restrict__ pz = a.z;
+    const int n_active = *n_active_p;
+    for (int k = blockIdx.x * FORCE_BLOCK + threadIdx.x; k < n_active; k += tstride) {
+        const int i = active_idx[k];
+        const double xi = px[i], yi = py[i], zi = pz[i];
+        double vx = a.vx[i], vy = a.vy[i], vz = a.vz[i];
+        const int cnt = nbr_cnt[i];
+        int j = nbr[i];  // row 0
+        PairAcc f = zero;
+        for (int kk = 0; kk < cnt; ++kk) {
+            const int jn = kk + 1 < cnt ? nbr[(size_t)(kk + 1) * npad + i] : 0;
+            pair_fast_branchy(f, true, px[j], py[j], pz[j], xi, yi, zi, c, fc);
+            j = jn;
+        }
+        double wx, wy, wz;
+        finish_atom(ss, f, vx, vy, vz, step, lambda, fc.hc, fc.mass, shift, wx, wy, wz, nh);
+        if (store_state) {
+            a.fx[i] = f.fx; a.fy[i] = f.fy; a.fz[i] = f.fz; a.u[i] = f.u; a.w[i] = f.w;
+            if (step) { a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz; }
+        } else {
+            a.vx[i] = wx; a.vy[i] = wy; a.vz[i] = wz;
+        }
+    }
+
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][threadIdx.x];
+    block_reduce<FORCE_BLOCK>(s);
+    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr,
+                                      (step ? FIN_STEP : 0) | (do_step & 2 ? FIN_DIST : 0) | (do_step & 8 ? FIN_P2P : 0),
+                                      cond_handle, peers);
+}
+
+// Two consecutive atoms per thread: every plane access is one 128-bit transaction, all of a pair's loads are issued
+// before the first use, and the neighbour loop advances both lists together (independent gather chains) with the
+// next rows of partner indices prefetched while the current ones are in flight.
+//   ROWS = 2: two list rows per trip (dense systems; 12 gathers in flight, 128 registers)
+//   ROWS = 1: one row per trip (dilute systems: few partners, occupancy matters more than unrolling)
+template <bool EXACT, int ROWS, bool MASKED>
+__global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
+    k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
+            double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
+            unsigned long long cond_handle, const ForceConsts fc, const Peers *peers)
+{
+    // do_step bits: 1 = MD step (both half-kicks fused in), 2 = multi-GPU (publish rank sums only), 4 = guarded,
+    //               8 = multi-GPU over peer memory (sums exchanged and finalized here), 16 = wait for the neighbours' ghosts
+    if (!force_prologue(do_step, sc, peers)) return;
     if (threadIdx.x == 0) { PROBE_MIN(0); }
     __shared__ SumsSmem ss;
 #pragma unroll
