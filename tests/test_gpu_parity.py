@@ -292,6 +292,45 @@ def test_nose_hoover_trajectory(name, mode):  # thermostat.rs:35-39, 59-65 (SURV
     assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
 
 
+@pytest.mark.parametrize("ensemble", ["nvt", "npt"])
+def test_long_run_statistics_match_oracle(ensemble):
+    """over long thermostat/barostat runs trajectories diverge chaotically, so the gate is statistical —
+    <T>, <P> and their spreads over the second half of a 3000-step run must agree with the oracle's run from the same
+    frame 0 within the sampling error; total momentum must not drift.  (512 atoms keep the CPU oracle's share short.)"""
+    o = liquid(8)
+    olj = orc.LennardJones()
+    st = to_gpu_state(md, o)
+    oth, gth = orc.Thermostat(orc.Thermostat.BERENDSEN, 1.0, 120.0), (md.Thermostat.Berendsen(1.0), 120.0)
+    oba = gba = None
+    if ensemble == "npt":
+        oba, gba = orc.Barostat(1.0, 5.0, 1.01325), (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
+    n_steps, every = 3000, 20
+    gt, gp, ot, op_ = [], [], [], []
+    with md.Solver() as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        for k in range(n_steps // every):
+            s.step(every, DT, thermostat=gth, barostat=gba)
+            if k >= n_steps // every // 2:
+                m = s.macro()
+                gt.append(m["temperature"]); gp.append(m["pressure"])
+        mom = np.abs(s.macro()["momentum"]).max()
+    orc.update_force(olj, o, mode="cells")
+    for k in range(n_steps // every):
+        orc.step(olj, o, DT, thermostat=oth, barostat=oba, mode="cells", n_steps=every)
+        if k >= n_steps // every // 2:
+            m = orc.macro(o)
+            ot.append(m["temperature"]); op_.append(m["pressure"])
+    gt, gp, ot, op_ = map(np.array, (gt, gp, ot, op_))
+    # 75 samples 20 steps apart: allow the mean to differ by half a standard deviation of the samples (several standard
+    # errors of the mean even for strongly correlated samples), the spreads by a factor 2
+    assert abs(gt.mean() - ot.mean()) <= 0.5 * ot.std() + 1e-9, (gt.mean(), ot.mean(), ot.std())
+    assert abs(gp.mean() - op_.mean()) <= 0.5 * op_.std() + 1e-9, (gp.mean(), op_.mean(), op_.std())
+    assert 0.5 <= gt.std() / ot.std() <= 2.0 and 0.5 <= gp.std() / op_.std() <= 2.0
+    assert abs(gt.mean() - 120.0) < 4.0
+    assert mom < 1e-9
+
+
 def test_graph_loop_equals_host_loop(mode):
     o = liquid(10)
     out = []
