@@ -69,6 +69,7 @@ struct Scalars {
     int nbr_max;       // largest neighbour count of the last build
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
+    int out_of_box;    // the last cell binning saw a coordinate outside [0, L): list builds use the generic minimum image
     int parity;        // fused one-kernel steps ping-pong x and v between two plane sets: which set is current
     unsigned long long epoch;  // multi-GPU peer-memory path: sequence number of the last finalized collective reduction
     unsigned long long wait_halo_ns, wait_sums_ns;  // time spent polling the mailboxes (block 0 / last block), accumulated
@@ -197,7 +198,7 @@ __device__ __forceinline__ int cell_coord(double x, double L, int nc)
 }
 
 __global__ void k_cell_count(int n, const double *__restrict__ x, const double *__restrict__ y,
-                             const double *__restrict__ z, const Scalars *__restrict__ sc, Grid g,
+                             const double *__restrict__ z, Scalars *sc, Grid g,
                              int *__restrict__ cell_of, int *__restrict__ cell_cnt)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +209,11 @@ __global__ void k_cell_count(int n, const double *__restrict__ x, const double *
     int c = (cx * g.nc[1] + cy) * g.nc[2] + cz;
     cell_of[i] = c;
     atomicAdd(&cell_cnt[c], 1);
+    // (inside md_step the drift kernel keeps every coordinate in [0, L); an uploaded State may hold anything)
+    const double xx = x[i], yy = y[i], zz = z[i];
+    if (xx < 0.0 || xx >= sc->box[0] || yy < 0.0 || yy >= sc->box[1] || zz < 0.0 || zz >= sc->box[2] || xx != xx ||
+        yy != yy || zz != zz)
+        sc->out_of_box = 1;
 }
 
 // Exclusive scan of cell counts: per-block scan (1024 items) → scan of block totals → add back.
@@ -333,7 +339,11 @@ __global__ void k_reorder(int n, const int *__restrict__ order, const int *__res
 // reference min-image distance is <= r_list — the predicate of potential.rs:181-204 widened by the skin,
 // evaluated in the reference's exact arithmetic so the pair set is the reference's, bit for bit.
 // Table layout nbr[k * npad + p]: a warp reads one coalesced row per k.
-template <bool SORT_BY_ID>
+// SHIFT: every dimension has at least 2*nsub + 3 cells.  Then a stencil cell that was wrapped around the box holds exactly
+// the partners the reference's single-shift rule moves by -/+L (|x_q - x_i| > L/2 there and < L/2 everywhere else), so the
+// image shift is a constant of the cell run — added with the reference's own operation (r + L, r - L; adding 0.0 is exact) —
+// and the two compares per axis and candidate of min_image() disappear from the inner loop (~100 → ~30 instructions).
+template <bool SORT_BY_ID, bool SHIFT>
 __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *__restrict__ cell_sorted,
                                                     const int *__restrict__ cell_start, Scalars *sc, Grid g,
                                                     double r_list, double r2_list, int *__restrict__ nbr,
@@ -364,12 +374,17 @@ __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *
             else if (hi > ncz) { z0a = lo; z1a = ncz; z0b = 0; z1b = hi - ncz; }
             else { z0a = lo; z1a = hi; }
         } else { z0a = 0; z1a = ncz; }
+        const bool in_box = sc->out_of_box == 0;
+        // which z run holds the wrapped cells, and which way the reference's rule shifts their atoms
+        const double szb = (ncz >= w && cz - g.nsub < 0) ? -Lz : Lz;
         for (int ia = 0; ia < nx; ++ia) {
             int qx = lox + ia;
+            const double sx = qx < 0 ? -Lx : (qx >= ncx ? Lx : 0.0);
             qx += (qx < 0) ? ncx : 0;
             qx -= (qx >= ncx) ? ncx : 0;
             for (int ib = 0; ib < ny; ++ib) {
                 int qy = loy + ib;
+                const double sy = qy < 0 ? -Ly : (qy >= ncy ? Ly : 0.0);
                 qy += (qy < 0) ? ncy : 0;
                 qy -= (qy >= ncy) ? ncy : 0;
                 const int base = (qx * ncy + qy) * ncz;
@@ -379,15 +394,29 @@ __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *
 #pragma unroll 1
                 for (int run = 0; run < 2; ++run) {
                     const int s = run ? sb : sa, e = run ? eb : ea;
-                    for (int q = s; q < e; ++q) {
-                        double rx = min_image(__dsub_rn(a.x[q], xi), Lx, hx);
-                        if (fabs(rx) > r_list) continue;
-                        double ry = min_image(__dsub_rn(a.y[q], yi), Ly, hy);
-                        double rz = min_image(__dsub_rn(a.z[q], zi), Lz, hz);
-                        double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                        if (r2 > r2_list || q == p) continue;
-                        if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
-                        ++cnt;
+                    if (SHIFT && in_box) {
+                        const double sz = run ? szb : 0.0;
+                        for (int q = s; q < e; ++q) {
+                            const double rx = __dadd_rn(__dsub_rn(a.x[q], xi), sx);
+                            if (fabs(rx) > r_list) continue;
+                            const double ry = __dadd_rn(__dsub_rn(a.y[q], yi), sy);
+                            const double rz = __dadd_rn(__dsub_rn(a.z[q], zi), sz);
+                            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                            if (r2 > r2_list || q == p) continue;
+                            if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
+                            ++cnt;
+                        }
+                    } else {
+                        for (int q = s; q < e; ++q) {
+                            double rx = min_image(__dsub_rn(a.x[q], xi), Lx, hx);
+                            if (fabs(rx) > r_list) continue;
+                            double ry = min_image(__dsub_rn(a.y[q], yi), Ly, hy);
+                            double rz = min_image(__dsub_rn(a.z[q], zi), Lz, hz);
+                            double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                            if (r2 > r2_list || q == p) continue;
+                            if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
+                            ++cnt;
+                        }
                     }
                 }
             }
@@ -1780,6 +1809,7 @@ __global__ void k_after_rebuild(Scalars *sc)
     sc->disp_next = 0.0;
     sc->inv_scale = 1.0;
     sc->need_rebuild = 0;
+    sc->out_of_box = 0;
 }
 
 __global__ void k_prepare(Scalars *sc, const Params *pr, long long n_steps, double psi)

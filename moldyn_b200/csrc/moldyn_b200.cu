@@ -460,14 +460,19 @@ int rebuild_lists(md_ctx *ctx)
     const double r2_list = sqrt_threshold(ctx->prm.r_list);
     for (int attempt = 0; attempt < 4; ++attempt) {
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
-        if (ctx->cfg.force_mode == MD_FORCE_EXACT)
-            k_build_list<true><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
-                                                                   ctx->d_sc, g, ctx->prm.r_list, r2_list, ctx->nbr,
-                                                                   ctx->nbr_cnt);
-        else
-            k_build_list<false><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,
-                                                                    ctx->d_sc, g, ctx->prm.r_list, r2_list, ctx->nbr,
-                                                                    ctx->nbr_cnt);
+        // image shift per cell run instead of per candidate when the box is wide enough in cells (see k_build_list)
+        const int need_cells = 2 * g.nsub + 3;
+        const bool shift = g.nc[0] >= need_cells && g.nc[1] >= need_cells && g.nc[2] >= need_cells;
+#define LAUNCH_BUILD(SORT, SHIFT)                                                                                     \
+    k_build_list<SORT, SHIFT><<<blocks_for(n, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start,     \
+                                                                 ctx->d_sc, g, ctx->prm.r_list, r2_list, ctx->nbr,   \
+                                                                 ctx->nbr_cnt)
+        if (ctx->cfg.force_mode == MD_FORCE_EXACT) {
+            if (shift) LAUNCH_BUILD(true, true); else LAUNCH_BUILD(true, false);
+        } else {
+            if (shift) LAUNCH_BUILD(false, true); else LAUNCH_BUILD(false, false);
+        }
+#undef LAUNCH_BUILD
         ctx->stats.kernel_launches += 2;
         CK(cudaGetLastError());
         TRY(pull_scalars(ctx));
