@@ -380,8 +380,9 @@ def run_ours(args, w):
         mine = {k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds", "peer_memory")}
         mine["wait_halo_us_per_step"] = (st1["wait_halo_ms"] - st0["wait_halo_ms"]) * 1e3 / args.steps
         mine["wait_sums_us_per_step"] = (st1["wait_sums_ms"] - st0["wait_sums_ms"]) * 1e3 / args.steps
-        for k in ("force_atoms", "force_tail", "drift_push"):
+        for k in ("force_atoms", "force_tail"):
             mine[k + "_us_per_step"] = (st1[k + "_ms"] - st0[k + "_ms"]) * 1e3 / args.steps
+        mine["rebuild_ms_each"] = (st1["drift_push_ms"] - st0["drift_push_ms"]) / max(st1["rebuilds"] - st0["rebuilds"], 1)
         dist.gather_object(mine, alls, dst=0)
         out["per_rank"] = alls
     if rank == 0:

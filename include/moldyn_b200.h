@@ -129,7 +129,7 @@ typedef struct md_stats {
     int32_t reserved1;
     double force_atoms_ms;    /* peer-memory path diagnostics: k_force first block start -> all atoms done,               */
     double force_tail_ms;     /*   -> mailbox exchange + finalize done,                                                  */
-    double drift_push_ms;     /*   k_kick_drift start -> neighbours' flags raised (last pushing block)                   */
+    double drift_push_ms;     /*   multi-GPU: wall time spent in list rebuilds so far (host clock around dist_rebuild)    */
 } md_stats;
 
 typedef struct md_ctx md_ctx;
