@@ -145,8 +145,9 @@ def cpu_reference_rate(w, sample_rows, threads=None):
     workload's own positions against ALL N partners → atoms/s of force evaluation ≈ atom-steps/s of the CPU
     solver (the Θ(N) parts of the step are negligible at these N)."""
     from oracle import oracle as orc
-    if threads:
-        orc.set_num_threads(threads)
+    # all the host threads the box offers — torchrun exports OMP_NUM_THREADS=1 to every rank, which is not what a CPU
+    # baseline should be measured with
+    orc.set_num_threads(threads or len(os.sched_getaffinity(0)))
     pos, vel, box = make_state(w)
     st = orc.State(pos, vel, ARGON_MASS, box)
     lj = orc.LennardJones() if w["cut"] is None else orc.LennardJones(r_cut=w["cut"][0], u_cut=w["cut"][1])
