@@ -56,7 +56,7 @@ def build_cli(force: bool = False) -> str:
         return CLI
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", CLI, *HOST_SRC, "-L", os.path.dirname(LIB),
-           "-lmoldyn_b200", "-Wl,-rpath,$ORIGIN"]
+           "-lmoldyn_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
     subprocess.check_call(cmd)
     return CLI
 

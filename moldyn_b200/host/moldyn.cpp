@@ -7,6 +7,11 @@
 
 #include <algorithm>
 #include <charconv>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -230,34 +235,17 @@ static std::vector<Vector3> get_bbs(const std::string &path)
     return bbs;
 }
 
-void StateToSave::save_to_file(const std::string &dir, size_t state_number) const
+// data/<n>.csv of one frame (save_data.rs:186-213)
+static void write_frame_csv(const StateToSave &st, const std::string &dir, size_t state_number)
 {
-    make_dirs(dir);
-    // bb.csv: row n = boundary box of frame n (save_data.rs:165-184).  The reference re-reads and re-writes the
-    // whole file per frame; appending is equivalent when the frame is the next row.
-    const std::string bb_path = dir + "/bb.csv";
-    std::vector<Vector3> bbs;
-    if (file_exists(bb_path)) bbs = get_bbs(bb_path);
-    if (bbs.size() > state_number) {
-        bbs[state_number] = boundary_box;
-        std::ofstream f(bb_path, std::ios::trunc);
-        f << "x,y,z\n";
-        for (auto &b : bbs) f << format_f64(b[0]) << ',' << format_f64(b[1]) << ',' << format_f64(b[2]) << '\n';
-    } else {
-        bool fresh = !file_exists(bb_path) || bbs.empty();
-        std::ofstream f(bb_path, fresh ? std::ios::trunc : std::ios::app);
-        if (fresh) f << "x,y,z\n";
-        f << format_f64(boundary_box[0]) << ',' << format_f64(boundary_box[1]) << ',' << format_f64(boundary_box[2])
-          << '\n';
-    }
     make_dirs(dir + "/data");
     const std::string path = dir + "/data/" + std::to_string(state_number) + ".csv";
     std::unique_ptr<FILE, int (*)(FILE *)> f(std::fopen(path.c_str(), "w"), std::fclose);
     if (!f) throw Error(MD_ERR_INVALID_ARGUMENT, "Can't write to file " + path);
     std::string buf;
-    buf.reserve(particles.size() * 140 + 128);
+    buf.reserve(st.particles.size() * 140 + 128);
     buf += "id,position_x,position_y,position_z,velocity_x,velocity_y,velocity_z\n";
-    for (auto &p : particles) {
+    for (auto &p : st.particles) {
         buf += std::to_string(p.id);
         for (double v : {p.position_x, p.position_y, p.position_z, p.velocity_x, p.velocity_y, p.velocity_z}) {
             buf.push_back(',');
@@ -267,6 +255,112 @@ void StateToSave::save_to_file(const std::string &dir, size_t state_number) cons
     }
     if (std::fwrite(buf.data(), 1, buf.size(), f.get()) != buf.size())
         throw Error(MD_ERR_INVALID_ARGUMENT, "Can't write");
+}
+
+// bb.csv: row n = boundary box of frame n (save_data.rs:165-184).  `bbs` is the file's content as known to the caller; the
+// reference re-reads and re-writes the whole file per frame, appending is equivalent when the frame is the next row.
+static void write_bb_row(std::vector<Vector3> &bbs, const std::string &dir, size_t state_number, const Vector3 &box)
+{
+    const std::string bb_path = dir + "/bb.csv";
+    if (bbs.size() > state_number) {
+        bbs[state_number] = box;
+        std::ofstream f(bb_path, std::ios::trunc);
+        f << "x,y,z\n";
+        for (auto &b : bbs) f << format_f64(b[0]) << ',' << format_f64(b[1]) << ',' << format_f64(b[2]) << '\n';
+    } else {
+        const bool fresh = !file_exists(bb_path) || bbs.empty();
+        std::ofstream f(bb_path, fresh ? std::ios::trunc : std::ios::app);
+        if (fresh) f << "x,y,z\n";
+        f << format_f64(box[0]) << ',' << format_f64(box[1]) << ',' << format_f64(box[2]) << '\n';
+        bbs.push_back(box);
+    }
+}
+
+void StateToSave::save_to_file(const std::string &dir, size_t state_number) const
+{
+    make_dirs(dir);
+    const std::string bb_path = dir + "/bb.csv";
+    std::vector<Vector3> bbs;
+    if (file_exists(bb_path)) bbs = get_bbs(bb_path);
+    write_bb_row(bbs, dir, state_number, boundary_box);
+    write_frame_csv(*this, dir, state_number);
+}
+
+struct FrameWriter::Impl {
+    std::string dir;
+    size_t depth;
+    std::vector<Vector3> bbs;
+    std::deque<std::pair<size_t, StateToSave>> queue;
+    std::mutex m;
+    std::condition_variable cv_push, cv_pop;
+    bool closing = false, busy = false;
+    std::exception_ptr error;
+    std::thread worker;
+
+    void run()
+    {
+        for (;;) {
+            std::pair<size_t, StateToSave> item;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_pop.wait(lk, [&] { return closing || !queue.empty(); });
+                if (queue.empty()) return;
+                item = std::move(queue.front());
+                queue.pop_front();
+                busy = true;
+            }
+            try {
+                write_bb_row(bbs, dir, item.first, item.second.boundary_box);
+                write_frame_csv(item.second, dir, item.first);
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(m);
+                if (!error) error = std::current_exception();
+            }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                busy = false;
+            }
+            cv_push.notify_all();
+        }
+    }
+};
+
+FrameWriter::FrameWriter(std::string dir, size_t depth) : impl_(new Impl)
+{
+    impl_->dir = std::move(dir);
+    impl_->depth = depth ? depth : 1;
+    make_dirs(impl_->dir);
+    const std::string bb_path = impl_->dir + "/bb.csv";
+    if (file_exists(bb_path)) impl_->bbs = get_bbs(bb_path);
+    impl_->worker = std::thread([this] { impl_->run(); });
+}
+
+FrameWriter::~FrameWriter()
+{
+    {
+        std::lock_guard<std::mutex> lk(impl_->m);
+        impl_->closing = true;
+    }
+    impl_->cv_pop.notify_all();
+    if (impl_->worker.joinable()) impl_->worker.join();
+    delete impl_;
+}
+
+void FrameWriter::push(size_t state_number, StateToSave frame)
+{
+    std::unique_lock<std::mutex> lk(impl_->m);
+    impl_->cv_push.wait(lk, [&] { return impl_->error || impl_->queue.size() < impl_->depth; });
+    if (impl_->error) std::rethrow_exception(impl_->error);
+    impl_->queue.emplace_back(state_number, std::move(frame));
+    lk.unlock();
+    impl_->cv_pop.notify_all();
+}
+
+void FrameWriter::finish()
+{
+    std::unique_lock<std::mutex> lk(impl_->m);
+    impl_->cv_push.wait(lk, [&] { return impl_->queue.empty() && !impl_->busy; });
+    if (impl_->error) std::rethrow_exception(impl_->error);
 }
 
 StateToSave StateToSave::load_from_file(const std::string &dir, size_t state_number)

@@ -85,6 +85,21 @@ struct StateToSave {
     static StateToSave load_from_file(const std::string &dir, size_t state_number);  // save_data.rs:215-230
 };
 
+// Frame output off the critical path: `solve` hands every downloaded frame to a writer thread and goes on
+// stepping on the GPU while the CSV text is produced; at most `depth` frames wait in memory.  The frames on disk are exactly
+// what StateToSave::save_to_file writes (save_data.rs:191-213); bb.csv is read once and then kept in memory instead of being
+// re-read for every frame (the reference's Θ(frames²) rewrite, save_data.rs:165-184).
+class FrameWriter {
+public:
+    FrameWriter(std::string dir, size_t depth = 2);
+    ~FrameWriter();                                   // joins; errors of the writer thread are dropped here
+    void push(size_t state_number, StateToSave frame);  // blocks while `depth` frames are pending; rethrows writer errors
+    void finish();                                    // waits for everything to be on disk; rethrows writer errors
+private:
+    struct Impl;
+    Impl *impl_;
+};
+
 // Shortest round-trip decimal in the layout of the `ryu` crate the reference's csv writer uses ("1.0", "1e-7").
 std::string format_f64(double v);
 

@@ -179,16 +179,19 @@ void cmd_solve(const std::string &dir, Args &a, size_t frames_per_save)
     s.upload(state, false);
     s.update_force();  // commands.rs:102
     if (frames_per_save == 0) frames_per_save = 1;
+    // frames go to a writer thread: the GPU steps the next chunk while the previous frame's CSV text is produced
     size_t frame = state_number, done = 0;
+    FrameWriter writer(dir, 2);
     while (done < iteration_count) {
         s.download(state);
-        StateToSave::from(state).save_to_file(dir, frame++);
+        writer.push(frame++, StateToSave::from(state));
         size_t chunk = std::min(frames_per_save, iteration_count - done);
         s.step((int64_t)chunk, dt, use_ba ? &bap : nullptr, use_th ? &thp : nullptr);
         done += chunk;
     }
     s.download(state);
-    StateToSave::from(state).save_to_file(dir, frame);
+    writer.push(frame, StateToSave::from(state));
+    writer.finish();
     md_stats stt = s.stats();
     std::fprintf(stderr, "Calculated. steps=%lld rebuilds=%lld kernel_launches=%lld\n", (long long)stt.steps,
                  (long long)stt.rebuilds, (long long)stt.kernel_launches);
@@ -275,6 +278,24 @@ int main(int argc, char **argv)
             ParticleDatabase::load_particles_data(dir);
             print_momentum(dir, 0, "First frame");
             print_momentum(dir, last_frame(dir), "Last frame");
+        } else if (command == "copy-frames") {
+            // extension (no GPU needed): frame -s is written again as the following -c frames through the asynchronous
+            // frame writer `solve` uses — exercises the writer thread, its back-pressure and the cached bb.csv
+            size_t from = 0, count = 0;
+            while (!a.done()) {
+                std::string o = a.next("option");
+                if (is(o, "-s", "--state-number")) from = std::stoul(a.next(o));
+                else if (is(o, "-c", "--iteration-count")) count = std::stoul(a.next(o));
+                else usage("unknown option for copy-frames: " + o);
+            }
+            StateToSave data = StateToSave::load_from_file(dir, from);
+            FrameWriter writer(dir, 2);
+            for (size_t k = 1; k <= count; ++k) {
+                StateToSave copy = data;
+                copy.boundary_box[0] = data.boundary_box[0] + (double)k;  // every row of bb.csv distinguishable
+                writer.push(from + k, std::move(copy));
+            }
+            writer.finish();
         } else if (command == "particle-count") {
             ParticleDatabase::load_particles_data(dir);
             std::printf("Particle count: %zu\n", StateToSave::load_from_file(dir, 0).into_state().count());

@@ -96,6 +96,26 @@ def test_potentials_file_commands(cli, tmp_path):  # cli/src/commands.rs:21-41
     assert set(data) == {"0,0", "0,1"} and data["0,1"]["LennardJones"]["r_cut"] == 0.34 * 2.5
 
 
+def test_async_frame_writer(cli, tmp_path):
+    """`solve` hands frames to a writer thread.  `copy-frames` drives the same FrameWriter without a GPU:
+    frames must land on disk byte-identical to the synchronous writer's, bb.csv must get one row per frame, in order."""
+    d = str(tmp_path / "run")
+    run(cli, "-f", d, "initialize", "-t", "u", "-s", 6, 6, 6, "-n", "Argon", "-m", 66.335, "-r", 0.071,
+        "-l", 3.338339, "-T", 273.15, "--seed", 3)
+    frame0 = open(os.path.join(d, "data", "0.csv")).read()
+    run(cli, "-f", d, "copy-frames", "-s", 0, "-c", 7)
+    for k in range(1, 8):
+        assert open(os.path.join(d, "data", f"{k}.csv")).read() == frame0
+    with open(os.path.join(d, "bb.csv")) as f:
+        rows = [[float(r[a]) for a in "xyz"] for r in csv.DictReader(f)]
+    assert len(rows) == 8
+    assert [r[0] - rows[0][0] for r in rows] == [float(k) for k in range(8)]
+    # a second run overwrites rows 1..3 in place (save_data.rs:170-176 semantics) and keeps the rest
+    run(cli, "-f", d, "copy-frames", "-s", 0, "-c", 3)
+    with open(os.path.join(d, "bb.csv")) as f:
+        assert len(list(csv.DictReader(f))) == 8
+
+
 def test_solve_without_gpu_fails_loudly(cli, tmp_path, kats):
     import torch
     if torch.cuda.is_available():
