@@ -159,6 +159,16 @@ MD_API int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const doub
 MD_API int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, double *potential,
                              double *virial, double box[3]);
 
+/* Device-side initializer: builds the State on the GPU instead of uploading it.
+ * UnitCell::{U,FCC}.initialize_particles_position (solver/src/initializer/position.rs:24-104; positions bit-identical)
+ * + initialize_velocities_maxwell_boltzmann (velocity.rs:6-29; the reference's RNG is unseeded, so the velocities match in
+ * distribution: first half sigma*N(0,1), second half the negated copy).  boundary_box = unit_cell * size, like
+ * `moldyn_cli initialize` (cli/src/commands.rs:43-80).  start may be NULL (= origin). */
+#define MD_CELL_UNIFORM 0
+#define MD_CELL_FCC 1
+MD_API int md_initialize_lattice(md_ctx *ctx, int cell_type, const int32_t size[3], const double start[3],
+                                 double unit_cell, double mass, double temperature, uint64_t seed);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* update_force(&potentials_db, &mut state) (potential.rs:158-216) on the resident state. */
 MD_API int md_update_force(md_ctx *ctx);

@@ -16,6 +16,7 @@ UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT = 0, 1
 LOOP_GRAPH, LOOP_HOST = 0, 1
 STEP_AUTO, STEP_SPLIT, STEP_FUSED = 0, 1, 2
+CELL_UNIFORM, CELL_FCC = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
 BAROSTAT_NONE, BAROSTAT_BERENDSEN = 0, 1
 
@@ -65,6 +66,7 @@ SYMBOLS = [
     "md_update_force_host", "md_calculate_host", "md_download_cells", "md_neighbour_counts",
     "md_neighbour_lists", "md_get_stats", "md_stream", "md_synchronize", "md_invalidate_lists", "md_time_kernels",
     "md_comm_unique_id", "md_comm_init", "md_local_count", "md_download_local", "md_plan_decomposition",
+    "md_initialize_lattice",
 ]
 
 _lib = None
@@ -114,6 +116,7 @@ def lib():
             "md_download_local": (C.c_int, [vp, pd, pd, pd, pd, pd, pd, pd]),
             "md_plan_decomposition": (C.c_int, [i64, pd, f64, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64),
                                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
+            "md_initialize_lattice": (C.c_int, [vp, C.c_int, pd, pd, f64, f64, f64, C.c_uint64]),
         }
         assert set(sig) == set(SYMBOLS)
         for name, (res, args) in sig.items():

@@ -1831,6 +1831,66 @@ __global__ void k_set_shift_to_vcom(Scalars *sc)
     sc->shift[0] = sc->vcom[0]; sc->shift[1] = sc->vcom[1]; sc->shift[2] = sc->vcom[2];
 }
 
+// ---- device-side initializer ---------------------------------------------------------
+// UnitCell::{U, FCC}.initialize_particles_position (solver/src/initializer/position.rs:24-104): cell (x, y, z) has index
+// x*sy*sz + y*sz + z; U puts one atom at start + (x, y, z)*l, FCC four atoms at the corner and the three face centres
+// (x, y+.5, z+.5), (x+.5, y, z+.5), (x+.5, y+.5, z), in this order.  Same operations as the reference: bit-identical.
+__global__ void k_init_lattice(int cells, int fcc, int sx, int sy, int sz, double x0, double y0, double z0, double l, Arrays a)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int z = c % sz, y = (c / sz) % sy, x = c / (sz * sy);
+    (void)sx;
+    const double fx = (double)x, fy = (double)y, fz = (double)z;
+    if (!fcc) {
+        a.x[c] = __dadd_rn(x0, __dmul_rn(fx, l)); a.y[c] = __dadd_rn(y0, __dmul_rn(fy, l)); a.z[c] = __dadd_rn(z0, __dmul_rn(fz, l));
+        return;
+    }
+    const double hx = __dadd_rn(fx, 0.5), hy = __dadd_rn(fy, 0.5), hz = __dadd_rn(fz, 0.5);
+    const int i = 4 * c;
+    a.x[i] = __dadd_rn(x0, __dmul_rn(fx, l));     a.y[i] = __dadd_rn(y0, __dmul_rn(fy, l));     a.z[i] = __dadd_rn(z0, __dmul_rn(fz, l));
+    a.x[i + 1] = __dadd_rn(x0, __dmul_rn(fx, l)); a.y[i + 1] = __dadd_rn(y0, __dmul_rn(hy, l)); a.z[i + 1] = __dadd_rn(z0, __dmul_rn(hz, l));
+    a.x[i + 2] = __dadd_rn(x0, __dmul_rn(hx, l)); a.y[i + 2] = __dadd_rn(y0, __dmul_rn(fy, l)); a.z[i + 2] = __dadd_rn(z0, __dmul_rn(hz, l));
+    a.x[i + 3] = __dadd_rn(x0, __dmul_rn(hx, l)); a.y[i + 3] = __dadd_rn(y0, __dmul_rn(hy, l)); a.z[i + 3] = __dadd_rn(z0, __dmul_rn(fz, l));
+}
+
+// initialize_velocities_maxwell_boltzmann (solver/src/initializer/velocity.rs:6-29): atom i < n/2 gets sigma * N(0,1) per
+// component, atom i + n/2 the negated copy (an odd last atom keeps zero velocity, as in the reference's loop).  The reference
+// draws from an unseeded thread_rng, so only the distribution can be matched: a counter-based generator (splitmix64 of
+// (seed, atom, component)) feeds Box-Muller in f64 — reproducible for a seed and independent of the launch geometry.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double standard_normal(unsigned long long seed, unsigned long long atom, int comp)
+{
+    const unsigned long long k = splitmix64(seed ^ splitmix64(atom * 3ull + (unsigned long long)comp));
+    const unsigned long long a = splitmix64(k), b = splitmix64(k ^ 0xd1b54a32d192ed03ull);
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740993.0);  // (0, 1)
+    const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__global__ void k_init_velocities(int n, double sigma, unsigned long long seed, Arrays a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = n / 2;
+    if (i < n) {  // forces, potential and virial of a fresh State are zero
+        a.fx[i] = 0.0; a.fy[i] = 0.0; a.fz[i] = 0.0; a.u[i] = 0.0; a.w[i] = 0.0;
+        if (i >= 2 * half) { a.vx[i] = 0.0; a.vy[i] = 0.0; a.vz[i] = 0.0; }
+    }
+    if (i >= half) return;
+    const double vx = sigma * standard_normal(seed, (unsigned long long)i, 0);
+    const double vy = sigma * standard_normal(seed, (unsigned long long)i, 1);
+    const double vz = sigma * standard_normal(seed, (unsigned long long)i, 2);
+    a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz;
+    a.vx[i + half] = -vx; a.vy[i + half] = -vy; a.vz[i + half] = -vz;
+}
+
 // ---- transfer helpers -------------------------------------------------------------------------------
 __global__ void k_deinterleave3(int n, const double *__restrict__ src, double *__restrict__ a,
                                 double *__restrict__ b, double *__restrict__ c)

@@ -823,15 +823,9 @@ int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, dou
     return MD_OK;
 }
 
-int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
-                    const double *potential, const double *virial, double mass, const double box[3])
+// (re)allocates the device-resident State of one GPU for n atoms
+static int alloc_state(md_ctx *ctx, int64_t n)
 {
-    TRY(check_ctx(ctx, false));
-    if (n <= 0 || n > (int64_t)1 << 30 || !pos || !vel || !box)
-        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: need n in [1, 2^30], pos, vel, box");
-    if (!(mass > 0.0) || !(box[0] > 0.0) || !(box[1] > 0.0) || !(box[2] > 0.0))
-        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: mass and box must be positive");
-    if (ctx->dist.on) return dist_upload(ctx, n, pos, vel, force, potential, virial, mass, box);
     cudaStream_t st = ctx->stream;
     if (n != ctx->n || !ctx->has_state) {
         CK(cudaStreamSynchronize(st));
@@ -877,32 +871,13 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         TRY(dev_alloc(ctx, &ctx->nbr_cnt, ctx->npad));
         ctx->grid = Grid{};
     }
-    ctx->mass = mass;
-    ctx->has_state = true;
-    ctx->list_valid = false;
-    ctx->force_valid = force != nullptr;
-    const int ni = (int)n;
-    const int nb = blocks_for(n, 256);
-    const size_t b3 = 3 * (size_t)n * sizeof(double), b1 = (size_t)n * sizeof(double);
-    CK(cudaMemcpyAsync(ctx->stage, pos, b3, cudaMemcpyHostToDevice, st));
-    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.x, ctx->cur.y, ctx->cur.z);
-    CK(cudaMemcpyAsync(ctx->stage, vel, b3, cudaMemcpyHostToDevice, st));
-    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.vx, ctx->cur.vy, ctx->cur.vz);
-    if (force) {
-        CK(cudaMemcpyAsync(ctx->stage, force, b3, cudaMemcpyHostToDevice, st));
-        k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.fx, ctx->cur.fy, ctx->cur.fz);
-    } else {
-        CK(cudaMemsetAsync(ctx->cur.fx, 0, b1, st));
-        CK(cudaMemsetAsync(ctx->cur.fy, 0, b1, st));
-        CK(cudaMemsetAsync(ctx->cur.fz, 0, b1, st));
-    }
-    if (potential) CK(cudaMemcpyAsync(ctx->cur.u, potential, b1, cudaMemcpyHostToDevice, st));
-    else CK(cudaMemsetAsync(ctx->cur.u, 0, b1, st));
-    if (virial) CK(cudaMemcpyAsync(ctx->cur.w, virial, b1, cudaMemcpyHostToDevice, st));
-    else CK(cudaMemsetAsync(ctx->cur.w, 0, b1, st));
-    k_iota<<<nb, 256, 0, st>>>(ni, ctx->cur.id);
-    ctx->stats.kernel_launches += 3 + (force ? 1 : 0);
+    return MD_OK;
+}
 
+// control words, skin, neighbour capacity and the macro parameters of a freshly written State (one GPU)
+static int finish_new_state(md_ctx *ctx, int64_t n, const double box[3])
+{
+    cudaStream_t st = ctx->stream;
     Scalars &h = *ctx->h_sc;
     memset(&h, 0, sizeof h);
     h.box[0] = box[0]; h.box[1] = box[1]; h.box[2] = box[2];
@@ -931,7 +906,82 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
     ctx->sums_c = ctx->prm.half_dt_m;
     ctx->sums_nh = true;
     CK(cudaGetLastError());
+    return MD_OK;
+}
+
+int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
+                    const double *potential, const double *virial, double mass, const double box[3])
+{
+    TRY(check_ctx(ctx, false));
+    if (n <= 0 || n > (int64_t)1 << 30 || !pos || !vel || !box)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: need n in [1, 2^30], pos, vel, box");
+    if (!(mass > 0.0) || !(box[0] > 0.0) || !(box[1] > 0.0) || !(box[2] > 0.0))
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: mass and box must be positive");
+    if (ctx->dist.on) return dist_upload(ctx, n, pos, vel, force, potential, virial, mass, box);
+    cudaStream_t st = ctx->stream;
+    TRY(alloc_state(ctx, n));
+    ctx->mass = mass;
+    ctx->has_state = true;
+    ctx->list_valid = false;
+    ctx->force_valid = force != nullptr;
+    const int ni = (int)n;
+    const int nb = blocks_for(n, 256);
+    const size_t b3 = 3 * (size_t)n * sizeof(double), b1 = (size_t)n * sizeof(double);
+    CK(cudaMemcpyAsync(ctx->stage, pos, b3, cudaMemcpyHostToDevice, st));
+    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.x, ctx->cur.y, ctx->cur.z);
+    CK(cudaMemcpyAsync(ctx->stage, vel, b3, cudaMemcpyHostToDevice, st));
+    k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.vx, ctx->cur.vy, ctx->cur.vz);
+    if (force) {
+        CK(cudaMemcpyAsync(ctx->stage, force, b3, cudaMemcpyHostToDevice, st));
+        k_deinterleave3<<<nb, 256, 0, st>>>(ni, ctx->stage, ctx->cur.fx, ctx->cur.fy, ctx->cur.fz);
+    } else {
+        CK(cudaMemsetAsync(ctx->cur.fx, 0, b1, st));
+        CK(cudaMemsetAsync(ctx->cur.fy, 0, b1, st));
+        CK(cudaMemsetAsync(ctx->cur.fz, 0, b1, st));
+    }
+    if (potential) CK(cudaMemcpyAsync(ctx->cur.u, potential, b1, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->cur.u, 0, b1, st));
+    if (virial) CK(cudaMemcpyAsync(ctx->cur.w, virial, b1, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->cur.w, 0, b1, st));
+    k_iota<<<nb, 256, 0, st>>>(ni, ctx->cur.id);
+    ctx->stats.kernel_launches += 3 + (force ? 1 : 0);
+
+    TRY(finish_new_state(ctx, n, box));
     CK(cudaStreamSynchronize(st));  // host buffers are only borrowed for the duration of the call
+    return MD_OK;
+}
+
+
+int md_initialize_lattice(md_ctx *ctx, int cell_type, const int32_t size[3], const double start[3], double unit_cell,
+                          double mass, double temperature, uint64_t seed)
+{
+    TRY(check_ctx(ctx, false));
+    if (!size || size[0] <= 0 || size[1] <= 0 || size[2] <= 0 || !(unit_cell > 0.0) || !(mass > 0.0) ||
+        !(temperature >= 0.0) || (cell_type != MD_CELL_UNIFORM && cell_type != MD_CELL_FCC))
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_initialize_lattice: bad arguments");
+    if (ctx->dist.on)
+        return ctx->fail(MD_ERR_UNSUPPORTED, "md_initialize_lattice on a decomposed context: initialise on one GPU or upload");
+    const int64_t cells = (int64_t)size[0] * size[1] * size[2];
+    const int64_t n = cells * (cell_type == MD_CELL_FCC ? 4 : 1);
+    if (n > (int64_t)1 << 30) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_initialize_lattice: more than 2^30 atoms");
+    const double box[3] = {unit_cell * (double)size[0], unit_cell * (double)size[1], unit_cell * (double)size[2]};
+    const double s0[3] = {start ? start[0] : 0.0, start ? start[1] : 0.0, start ? start[2] : 0.0};
+    cudaStream_t st = ctx->stream;
+    TRY(alloc_state(ctx, n));
+    ctx->mass = mass;
+    ctx->has_state = true;
+    ctx->list_valid = false;
+    ctx->force_valid = false;
+    const int ni = (int)n, nb = blocks_for(n, 256);
+    k_init_lattice<<<blocks_for(cells, 256), 256, 0, st>>>((int)cells, cell_type == MD_CELL_FCC ? 1 : 0, size[0], size[1],
+                                                         size[2], s0[0], s0[1], s0[2], unit_cell, ctx->cur);
+    // velocity.rs:8-11: sigma = sqrt(K_B * (T * 0.01) / mass)
+    const double sigma = std::sqrt(K_B * (temperature * 0.01) / mass);
+    k_init_velocities<<<nb, 256, 0, st>>>(ni, sigma, (unsigned long long)seed, ctx->cur);
+    k_iota<<<nb, 256, 0, st>>>(ni, ctx->cur.id);
+    ctx->stats.kernel_launches += 3;
+    TRY(finish_new_state(ctx, n, box));
+    CK(cudaStreamSynchronize(st));
     return MD_OK;
 }
 

@@ -224,6 +224,15 @@ class Solver:
     def update_force(self):
         self._ck(_ffi.lib().md_update_force(self._ctx))
 
+    def initialize_lattice(self, size, unit_cell, mass, temperature, cell="u", start=None, seed=0):
+        """`moldyn_cli initialize` on the device (position.rs:24-104, velocity.rs:6-29): no host State, no upload."""
+        sz = np.ascontiguousarray(size, dtype=np.int32).reshape(3)
+        st = None if start is None else _f64(start).reshape(3)
+        kind = {"u": _ffi.CELL_UNIFORM, "fcc": _ffi.CELL_FCC}[cell]
+        self._ck(_ffi.lib().md_initialize_lattice(self._ctx, kind, _ptr(sz), _ptr(st) if st is not None else None,
+                                                  float(unit_cell), float(mass), float(temperature), int(seed)))
+        self.n = int(sz.prod()) * (4 if cell == "fcc" else 1)
+
     def step(self, n_steps, dt, thermostat=None, barostat=None):
         """n_steps × Integrator::calculate. thermostat=(Thermostat, target_K), barostat=(Barostat, target_P)."""
         th = thermostat[0]._c(thermostat[1]) if thermostat else None

@@ -331,6 +331,36 @@ def test_long_run_statistics_match_oracle(ensemble):
     assert mom < 1e-9
 
 
+@pytest.mark.parametrize("cell", ["u", "fcc"])
+def test_device_side_initializer(cell):
+    """`initialize` on the device.  Positions and box are bit-identical to the reference's formulas
+    (position.rs:24-104, oracle's restatement); velocities can only match in distribution (the reference's RNG is
+    unseeded): second half = negated first half exactly, zero net momentum, variance sigma^2 = K_B*T/100/m."""
+    side, lc, t_init, mass = (24, orc.GAS_CELL, 273.15, orc.ARGON_MASS) if cell == "u" else (12, 0.5256, 120.0, orc.ARGON_MASS)
+    n = side ** 3 * (1 if cell == "u" else 4)
+    with md.Solver() as s:
+        s.initialize_lattice((side, side, side), lc, mass, t_init, cell=cell, seed=5)
+        st = md.State(np.zeros((n, 3)), np.zeros((n, 3)), mass, np.ones(3))
+        s.download(st)
+        m = s.macro()
+        s.update_force()
+        s.step(10, DT, thermostat=(md.Thermostat.Berendsen(10.0), t_init))   # the State is usable right away
+        assert s.stats()["steps"] == 10
+    want = orc.argon_lattice(side, lc, t_init, seed=1, kind=cell).pos   # the oracle's restatement of position.rs:24-104
+    assert np.array_equal(st.position, want)
+    assert np.array_equal(st.boundary_box, np.array([lc * side] * 3))
+    half = n // 2
+    assert np.array_equal(st.velocity[half:2 * half], -st.velocity[:half])
+    sigma2 = orc.K_B * (t_init * 0.01) / mass
+    v = st.velocity[:half].ravel()
+    assert abs(v.mean()) < 4.0 * np.sqrt(sigma2 / v.size)
+    assert abs(v.var() / sigma2 - 1.0) < 5.0 * np.sqrt(2.0 / v.size)
+    assert abs(np.mean(v ** 4) / (3.0 * sigma2 ** 2) - 1.0) < 0.1          # Gaussian kurtosis
+    assert np.abs(m["momentum"]).max() < 1e-9
+    assert abs(m["temperature"] / t_init - 1.0) < 0.05
+    assert not st.force.any() and not st.potential.any()
+
+
 def test_graph_loop_equals_host_loop(mode):
     o = liquid(10)
     out = []
