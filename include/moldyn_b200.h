@@ -46,6 +46,10 @@ typedef enum md_status {
 #define MD_FORCE_FAST 0  /* r^2-based LJ, FMA allowed, neighbour order = cell order (default) */
 #define MD_FORCE_EXACT 1 /* the reference's operation order (potential.rs:181-211) without FMA and with
                             partners summed in ascending particle index: bit-identical to update_force */
+#define MD_FORCE_FAST_UNION 2 /* MD_FORCE_FAST with union lists per atom pair for dense systems on one GPU (k_build_union): one
+                                gather serves both atoms of a thread.  Opt-in: measured slower on B200 (C5 k_force 0.311 vs
+                                0.245 ms) — after the 256-bit gathers the dense loop is bound by pair arithmetic, and the union
+                                evaluates 25 % more pairs */
 /* loop_mode */
 #define MD_LOOP_GRAPH 0 /* steady-state steps run inside one conditional (WHILE) CUDA graph (default) */
 #define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check) */
@@ -126,7 +130,7 @@ typedef struct md_stats {
     double wait_halo_ms;      /* multi-GPU peer-memory path: time block 0 of k_force polled for the neighbours' ghosts, */
     double wait_sums_ms;      /* and the last block polled for the other ranks' reduction sums (since the last upload)   */
     int32_t peer_memory;      /* 1: halo and reduction go through peer memory (NVLink stores), 0: NCCL send/recv path     */
-    int32_t reserved1;
+    int32_t union_lists;      /* 1: the last rebuild produced union lists per atom pair (dense systems, FAST mode, one GPU) */
     double force_atoms_ms;    /* peer-memory path diagnostics: k_force first block start -> all atoms done,               */
     double force_tail_ms;     /*   -> mailbox exchange + finalize done,                                                  */
     double drift_push_ms;     /*   multi-GPU: wall time spent in list rebuilds so far (host clock around dist_rebuild)    */

@@ -71,6 +71,8 @@ struct Scalars {
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     int out_of_box;    // the last cell binning saw a coordinate outside [0, L): list builds use the generic minimum image
     int parity;        // fused one-kernel steps ping-pong x and v between two plane sets: which set is current
+    int union_max;     // largest union-list length of the last k_build_union (entries per atom pair)
+    int union_fail;    // k_build_union could not run (a coordinate outside the box): fall back to per-atom lists
     unsigned long long epoch;  // multi-GPU peer-memory path: sequence number of the last finalized collective reduction
     unsigned long long wait_halo_ns, wait_sums_ns;  // time spent polling the mailboxes (block 0 / last block), accumulated
     unsigned long long t_start;                     // %globaltimer when the first block of the running k_force started
@@ -448,6 +450,162 @@ __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *
         atomicMax(&sc->nbr_max, wmax);
         atomicAdd(&sc->nbr_total, (unsigned long long)wsum);
         if (wmax > g.cap) atomicExch(&sc->nbr_overflow, 1);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K2 for dense systems, FAST mode: UNION lists.  The force kernel gives two consecutive (cell-sorted, hence spatially
+// adjacent) atoms A = 2t, B = 2t+1 to one thread, and the dense loop is bound by the L1's gather rate (one pass per lane and
+// partner).  A and B share ~3/4 of their partners, so thread t gets ONE list: every atom within r_list of A or of B, each
+// entry tagged with two membership bits (bit 30: in A's list, bit 31: in B's).  A partner is then gathered once and
+// evaluated against both atoms: ~1.25x the pair arithmetic for ~0.63x the gathers.  The membership bits make the union
+// exactly equivalent to the two per-atom lists (md_neighbour_lists reconstructs them from the bits).
+//
+// One thread scans A's stencil once, testing both atoms, then the cells of B's stencil that A's stencil does not cover
+// (B only).  Requires >= 2*nsub + 5 cells per dimension and every coordinate inside the box: the periodic image of a stencil
+// cell is then a per-run constant for A (cell wrap) and for B (nearest image by cell distance), added with the reference's
+// own r + L / r - L — same exact predicate as k_build_list<.., SHIFT = true>.
+constexpr int UNION_A = 1 << 30;
+constexpr unsigned int UNION_B = 1u << 31;
+constexpr int UNION_IDX = (1 << 30) - 1;
+
+__device__ __forceinline__ double image_shift(int q, int b, int nc, double L)
+{
+    const int d = q - b;
+    return 2 * d > nc ? -L : (2 * d < -nc ? L : 0.0);
+}
+
+__device__ __forceinline__ int cell_dist(int q, int a, int nc)
+{
+    const int d = abs(q - a);
+    return min(d, nc - d);
+}
+
+__global__ void __launch_bounds__(128) k_build_union(int n, Arrays a, const int *__restrict__ cell_sorted,
+                                                     const int *__restrict__ cell_start, Scalars *sc, Grid g,
+                                                     double r_list, double r2_list, int *__restrict__ nbr_u,
+                                                     int *__restrict__ cnt_u, int cap_u, int pstride,
+                                                     int *__restrict__ nbr_cnt)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int npairs = (n + 1) >> 1;
+    int cnt = 0, cnt_a = 0, cnt_b = 0;
+    if (sc->out_of_box) {
+        if (t == 0) sc->union_fail = 1;
+        return;
+    }
+    if (t < npairs) {
+        const int A = 2 * t;
+        const bool has_b = A + 1 < n;
+        const int B = has_b ? A + 1 : A;
+        const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+        const double xa = a.x[A], ya = a.y[A], za = a.z[A];
+        const double xb = a.x[B], yb = a.y[B], zb = a.z[B];
+        const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2], ns = g.nsub, w = 2 * g.nsub + 1;
+        const int ca = cell_sorted[A], cb = cell_sorted[B];
+        const int az = ca % ncz, ay = (ca / ncz) % ncy, ax = ca / (ncz * ncy);
+        const int bz = cb % ncz, by = (cb / ncz) % ncy, bx = cb / (ncz * ncy);
+        auto emit = [&](int q, bool in_a, bool in_b) {
+            if (cnt < cap_u) nbr_u[(size_t)cnt * pstride + t] = (int)((unsigned int)q | (in_a ? (unsigned int)UNION_A : 0u) | (in_b ? UNION_B : 0u));
+            ++cnt;
+            cnt_a += in_a ? 1 : 0;
+            cnt_b += in_b ? 1 : 0;
+        };
+        // ---- pass 1: A's stencil, both atoms ----
+        int z0a, z1a, z0b = 0, z1b = 0;
+        {
+            const int lo = az - ns, hi = az + ns + 1;
+            if (lo < 0) { z0a = 0; z1a = hi; z0b = lo + ncz; z1b = ncz; }
+            else if (hi > ncz) { z0a = lo; z1a = ncz; z0b = 0; z1b = hi - ncz; }
+            else { z0a = lo; z1a = hi; }
+        }
+        const double sza_b = (az - ns < 0) ? -Lz : Lz;  // A's shift for the wrapped z run
+        for (int ia = 0; ia < w; ++ia) {
+            int qx = ax - ns + ia;
+            const double sxa = qx < 0 ? -Lx : (qx >= ncx ? Lx : 0.0);
+            qx += (qx < 0) ? ncx : 0;
+            qx -= (qx >= ncx) ? ncx : 0;
+            const double sxb = image_shift(qx, bx, ncx, Lx);
+            for (int ib = 0; ib < w; ++ib) {
+                int qy = ay - ns + ib;
+                const double sya = qy < 0 ? -Ly : (qy >= ncy ? Ly : 0.0);
+                qy += (qy < 0) ? ncy : 0;
+                qy -= (qy >= ncy) ? ncy : 0;
+                const double syb = image_shift(qy, by, ncy, Ly);
+                const int base = (qx * ncy + qy) * ncz;
+                const int sa = cell_start[base + z0a], ea = cell_start[base + z1a];
+                const int sb = (z1b > z0b) ? cell_start[base + z0b] : 0, eb = (z1b > z0b) ? cell_start[base + z1b] : 0;
+#pragma unroll 1
+                for (int run = 0; run < 2; ++run) {
+                    const int s = run ? sb : sa, e = run ? eb : ea;
+                    const double sza = run ? sza_b : 0.0;
+                    const double szb = image_shift(run ? z0b : z0a, bz, ncz, Lz);  // constant over a run (>= 2ns+5 cells)
+                    for (int q = s; q < e; ++q) {
+                        const double xq = a.x[q];
+                        const double rxa = __dadd_rn(__dsub_rn(xq, xa), sxa), rxb = __dadd_rn(__dsub_rn(xq, xb), sxb);
+                        if (fabs(rxa) > r_list && fabs(rxb) > r_list) continue;
+                        const double yq = a.y[q], zq = a.z[q];
+                        const double rya = __dadd_rn(__dsub_rn(yq, ya), sya), rza = __dadd_rn(__dsub_rn(zq, za), sza);
+                        const double ryb = __dadd_rn(__dsub_rn(yq, yb), syb), rzb = __dadd_rn(__dsub_rn(zq, zb), szb);
+                        const double r2a = __dadd_rn(__dadd_rn(__dmul_rn(rxa, rxa), __dmul_rn(rya, rya)), __dmul_rn(rza, rza));
+                        const double r2b = __dadd_rn(__dadd_rn(__dmul_rn(rxb, rxb), __dmul_rn(ryb, ryb)), __dmul_rn(rzb, rzb));
+                        const bool in_a = r2a <= r2_list && q != A;
+                        const bool in_b = has_b && r2b <= r2_list && q != B;
+                        if (in_a || in_b) emit(q, in_a, in_b);
+                    }
+                }
+            }
+        }
+        // ---- pass 2: cells of B's stencil outside A's stencil, B only ----
+        if (has_b && cb != ca) {
+            for (int ia = 0; ia < w; ++ia) {
+                int qx = bx - ns + ia;
+                const double sx = qx < 0 ? -Lx : (qx >= ncx ? Lx : 0.0);
+                qx += (qx < 0) ? ncx : 0;
+                qx -= (qx >= ncx) ? ncx : 0;
+                const bool in_x = cell_dist(qx, ax, ncx) <= ns;
+                for (int ib = 0; ib < w; ++ib) {
+                    int qy = by - ns + ib;
+                    const double sy = qy < 0 ? -Ly : (qy >= ncy ? Ly : 0.0);
+                    qy += (qy < 0) ? ncy : 0;
+                    qy -= (qy >= ncy) ? ncy : 0;
+                    const bool in_xy = in_x && cell_dist(qy, ay, ncy) <= ns;
+                    for (int ic = 0; ic < w; ++ic) {
+                        int qz = bz - ns + ic;
+                        const double sz = qz < 0 ? -Lz : (qz >= ncz ? Lz : 0.0);
+                        qz += (qz < 0) ? ncz : 0;
+                        qz -= (qz >= ncz) ? ncz : 0;
+                        if (in_xy && cell_dist(qz, az, ncz) <= ns) continue;  // pass 1 has seen this cell
+                        const int c = (qx * ncy + qy) * ncz + qz;
+                        for (int q = cell_start[c]; q < cell_start[c + 1]; ++q) {
+                            const double rx = __dadd_rn(__dsub_rn(a.x[q], xb), sx);
+                            if (fabs(rx) > r_list) continue;
+                            const double ry = __dadd_rn(__dsub_rn(a.y[q], yb), sy), rz = __dadd_rn(__dsub_rn(a.z[q], zb), sz);
+                            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                            if (r2 <= r2_list && q != B) emit(q, false, true);
+                        }
+                    }
+                }
+            }
+        }
+        cnt_u[t] = min(cnt, cap_u);
+        nbr_cnt[A] = cnt_a;
+        if (has_b) nbr_cnt[B] = cnt_b;
+    }
+    // statistics (integer atomics — order-independent): per-atom max / total as for k_build_list, plus the union length
+    int wmax = max(cnt_a, cnt_b), umax = cnt;
+    unsigned int wsum = (unsigned int)(cnt_a + cnt_b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && wsum) {
+        atomicMax(&sc->nbr_max, wmax);
+        atomicMax(&sc->union_max, umax);
+        atomicAdd(&sc->nbr_total, (unsigned long long)wsum);
+        if (umax > cap_u) atomicExch(&sc->nbr_overflow, 1);
     }
 }
 
@@ -911,7 +1069,9 @@ __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, do
     }
     double r2 = rx * rx + ry * ry + rz * rz;
     bool in = active && (r2 <= fc.rc2);
-    double inv = rcp_nr(in ? r2 : 1.0);
+    // r2 > 0 for every lane: masked lanes gather an atom that is not one of the thread's own (see safe_dummy), so the
+    // reciprocal needs no guard — whatever it yields for a masked or out-of-range pair is discarded by the select below
+    double inv = rcp_nr(r2);
     double s2 = fc.sigma2 * inv;
     double s6 = s2 * s2 * s2;
     double s12 = s6 * s6;
@@ -1065,6 +1225,14 @@ __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const A
 // one-trip-ahead index prefetch leaves the warp waiting on DRAM every trip.  Each thread therefore keeps a ring of the next
 // RING_D trips' index rows (two rows per trip) in shared memory, filled by cp.async — no registers, no barrier (a thread only
 // reads what it copied), ~RING_D trips of DRAM latency hidden.
+// Address masked lanes gather from: warp-uniform (one L1 pass), a real atom, and never one of the warp's own 64 atoms — so
+// its distance to the lane's atoms is positive and the pair term stays finite before it is masked out.  (n >= 128 on this path.)
+__device__ __forceinline__ int safe_dummy(int i0, int n)
+{
+    const int w0 = i0 & ~63;
+    return w0 + 64 < n ? w0 + 64 : w0 - 64;
+}
+
 constexpr int RING_D = 8;
 struct IndexRing {
     int2 r[RING_D][2][FORCE_BLOCK];
@@ -1074,7 +1242,7 @@ template <bool WRAP>
 __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, const double4 *__restrict__ q4,
                                                      const int2 *__restrict__ row, size_t stride, int2 C, int i0,
                                                      double2 X, double2 Y, double2 Z, const LjConst &c,
-                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w)
+                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w, int n)
 {
     const int l = threadIdx.x;
     const int kmax = max(C.x, C.y);
@@ -1112,7 +1280,7 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
             : "l"(q4 + (J)));                                                                             \
     } while (0)
     // masked lanes (list shorter than the warp's longest) all gather the same address: one L1 pass instead of 32
-    i0 &= ~63;
+    i0 = safe_dummy(i0, n);
     double2 pa0, pa1, pb0, pb1;
     double za0, za1, zb0, zb1;
     pa0 = pa1 = pb0 = pb1 = make_double2(0.0, 0.0);
@@ -1143,6 +1311,78 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
     }
 #undef MD_FETCH_ROWS
 #undef MD_GATHER
+    cp_async_wait_all();
+}
+
+// Dense systems with UNION lists (k_build_union): one entry = one gather, evaluated against both atoms of the thread under
+// the entry's membership bits.  Same ring / pipeline structure as neighbour_loop_dense, half the gathers per pair term.
+template <bool WRAP>
+__device__ __forceinline__ void neighbour_loop_union(PairAcc &f0, PairAcc &f1, const double4 *__restrict__ q4,
+                                                     const int *__restrict__ row, size_t stride, int cnt, int i0,
+                                                     double2 X, double2 Y, double2 Z, const LjConst &c,
+                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w, int n)
+{
+    const int l = threadIdx.x;
+    const int ntrips = (cnt + 1) >> 1;
+    int *slots = reinterpret_cast<int *>(&ring.r[0][0][0]);  // [RING_D][2][FORCE_BLOCK] ints
+#define MD_SLOT(D, H) slots[((D) * 2 + (H)) * FORCE_BLOCK + l]
+#define MD_CP4(DST, SRC) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(DST)), "l"(SRC) : "memory")
+#pragma unroll
+    for (int d = 0; d < RING_D; ++d) {
+        if (d < ntrips) {
+            MD_CP4(&MD_SLOT(d, 0), row + (size_t)(2 * d) * stride);
+            if (2 * d + 1 < cnt) MD_CP4(&MD_SLOT(d, 1), row + (size_t)(2 * d + 1) * stride);
+        }
+        cp_async_commit();
+    }
+    i0 = safe_dummy(i0, n);  // masked entries gather one common address
+#define MD_FETCH_ENTRIES(T, EA, EB)                                                                   \
+    do {                                                                                              \
+        const int slot_ = (T) % RING_D;                                                               \
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING_D - 1) : "memory");                         \
+        EA = MD_SLOT(slot_, 0);                                                                       \
+        EB = 2 * (T) + 1 < cnt ? MD_SLOT(slot_, 1) : i0;                                              \
+        const int tn_ = (T) + RING_D;                                                                 \
+        if (tn_ < ntrips) {                                                                           \
+            MD_CP4(&MD_SLOT(slot_, 0), row + (size_t)(2 * tn_) * stride);                             \
+            if (2 * tn_ + 1 < cnt) MD_CP4(&MD_SLOT(slot_, 1), row + (size_t)(2 * tn_ + 1) * stride);  \
+        }                                                                                             \
+        cp_async_commit();                                                                            \
+    } while (0)
+#define MD_GATHER(J, XY, ZZ)                                                                              \
+    do {                                                                                                  \
+        double w_;                                                                                        \
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"                                                    \
+            : "=d"(XY.x), "=d"(XY.y), "=d"(ZZ), "=d"(w_)                                                  \
+            : "l"(q4 + (J)));                                                                             \
+    } while (0)
+    double2 pa = make_double2(0.0, 0.0), pb = pa;
+    double za = 0.0, zb = 0.0;
+    int ea = i0, eb = i0;
+    if (ntrips > 0) {
+        MD_FETCH_ENTRIES(0, ea, eb);
+        MD_GATHER(ea & UNION_IDX, pa, za);
+        MD_GATHER(eb & UNION_IDX, pb, zb);
+    }
+    for (int t = 0; t < ntrips; ++t) {
+        double2 na = pa, nb = pb;
+        double ya = za, yb = zb;
+        int fa = i0, fb = i0;
+        if (t + 1 < ntrips) {
+            MD_FETCH_ENTRIES(t + 1, fa, fb);
+            MD_GATHER(fa & UNION_IDX, na, ya);
+            MD_GATHER(fb & UNION_IDX, nb, yb);
+        }
+        pair_fast<WRAP>(f0, (ea & UNION_A) != 0, pa.x, pa.y, za, X.x, Y.x, Z.x, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f1, ea < 0, pa.x, pa.y, za, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f0, (eb & UNION_A) != 0, pb.x, pb.y, zb, X.x, Y.x, Z.x, c, fc, need_u, need_w);
+        pair_fast<WRAP>(f1, eb < 0, pb.x, pb.y, zb, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pa = na; pb = nb; za = ya; zb = yb; ea = fa; eb = fb;
+    }
+#undef MD_FETCH_ENTRIES
+#undef MD_GATHER
+#undef MD_SLOT
+#undef MD_CP4
     cp_async_wait_all();
 }
 
@@ -1310,7 +1550,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, 5)
 // next rows of partner indices prefetched while the current ones are in flight.
 //   ROWS = 2: two list rows per trip (dense systems; 12 gathers in flight, 128 registers)
 //   ROWS = 1: one row per trip (dilute systems: few partners, occupancy matters more than unrolling)
-template <bool EXACT, int ROWS, bool MASKED>
+// UNION (dense only): nbr / nbr_cnt are the union table and its per-thread lengths (k_build_union), npad its row stride * 2
+template <bool EXACT, int ROWS, bool MASKED, bool UNION = false>
 __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB : MD_FORCE_MINB_DILUTE)
     k_force(int n, Arrays a, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad, int cap,
             double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
@@ -1382,8 +1623,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
         } else {
             X = reinterpret_cast<const double2 *>(px)[t]; Y = reinterpret_cast<const double2 *>(py)[t];
             Z = reinterpret_cast<const double2 *>(pz)[t];
-            C = reinterpret_cast<const int2 *>(nbr_cnt)[t];
-            J0 = row[0];
+            if (UNION) { C = make_int2(nbr_cnt[t], 0); J0 = make_int2(0, 0); }
+            else { C = reinterpret_cast<const int2 *>(nbr_cnt)[t]; J0 = row[0]; }
             if (!MASKED) {  // dense: the velocities are fetched after the (long) neighbour loop — 12 registers less in it
                 VX = reinterpret_cast<double2 *>(a.vx)[t]; VY = reinterpret_cast<double2 *>(a.vy)[t];
                 VZ = reinterpret_cast<double2 *>(a.vz)[t];
@@ -1406,10 +1647,15 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
                 const double m = wrap_margin;
                 const bool near = X.x < m || X.x > c.Lx - m || Y.x < m || Y.x > c.Ly - m || Z.x < m || Z.x > c.Lz - m ||
                                   X.y < m || X.y > c.Lx - m || Y.y < m || Y.y > c.Ly - m || Z.y < m || Z.y > c.Lz - m;
-                if (__any_sync(__activemask(), near))
-                    neighbour_loop_dense<true>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w);
+                const bool wrap = __any_sync(__activemask(), near);
+                if (UNION) {
+                    const int *urow = nbr + t;  // entry k of thread t: nbr[k * (npad / 2) + t]
+                    if (wrap) neighbour_loop_union<true>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
+                    else neighbour_loop_union<false>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
+                } else if (wrap)
+                    neighbour_loop_dense<true>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
                 else
-                    neighbour_loop_dense<false>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w);
+                    neighbour_loop_dense<false>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
             } else {
                 neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             }
@@ -1824,6 +2070,8 @@ __global__ void k_reset_list_stats(Scalars *sc)
     sc->nbr_max = 0;
     sc->nbr_overflow = 0;
     sc->nbr_total = 0ull;
+    sc->union_max = 0;
+    sc->union_fail = 0;
 }
 
 __global__ void k_set_shift_to_vcom(Scalars *sc)

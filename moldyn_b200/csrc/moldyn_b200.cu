@@ -110,6 +110,11 @@ struct md_ctx {
     int act_alloc = 0, sparse_grid = 1;
     bool sparse = false;                              // dilute + FAST: the last rebuild left a valid active list
     double rebuild_host_ms = 0.0;                     // multi-GPU: wall time spent in list rebuilds (host clock, synchronised)
+    // dense + FAST on one GPU: union lists per atom pair (k_build_union), see md_kernels.cuh
+    int *nbr_u = nullptr, *cnt_u = nullptr;
+    size_t nbr_u_alloc = 0;
+    int cap_u = 0;
+    bool union_valid = false;
     double *hot_slab = nullptr;                       // one GPU: x, y, z, vx, vy, vz of both plane sets in one allocation,
                                                       // so one L2 access-policy window can pin the current set (apply_l2_window)
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
@@ -395,6 +400,22 @@ int ensure_nbr_capacity(md_ctx *ctx, int cap)
     return MD_OK;
 }
 
+int ensure_union_capacity(md_ctx *ctx, int cap_u)
+{
+    const size_t need = (size_t)cap_u * (size_t)(ctx->npad / 2);
+    if (need > ctx->nbr_u_alloc) {
+        dev_free(ctx, ctx->nbr_u);
+        ctx->nbr_u = nullptr;
+        ctx->nbr_u_alloc = 0;
+        TRY(dev_alloc(ctx, &ctx->nbr_u, need));
+        ctx->nbr_u_alloc = need;
+    }
+    if (!ctx->cnt_u) TRY(dev_alloc(ctx, &ctx->cnt_u, (size_t)ctx->npad / 2 + 1));
+    ctx->cap_u = cap_u;
+    drop_graph(ctx);
+    return MD_OK;
+}
+
 // Largest double t with sqrt(t) <= r (IEEE sqrt is correctly rounded and monotonic): turns the reference's
 // `norm(r) > r_cut` test into a comparison of squares with the identical outcome for every input.
 double sqrt_threshold(double r)
@@ -489,7 +510,34 @@ int rebuild_lists(md_ctx *ctx)
     drop_graph(ctx);  // array pointers are baked into the captured kernels
 
     const double r2_list = sqrt_threshold(ctx->prm.r_list);
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    // Dense systems in FAST mode on one GPU: union lists per atom pair (half the gathers in the force kernel).
+    ctx->union_valid = false;
+    {
+        const bool allowed = ctx->cfg.force_mode == MD_FORCE_FAST_UNION;  // opt-in, see include/moldyn_b200.h
+        const double volume = box[0] * box[1] * box[2];
+        const double in_list = (double)n / volume * 4.18879020478639 * ctx->prm.r_list * ctx->prm.r_list * ctx->prm.r_list;
+        const int need_cells = 2 * g.nsub + 5;
+        bool want = allowed && ctx->cfg.force_mode != MD_FORCE_EXACT && in_list >= 12.0 && g.nc[0] >= need_cells &&
+                    g.nc[1] >= need_cells && g.nc[2] >= need_cells && n >= 128;
+        for (int attempt = 0; want && attempt < 4; ++attempt) {
+            if (ctx->cap_u == 0) TRY(ensure_union_capacity(ctx, ((int)(in_list * 1.45) + 32 + 7) / 8 * 8));
+            k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
+            k_build_union<<<blocks_for((n + 1) / 2, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start, ctx->d_sc,
+                                                                      g, ctx->prm.r_list, r2_list, ctx->nbr_u, ctx->cnt_u,
+                                                                      ctx->cap_u, ctx->npad / 2, ctx->nbr_cnt);
+            ctx->stats.kernel_launches += 2;
+            CK(cudaGetLastError());
+            TRY(pull_scalars(ctx));
+            if (ctx->h_sc->union_fail) break;  // a coordinate outside the box: per-atom lists with the generic minimum image
+            if (!ctx->h_sc->nbr_overflow) {
+                ctx->union_valid = (double)ctx->h_sc->nbr_total / (double)n >= 8.0;  // the dense kernel is the right one
+                break;
+            }
+            if (attempt == 3) return ctx->fail(MD_ERR_NEIGHBOUR_OVERFLOW, "union list overflow (max %d)", ctx->h_sc->union_max);
+            TRY(ensure_union_capacity(ctx, ((int)(ctx->h_sc->union_max * 1.15) + 8 + 7) / 8 * 8));
+        }
+    }
+    for (int attempt = 0; !ctx->union_valid && attempt < 4; ++attempt) {
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         // image shift per cell run instead of per candidate when the box is wide enough in cells (see k_build_list)
         const int need_cells = 2 * g.nsub + 3;
@@ -518,7 +566,7 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.rebuilds += 1;
     ctx->stats.nbr_max = ctx->h_sc->nbr_max;
     ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
-    ctx->dense = ctx->stats.nbr_mean >= 8.0;
+    ctx->dense = ctx->stats.nbr_mean >= 8.0 && n >= 128;  // (the dense kernel's masked lanes need a foreign warp's atom)
     ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT;
     TRY(refresh_q4(ctx));
     TRY(build_active_list(ctx, n));
@@ -574,6 +622,10 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
                                                          ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
                                                          kick ? 1 : 0, cond, fc, nullptr)
     if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
+    else if (ctx->dense && ctx->union_valid)
+        k_force<false, 2, true, true><<<ctx->force_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
+            n, ctx->cur, ctx->nbr_u, ctx->cnt_u, ctx->npad, ctx->cap_u, ctx->d_partials, ctx->d_sc, ctx->d_pr, kick ? 1 : 0,
+            cond, fc, nullptr);
     else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
     else if (ctx->sparse)
         k_force_sparse<<<ctx->sparse_grid, FORCE_BLOCK, 0, ctx->stream>>>(
@@ -644,6 +696,11 @@ int choose_grids(md_ctx *ctx)
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, 1, false>, FORCE_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, 2, true>, FORCE_BLOCK, 0));
+    {
+        int occ_u = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_force<false, 2, true, true>, FORCE_BLOCK, 0));
+        occ[1] = std::min(occ[1], occ_u);
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, MD_DILUTE_ROWS, false>, FORCE_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
     const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
@@ -835,6 +892,8 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         dev_free(ctx, ctx->cell_of); dev_free(ctx, ctx->cell_sorted); dev_free(ctx, ctx->order);
         dev_free(ctx, ctx->nbr_cnt); dev_free(ctx, ctx->nbr);
         ctx->nbr = nullptr; ctx->nbr_alloc = 0;
+        dev_free(ctx, ctx->nbr_u); dev_free(ctx, ctx->cnt_u);
+        ctx->nbr_u = nullptr; ctx->cnt_u = nullptr; ctx->nbr_u_alloc = 0; ctx->cap_u = 0; ctx->union_valid = false;
         ctx->owned.erase(std::remove_if(ctx->owned.begin(), ctx->owned.end(), [](const DevBuf &b) { return !b.p; }),
                          ctx->owned.end());
         ctx->n = n;
@@ -1358,6 +1417,27 @@ static int fetch_lists(md_ctx *ctx, std::vector<int> &cnt, std::vector<int> &id,
     id.resize(n);
     CK(cudaMemcpyAsync(cnt.data(), ctx->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(id.data(), ctx->cur.id, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nbr && ctx->union_valid) {
+        // union lists (k_build_union): the two membership bits of an entry give back the per-atom lists, in the layout
+        // nbr[k * npad + p] the callers expect
+        const size_t pstride = (size_t)ctx->npad / 2, npairs = (n + 1) / 2;
+        std::vector<int> u((size_t)ctx->cap_u * pstride), cu(npairs);
+        CK(cudaMemcpyAsync(u.data(), ctx->nbr_u, sizeof(int) * u.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cu.data(), ctx->cnt_u, sizeof(int) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int cmax = 1;
+        for (size_t p = 0; p < n; ++p) cmax = std::max(cmax, cnt[p]);
+        nbr->assign((size_t)cmax * ctx->npad, 0);
+        std::vector<int> fill(n, 0);
+        for (size_t t = 0; t < npairs; ++t)
+            for (int k = 0; k < cu[t]; ++k) {
+                const unsigned int e = (unsigned int)u[(size_t)k * pstride + t];
+                const int q = (int)(e & 0x3fffffffu);
+                if (e & (1u << 30)) (*nbr)[(size_t)fill[2 * t]++ * ctx->npad + 2 * t] = q;
+                if ((e & (1u << 31)) && 2 * t + 1 < n) (*nbr)[(size_t)fill[2 * t + 1]++ * ctx->npad + 2 * t + 1] = q;
+            }
+        return MD_OK;
+    }
     if (nbr) {
         nbr->resize((size_t)ctx->grid.cap * ctx->npad);
         CK(cudaMemcpyAsync(nbr->data(), ctx->nbr, sizeof(int) * nbr->size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1403,6 +1483,7 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->wait_halo_ms = (double)ctx->h_sc->wait_halo_ns * 1e-6;  // as of the last time the host looked at the device
     out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
     out->peer_memory = ctx->dist.p2p ? 1 : 0;
+    out->union_lists = ctx->union_valid ? 1 : 0;
     out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
     out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;
     out->drift_push_ms = ctx->rebuild_host_ms;  // (field reused: the drift kernel no longer has a push phase to time)

@@ -26,7 +26,7 @@ def mode(request):
 
 
 def make_solver(mode, **kw):
-    return md.Solver(exact=(mode == "exact"), **kw)
+    return md.Solver(exact=(mode == "exact"), union_lists=(mode == "fast_union"), **kw)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -152,6 +152,7 @@ SYSTEMS = {
     "liquid1000": lambda: (liquid(10), None),
     "liquid4096_3.5sigma": lambda: (liquid(16), LONG_CUT),
     "liquid_small_box": lambda: (liquid(5), None),   # box 1.81 nm: fewer than 3 cells per axis
+    "liquid5832": lambda: (liquid(18), None),        # 13 cells per axis: the dense FAST path uses union lists
 }
 
 
@@ -179,7 +180,7 @@ def test_forces_match_oracle(name, mode):
         assert np.all(np.abs(st.temp - o.vir) <= 1e-10 * (scale * olj.r_cut + 1e-300) + 1e-300)
 
 
-@pytest.mark.parametrize("name", ["dense_gas3000", "liquid1000", "gas1000"])
+@pytest.mark.parametrize("name", ["dense_gas3000", "liquid1000", "gas1000", "liquid5832"])
 def test_cells_and_neighbour_sets_bit_exact(name, mode):
     o, cut = SYSTEMS[name]()
     olj, plj = lj_pair(md, *(cut or (None, None)))
@@ -191,6 +192,7 @@ def test_cells_and_neighbour_sets_bit_exact(name, mode):
         cell, dims = s.cells()
         off, partners = s.neighbour_lists()
         skin = s.stats()["skin"]
+        assert s.stats()["union_lists"] == 0
     # cell assignment: c_d = min(nc_d-1, (int)(frac(x_d / L_d) * nc_d)), linear index (cx*ny + cy)*nz + cz
     c = []
     for d in range(3):
@@ -205,12 +207,42 @@ def test_cells_and_neighbour_sets_bit_exact(name, mode):
     assert np.array_equal(partners, wpartners)
 
 
+def test_union_lists_opt_in():
+    """MD_FORCE_FAST_UNION (k_build_union + the union force loop): pair sets — reconstructed from the membership bits —
+    bit-exact, forces within the FAST bar, 100-step NVT trajectory within 1e-8 of the oracle."""
+    o, _ = SYSTEMS["liquid5832"]()
+    olj, plj = lj_pair(md)
+    ref = o.copy()
+    orc.update_force(olj, ref, mode="cells")
+    st = to_gpu_state(md, o)
+    gth, oth = (md.Thermostat.Berendsen(10.0), 120.0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, 120.0)
+    with make_solver("fast_union") as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        assert s.stats()["union_lists"] == 1
+        off, partners = s.neighbour_lists()
+        skin = s.stats()["skin"]
+        s.download(st)
+        f0 = st.force.copy()
+        s.step(100, DT, thermostat=gth)
+        s.download(st)
+    woff, wpartners = orc.neighbour_sets(o.pos, o.box, olj.r_cut + skin)
+    assert np.array_equal(off, woff) and np.array_equal(partners, wpartners)
+    scale = force_scale(olj, ref)
+    rms = np.sqrt((ref.force ** 2).sum(axis=1).mean())
+    assert np.all(np.abs(f0 - ref.force) <= 1e-10 * np.maximum(scale, rms)[:, None])
+    run_oracle(olj, o, 100, oth)
+    dx = np.abs(st.position - o.pos)
+    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+
+
 def run_oracle(olj, o, n_steps, th=None, ba=None):
     orc.update_force(olj, o, mode="cells")
     orc.step(olj, o, DT, thermostat=th, barostat=ba, mode="cells", n_steps=n_steps)
 
 
-@pytest.mark.parametrize("name", ["liquid1000", "dense_gas3000", "gas1000"])
+@pytest.mark.parametrize("name", ["liquid1000", "dense_gas3000", "gas1000", "liquid5832"])
 def test_nve_trajectory_100_steps(name, mode):
     o, cut = SYSTEMS[name]()
     olj, plj = lj_pair(md, *(cut or (None, None)))
