@@ -1015,6 +1015,7 @@ constexpr int FORCE_BLOCK = 128;
 // as c[bank][offset] operands instead of occupying ~20 registers per thread.
 struct ForceConsts {
     double sigma, sigma2, eps4, eps24, r_cut, rc2, u_cut;
+    double c6, c12, d6, d12;  // 24 eps sigma^6, 48 eps sigma^12, 4 eps sigma^6, 4 eps sigma^12 (dense FAST pair term)
     double hc;    // dt / (2 m)
     double mass;
 };
@@ -1071,16 +1072,16 @@ __device__ __forceinline__ void pair_fast(PairAcc &a, bool active, double xj, do
     bool in = active && (r2 <= fc.rc2);
     // r2 > 0 for every lane: masked lanes gather an atom that is not one of the thread's own (see safe_dummy), so the
     // reciprocal needs no guard — whatever it yields for a masked or out-of-range pair is discarded by the select below
-    double inv = rcp_nr(r2);
-    double s2 = fc.sigma2 * inv;
-    double s6 = s2 * s2 * s2;
-    double s12 = s6 * s6;
-    double fr = fc.eps24 * inv * (s6 - 2.0 * s12);  // F / r
+    // with y = 1/r^2:  F/r = 24 eps (s^6 - 2 s^12) / r^2 = y^4 (c6 - c12 y^3),  U = y^3 (d12 y^3 - d6) - u_cut
+    const double y = rcp_nr(r2);
+    const double y2 = y * y;
+    const double y3 = y2 * y;
+    double fr = (y2 * y2) * fma(-fc.c12, y3, fc.c6);  // F / r
     fr = in ? fr : 0.0;
     a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
     // per-atom potential / virial: uniform flags — steady-state steps of a batch only need what feeds the controls
     if (need_u) {
-        double pu = fc.eps4 * (s12 - s6) - fc.u_cut;
+        const double pu = fma(y3, fma(fc.d12, y3, -fc.d6), -fc.u_cut);
         a.u += in ? pu : 0.0;
     }
     if (need_w) a.w += fr * r2;
