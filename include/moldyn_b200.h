@@ -51,8 +51,12 @@ typedef enum md_status {
                                 0.245 ms) — after the 256-bit gathers the dense loop is bound by pair arithmetic, and the union
                                 evaluates 25 % more pairs */
 /* loop_mode */
-#define MD_LOOP_GRAPH 0 /* steady-state steps run inside one conditional (WHILE) CUDA graph (default) */
-#define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check) */
+#define MD_LOOP_GRAPH 0 /* default: CUDA-graph loop, currently MD_LOOP_CHUNK (measured faster than MD_LOOP_WHILE on B200:
+                           36.8 vs 41.1 us/step at 10^6 atoms, 14.3 vs 17.5 at 32768 — same bits) */
+#define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check, ncu) */
+#define MD_LOOP_CHUNK 2 /* pre-enqueued graphs of 16 guarded steps (a step is a no-op once the device says "rebuild" or
+                           "done"): no conditional node per iteration */
+#define MD_LOOP_WHILE 3 /* ONE conditional (WHILE) graph; the force kernel's last block sets the loop condition */
 
 /* step_mode */
 #define MD_STEP_AUTO 0  /* the faster of the two below as measured on B200: currently MD_STEP_SPLIT everywhere */

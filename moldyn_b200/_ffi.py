@@ -14,7 +14,7 @@ ERR_NAMES = {
 }
 UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT, FORCE_FAST_UNION = 0, 1, 2
-LOOP_GRAPH, LOOP_HOST = 0, 1
+LOOP_GRAPH, LOOP_HOST, LOOP_CHUNK, LOOP_WHILE = 0, 1, 2, 3
 STEP_AUTO, STEP_SPLIT, STEP_FUSED = 0, 1, 2
 CELL_UNIFORM, CELL_FCC = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2

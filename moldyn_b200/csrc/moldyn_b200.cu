@@ -110,6 +110,7 @@ struct md_ctx {
     int act_alloc = 0, sparse_grid = 1;
     bool sparse = false;                              // dilute + FAST: the last rebuild left a valid active list
     double rebuild_host_ms = 0.0;                     // multi-GPU: wall time spent in list rebuilds (host clock, synchronised)
+    long long epoch_start_step = 0, last_epoch_len = 128;  // list epochs in steps: sizes the chunk look-ahead
     // dense + FAST on one GPU: union lists per atom pair (k_build_union), see md_kernels.cuh
     int *nbr_u = nullptr, *cnt_u = nullptr;
     size_t nbr_u_alloc = 0;
@@ -572,6 +573,8 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.kernel_launches += 1;
     CK(cudaGetLastError());
     ctx->stats.rebuilds += 1;
+    if (ctx->stats.steps > ctx->epoch_start_step) ctx->last_epoch_len = ctx->stats.steps - ctx->epoch_start_step;
+    ctx->epoch_start_step = ctx->stats.steps;
     ctx->stats.nbr_max = ctx->h_sc->nbr_max;
     ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
     ctx->dense = ctx->stats.nbr_mean >= 8.0 && n >= 128;  // (the dense kernel's masked lanes need a foreign warp's atom)
@@ -621,24 +624,24 @@ int build_active_list(md_ctx *ctx, int n)
     return MD_OK;
 }
 
-int launch_force(md_ctx *ctx, bool kick, unsigned long long cond)
+int launch_force(md_ctx *ctx, bool kick, unsigned long long cond, int guarded = 0)
 {
     const int n = (int)ctx->n;
     const ForceConsts fc = force_consts(ctx);
 #define LAUNCH_FORCE(E, R, M, GRID)                                                                                  \
     k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
                                                          ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
-                                                         kick ? 1 : 0, cond, fc, nullptr)
+                                                         (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr)
     if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
     else if (ctx->dense && ctx->union_valid)
         k_force<false, 2, true, true><<<ctx->force_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, ctx->cur, ctx->nbr_u, ctx->cnt_u, ctx->npad, ctx->cap_u, ctx->d_partials, ctx->d_sc, ctx->d_pr, kick ? 1 : 0,
-            cond, fc, nullptr);
+            n, ctx->cur, ctx->nbr_u, ctx->cnt_u, ctx->npad, ctx->cap_u, ctx->d_partials, ctx->d_sc, ctx->d_pr,
+            (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr);
     else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
     else if (ctx->sparse)
         k_force_sparse<<<ctx->sparse_grid, FORCE_BLOCK, 0, ctx->stream>>>(
             n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->act_idx, ctx->act_scan + n, ctx->d_partials, ctx->d_sc,
-            ctx->d_pr, kick ? 1 : 0, cond, fc, nullptr);
+            ctx->d_pr, (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr);
     else LAUNCH_FORCE(false, MD_DILUTE_ROWS, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
     return MD_OK;
@@ -661,7 +664,7 @@ void fused_views(const md_ctx *ctx, Arrays *p0, Arrays *p1)
     *p1 = ctx->parity_host ? ctx->cur : other;
 }
 
-int launch_fused_step(md_ctx *ctx, unsigned long long cond)
+int launch_fused_step(md_ctx *ctx, unsigned long long cond, int guarded = 0)
 {
     const int n = (int)ctx->n;
     const ForceConsts fc = force_consts(ctx);
@@ -669,10 +672,12 @@ int launch_fused_step(md_ctx *ctx, unsigned long long cond)
     fused_views(ctx, &p0, &p1);
     if (ctx->cfg.force_mode == MD_FORCE_EXACT)
         k_step_dilute<true><<<ctx->step_grid[0], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, 0, cond, fc);
+            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,
+            guarded ? 4 : 0, cond, fc);
     else
         k_step_dilute<false><<<ctx->step_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, 0, cond, fc);
+            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,
+            guarded ? 4 : 0, cond, fc);
     return MD_OK;
 }
 
@@ -753,6 +758,29 @@ int build_graph(md_ctx *ctx)
     return MD_OK;
 }
 
+// MD_LOOP_CHUNK: STEP_CHUNK guarded steps captured once per list epoch; the host enqueues a few of them ahead.
+constexpr int STEP_CHUNK = 16;
+int build_chunk_graph(md_ctx *ctx, bool fused)
+{
+    drop_graph(ctx);
+    const int64_t launches = ctx->stats.kernel_launches;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < STEP_CHUNK; ++k) {
+        if (fused) {
+            launch_fused_step(ctx, 0ull, 1);
+        } else {
+            launch_kick_drift(ctx, 1);
+            launch_force(ctx, true, 0ull, 1);
+        }
+    }
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->dist_graph);
+    ctx->stats.kernel_launches = launches;
+    if (e != cudaSuccess) return ctx->fail(MD_ERR_CUDA, "graph capture of the step chunk failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&ctx->dist_graph_exec, ctx->dist_graph, 0));
+    ctx->graph_fused = fused;
+    return MD_OK;
+}
+
 int flush_pending_scale(md_ctx *ctx)
 {
     const int n = (int)ctx->n_own;
@@ -819,7 +847,11 @@ int md_create(const md_config *cfg, md_ctx **out)
     md_ctx *ctx = new md_ctx();
     if (cfg) ctx->cfg = *cfg;
     if (const char *e = std::getenv("MOLDYN_B200_LOOP"))  // profiling aid: ncu cannot see kernels of conditional graphs
+    {
         if (!strcmp(e, "host")) ctx->cfg.loop_mode = MD_LOOP_HOST;
+        if (!strcmp(e, "chunk")) ctx->cfg.loop_mode = MD_LOOP_CHUNK;
+        if (!strcmp(e, "while")) ctx->cfg.loop_mode = MD_LOOP_WHILE;
+    }
     ctx->device = ctx->cfg.device;
     auto bail = [&](cudaError_t e, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e) +
@@ -1210,11 +1242,23 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
                 if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
             }
         } else {
-            if (ctx->graph_ok && ctx->graph_fused != fused) drop_graph(ctx);
-            if (!ctx->graph_ok) TRY(build_graph(ctx));
             long long before = ctx->h_sc->steps_done;
-            CK(cudaGraphLaunch(ctx->graph_exec, st));
-            ctx->stats.graph_launches += 1;
+            if (ctx->cfg.loop_mode != MD_LOOP_WHILE) {
+                if (ctx->dist_graph_exec && ctx->graph_fused != fused) drop_graph(ctx);
+                if (!ctx->dist_graph_exec) TRY(build_chunk_graph(ctx, fused));
+                // look ahead as far as the list is expected to last (the previous epoch's length), at most 8 chunks: steps
+                // enqueued past a rebuild request are no-ops, but each still costs a launch
+                const long long since = ctx->stats.steps - ctx->epoch_start_step;
+                const long long expect = std::max<long long>(STEP_CHUNK, ctx->last_epoch_len - since);
+                const int chunks = (int)std::min<long long>(8, (std::min<long long>(remaining, expect) + STEP_CHUNK - 1) / STEP_CHUNK);
+                for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(ctx->dist_graph_exec, st));
+                ctx->stats.graph_launches += chunks;
+            } else {
+                if (ctx->graph_ok && ctx->graph_fused != fused) drop_graph(ctx);
+                if (!ctx->graph_ok) TRY(build_graph(ctx));
+                CK(cudaGraphLaunch(ctx->graph_exec, st));
+                ctx->stats.graph_launches += 1;
+            }
             TRY(pull_scalars(ctx));
             long long ran = ctx->h_sc->steps_done - before;
             ctx->stats.kernel_launches += (fused ? 1 : 2) * ran;

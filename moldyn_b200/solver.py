@@ -153,11 +153,12 @@ class State:
 class Solver:
     """Device-resident session: owns an md_ctx. `exact=True` selects MD_FORCE_EXACT (bit-identical forces)."""
 
-    def __init__(self, device=0, exact=False, host_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
+    def __init__(self, device=0, exact=False, host_loop=False, while_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
                  cell_atoms=0.0, step_mode="auto", union_lists=False):
         self._ctx = C.c_void_p()
         cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else (_ffi.FORCE_FAST_UNION if union_lists else _ffi.FORCE_FAST),
-                          _ffi.LOOP_HOST if host_loop else _ffi.LOOP_GRAPH, max_neighbours, cell_subdiv,
+                          _ffi.LOOP_HOST if host_loop else (_ffi.LOOP_WHILE if while_loop else _ffi.LOOP_GRAPH),
+                          max_neighbours, cell_subdiv,
                           {"auto": _ffi.STEP_AUTO, "split": _ffi.STEP_SPLIT, "fused": _ffi.STEP_FUSED}[step_mode], skin,
                           cell_atoms)
         L = _ffi.lib()

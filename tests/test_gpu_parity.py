@@ -394,21 +394,24 @@ def test_device_side_initializer(cell):
 
 
 def test_graph_loop_equals_host_loop(mode):
+    """The three loop drivers — chunked graphs of guarded steps (default), the conditional WHILE graph, and one host round
+    trip per step — run the same kernels on the same data: identical bits."""
     o = liquid(10)
     out = []
-    for host_loop in (False, True):
+    for kw in ({}, {"while_loop": True}, {"host_loop": True}):
         st = to_gpu_state(md, o)
-        with make_solver(mode, host_loop=host_loop) as s:
+        with make_solver(mode, **kw) as s:
             s.upload(st, with_forces=False)
             s.update_force()
             s.step(150, DT, thermostat=(md.Thermostat.Berendsen(10.0), 120.0),
                    barostat=(md.Barostat.Berendsen(1.0, 5.0), 1.01325))
             s.download(st)
             out.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.boundary_box.copy(), s.stats()))
-    for a, b in zip(out[0][:4], out[1][:4]):
-        assert np.array_equal(a, b)
-    assert out[0][4]["graph_launches"] > 0 and out[1][4]["graph_launches"] == 0
-    assert out[0][4]["rebuilds"] == out[1][4]["rebuilds"]
+    for other in out[1:]:
+        for a, b in zip(out[0][:4], other[:4]):
+            assert np.array_equal(a, b)
+        assert out[0][4]["rebuilds"] == other[4]["rebuilds"]
+    assert out[0][4]["graph_launches"] > 0 and out[1][4]["graph_launches"] > 0 and out[2][4]["graph_launches"] == 0
 
 
 @pytest.mark.parametrize("host_loop", [False, True])
