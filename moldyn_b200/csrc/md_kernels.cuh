@@ -1047,6 +1047,15 @@ __device__ __forceinline__ double rcp_nr(double x)
     return fma(y, e, y);
 }
 
+// A load the compiler can neither hoist nor keep live across a loop: per-block constants that are only needed between two
+// long neighbour loops are re-read (L1/L2 hits) instead of occupying registers inside them.
+__device__ __forceinline__ double ld_pinned(const double *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // branch-free single-shift minimum image (same rule as min_image): two compares, a select, one add
 __device__ __forceinline__ double min_image_sel(double r, double L, double h)
 {
@@ -1222,6 +1231,48 @@ __device__ __forceinline__ void neighbour_loop(PairAcc &f0, PairAcc &f1, const A
     }
 }
 
+// ---- dense pair term ---------------------------------------------------------------------------------------------------
+// What the SASS of the first dense loop showed (cuobjdump, 4 pair terms per trip: 227 instructions, 84 of them FP64): the
+// uniform need_u / need_w flags had been if-converted — potential and virial were computed for every pair and dropped by a
+// select (16 FP64 + 12 FSEL per trip).  The flags are therefore a template parameter (UW: 0 = forces only, 1 = + virial,
+// 2 = + potential); one of six loop instances runs per launch.  Same arithmetic in the same order: bit-identical results.
+
+// single-shift minimum image, same rule as min_image (r > h → r - L, r < -h → r + L) written as |r| > h → r - copysign(L, r):
+// one FP64 compare instead of two, the sign work on the integer pipe
+__device__ __forceinline__ double min_image_abs(double r, double L, double h)
+{
+    const int hi = __double2hiint(r);
+    const double ar = __hiloint2double(hi & 0x7fffffff, __double2loint(r));
+    const double s = __hiloint2double(__double2hiint(L) | (~hi & 0x80000000), __double2loint(L));  // -copysign(L, r), L > 0
+    return r + (ar > h ? s : 0.0);
+}
+
+template <bool WRAP, int UW>
+__device__ __forceinline__ void pair_dense(PairAcc &a, bool active, double xj, double yj, double zj, double xi, double yi,
+                                           double zi, const LjConst &c, const ForceConsts &fc)
+{
+    double rx = xj - xi, ry = yj - yi, rz = zj - zi;
+    if (WRAP) {
+        rx = min_image_abs(rx, c.Lx, c.hx);
+        ry = min_image_abs(ry, c.Ly, c.hy);
+        rz = min_image_abs(rz, c.Lz, c.hz);
+    }
+    const double r2 = rx * rx + ry * ry + rz * rz;
+    const bool in = active && (r2 <= fc.rc2);
+    // see pair_fast: r2 > 0 on every lane, masked and out-of-range pairs are zeroed by the select
+    const double y = rcp_nr(r2);
+    const double y2 = y * y;
+    const double y3 = y2 * y;
+    double fr = (y2 * y2) * fma(-fc.c12, y3, fc.c6);  // F / r
+    fr = in ? fr : 0.0;
+    a.fx += fr * rx; a.fy += fr * ry; a.fz += fr * rz;
+    if (UW >= 2) {
+        const double pu = fma(y3, fma(fc.d12, y3, -fc.d6), -fc.u_cut);
+        a.u += in ? pu : 0.0;
+    }
+    if (UW >= 1) a.w += fr * r2;
+}
+
 // Dense systems (hundreds of listed partners per atom): the neighbour table is far larger than L2 and streams from HBM, so a
 // one-trip-ahead index prefetch leaves the warp waiting on DRAM every trip.  Each thread therefore keeps a ring of the next
 // RING_D trips' index rows (two rows per trip) in shared memory, filled by cp.async — no registers, no barrier (a thread only
@@ -1239,11 +1290,11 @@ struct IndexRing {
     int2 r[RING_D][2][FORCE_BLOCK];
 };
 
-template <bool WRAP>
+template <bool WRAP, int UW>
 __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, const double4 *__restrict__ q4,
                                                      const int2 *__restrict__ row, size_t stride, int2 C, int i0,
                                                      double2 X, double2 Y, double2 Z, const LjConst &c,
-                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w, int n)
+                                                     const ForceConsts &fc, IndexRing &ring, int n)
 {
     const int l = threadIdx.x;
     const int kmax = max(C.x, C.y);
@@ -1257,6 +1308,7 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
         }
         cp_async_commit();
     }
+    const int2 *refill = row + (size_t)(2 * RING_D) * stride;
     // software pipeline: the gathers of trip t+1 are in flight while the pair terms of trip t are computed.
 #define MD_FETCH_ROWS(T, JA, JB)                                                                           \
     do {                                                                                                   \
@@ -1266,10 +1318,11 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
         JB = ring.r[slot_][1][l];                                                                          \
         const int tn_ = (T) + RING_D; /* refill the slot with the rows of trip T + RING_D */               \
         if (tn_ < ntrips) {                                                                                \
-            cp_async8(&ring.r[slot_][0][l], row + (size_t)(2 * tn_) * stride);                             \
-            if (2 * tn_ + 1 < kmax) cp_async8(&ring.r[slot_][1][l], row + (size_t)(2 * tn_ + 1) * stride); \
+            cp_async8(&ring.r[slot_][0][l], refill);                                                       \
+            if (2 * tn_ + 1 < kmax) cp_async8(&ring.r[slot_][1][l], refill + stride);                      \
         }                                                                                                  \
         cp_async_commit();                                                                                 \
+        refill += 2 * stride; /* walks the table two rows per trip: no 64-bit multiply per refill */       \
     } while (0)
     // one 256-bit load per partner (LDG.E.256, new with sm_100): a divergent gather costs the L1 one pass per lane and
     // instruction, and this loop is co-limited by exactly that — half the passes of an (x, y) + z pair of loads
@@ -1303,10 +1356,10 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
             MD_GATHER(k + 3 < C.x ? Jb.x : i0, nb0, yb0); MD_GATHER(k + 3 < C.y ? Jb.y : i0, nb1, yb1);
         }
         const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
-        pair_fast<WRAP>(f0, a0, pa0.x, pa0.y, za0, X.x, Y.x, Z.x, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f1, a1, pa1.x, pa1.y, za1, X.y, Y.y, Z.y, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f0, b0, pb0.x, pb0.y, zb0, X.x, Y.x, Z.x, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f1, b1, pb1.x, pb1.y, zb1, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pair_dense<WRAP, UW>(f0, a0, pa0.x, pa0.y, za0, X.x, Y.x, Z.x, c, fc);
+        pair_dense<WRAP, UW>(f1, a1, pa1.x, pa1.y, za1, X.y, Y.y, Z.y, c, fc);
+        pair_dense<WRAP, UW>(f0, b0, pb0.x, pb0.y, zb0, X.x, Y.x, Z.x, c, fc);
+        pair_dense<WRAP, UW>(f1, b1, pb1.x, pb1.y, zb1, X.y, Y.y, Z.y, c, fc);
         pa0 = na0; pa1 = na1; pb0 = nb0; pb1 = nb1;
         za0 = ya0; za1 = ya1; zb0 = yb0; zb1 = yb1;
     }
@@ -1568,12 +1621,12 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
     // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
     const bool store_state = !(do_step & 1) || sc->steps_left <= 1;
     const bool nh = pr->th_kind == 2 || !(do_step & 1);  // a plain force evaluation keeps every stored sum valid
-    const double lambda = sc->lambda;
+    const double lambda = MASKED ? 1.0 : sc->lambda;
     LjConst c;
     c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
     c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
     c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
-    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    const double shift[3] = {MASKED ? 0.0 : sc->shift[0], MASKED ? 0.0 : sc->shift[1], MASKED ? 0.0 : sc->shift[2]};
     // partners listed at the last build are now at most r_list + skin away (each atom moved < skin/2)
     const double wrap_margin = (2.0 * pr->r_list - pr->r_cut) * 1.02;
     const int npairs = (n + 1) >> 1;
@@ -1653,10 +1706,18 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
                     const int *urow = nbr + t;  // entry k of thread t: nbr[k * (npad / 2) + t]
                     if (wrap) neighbour_loop_union<true>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
                     else neighbour_loop_union<false>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
-                } else if (wrap)
-                    neighbour_loop_dense<true>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
-                else
-                    neighbour_loop_dense<false>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
+                }
+                else {
+                    // uniform over the grid: one of six loop instances runs per launch
+                    const int uw = need_u ? 2 : (need_w ? 1 : 0);
+#define MD_DENSE_CALL(W, U) neighbour_loop_dense<W, U>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, n)
+                    if (wrap) {
+                        if (uw == 0) MD_DENSE_CALL(true, 0); else if (uw == 1) MD_DENSE_CALL(true, 1); else MD_DENSE_CALL(true, 2);
+                    } else {
+                        if (uw == 0) MD_DENSE_CALL(false, 0); else if (uw == 1) MD_DENSE_CALL(false, 1); else MD_DENSE_CALL(false, 2);
+                    }
+#undef MD_DENSE_CALL
+                }
             } else {
                 neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             }
@@ -1666,8 +1727,12 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
             VZ = reinterpret_cast<double2 *>(a.vz)[t];
         }
         double2 WX, WY, WZ;
-        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
-        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y, nh);
+        // dense: lambda and the sum shift are re-read here rather than carried through the neighbour loop (7 registers)
+        const double lam = MASKED ? ld_pinned(&sc->lambda) : lambda;
+        const double sh[3] = {MASKED ? ld_pinned(&sc->shift[0]) : shift[0], MASKED ? ld_pinned(&sc->shift[1]) : shift[1],
+                              MASKED ? ld_pinned(&sc->shift[2]) : shift[2]};
+        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lam, fc.hc, fc.mass, sh, WX.x, WY.x, WZ.x, nh);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lam, fc.hc, fc.mass, sh, WX.y, WY.y, WZ.y, nh);
         else { WX.y = WY.y = WZ.y = 0.0; }
         if (!has1) {  // odd tail: scalar stores only (slot i0+1 may hold a ghost atom in the distributed layout)
             if (store_state) {
