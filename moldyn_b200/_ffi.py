@@ -73,7 +73,9 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree library; MOLDYN_B200_LIBRARY points at another build of the same sources (kernel A/B runs on the
+    GPU box, see scripts/gpu_round1_final.sh) — still a CUDA build of this repo, never a fallback."""
+    return os.environ.get("MOLDYN_B200_LIBRARY") or _build.LIB
 
 
 def lib():

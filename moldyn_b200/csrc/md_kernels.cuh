@@ -92,6 +92,12 @@ __device__ __forceinline__ bool halted(const Scalars *sc)
     return sc->need_rebuild != 0 || sc->error != 0 || sc->steps_left <= 0;
 }
 
+// Programmatic dependent launch (opt-in, MOLDYN_B200_PDL=1; single-GPU chunk graphs): a step kernel launched with the
+// programmatic-serialization attribute becomes resident while its predecessor drains and blocks here until the predecessor
+// has completed and its memory operations are visible.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long gtime()
 {
     unsigned long long t;
@@ -1460,6 +1466,7 @@ __global__ void k_flag_active(int n, const int *__restrict__ nbr_cnt, int *__res
 // shared by the force kernels: guarded early-out, phase clock, wait for the neighbours' ghosts (peer-memory path)
 __device__ __forceinline__ bool force_prologue(int do_step, Scalars *sc, const Peers *peers)
 {
+    if (do_step & 32) { pdl_wait(); pdl_launch_dependents(); }
     if ((do_step & 4) && halted(sc)) return false;  // uniform over the grid: nobody takes a ticket
     if ((do_step & 8) && threadIdx.x == 0) atomicMin(&sc->t_start, gtime());
     if (do_step & 16) {
@@ -1612,7 +1619,8 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
             unsigned long long cond_handle, const ForceConsts fc, const Peers *peers)
 {
     // do_step bits: 1 = MD step (both half-kicks fused in), 2 = multi-GPU (publish rank sums only), 4 = guarded,
-    //               8 = multi-GPU over peer memory (sums exchanged and finalized here), 16 = wait for the neighbours' ghosts
+    //               8 = multi-GPU over peer memory (sums exchanged and finalized here), 16 = wait for the neighbours' ghosts,
+    //               32 = launched as a programmatic dependent (wait for the predecessor first)
     if (!force_prologue(do_step, sc, peers)) return;
     if (threadIdx.x == 0) { PROBE_MIN(0); }
     __shared__ SumsSmem ss;
@@ -1829,8 +1837,21 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
                                                     const Params *__restrict__ pr, int guarded, int write_q4,
                                                     const HaloPush h)
 {
-    if (guarded && halted(sc)) return;
+    // guarded bits: 1 = return at once when the loop is halted, 2 = launched as a programmatic dependent of k_force
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double2 x, y, z;
+    const bool early = (guarded & 2) && 2 * t + 1 < n;
+    if (guarded & 2) {
+        // positions were last written by the previous k_kick_drift, which completed before our predecessor (k_force) did
+        // anything: they can be fetched while k_force drains.  Everything else waits.
+        if (early) {
+            x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
+            z = reinterpret_cast<double2 *>(a.z)[t];
+        }
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+    if ((guarded & 1) && halted(sc)) return;
     // block-uniform: does this block hold face atoms?  (512 atoms per block)
     const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
     const bool pushes = (h.m[0] | h.m[1]) != 0 && (b_lo < h.m[0] || b_hi > n - h.m[1]);
@@ -1843,8 +1864,10 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
             const double lambda = sc->lambda, mup = sc->mu_pending;
             const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
             const bool half = sc->vel_is_half != 0;
-            double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
-                    z = reinterpret_cast<double2 *>(a.z)[t];
+            if (!early) {
+                x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
+                z = reinterpret_cast<double2 *>(a.z)[t];
+            }
             double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
                     uz = reinterpret_cast<double2 *>(a.vz)[t];
             if (!half) {

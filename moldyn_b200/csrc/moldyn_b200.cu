@@ -586,11 +586,42 @@ int rebuild_lists(md_ctx *ctx)
     return MD_OK;
 }
 
-int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr)
+// Programmatic dependent launch of the step kernels inside the single-GPU chunk graph (opt-in: MOLDYN_B200_PDL=1).
+// The launch attribute turns the kernel -> kernel edge of the captured graph into a programmatic one; the kernels
+// themselves start with griddepcontrol.wait (pdl_wait), so nothing is read before the predecessor has completed.
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("MOLDYN_B200_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr, bool pdl = false)
 {
     const int n = (int)ctx->n_own;
-    k_kick_drift<<<std::max(1, blocks_for((n + 1) / 2, 256)), 256, 0, ctx->stream>>>(
-        n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded, ctx->use_q4 ? 1 : 0, push ? *push : HaloPush{});
+    const int blocks = std::max(1, blocks_for((n + 1) / 2, 256));
+    if (pdl) {
+        CK(launch_pdl(k_kick_drift, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded | 2,
+                      ctx->use_q4 ? 1 : 0, push ? *push : HaloPush{}));
+        return MD_OK;
+    }
+    k_kick_drift<<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded, ctx->use_q4 ? 1 : 0,
+                                                  push ? *push : HaloPush{});
     return MD_OK;
 }
 
@@ -624,14 +655,23 @@ int build_active_list(md_ctx *ctx, int n)
     return MD_OK;
 }
 
-int launch_force(md_ctx *ctx, bool kick, unsigned long long cond, int guarded = 0)
+int launch_force(md_ctx *ctx, bool kick, unsigned long long cond, int guarded = 0, bool pdl = false)
 {
     const int n = (int)ctx->n;
     const ForceConsts fc = force_consts(ctx);
+    if (pdl && (ctx->sparse || (ctx->dense && ctx->union_valid))) pdl = false;  // opt-in variants keep plain launches
+    const int flags = (kick ? 1 : 0) | (guarded ? 4 : 0) | (pdl ? 32 : 0);
 #define LAUNCH_FORCE(E, R, M, GRID)                                                                                  \
-    k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,           \
-                                                         ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,    \
-                                                         (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr)
+    do {                                                                                                             \
+        if (pdl)                                                                                                     \
+            CK(launch_pdl(k_force<E, R, M>, dim3(GRID), dim3(FORCE_BLOCK), ctx->stream, n, ctx->cur, ctx->nbr,       \
+                          ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, cond, \
+                          fc, (const Peers *)nullptr));                                                              \
+        else                                                                                                         \
+            k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,   \
+                                                                 ctx->grid.cap, ctx->d_partials, ctx->d_sc,       \
+                                                                 ctx->d_pr, flags, cond, fc, nullptr);            \
+    } while (0)
     if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
     else if (ctx->dense && ctx->union_valid)
         k_force<false, 2, true, true><<<ctx->force_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
@@ -765,16 +805,20 @@ int build_chunk_graph(md_ctx *ctx, bool fused)
     drop_graph(ctx);
     const int64_t launches = ctx->stats.kernel_launches;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    for (int k = 0; k < STEP_CHUNK; ++k) {
+    int rc = MD_OK;
+    for (int k = 0; k < STEP_CHUNK && rc == MD_OK; ++k) {
         if (fused) {
             launch_fused_step(ctx, 0ull, 1);
         } else {
-            launch_kick_drift(ctx, 1);
-            launch_force(ctx, true, 0ull, 1);
+            // programmatic edges inside the chunk; its first kernel depends on the previous graph launch as a whole
+            const bool pdl = pdl_enabled();
+            rc = launch_kick_drift(ctx, 1, nullptr, pdl && k > 0);
+            if (rc == MD_OK) rc = launch_force(ctx, true, 0ull, 1, pdl);
         }
     }
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->dist_graph);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->dist_graph);  // always leave capture mode
     ctx->stats.kernel_launches = launches;
+    if (rc != MD_OK) return rc;
     if (e != cudaSuccess) return ctx->fail(MD_ERR_CUDA, "graph capture of the step chunk failed: %s", cudaGetErrorString(e));
     CK(cudaGraphInstantiate(&ctx->dist_graph_exec, ctx->dist_graph, 0));
     ctx->graph_fused = fused;

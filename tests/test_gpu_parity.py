@@ -589,3 +589,48 @@ def test_full_size_sampled_rows_and_invariants(n_side, cut):
     e0, e1 = m0["kinetic"] + m0["potential"], m1["kinetic"] + m1["potential"]
     assert abs(e1 - e0) <= 1e-3 * abs(m0["kinetic"])       # NVE energy conservation at dt = 2 fs (oracle: 1.1e-4)
     assert np.abs(m1["momentum"]).max() <= 1e-9 * o.n       # Σ m v stays ~0
+
+
+# ---------------------------------------------------------------------------------------------------
+# programmatic dependent launch of the step kernels (MOLDYN_B200_PDL, read once per process → a child process each)
+_PDL_CHILD = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import moldyn_b200 as md
+from helpers import liquid, gas, to_gpu_state
+for name, o, T in (("liquid", liquid(12), 120.0), ("gas", gas(16), 300.0)):
+    for exact in (False, True):
+        st = to_gpu_state(md, o)
+        with md.Solver(exact=exact) as s:
+            s.upload(st, with_forces=False)
+            s.update_force()
+            for k in (1, 37, 200):
+                s.step(k, 0.002, thermostat=(md.Thermostat.Berendsen(10.0), T),
+                       barostat=(md.Barostat.Berendsen(1.0, 5.0), 1.01325))
+            s.download(st)
+            stats = s.stats()
+        h = hashlib.sha256()
+        for a in (st.position, st.velocity, st.force, st.potential, st.temp, st.boundary_box):
+            h.update(np.ascontiguousarray(a).tobytes())
+        print(name, exact, h.hexdigest(), stats["graph_launches"] > 0, stats["rebuilds"])
+"""
+
+
+def test_programmatic_dependent_launch_is_bit_identical():
+    """MOLDYN_B200_PDL=1 turns the kernel → kernel edges of the step graph into programmatic ones (the kernels wait with
+    griddepcontrol.wait before reading anything; k_kick_drift fetches its positions ahead of the wait).  Scheduling only:
+    NPT trajectories through the graph loop must not change by a bit."""
+    import os
+    import subprocess
+    import sys
+    tests = os.path.dirname(os.path.abspath(__file__))
+    code = _PDL_CHILD.format(root=os.path.dirname(tests), tests=tests)
+    outs = []
+    for pdl in ("0", "1"):
+        env = dict(os.environ, MOLDYN_B200_PDL=pdl)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines())
+    assert len(outs[0]) == 4 and outs[0] == outs[1]
+    assert all(line.split()[3] == "True" for line in outs[0])  # the graph loop ran
