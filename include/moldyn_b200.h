@@ -50,6 +50,9 @@ typedef enum md_status {
                                 gather serves both atoms of a thread.  Opt-in: measured slower on B200 (C5 k_force 0.311 vs
                                 0.245 ms) — after the 256-bit gathers the dense loop is bound by pair arithmetic, and the union
                                 evaluates 25 % more pairs */
+#define MD_FORCE_FAST_COOP 3 /* MD_FORCE_FAST with the warp-cooperative force kernel for dense systems on one GPU (k_force_coop:
+                               the 32 lanes of a warp share one atom's list, stored atom-major, so a gather touches a few
+                               128-byte lines instead of 32 — the per-thread loop is bound by the L1 tag stage) */
 /* loop_mode */
 #define MD_LOOP_GRAPH 0 /* default: CUDA-graph loop, currently MD_LOOP_CHUNK (measured faster than MD_LOOP_WHILE on B200:
                            36.8 vs 41.1 us/step at 10^6 atoms, 14.3 vs 17.5 at 32768 — same bits) */
@@ -124,7 +127,7 @@ typedef struct md_stats {
     int32_t cells[3];         /* current cell grid */
     int32_t nbr_capacity;     /* neighbour slots per atom */
     int32_t nbr_max;          /* largest neighbour count seen at the last rebuild */
-    int32_t reserved0;
+    int32_t coop_lists;       /* 1: the last rebuild produced the atom-major table of the warp-cooperative dense force kernel */
     double skin;              /* skin in use */
     double nbr_mean;          /* mean neighbour count at the last rebuild */
     int64_t n_owned;          /* atoms this rank owns (== n on one GPU) */

@@ -13,7 +13,7 @@ ERR_NAMES = {
     5: "MD_ERR_NEIGHBOUR_OVERFLOW", 6: "MD_ERR_NO_STATE", 7: "MD_ERR_NONFINITE", 8: "MD_ERR_DECOMPOSITION",
 }
 UNIQUE_ID_BYTES = 128
-FORCE_FAST, FORCE_EXACT, FORCE_FAST_UNION = 0, 1, 2
+FORCE_FAST, FORCE_EXACT, FORCE_FAST_UNION, FORCE_FAST_COOP = 0, 1, 2, 3
 LOOP_GRAPH, LOOP_HOST, LOOP_CHUNK, LOOP_WHILE = 0, 1, 2, 3
 STEP_AUTO, STEP_SPLIT, STEP_FUSED = 0, 1, 2
 CELL_UNIFORM, CELL_FCC = 0, 1
@@ -53,7 +53,7 @@ class MacroOut(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("graph_launches", C.c_int64), ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32),
-                ("nbr_max", C.c_int32), ("reserved0", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
+                ("nbr_max", C.c_int32), ("coop_lists", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
                 ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64), ("fused_steps", C.c_int64), ("wait_halo_ms", C.c_double),
                 ("wait_sums_ms", C.c_double), ("peer_memory", C.c_int32), ("union_lists", C.c_int32),
                 ("force_atoms_ms", C.c_double), ("force_tail_ms", C.c_double), ("drift_push_ms", C.c_double)]

@@ -1376,11 +1376,11 @@ __device__ __forceinline__ void neighbour_loop_dense(PairAcc &f0, PairAcc &f1, c
 
 // Dense systems with UNION lists (k_build_union): one entry = one gather, evaluated against both atoms of the thread under
 // the entry's membership bits.  Same ring / pipeline structure as neighbour_loop_dense, half the gathers per pair term.
-template <bool WRAP>
+template <bool WRAP, int UW>
 __device__ __forceinline__ void neighbour_loop_union(PairAcc &f0, PairAcc &f1, const double4 *__restrict__ q4,
                                                      const int *__restrict__ row, size_t stride, int cnt, int i0,
                                                      double2 X, double2 Y, double2 Z, const LjConst &c,
-                                                     const ForceConsts &fc, IndexRing &ring, bool need_u, bool need_w, int n)
+                                                     const ForceConsts &fc, IndexRing &ring, int n)
 {
     const int l = threadIdx.x;
     const int ntrips = (cnt + 1) >> 1;
@@ -1433,10 +1433,10 @@ __device__ __forceinline__ void neighbour_loop_union(PairAcc &f0, PairAcc &f1, c
             MD_GATHER(fa & UNION_IDX, na, ya);
             MD_GATHER(fb & UNION_IDX, nb, yb);
         }
-        pair_fast<WRAP>(f0, (ea & UNION_A) != 0, pa.x, pa.y, za, X.x, Y.x, Z.x, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f1, ea < 0, pa.x, pa.y, za, X.y, Y.y, Z.y, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f0, (eb & UNION_A) != 0, pb.x, pb.y, zb, X.x, Y.x, Z.x, c, fc, need_u, need_w);
-        pair_fast<WRAP>(f1, eb < 0, pb.x, pb.y, zb, X.y, Y.y, Z.y, c, fc, need_u, need_w);
+        pair_dense<WRAP, UW>(f0, (ea & UNION_A) != 0, pa.x, pa.y, za, X.x, Y.x, Z.x, c, fc);
+        pair_dense<WRAP, UW>(f1, ea < 0, pa.x, pa.y, za, X.y, Y.y, Z.y, c, fc);
+        pair_dense<WRAP, UW>(f0, (eb & UNION_A) != 0, pb.x, pb.y, zb, X.x, Y.x, Z.x, c, fc);
+        pair_dense<WRAP, UW>(f1, eb < 0, pb.x, pb.y, zb, X.y, Y.y, Z.y, c, fc);
         pa = na; pb = nb; za = ya; zb = yb; ea = fa; eb = fb;
     }
 #undef MD_FETCH_ENTRIES
@@ -1710,22 +1710,20 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
                 const bool near = X.x < m || X.x > c.Lx - m || Y.x < m || Y.x > c.Ly - m || Z.x < m || Z.x > c.Lz - m ||
                                   X.y < m || X.y > c.Lx - m || Y.y < m || Y.y > c.Ly - m || Z.y < m || Z.y > c.Lz - m;
                 const bool wrap = __any_sync(__activemask(), near);
-                if (UNION) {
-                    const int *urow = nbr + t;  // entry k of thread t: nbr[k * (npad / 2) + t]
-                    if (wrap) neighbour_loop_union<true>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
-                    else neighbour_loop_union<false>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, need_u, need_w, n);
+                // uniform over the grid: one of six loop instances runs per launch
+                const int uw = need_u ? 2 : (need_w ? 1 : 0);
+                const int *urow = nbr + t;  // UNION: entry k of thread t is nbr[k * (npad / 2) + t]
+#define MD_DENSE_CALL(W, U)                                                                                       \
+    do {                                                                                                          \
+        if (UNION) neighbour_loop_union<W, U>(f0, f1, a.q4, urow, stride, C.x, i0, X, Y, Z, c, fc, ring, n);      \
+        else neighbour_loop_dense<W, U>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, n);               \
+    } while (0)
+                if (wrap) {
+                    if (uw == 0) MD_DENSE_CALL(true, 0); else if (uw == 1) MD_DENSE_CALL(true, 1); else MD_DENSE_CALL(true, 2);
+                } else {
+                    if (uw == 0) MD_DENSE_CALL(false, 0); else if (uw == 1) MD_DENSE_CALL(false, 1); else MD_DENSE_CALL(false, 2);
                 }
-                else {
-                    // uniform over the grid: one of six loop instances runs per launch
-                    const int uw = need_u ? 2 : (need_w ? 1 : 0);
-#define MD_DENSE_CALL(W, U) neighbour_loop_dense<W, U>(f0, f1, a.q4, row, stride, C, i0, X, Y, Z, c, fc, ring, n)
-                    if (wrap) {
-                        if (uw == 0) MD_DENSE_CALL(true, 0); else if (uw == 1) MD_DENSE_CALL(true, 1); else MD_DENSE_CALL(true, 2);
-                    } else {
-                        if (uw == 0) MD_DENSE_CALL(false, 0); else if (uw == 1) MD_DENSE_CALL(false, 1); else MD_DENSE_CALL(false, 2);
-                    }
 #undef MD_DENSE_CALL
-                }
             } else {
                 neighbour_loop<ROWS, false, true>(f0, f1, a, row, stride, last_row, C, i0, X, Y, Z, c, fc, J0);
             }
@@ -1765,6 +1763,221 @@ __global__ void __launch_bounds__(FORCE_BLOCK, (EXACT || MASKED) ? MD_FORCE_MINB
         }
     }
     if (threadIdx.x == 0) { PROBE_MAX(1); }
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][threadIdx.x];
+    block_reduce<FORCE_BLOCK>(s);
+    grid_reduce_finalize<FORCE_BLOCK>(s, partials, sc, pr,
+                                      (do_step & 1 ? FIN_STEP : 0) | (do_step & 2 ? FIN_DIST : 0) | (do_step & 8 ? FIN_P2P : 0),
+                                      cond_handle, peers);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Dense systems, warp-cooperative variant (MD_FORCE_FAST_COOP).
+//
+// ncu on k_force<.., MASKED> (profiles/r01_ncu_c5_v10): 363 k L1 wavefronts per SM in 359 k active cycles — the per-thread
+// Verlet loop is bound by the L1 tag stage, not by FP64 (31 % busy): lane l gathers partner k of ITS atom, 32 lanes hit 32
+// different 128-byte lines, one wavefront each.  Here the 32 lanes of a warp work on ONE atom at a time: lane l takes list
+// entries l, l + 32, ...  The list is stored atom-major (k_transpose_list), so the index read is one coalesced line, and
+// since a list is the concatenation of ascending index runs (one per stencil cell run) consecutive entries are mostly
+// consecutive atoms: four partners share a 128-byte line of the packed copy q4 and a gather costs ~8-12 wavefronts instead
+// of 32.  The per-lane partial forces are folded with xor-shuffles (fixed order: deterministic) and handed to the lane
+// that owns the atom, so everything after the neighbour phase is k_force's (two atoms per thread, 128-bit plane accesses).
+// Index rows are staged COOP_STAGES atoms ahead in a per-warp shared-memory ring by cp.async (a lane reads back only what
+// it copied: no barrier).
+constexpr int COOP_ROWS = 7;     // rows of 32 entries gathered from registers per atom (224 partners); longer lists take the tail loop
+constexpr int COOP_STAGES = 4;
+#ifndef MD_COOP_MINB
+#define MD_COOP_MINB 4
+#endif
+
+// nbr[k * npad + i] (k-major, one coalesced row per partner slot) -> nbrT[i * capT + k] (atom-major); 32 x 32 tiles
+__global__ void __launch_bounds__(256) k_transpose_list(int n, int cap, int npad, int capT, const int *__restrict__ nbr,
+                                                        int *__restrict__ nbrT)
+{
+    __shared__ int tile[32][33];
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int k = k0 + ty + r, i = i0 + tx;
+        tile[ty + r][tx] = (k < cap && i < n) ? nbr[(size_t)k * npad + i] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int i = i0 + ty + r, k = k0 + tx;
+        if (i < n && k < capT) nbrT[(size_t)i * capT + k] = tile[tx][ty + r];
+    }
+}
+
+// R rows of one atom's list, straight-line: R gathers, then R pair terms.  (With the row count as a run-time condition
+// ptxas sinks every gather into the branch that uses it, right in front of its pair term — the latencies then add up.)
+template <bool WRAP, int UW, int R>
+__device__ __forceinline__ void coop_rows(PairAcc &acc, const double4 *__restrict__ q4, const int *ring_stage, int cnt,
+                                          int dummy, double xi, double yi, double zi, const LjConst &c,
+                                          const ForceConsts &fc)
+{
+    const int lane = threadIdx.x & 31;
+#define MD_ROW(M)                                                                                         \
+    double2 p##M = make_double2(0.0, 0.0);                                                                \
+    double z##M = 0.0;                                                                                    \
+    if ((M) < R) {                                                                                        \
+        const int k_ = (M) * 32 + lane;                                                                   \
+        const int j_ = k_ < cnt ? ring_stage[k_] : dummy; /* entries past the list share one address */   \
+        double w_;                                                                                        \
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"                                           \
+                     : "=d"(p##M.x), "=d"(p##M.y), "=d"(z##M), "=d"(w_)                                   \
+                     : "l"(q4 + j_));                                                                     \
+    }
+    MD_ROW(0) MD_ROW(1) MD_ROW(2) MD_ROW(3) MD_ROW(4) MD_ROW(5) MD_ROW(6)
+#undef MD_ROW
+#define MD_TERM(M) \
+    if ((M) < R) pair_dense<WRAP, UW>(acc, (M) * 32 + lane < cnt, p##M.x, p##M.y, z##M, xi, yi, zi, c, fc);
+    MD_TERM(0) MD_TERM(1) MD_TERM(2) MD_TERM(3) MD_TERM(4) MD_TERM(5) MD_TERM(6)
+#undef MD_TERM
+}
+
+template <bool WRAP, int UW>
+__device__ __forceinline__ void coop_atom(PairAcc &acc, const double4 *__restrict__ q4, const int *__restrict__ lst,
+                                          const int *ring_stage, int cnt, int dummy, double xi, double yi, double zi,
+                                          const LjConst &c, const ForceConsts &fc)
+{
+    static_assert(COOP_ROWS == 7, "coop_rows is written out for seven rows");
+    const int rows = (cnt + 31) >> 5;  // warp-uniform
+#define MD_CASE(R) case R: coop_rows<WRAP, UW, R>(acc, q4, ring_stage, cnt, dummy, xi, yi, zi, c, fc); break
+    switch (min(rows, COOP_ROWS)) {
+        MD_CASE(1); MD_CASE(2); MD_CASE(3); MD_CASE(4); MD_CASE(5); MD_CASE(6); MD_CASE(7);
+        default: break;
+    }
+#undef MD_CASE
+    const int lane = threadIdx.x & 31;
+    for (int m = COOP_ROWS; m < rows; ++m) {  // lists beyond COOP_ROWS * 32 entries: straight from the table
+        const int k = m * 32 + lane;
+        const int j = k < cnt ? lst[k] : dummy;
+        const double4 q = q4[j];
+        pair_dense<WRAP, UW>(acc, k < cnt, q.x, q.y, q.z, xi, yi, zi, c, fc);
+    }
+}
+
+__global__ void __launch_bounds__(FORCE_BLOCK, MD_COOP_MINB)
+    k_force_coop(int n, Arrays a, const int *__restrict__ nbrT, const int *__restrict__ nbr_cnt, int capT,
+                 double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int do_step,
+                 unsigned long long cond_handle, const ForceConsts fc, const Peers *peers)
+{
+    if (!force_prologue(do_step, sc, peers)) return;
+    __shared__ SumsSmem ss;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) ss.v[q][threadIdx.x] = 0.0;
+    __shared__ int ring_store[FORCE_BLOCK / 32][COOP_STAGES][COOP_ROWS * 32];
+    const bool store_state = !(do_step & 1) || sc->steps_left <= 1;
+    const bool nh = pr->th_kind == 2 || !(do_step & 1);
+    const bool need_u = store_state, need_w = store_state || pr->ba_kind != 0;
+    const int uw = need_u ? 2 : (need_w ? 1 : 0);
+    LjConst c;
+    c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
+    c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
+    c.hxi = c.hyi = c.hzi = 0;
+    const double wrap_margin = (2.0 * pr->r_list - pr->r_cut) * 1.02;  // see k_force
+    const int npairs = (n + 1) >> 1;
+    const int tstride = gridDim.x * FORCE_BLOCK;
+    const int lane = threadIdx.x & 31;
+    int(*ring)[COOP_ROWS * 32] = ring_store[threadIdx.x >> 5];
+    for (int tb = blockIdx.x * FORCE_BLOCK + threadIdx.x - lane; tb < npairs; tb += tstride) {  // warp-uniform
+        const int t = tb + lane;
+        const bool valid = t < npairs;
+        const int i0 = 2 * t;
+        const bool has1 = valid && i0 + 1 < n;
+        int2 C = valid ? reinterpret_cast<const int2 *>(nbr_cnt)[t] : make_int2(0, 0);
+        if (!has1) C.y = 0;
+        const int base = 2 * tb;                       // first atom of the warp's tile (multiple of 64)
+        const int na = min(64, n - base);              // atoms in the tile
+        const int dummy = safe_dummy(base, n);         // never one of the tile's atoms (n >= 128 on this path)
+        PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // stage the index rows of atom A (a lane copies the entries it will read itself); one commit group per atom
+#define MD_STAGE_ATOM(A)                                                                                          \
+    do {                                                                                                          \
+        const int a_ = (A);                                                                                       \
+        if (a_ < na) {                                                                                            \
+            const int cnt_ = __shfl_sync(0xffffffffu, (a_ & 1) ? C.y : C.x, a_ >> 1);                             \
+            const int *src_ = nbrT + (size_t)(base + a_) * capT;                                                  \
+            int *dst_ = ring[a_ % COOP_STAGES];                                                                   \
+            _Pragma("unroll") for (int m = 0; m < COOP_ROWS; ++m) {                                               \
+                const int k_ = m * 32 + lane;                                                                     \
+                if (k_ < cnt_)                                                                                    \
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_ + k_)), "l"(src_ + k_) \
+                                 : "memory");                                                                     \
+            }                                                                                                     \
+        }                                                                                                         \
+        cp_async_commit();                                                                                        \
+    } while (0)
+#pragma unroll
+        for (int s = 0; s < COOP_STAGES - 1; ++s) MD_STAGE_ATOM(s);
+        for (int at = 0; at < na; ++at) {
+            MD_STAGE_ATOM(at + COOP_STAGES - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(COOP_STAGES - 1) : "memory");
+            const int cnt = __shfl_sync(0xffffffffu, (at & 1) ? C.y : C.x, at >> 1);
+            const int i = base + at;
+            const double4 qi = a.q4[i];  // warp-uniform address
+            const double m = wrap_margin;
+            const bool wrap = qi.x < m || qi.x > c.Lx - m || qi.y < m || qi.y > c.Ly - m || qi.z < m || qi.z > c.Lz - m;
+            PairAcc acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const int *lst = nbrT + (size_t)i * capT;
+            const int *stage = ring[at % COOP_STAGES];
+#define MD_COOP_CALL(W, U) coop_atom<W, U>(acc, a.q4, lst, stage, cnt, dummy, qi.x, qi.y, qi.z, c, fc)
+            if (wrap) {
+                if (uw == 0) MD_COOP_CALL(true, 0); else if (uw == 1) MD_COOP_CALL(true, 1); else MD_COOP_CALL(true, 2);
+            } else {
+                if (uw == 0) MD_COOP_CALL(false, 0); else if (uw == 1) MD_COOP_CALL(false, 1); else MD_COOP_CALL(false, 2);
+            }
+#undef MD_COOP_CALL
+            // fixed-order fold over the lanes
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc.fx += __shfl_xor_sync(0xffffffffu, acc.fx, o);
+                acc.fy += __shfl_xor_sync(0xffffffffu, acc.fy, o);
+                acc.fz += __shfl_xor_sync(0xffffffffu, acc.fz, o);
+                if (uw >= 1) acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                if (uw >= 2) acc.u += __shfl_xor_sync(0xffffffffu, acc.u, o);
+            }
+            if (lane == (at >> 1)) {
+                if (at & 1) f1 = acc; else f0 = acc;
+            }
+        }
+#undef MD_STAGE_ATOM
+        cp_async_wait_all();
+        if (!valid) continue;
+        // ---- from here on: k_force's epilogue for the two atoms this thread owns -------------------------------------
+        double2 VX = reinterpret_cast<double2 *>(a.vx)[t], VY = reinterpret_cast<double2 *>(a.vy)[t],
+                VZ = reinterpret_cast<double2 *>(a.vz)[t];
+        double2 WX, WY, WZ;
+        const double lam = ld_pinned(&sc->lambda);
+        const double sh[3] = {ld_pinned(&sc->shift[0]), ld_pinned(&sc->shift[1]), ld_pinned(&sc->shift[2])};
+        finish_atom(ss, f0, VX.x, VY.x, VZ.x, (do_step & 1) != 0, lam, fc.hc, fc.mass, sh, WX.x, WY.x, WZ.x, nh);
+        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, (do_step & 1) != 0, lam, fc.hc, fc.mass, sh, WX.y, WY.y, WZ.y, nh);
+        else { WX.y = WY.y = WZ.y = 0.0; }
+        if (!has1) {
+            if (store_state) {
+                a.fx[i0] = f0.fx; a.fy[i0] = f0.fy; a.fz[i0] = f0.fz; a.u[i0] = f0.u; a.w[i0] = f0.w;
+                if (do_step & 1) { a.vx[i0] = VX.x; a.vy[i0] = VY.x; a.vz[i0] = VZ.x; }
+            } else {
+                a.vx[i0] = WX.x; a.vy[i0] = WY.x; a.vz[i0] = WZ.x;
+            }
+        } else if (store_state) {
+            reinterpret_cast<double2 *>(a.fx)[t] = make_double2(f0.fx, f1.fx);
+            reinterpret_cast<double2 *>(a.fy)[t] = make_double2(f0.fy, f1.fy);
+            reinterpret_cast<double2 *>(a.fz)[t] = make_double2(f0.fz, f1.fz);
+            reinterpret_cast<double2 *>(a.u)[t] = make_double2(f0.u, f1.u);
+            reinterpret_cast<double2 *>(a.w)[t] = make_double2(f0.w, f1.w);
+            if (do_step & 1) {
+                reinterpret_cast<double2 *>(a.vx)[t] = VX; reinterpret_cast<double2 *>(a.vy)[t] = VY;
+                reinterpret_cast<double2 *>(a.vz)[t] = VZ;
+            }
+        } else {
+            reinterpret_cast<double2 *>(a.vx)[t] = WX; reinterpret_cast<double2 *>(a.vy)[t] = WY;
+            reinterpret_cast<double2 *>(a.vz)[t] = WZ;
+        }
+    }
     Sums s;
 #pragma unroll
     for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][threadIdx.x];

@@ -116,6 +116,11 @@ struct md_ctx {
     size_t nbr_u_alloc = 0;
     int cap_u = 0;
     bool union_valid = false;
+    // dense + FAST on one GPU: atom-major copy of the lists for the warp-cooperative force kernel (k_force_coop)
+    int *nbr_t = nullptr;
+    size_t nbr_t_alloc = 0;
+    int cap_t = 0, coop_grid = 1;
+    bool coop_valid = false;
     double *hot_slab = nullptr;                       // one GPU: x, y, z, vx, vy, vz of both plane sets in one allocation,
                                                       // so one L2 access-policy window can pin the current set (apply_l2_window)
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
@@ -488,6 +493,37 @@ int apply_l2_window(md_ctx *ctx)
     return MD_OK;
 }
 
+// Warp-cooperative dense force kernel (k_force_coop): needs the lists atom-major.  Dense systems, FAST arithmetic, one GPU.
+bool coop_wanted(const md_ctx *ctx)
+{
+    static const int env = [] { const char *e = std::getenv("MOLDYN_B200_DENSE_COOP"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    if (ctx->cfg.force_mode == MD_FORCE_FAST_COOP) return true;
+    return ctx->cfg.force_mode == MD_FORCE_FAST && env == 1;
+}
+
+int build_coop_table(md_ctx *ctx, int n)
+{
+    ctx->coop_valid = false;
+    if (!coop_wanted(ctx) || !ctx->dense || ctx->union_valid || ctx->dist.on || n < 128) return MD_OK;
+    const int cap = ctx->grid.cap;
+    const int cap_t = (cap + 31) / 32 * 32;
+    const size_t need = (size_t)ctx->npad * (size_t)cap_t;
+    if (need > ctx->nbr_t_alloc) {
+        dev_free(ctx, ctx->nbr_t);
+        ctx->nbr_t = nullptr;
+        ctx->nbr_t_alloc = 0;
+        TRY(dev_alloc(ctx, &ctx->nbr_t, need));
+        ctx->nbr_t_alloc = need;
+    }
+    ctx->cap_t = cap_t;
+    dim3 grid((unsigned)blocks_for(n, 32), (unsigned)(cap_t / 32));
+    k_transpose_list<<<grid, 256, 0, ctx->stream>>>(n, cap, ctx->npad, cap_t, ctx->nbr, ctx->nbr_t);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    ctx->coop_valid = true;
+    return MD_OK;
+}
+
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
 // (no pending barostat scaling).
 int rebuild_lists(md_ctx *ctx)
@@ -580,6 +616,7 @@ int rebuild_lists(md_ctx *ctx)
     ctx->dense = ctx->stats.nbr_mean >= 8.0 && n >= 128;  // (the dense kernel's masked lanes need a foreign warp's atom)
     ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT;
     TRY(refresh_q4(ctx));
+    TRY(build_coop_table(ctx, n));
     TRY(build_active_list(ctx, n));
     TRY(apply_l2_window(ctx));
     ctx->list_valid = true;
@@ -677,7 +714,16 @@ int launch_force(md_ctx *ctx, bool kick, unsigned long long cond, int guarded = 
         k_force<false, 2, true, true><<<ctx->force_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
             n, ctx->cur, ctx->nbr_u, ctx->cnt_u, ctx->npad, ctx->cap_u, ctx->d_partials, ctx->d_sc, ctx->d_pr,
             (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr);
-    else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
+    else if (ctx->dense && ctx->coop_valid) {
+        if (pdl)
+            CK(launch_pdl(k_force_coop, dim3(ctx->coop_grid), dim3(FORCE_BLOCK), ctx->stream, n, ctx->cur, (const int *)ctx->nbr_t,
+                          (const int *)ctx->nbr_cnt, ctx->cap_t, ctx->d_partials, ctx->d_sc, (const Params *)ctx->d_pr, flags, cond,
+                          fc, (const Peers *)nullptr));
+        else
+            k_force_coop<<<ctx->coop_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr_t, ctx->nbr_cnt, ctx->cap_t,
+                                                                         ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, cond, fc,
+                                                                         nullptr);
+    } else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
     else if (ctx->sparse)
         k_force_sparse<<<ctx->sparse_grid, FORCE_BLOCK, 0, ctx->stream>>>(
             n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->act_idx, ctx->act_scan + n, ctx->d_partials, ctx->d_sc,
@@ -758,6 +804,9 @@ int choose_grids(md_ctx *ctx)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
     const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
     for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
+    int occ_c = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_force_coop, FORCE_BLOCK, 0));
+    ctx->coop_grid = std::max(1, std::min(pair_blocks, sms * std::max(occ_c, 1)));
     int occ_sp = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, k_force_sparse, FORCE_BLOCK, 0));
     ctx->sparse_grid = std::max(1, std::min(pair_blocks, sms * std::max(occ_sp, 1)));
@@ -978,6 +1027,8 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         ctx->nbr = nullptr; ctx->nbr_alloc = 0;
         dev_free(ctx, ctx->nbr_u); dev_free(ctx, ctx->cnt_u);
         ctx->nbr_u = nullptr; ctx->cnt_u = nullptr; ctx->nbr_u_alloc = 0; ctx->cap_u = 0; ctx->union_valid = false;
+        dev_free(ctx, ctx->nbr_t);
+        ctx->nbr_t = nullptr; ctx->nbr_t_alloc = 0; ctx->cap_t = 0; ctx->coop_valid = false;
         ctx->owned.erase(std::remove_if(ctx->owned.begin(), ctx->owned.end(), [](const DevBuf &b) { return !b.p; }),
                          ctx->owned.end());
         ctx->n = n;
@@ -1006,7 +1057,7 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         ctx->partial_blocks = std::max(std::max(ctx->force_grid[0], ctx->force_grid[1]),
                                        std::max(ctx->force_grid[2], ctx->reduce_grid));
         ctx->partial_blocks = std::max(ctx->partial_blocks, std::max(ctx->step_grid[0], ctx->step_grid[1]));
-        ctx->partial_blocks = std::max(ctx->partial_blocks, ctx->sparse_grid);
+        ctx->partial_blocks = std::max(ctx->partial_blocks, std::max(ctx->sparse_grid, ctx->coop_grid));
         TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
         TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
@@ -1580,6 +1631,7 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
     out->peer_memory = ctx->dist.p2p ? 1 : 0;
     out->union_lists = ctx->union_valid ? 1 : 0;
+    out->coop_lists = ctx->coop_valid ? 1 : 0;
     out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
     out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;
     out->drift_push_ms = ctx->rebuild_host_ms;  // (field reused: the drift kernel no longer has a push phase to time)

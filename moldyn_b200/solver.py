@@ -154,9 +154,10 @@ class Solver:
     """Device-resident session: owns an md_ctx. `exact=True` selects MD_FORCE_EXACT (bit-identical forces)."""
 
     def __init__(self, device=0, exact=False, host_loop=False, while_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
-                 cell_atoms=0.0, step_mode="auto", union_lists=False):
+                 cell_atoms=0.0, step_mode="auto", union_lists=False, coop=False):
         self._ctx = C.c_void_p()
-        cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else (_ffi.FORCE_FAST_UNION if union_lists else _ffi.FORCE_FAST),
+        fast = _ffi.FORCE_FAST_UNION if union_lists else (_ffi.FORCE_FAST_COOP if coop else _ffi.FORCE_FAST)
+        cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else fast,
                           _ffi.LOOP_HOST if host_loop else (_ffi.LOOP_WHILE if while_loop else _ffi.LOOP_GRAPH),
                           max_neighbours, cell_subdiv,
                           {"auto": _ffi.STEP_AUTO, "split": _ffi.STEP_SPLIT, "fused": _ffi.STEP_FUSED}[step_mode], skin,
@@ -286,7 +287,7 @@ class Solver:
                 "graph_launches": s.graph_launches, "cells": list(s.cells), "nbr_capacity": s.nbr_capacity,
                 "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean, "n_owned": s.n_owned,
                 "n_ghost": s.n_ghost, "migrated": s.migrated, "fused_steps": s.fused_steps, "wait_halo_ms": s.wait_halo_ms,
-                "wait_sums_ms": s.wait_sums_ms, "peer_memory": s.peer_memory, "union_lists": s.union_lists, "force_atoms_ms": s.force_atoms_ms,
+                "wait_sums_ms": s.wait_sums_ms, "peer_memory": s.peer_memory, "union_lists": s.union_lists, "coop_lists": s.coop_lists, "force_atoms_ms": s.force_atoms_ms,
                 "force_tail_ms": s.force_tail_ms, "drift_push_ms": s.drift_push_ms}
 
     def stream(self):

@@ -153,6 +153,7 @@ SYSTEMS = {
     "liquid4096_3.5sigma": lambda: (liquid(16), LONG_CUT),
     "liquid_small_box": lambda: (liquid(5), None),   # box 1.81 nm: fewer than 3 cells per axis
     "liquid5832": lambda: (liquid(18), None),        # 13 cells per axis: the dense FAST path uses union lists
+    "liquid729": lambda: (liquid(9), None),          # odd atom count: the last thread owns one atom
 }
 
 
@@ -235,6 +236,50 @@ def test_union_lists_opt_in():
     dx = np.abs(st.position - o.pos)
     assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
     assert np.abs(st.velocity - o.vel).max() <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["liquid4096_3.5sigma", "liquid5832", "dense_gas3000", "liquid1000", "liquid729"])
+def test_warp_cooperative_dense_kernel(name):
+    """MD_FORCE_FAST_COOP (k_transpose_list + k_force_coop: one warp per atom over an atom-major list): per-atom force,
+    potential and virial within the FAST bar, 100-step NVT and NPT trajectories within 1e-8 of the oracle (forces-only,
+    + virial and + potential instances of the loop all run), run-to-run bit-reproducible."""
+    o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    ref = o.copy()
+    orc.update_force(olj, ref, mode="cells")
+    scale = force_scale(olj, ref)
+    rms = np.sqrt((ref.force ** 2).sum(axis=1).mean())
+    T0 = 120.0 if name.startswith("liquid") else 273.15
+    runs = []
+    for ensemble in ("nvt", "npt", "npt"):
+        st = to_gpu_state(md, o)
+        gth, oth = (md.Thermostat.Berendsen(10.0), T0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, T0)
+        gba = oba = None
+        if ensemble == "npt":
+            gba, oba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325), orc.Barostat(1.0, 5.0, 1.01325)
+        with md.Solver(coop=True) as s:
+            s.set_potential(plj)
+            s.upload(st, with_forces=False)
+            s.update_force()
+            assert s.stats()["coop_lists"] == 1 and s.stats()["nbr_mean"] >= 8.0
+            s.download(st)
+            assert np.all(np.abs(st.force - ref.force) <= 1e-10 * np.maximum(scale, rms)[:, None])
+            assert np.all(np.abs(st.potential - ref.pot) <= 1e-10 * np.maximum(np.abs(ref.pot), 1.0))
+            assert np.all(np.abs(st.temp - ref.vir) <= 1e-10 * np.maximum(np.abs(ref.vir), 1.0))
+            for k in (1, 36, 63):
+                s.step(k, DT, thermostat=gth, barostat=gba)
+            s.download(st)
+            m = s.macro()
+        r = o.copy()
+        run_oracle(olj, r, 100, oth, oba)
+        dx = np.abs(st.position - r.pos)
+        assert np.minimum(dx, np.abs(dx - r.box)).max() <= 1e-8
+        assert np.abs(st.velocity - r.vel).max() <= 1e-8
+        assert np.abs(st.boundary_box - r.box).max() <= 1e-9
+        runs.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.temp.copy(), m["pressure"]))
+    for a, b in zip(runs[1][:4], runs[2][:4]):
+        assert np.array_equal(a, b)
+    assert runs[1][4] == runs[2][4]
 
 
 def run_oracle(olj, o, n_steps, th=None, ba=None):
