@@ -40,7 +40,7 @@ NCU_TRAFFIC = {
     ("c3", "k_force"): (66.93e6, "profiles/r01_ncu_c3_v7_k_force_k_kick_drift.txt"),
     ("c3", "k_kick_drift"): (48.03e6, "profiles/r01_ncu_c3_v7_k_force_k_kick_drift.txt"),
     ("c3", "k_step_dilute"): (73.33e6, "profiles/r01_ncu_c3_v1_k_step_dilute.txt"),
-    ("c5", "k_force"): (236.22e6, "profiles/r01_ncu_c5_v9_k_force.txt"),
+    ("c5", "k_force"): (235.19e6, "profiles/r01_ncu_c5_v10_k_force.txt"),
 }
 ALGO_FLOP_PAIR = 42         # flop per directed in-range pair
 ALGO_FLOP_ATOM = 30

@@ -51,8 +51,9 @@ typedef enum md_status {
                                 0.245 ms) — after the 256-bit gathers the dense loop is bound by pair arithmetic, and the union
                                 evaluates 25 % more pairs */
 #define MD_FORCE_FAST_COOP 3 /* MD_FORCE_FAST with the warp-cooperative force kernel for dense systems on one GPU (k_force_coop:
-                               the 32 lanes of a warp share one atom's list, stored atom-major, so a gather touches a few
-                               128-byte lines instead of 32 — the per-thread loop is bound by the L1 tag stage) */
+                               the 32 lanes of a warp share one atom's list, stored atom-major, so a gather touches fewer
+                               128-byte lines — the per-thread loop is bound by the L1 data pipe).  Opt-in: measured slower
+                               on B200 (C5 k_force 0.247 vs 0.221 ms: -28 % L1 wavefronts, +16 % instructions) */
 /* loop_mode */
 #define MD_LOOP_GRAPH 0 /* default: CUDA-graph loop, currently MD_LOOP_CHUNK (measured faster than MD_LOOP_WHILE on B200:
                            36.8 vs 41.1 us/step at 10^6 atoms, 14.3 vs 17.5 at 32768 — same bits) */
