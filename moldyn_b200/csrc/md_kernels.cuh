@@ -79,6 +79,8 @@ struct Scalars {
     unsigned long long force_atoms_ns, force_tail_ns, drift_push_ns;  // accumulated phase times (multi-GPU diagnostics)
     unsigned long long nbr_total;
     unsigned long long probe[8];  // MD_TIMING_PROBES: %globaltimer stamps of k_force phases
+    unsigned long long fin_seq;     // number of last-block epilogues completed so far (release-stored at their very end)
+    unsigned long long chunk_fin0;  // fin_seq when the running step chunk started (early-start k_kick_drift, see there)
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
     // multi-GPU rebuild bookkeeping
     int n_stay, n_left, n_right, n_lost;
@@ -97,6 +99,29 @@ __device__ __forceinline__ bool halted(const Scalars *sc)
 // has completed and its memory operations are visible.  Without the attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// gpu-scope acquire / release accesses of the step-control words (L2, never a stale L1 line)
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// halted(), read through L2: for a kernel that runs while its predecessor is still finishing
+__device__ __forceinline__ bool halted_now(const Scalars *sc)
+{
+    return __ldcg(&sc->need_rebuild) != 0 || __ldcg(&sc->error) != 0 || __ldcg(&sc->steps_left) <= 0;
+}
 
 __device__ __forceinline__ unsigned long long gtime()
 {
@@ -948,6 +973,8 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
         }
         finalize(sc, &sc_in, &pr_in, acc, mode);
         sc->ticket = 0;
+        // everything above is visible to whoever acquires the new sequence number (early-start k_kick_drift)
+        st_release_gpu(&sc->fin_seq, sc_in.fin_seq + 1);
         PROBE(4);
         if (cond_handle) {
             unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
@@ -2008,17 +2035,18 @@ __device__ __forceinline__ void drift_one(double &x, double u, double lambda, do
 __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const Scalars *__restrict__ sc,
                                                 const Params *__restrict__ pr, bool write_q4)
 {
-    const double c = pr->half_dt_m, dt = pr->dt, lambda = sc->lambda, mup = sc->mu_pending;
-    double ux = a.vx[i], uy = a.vy[i], uz = a.vz[i];
-    if (!sc->vel_is_half) {
-        ux = __dadd_rn(ux, __dmul_rn(a.fx[i], c)); uy = __dadd_rn(uy, __dmul_rn(a.fy[i], c));
-        uz = __dadd_rn(uz, __dmul_rn(a.fz[i], c));
+    // (L2 reads: under an early start this kernel runs while its predecessor is finishing, see k_kick_drift)
+    const double c = pr->half_dt_m, dt = pr->dt, lambda = __ldcg(&sc->lambda), mup = __ldcg(&sc->mu_pending);
+    double ux = __ldcg(a.vx + i), uy = __ldcg(a.vy + i), uz = __ldcg(a.vz + i);
+    if (!__ldcg(&sc->vel_is_half)) {
+        ux = __dadd_rn(ux, __dmul_rn(__ldcg(a.fx + i), c)); uy = __dadd_rn(uy, __dmul_rn(__ldcg(a.fy + i), c));
+        uz = __dadd_rn(uz, __dmul_rn(__ldcg(a.fz + i), c));
         a.vx[i] = ux; a.vy[i] = uy; a.vz[i] = uz;
     }
-    double x = a.x[i], y = a.y[i], z = a.z[i];
-    drift_one(x, ux, lambda, mup, dt, sc->box[0]);
-    drift_one(y, uy, lambda, mup, dt, sc->box[1]);
-    drift_one(z, uz, lambda, mup, dt, sc->box[2]);
+    double x = __ldcg(a.x + i), y = __ldcg(a.y + i), z = __ldcg(a.z + i);
+    drift_one(x, ux, lambda, mup, dt, __ldcg(&sc->box[0]));
+    drift_one(y, uy, lambda, mup, dt, __ldcg(&sc->box[1]));
+    drift_one(z, uz, lambda, mup, dt, __ldcg(&sc->box[2]));
     a.x[i] = x; a.y[i] = y; a.z[i] = z;
     if (write_q4) a.q4[i] = make_double4(x, y, z, 0.0);
 }
@@ -2048,23 +2076,70 @@ __device__ __forceinline__ void push_atom(const HaloPush &h, int i, int n, doubl
 
 __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars *sc,
                                                     const Params *__restrict__ pr, int guarded, int write_q4,
-                                                    const HaloPush h)
+                                                    int early_k, unsigned force_grid, const HaloPush h)
 {
-    // guarded bits: 1 = return at once when the loop is halted, 2 = launched as a programmatic dependent of k_force
+    // guarded bits: 1 = return at once when the loop is halted, 2 = launched as a programmatic dependent of k_force,
+    //               4 = early start (with 2; single-GPU chunk graph, step early_k >= 1 of the chunk), see below
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    double2 x, y, z;
-    const bool early = (guarded & 2) && 2 * t + 1 < n;
+    double2 x, y, z, ux, uy, uz;
+    bool have_x = false, have_u = false;
     if (guarded & 2) {
+        pdl_launch_dependents();  // k_force of this step may become resident; it waits for this grid to complete
         // positions were last written by the previous k_kick_drift, which completed before our predecessor (k_force) did
-        // anything: they can be fetched while k_force drains.  Everything else waits.
-        if (early) {
-            x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
-            z = reinterpret_cast<double2 *>(a.z)[t];
+        // anything: they can be fetched while k_force drains.
+        if (2 * t + 1 < n) {
+            x = __ldcg(reinterpret_cast<const double2 *>(a.x) + t); y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t);
+            z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
+            have_x = true;
         }
-        pdl_wait();
-        pdl_launch_dependents();
+        bool waited = false;
+        if (guarded & 4) {
+            // Early start.  The predecessor's tail — one block folding 592 partial sums and computing lambda, myu and the
+            // rebuild decision while 147 SMs idle — is hidden behind this kernel's loads: (a) once every block of k_force has
+            // taken its ticket, all velocities u' are final (each block fences before the ticket): fetch them; (b) once the
+            // last block has release-stored the sequence number of this step, the controls are final: drift and store.
+            // One thread per block polls (bounded); on a timeout, or on anything unexpected, the block falls back to
+            // griddepcontrol.wait — always correct, the flags only ever let it start sooner.
+            __shared__ int verdict;  // 0 = go, 1 = fall back to the full wait, 2 = halted: nothing to do
+            const unsigned long long expect = __ldcg(&sc->chunk_fin0) + (unsigned long long)early_k;
+            if (threadIdx.x == 0) {
+                int v = 1;
+                if (halted_now(sc)) v = 2;  // halted before our predecessor started: it is a no-op and raises no flag
+                else
+                    for (int spin = 0; spin < 4096; ++spin) {
+                        if (ld_acquire_gpu(&sc->fin_seq) >= expect) { v = 3; break; }  // the whole predecessor is done
+                        if (ld_acquire_gpu(&sc->ticket) == force_grid) { v = 0; break; }
+                        __nanosleep(64);
+                    }
+                verdict = v;
+            }
+            __syncthreads();
+            if (verdict == 2) return;
+            if (verdict == 3) waited = true;
+            else if (verdict == 0) {
+                if (have_x) {
+                    ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t); uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t);
+                    uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
+                    have_u = true;
+                }
+                __syncthreads();  // verdict is rewritten below
+                if (threadIdx.x == 0) {
+                    int v = 1;
+                    for (int spin = 0; spin < 4096; ++spin) {
+                        if (ld_acquire_gpu(&sc->fin_seq) >= expect) { v = 0; break; }
+                        __nanosleep(64);
+                    }
+                    verdict = v;
+                }
+                __syncthreads();
+                waited = verdict == 0;
+            }
+        }
+        if (!waited) pdl_wait();
     }
-    if ((guarded & 1) && halted(sc)) return;
+    if ((guarded & 1) && halted_now(sc)) return;
+    // first step of a chunk (plain launch: everything before it is complete): the sequence number the chunk counts from
+    if ((guarded & 4) && early_k == 0 && t == 0) sc->chunk_fin0 = __ldcg(&sc->fin_seq);
     // block-uniform: does this block hold face atoms?  (512 atoms per block)
     const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
     const bool pushes = (h.m[0] | h.m[1]) != 0 && (b_lo < h.m[0] || b_hi > n - h.m[1]);
@@ -2074,18 +2149,20 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
             if (pushes) push_atom(h, 2 * t, n, a.x[2 * t], a.y[2 * t], a.z[2 * t]);
         } else {
             const double c = pr->half_dt_m, dt = pr->dt;
-            const double lambda = sc->lambda, mup = sc->mu_pending;
-            const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-            const bool half = sc->vel_is_half != 0;
-            if (!early) {
+            const double lambda = __ldcg(&sc->lambda), mup = __ldcg(&sc->mu_pending);
+            const double Lx = __ldcg(&sc->box[0]), Ly = __ldcg(&sc->box[1]), Lz = __ldcg(&sc->box[2]);
+            const bool half = __ldcg(&sc->vel_is_half) != 0;
+            if (!have_x) {
                 x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
                 z = reinterpret_cast<double2 *>(a.z)[t];
             }
-            double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
-                    uz = reinterpret_cast<double2 *>(a.vz)[t];
+            if (!have_u) {
+                ux = reinterpret_cast<double2 *>(a.vx)[t]; uy = reinterpret_cast<double2 *>(a.vy)[t];
+                uz = reinterpret_cast<double2 *>(a.vz)[t];
+            }
             if (!half) {
-                const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
-                              fz = reinterpret_cast<const double2 *>(a.fz)[t];
+                const double2 fx = __ldcg(reinterpret_cast<const double2 *>(a.fx) + t), fy = __ldcg(reinterpret_cast<const double2 *>(a.fy) + t),
+                              fz = __ldcg(reinterpret_cast<const double2 *>(a.fz) + t);
                 ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
                 uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
                 uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));

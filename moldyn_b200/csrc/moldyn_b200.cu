@@ -626,10 +626,25 @@ int rebuild_lists(md_ctx *ctx)
 // Programmatic dependent launch of the step kernels inside the single-GPU chunk graph (opt-in: MOLDYN_B200_PDL=1).
 // The launch attribute turns the kernel -> kernel edge of the captured graph into a programmatic one; the kernels
 // themselves start with griddepcontrol.wait (pdl_wait), so nothing is read before the predecessor has completed.
-bool pdl_enabled()
+// 0 = off, 1 = programmatic edges, 2 = programmatic edges + early-start k_kick_drift (flag protocol, see the kernel)
+int pdl_level()
 {
-    static const bool on = [] { const char *e = std::getenv("MOLDYN_B200_PDL"); return e && e[0] == '1'; }();
-    return on;
+    static const int level = [] {
+        const char *e = std::getenv("MOLDYN_B200_PDL");
+        return e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
+    }();
+    return level;
+}
+
+// grid of the force kernel launch_force() would pick right now (the early-start drift compares the ticket with it)
+unsigned current_force_grid(const md_ctx *ctx)
+{
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT) return (unsigned)ctx->force_grid[0];
+    if (ctx->dense && ctx->union_valid) return (unsigned)ctx->force_grid[1];
+    if (ctx->dense && ctx->coop_valid) return (unsigned)ctx->coop_grid;
+    if (ctx->dense) return (unsigned)ctx->force_grid[1];
+    if (ctx->sparse) return (unsigned)ctx->sparse_grid;
+    return (unsigned)ctx->force_grid[2];
 }
 
 template <typename... KArgs, typename... Args>
@@ -648,17 +663,20 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
-int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr, bool pdl = false)
+// early_k >= 0: step index inside a chunk graph whose drifts use the early-start protocol (guarded bit 4)
+int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr, bool pdl = false, int early_k = -1)
 {
     const int n = (int)ctx->n_own;
     const int blocks = std::max(1, blocks_for((n + 1) / 2, 256));
+    const int g = guarded | (early_k >= 0 ? 4 : 0);
+    const unsigned fgrid = current_force_grid(ctx);
     if (pdl) {
-        CK(launch_pdl(k_kick_drift, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded | 2,
-                      ctx->use_q4 ? 1 : 0, push ? *push : HaloPush{}));
+        CK(launch_pdl(k_kick_drift, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, (const Params *)ctx->d_pr,
+                      g | 2, ctx->use_q4 ? 1 : 0, std::max(early_k, 0), fgrid, push ? *push : HaloPush{}));
         return MD_OK;
     }
-    k_kick_drift<<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded, ctx->use_q4 ? 1 : 0,
-                                                  push ? *push : HaloPush{});
+    k_kick_drift<<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, g, ctx->use_q4 ? 1 : 0,
+                                                  std::max(early_k, 0), fgrid, push ? *push : HaloPush{});
     return MD_OK;
 }
 
@@ -860,8 +878,10 @@ int build_chunk_graph(md_ctx *ctx, bool fused)
             launch_fused_step(ctx, 0ull, 1);
         } else {
             // programmatic edges inside the chunk; its first kernel depends on the previous graph launch as a whole
-            const bool pdl = pdl_enabled();
-            rc = launch_kick_drift(ctx, 1, nullptr, pdl && k > 0);
+            const int level = pdl_level();
+            const bool pdl = level >= 1;
+            const bool early = level >= 2 && !ctx->sparse && !(ctx->dense && ctx->union_valid);  // (those keep plain force launches)
+            rc = launch_kick_drift(ctx, 1, nullptr, pdl && k > 0, early ? k : -1);
             if (rc == MD_OK) rc = launch_force(ctx, true, 0ull, 1, pdl);
         }
     }

@@ -672,10 +672,10 @@ def test_programmatic_dependent_launch_is_bit_identical():
     tests = os.path.dirname(os.path.abspath(__file__))
     code = _PDL_CHILD.format(root=os.path.dirname(tests), tests=tests)
     outs = []
-    for pdl in ("0", "1"):
+    for pdl in ("0", "1", "2"):  # 2 = + early-start k_kick_drift (ticket / sequence-number protocol)
         env = dict(os.environ, MOLDYN_B200_PDL=pdl)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines())
-    assert len(outs[0]) == 4 and outs[0] == outs[1]
+    assert len(outs[0]) == 4 and outs[0] == outs[1] == outs[2]
     assert all(line.split()[3] == "True" for line in outs[0])  # the graph loop ran
