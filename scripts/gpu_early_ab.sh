@@ -25,13 +25,12 @@ PY
   lap "bench $name"
 }
 Q="--e2e-steps 0 --cpu-rows -1"
-for w in c3 c2 c1 c5; do
+for w in ${EARLY_WORKLOADS:-c3 c2 c1 c5 big}; do
   S=""; [ $w = c5 ] && S="--steps 2000 --warmup 500"
   bench ${w}_default -- --workload $w $Q $S
+  bench ${w}_pdl1 MOLDYN_B200_PDL=1 -- --workload $w $Q $S
   bench ${w}_pdl2 MOLDYN_B200_PDL=2 -- --workload $w $Q $S
 done
-bench big_default -- --workload big $Q
-bench big_pdl2 MOLDYN_B200_PDL=2 -- --workload big $Q
 MOLDYN_B200_PDL=2 timeout 420 python -m pytest tests/test_gpu_parity.py tests/test_cli.py -x -q -m gpu > $O/early_pytest2.log 2>&1; echo "pytest(PDL=2, parity+cli) rc=$?" | tee -a $O/early_timing.log
 tail -4 $O/early_pytest2.log
 lap "pytest PDL=2"
