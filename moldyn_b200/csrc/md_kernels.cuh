@@ -2032,26 +2032,37 @@ __device__ __forceinline__ void drift_one(double &x, double u, double lambda, do
     else if (x >= L) x = __dsub_rn(x, L);
 }
 
-__device__ __forceinline__ void kick_drift_tail(int i, Arrays a, const double *ctl, bool half,
-                                                const Params *__restrict__ pr, bool write_q4)
+// L2 (PDL = true: the kernel may run while its predecessor is finishing, never trust an L1 line) or plain loads
+template <bool PDL, typename T>
+__device__ __forceinline__ T ld_state(const T *p)
 {
-    // ctl = {lambda, mu_pending, Lx, Ly, Lz} (the block's copy of the step controls, see k_kick_drift)
-    // (L2 reads: under an early start this kernel runs while its predecessor is finishing)
-    const double c = pr->half_dt_m, dt = pr->dt, lambda = ctl[0], mup = ctl[1];
-    double ux = __ldcg(a.vx + i), uy = __ldcg(a.vy + i), uz = __ldcg(a.vz + i);
+    if constexpr (PDL) return __ldcg(p);
+    else return *p;
+}
+
+template <bool PDL>
+__device__ __forceinline__ void kick_drift_tail(int i, Arrays a, double lambda, double mup, double Lx, double Ly, double Lz,
+                                                bool half, const Params *__restrict__ pr, bool write_q4)
+{
+    const double c = pr->half_dt_m, dt = pr->dt;
+    double ux = ld_state<PDL>(a.vx + i), uy = ld_state<PDL>(a.vy + i), uz = ld_state<PDL>(a.vz + i);
     if (!half) {
-        ux = __dadd_rn(ux, __dmul_rn(__ldcg(a.fx + i), c)); uy = __dadd_rn(uy, __dmul_rn(__ldcg(a.fy + i), c));
-        uz = __dadd_rn(uz, __dmul_rn(__ldcg(a.fz + i), c));
+        ux = __dadd_rn(ux, __dmul_rn(ld_state<PDL>(a.fx + i), c)); uy = __dadd_rn(uy, __dmul_rn(ld_state<PDL>(a.fy + i), c));
+        uz = __dadd_rn(uz, __dmul_rn(ld_state<PDL>(a.fz + i), c));
         a.vx[i] = ux; a.vy[i] = uy; a.vz[i] = uz;
     }
-    double x = __ldcg(a.x + i), y = __ldcg(a.y + i), z = __ldcg(a.z + i);
-    drift_one(x, ux, lambda, mup, dt, ctl[2]);
-    drift_one(y, uy, lambda, mup, dt, ctl[3]);
-    drift_one(z, uz, lambda, mup, dt, ctl[4]);
+    double x = ld_state<PDL>(a.x + i), y = ld_state<PDL>(a.y + i), z = ld_state<PDL>(a.z + i);
+    drift_one(x, ux, lambda, mup, dt, Lx);
+    drift_one(y, uy, lambda, mup, dt, Ly);
+    drift_one(z, uz, lambda, mup, dt, Lz);
     a.x[i] = x; a.y[i] = y; a.z[i] = z;
     if (write_q4) a.q4[i] = make_double4(x, y, z, 0.0);
 }
 
+// Multi-GPU over peer memory: the face atoms of a slab are a prefix [0, m_left) and a suffix [n - m_right, n) of its
+// cell-sorted order (ghosts are selected by x cell layer), so the drift kernel itself stores their new positions into the
+// neighbours' ghost slots — plain NVLink stores into the neighbour's HBM, no fence here.  The kernel boundary orders them;
+// the first thing k_force does is raise the step's sequence flag in both neighbours' mailboxes and poll its own.
 struct HaloPush {
     int m[2];                    // face atoms for the left / right neighbour (0, 0: nothing to push, e.g. single GPU)
     double *x[2], *y[2], *z[2];  // the neighbour's planes (mapped), already offset to the first ghost slot we own there
@@ -2071,16 +2082,21 @@ __device__ __forceinline__ void push_atom(const HaloPush &h, int i, int n, doubl
     }
 }
 
+// PDL = false: plain launch, the predecessor is complete (every launch but the ones below).  PDL = true: launched as a
+// programmatic dependent of k_force inside a single-GPU chunk graph (MOLDYN_B200_PDL, opt-in).
+template <bool PDL>
 __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars *sc,
                                                     const Params *__restrict__ pr, int guarded, int write_q4,
                                                     int early_k, unsigned force_grid, const HaloPush h)
 {
-    // guarded bits: 1 = return at once when the loop is halted, 2 = launched as a programmatic dependent of k_force,
-    //               4 = early start (with 2; single-GPU chunk graph, step early_k >= 1 of the chunk), see below
+    // guarded bits: 1 = return at once when the loop is halted, 2 = programmatic dependent (== PDL),
+    //               4 = the chunk's drifts start early (with 2: step early_k >= 1 of the chunk; step 0 is a plain launch)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     double2 x, y, z, ux, uy, uz;
     bool have_x = false, have_u = false;
-    if (guarded & 2) {
+    double lambda, mup, Lx, Ly, Lz;
+    bool half;
+    if constexpr (PDL) {
         pdl_launch_dependents();  // k_force of this step may become resident; it waits for this grid to complete
         // positions were last written by the previous k_kick_drift, which completed before our predecessor (k_force) did
         // anything: they can be fetched while k_force drains.
@@ -2136,34 +2152,38 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
             }
         }
         if (!waited) pdl_wait();
+        // The step controls, once per block through L2 (never a stale L1 line, and not 2000 blocks x 8 warps hammering one
+        // L2 slice with the same nine words: measured 13 -> 26 us per launch at 10^6 atoms when every thread read them itself).
+        __shared__ double ctl[5];   // lambda, mu_pending, Lx, Ly, Lz
+        __shared__ int ctl_half, ctl_halted;
+        if (threadIdx.x == 0) {
+            const double l0 = __ldcg(&sc->lambda), l1 = __ldcg(&sc->mu_pending), l2 = __ldcg(&sc->box[0]),
+                         l3 = __ldcg(&sc->box[1]), l4 = __ldcg(&sc->box[2]);
+            ctl_half = __ldcg(&sc->vel_is_half);
+            ctl_halted = halted_now(sc) ? 1 : 0;
+            ctl[0] = l0; ctl[1] = l1; ctl[2] = l2; ctl[3] = l3; ctl[4] = l4;
+        }
+        __syncthreads();
+        if ((guarded & 1) && ctl_halted) return;
+        lambda = ctl[0]; mup = ctl[1]; Lx = ctl[2]; Ly = ctl[3]; Lz = ctl[4];
+        half = ctl_half != 0;
+    } else {
+        if ((guarded & 1) && halted(sc)) return;
+        lambda = sc->lambda; mup = sc->mu_pending;
+        Lx = sc->box[0]; Ly = sc->box[1]; Lz = sc->box[2];
+        half = sc->vel_is_half != 0;
+        // first step of a chunk whose later drifts start early: the sequence number the chunk counts from
+        if ((guarded & 4) && early_k == 0 && t == 0) sc->chunk_fin0 = sc->fin_seq;
     }
-    // The step controls, once per block through L2 (never a stale L1 line, and not 2000 blocks x 8 warps hammering one L2
-    // slice with the same nine words: measured 13 -> 26 us per launch at 10^6 atoms when every thread read them itself).
-    __shared__ double ctl[5];   // lambda, mu_pending, Lx, Ly, Lz
-    __shared__ int ctl_half, ctl_halted;
-    if (threadIdx.x == 0) {
-        const double l0 = __ldcg(&sc->lambda), l1 = __ldcg(&sc->mu_pending), l2 = __ldcg(&sc->box[0]),
-                     l3 = __ldcg(&sc->box[1]), l4 = __ldcg(&sc->box[2]);
-        ctl_half = __ldcg(&sc->vel_is_half);
-        ctl_halted = halted_now(sc) ? 1 : 0;
-        ctl[0] = l0; ctl[1] = l1; ctl[2] = l2; ctl[3] = l3; ctl[4] = l4;
-    }
-    __syncthreads();
-    if ((guarded & 1) && ctl_halted) return;
-    // first step of a chunk (plain launch: everything before it is complete): the sequence number the chunk counts from
-    if ((guarded & 4) && early_k == 0 && t == 0) sc->chunk_fin0 = __ldcg(&sc->fin_seq);
     // block-uniform: does this block hold face atoms?  (512 atoms per block)
     const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
     const bool pushes = (h.m[0] | h.m[1]) != 0 && (b_lo < h.m[0] || b_hi > n - h.m[1]);
     if (2 * t < n) {
         if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
-            kick_drift_tail(2 * t, a, ctl, ctl_half != 0, pr, write_q4 != 0);
+            kick_drift_tail<PDL>(2 * t, a, lambda, mup, Lx, Ly, Lz, half, pr, write_q4 != 0);
             if (pushes) push_atom(h, 2 * t, n, a.x[2 * t], a.y[2 * t], a.z[2 * t]);
         } else {
             const double c = pr->half_dt_m, dt = pr->dt;
-            const double lambda = ctl[0], mup = ctl[1];
-            const double Lx = ctl[2], Ly = ctl[3], Lz = ctl[4];
-            const bool half = ctl_half != 0;
             if (!have_x) {
                 x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
                 z = reinterpret_cast<double2 *>(a.z)[t];
@@ -2173,8 +2193,9 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
                 uz = reinterpret_cast<double2 *>(a.vz)[t];
             }
             if (!half) {
-                const double2 fx = __ldcg(reinterpret_cast<const double2 *>(a.fx) + t), fy = __ldcg(reinterpret_cast<const double2 *>(a.fy) + t),
-                              fz = __ldcg(reinterpret_cast<const double2 *>(a.fz) + t);
+                const double2 fx = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fx) + t),
+                              fy = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fy) + t),
+                              fz = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fz) + t);
                 ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
                 uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
                 uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));

@@ -671,11 +671,11 @@ int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullp
     const int g = guarded | (early_k >= 0 ? 4 : 0);
     const unsigned fgrid = current_force_grid(ctx);
     if (pdl) {
-        CK(launch_pdl(k_kick_drift, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, (const Params *)ctx->d_pr,
+        CK(launch_pdl(k_kick_drift<true>, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, (const Params *)ctx->d_pr,
                       g | 2, ctx->use_q4 ? 1 : 0, std::max(early_k, 0), fgrid, push ? *push : HaloPush{}));
         return MD_OK;
     }
-    k_kick_drift<<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, g, ctx->use_q4 ? 1 : 0,
+    k_kick_drift<false><<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, g, ctx->use_q4 ? 1 : 0,
                                                   std::max(early_k, 0), fgrid, push ? *push : HaloPush{});
     return MD_OK;
 }
