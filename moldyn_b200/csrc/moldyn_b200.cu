@@ -143,6 +143,16 @@ struct md_ctx {
     cudaGraphConditionalHandle cond = 0;
     bool graph_ok = false;
     bool graph_fused = false;  // the captured body is the fused one-kernel step
+    // single-GPU chunk graphs, kept by what is baked into them (see ChunkKey): a rebuild swaps the two plane sets, so the
+    // graphs of two consecutive list epochs alternate — two entries make re-capture + re-instantiation a once-only cost
+    struct ChunkGraph {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        std::vector<unsigned char> key;
+        unsigned long long stamp = 0;
+    } chunk_cache[2];
+    unsigned long long chunk_stamp = 0;
+    long long chunk_hits = 0, chunk_builds = 0;
 
     md_stats stats{};
 
@@ -865,11 +875,58 @@ int build_graph(md_ctx *ctx)
     return MD_OK;
 }
 
-// MD_LOOP_CHUNK: STEP_CHUNK guarded steps captured once per list epoch; the host enqueues a few of them ahead.
+// MD_LOOP_CHUNK: STEP_CHUNK guarded steps captured per list epoch; the host enqueues a few of them ahead.
 constexpr int STEP_CHUNK = 16;
-int build_chunk_graph(md_ctx *ctx, bool fused)
+
+void drop_chunk_cache(md_ctx *ctx)
 {
-    drop_graph(ctx);
+    for (auto &c : ctx->chunk_cache) {
+        if (c.exec) cudaGraphExecDestroy(c.exec);
+        if (c.graph) cudaGraphDestroy(c.graph);
+        c.exec = nullptr;
+        c.graph = nullptr;
+        c.key.clear();
+    }
+}
+
+// Everything launch_kick_drift / launch_force / launch_fused_step bake into a captured chunk: kernel variant selectors, grids
+// and every argument.  Equal keys mean byte-identical launches, so a cached graph may be replayed whatever happened in between.
+std::vector<unsigned char> chunk_key(const md_ctx *ctx, bool fused)
+{
+    std::vector<unsigned char> k;
+    auto put = [&k](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; k.insert(k.end(), b, b + n); };
+    auto put_ptr = [&put](const void *p) { put(&p, sizeof p); };
+    auto put_i = [&put](long long v) { put(&v, sizeof v); };
+    // Arrays hold only pointers; copy them field by field (no padding bytes in the key)
+    for (const Arrays *a : {&ctx->cur, &ctx->alt})
+        for (const void *q : {(const void *)a->x, (const void *)a->y, (const void *)a->z, (const void *)a->vx, (const void *)a->vy,
+                              (const void *)a->vz, (const void *)a->fx, (const void *)a->fy, (const void *)a->fz,
+                              (const void *)a->u, (const void *)a->w, (const void *)a->id, (const void *)a->q4})
+            put_ptr(q);
+    for (const void *q : {(const void *)ctx->nbr, (const void *)ctx->nbr_cnt, (const void *)ctx->nbr_u, (const void *)ctx->cnt_u,
+                          (const void *)ctx->nbr_t, (const void *)ctx->act_idx, (const void *)ctx->act_scan,
+                          (const void *)ctx->d_partials, (const void *)ctx->d_sc, (const void *)ctx->d_pr})
+        put_ptr(q);
+    const ForceConsts fc = force_consts(ctx);
+    for (double v : {fc.sigma, fc.sigma2, fc.eps4, fc.eps24, fc.r_cut, fc.rc2, fc.u_cut, fc.c6, fc.c12, fc.d6, fc.d12, fc.hc, fc.mass})
+        put(&v, sizeof v);
+    for (long long v : {(long long)ctx->n, (long long)ctx->n_own, (long long)ctx->npad, (long long)ctx->grid.cap,
+                        (long long)ctx->cap_u, (long long)ctx->cap_t, (long long)ctx->cfg.force_mode, (long long)ctx->dense,
+                        (long long)ctx->union_valid, (long long)ctx->coop_valid, (long long)ctx->sparse, (long long)ctx->use_q4,
+                        (long long)fused, (long long)ctx->parity_host, (long long)ctx->force_grid[0], (long long)ctx->force_grid[1],
+                        (long long)ctx->force_grid[2], (long long)ctx->coop_grid, (long long)ctx->sparse_grid,
+                        (long long)ctx->step_grid[0], (long long)ctx->step_grid[1], (long long)pdl_level()})
+        put_i(v);
+    return k;
+}
+
+int build_chunk_graph(md_ctx *ctx, bool fused, md_ctx::ChunkGraph *slot)
+{
+    if (slot->exec) cudaGraphExecDestroy(slot->exec);
+    if (slot->graph) cudaGraphDestroy(slot->graph);
+    slot->exec = nullptr;
+    slot->graph = nullptr;
+    slot->key.clear();
     const int64_t launches = ctx->stats.kernel_launches;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int rc = MD_OK;
@@ -885,12 +942,33 @@ int build_chunk_graph(md_ctx *ctx, bool fused)
             if (rc == MD_OK) rc = launch_force(ctx, true, 0ull, 1, pdl);
         }
     }
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->dist_graph);  // always leave capture mode
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &slot->graph);  // always leave capture mode
     ctx->stats.kernel_launches = launches;
     if (rc != MD_OK) return rc;
     if (e != cudaSuccess) return ctx->fail(MD_ERR_CUDA, "graph capture of the step chunk failed: %s", cudaGetErrorString(e));
-    CK(cudaGraphInstantiate(&ctx->dist_graph_exec, ctx->dist_graph, 0));
-    ctx->graph_fused = fused;
+    CK(cudaGraphInstantiate(&slot->exec, slot->graph, 0));
+    slot->key = chunk_key(ctx, fused);
+    ctx->chunk_builds += 1;
+    return MD_OK;
+}
+
+// the cached chunk graph for the current state of the context, built on a miss (evicting the older entry)
+int get_chunk_graph(md_ctx *ctx, bool fused, cudaGraphExec_t *exec)
+{
+    const std::vector<unsigned char> key = chunk_key(ctx, fused);
+    md_ctx::ChunkGraph *hit = nullptr, *victim = &ctx->chunk_cache[0];
+    for (auto &c : ctx->chunk_cache) {
+        if (c.exec && c.key == key) hit = &c;
+        if (c.stamp < victim->stamp) victim = &c;
+    }
+    if (!hit) {
+        TRY(build_chunk_graph(ctx, fused, victim));
+        hit = victim;
+    } else {
+        ctx->chunk_hits += 1;
+    }
+    hit->stamp = ++ctx->chunk_stamp;
+    *exec = hit->exec;
     return MD_OK;
 }
 
@@ -1002,6 +1080,7 @@ void md_destroy(md_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drop_graph(ctx);
+    drop_chunk_cache(ctx);
     for (int k = 0; k < ctx->dist.n_ipc_opened; ++k) cudaIpcCloseMemHandle(ctx->dist.ipc_opened[k]);
     if (ctx->dist.comm) ncclCommDestroy(ctx->dist.comm);
     if (ctx->dist.h_cnt) cudaFreeHost(ctx->dist.h_cnt);
@@ -1359,14 +1438,14 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
         } else {
             long long before = ctx->h_sc->steps_done;
             if (ctx->cfg.loop_mode != MD_LOOP_WHILE) {
-                if (ctx->dist_graph_exec && ctx->graph_fused != fused) drop_graph(ctx);
-                if (!ctx->dist_graph_exec) TRY(build_chunk_graph(ctx, fused));
+                cudaGraphExec_t chunk_exec = nullptr;
+                TRY(get_chunk_graph(ctx, fused, &chunk_exec));
                 // look ahead as far as the list is expected to last (the previous epoch's length), at most 8 chunks: steps
                 // enqueued past a rebuild request are no-ops, but each still costs a launch
                 const long long since = ctx->stats.steps - ctx->epoch_start_step;
                 const long long expect = std::max<long long>(STEP_CHUNK, ctx->last_epoch_len - since);
                 const int chunks = (int)std::min<long long>(8, (std::min<long long>(remaining, expect) + STEP_CHUNK - 1) / STEP_CHUNK);
-                for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(ctx->dist_graph_exec, st));
+                for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(chunk_exec, st));
                 ctx->stats.graph_launches += chunks;
             } else {
                 if (ctx->graph_ok && ctx->graph_fused != fused) drop_graph(ctx);
