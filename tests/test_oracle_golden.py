@@ -1,5 +1,7 @@
 """Pins the CPU oracle against every golden value in the reference's own tests
 (solver/src/lib.rs, cli/src/tests.rs — see tests/golden/reference_kats.json for file:line)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -198,3 +200,23 @@ def test_barostat_scales_box():  # barostat.rs:21-49
     mu = np.cbrt(1.0 + 0.002 * 1.0 / 0.1 * (p0 - 0.101325))
     assert abs(ba.myu / mu - 1.0) < 4e-16  # numpy's cbrt and glibc's may differ in the last bit
     assert np.array_equal(st.box, box0 * ba.myu)
+
+
+def test_oracle_many_body_fixtures():
+    """Many-body forces and NVT/NPT trajectories have no enabled test in the reference ("parity unpinned"): the
+    restated oracle is their only anchor.  tests/golden/oracle_fixtures.npz (tests/golden/make_oracle_fixtures.py) freezes its
+    answers bit for bit — both scan modes — so a toolchain or source change that moves one bit of the checker is caught here."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_fixtures", os.path.join(here, "golden", "make_oracle_fixtures.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got = mod.build()
+    want = np.load(os.path.join(here, "golden", "oracle_fixtures.npz"))
+    assert set(got) == set(want.files)
+    for key in want.files:
+        assert np.array_equal(got[key], want[key]), key
+    # the Θ(N) cell-list variant reproduces the frozen many-body forces as well
+    o = orc.State(want["liquid216_pos"].copy(), np.zeros_like(want["liquid216_pos"]), orc.ARGON_MASS, want["liquid216_box"].copy())
+    orc.update_force(orc.LennardJones(), o, mode="cells")
+    assert np.array_equal(o.force, want["liquid216_force"]) and np.array_equal(o.vir, want["liquid216_vir"])
