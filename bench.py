@@ -215,7 +215,7 @@ def run_ours(args, w):
         else (lambda: None)
 
     s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv,
-                  step_mode=args.step_mode, union_lists=args.dense_kernel == "union", coop=args.dense_kernel == "coop")
+                  chunk_loop=args.loop == "chunk", host_loop=args.loop == "host")
     if world > 1:
         from moldyn_b200 import distributed as mdd
         mdd.init_solver_comm(s)
@@ -257,10 +257,8 @@ def run_ours(args, w):
         # --- per-kernel device times (CUDA events on the launching stream, host-stepped) -----------------
         kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
         per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt}
-        f_ms, k_ms, s_ms = per["force"], per["kick_drift"], per["fused_step"]
-        if s_ms is not None and kt["fused_step"][1] >= kt["force"][1]:
-            dominant, dom_ms, dom_bytes = "k_step_dilute", s_ms, ALGO_BYTES_FUSED_STEP
-        elif f_ms >= k_ms:
+        f_ms, k_ms, s_ms = per["force"], per["kick_drift"], per["loop_barrier"]
+        if f_ms >= k_ms:
             dominant, dom_ms, dom_bytes = "k_force", f_ms, ALGO_BYTES_FORCE
         else:
             dominant, dom_ms, dom_bytes = "k_kick_drift", k_ms, ALGO_BYTES_KICK_DRIFT
@@ -377,7 +375,7 @@ def run_ours(args, w):
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
         "graph_launches_in_timed_region": st1["graph_launches"] - st0["graph_launches"],
-        "fused_steps_in_timed_region": st1["fused_steps"] - st0["fused_steps"],
+        "loop_launches_in_timed_region": st1["loop_launches"] - st0["loop_launches"],
         "state_check": {"temperature": macro["temperature"], "pressure": macro["pressure"],
                         "momentum_abs_max": float(np.abs(macro["momentum"]).max())},
     }
@@ -388,7 +386,8 @@ def run_ours(args, w):
         mine["wait_sums_us_per_step"] = (st1["wait_sums_ms"] - st0["wait_sums_ms"]) * 1e3 / args.steps
         for k in ("force_atoms", "force_tail"):
             mine[k + "_us_per_step"] = (st1[k + "_ms"] - st0[k + "_ms"]) * 1e3 / args.steps
-        mine["rebuild_ms_each"] = (st1["drift_push_ms"] - st0["drift_push_ms"]) / max(st1["rebuilds"] - st0["rebuilds"], 1)
+        mine["rebuild_ms_each"] = (st1["rebuild_ms"] - st0["rebuild_ms"]) / max(st1["rebuilds"] - st0["rebuilds"], 1)
+        mine["loop_phase_us_per_step"] = [(a - b) * 1e3 / args.steps for a, b in zip(st1["loop_phase_ms"], st0["loop_phase_ms"])]
         dist.gather_object(mine, alls, dst=0)
         out["per_rank"] = alls
     if rank == 0:
@@ -408,10 +407,9 @@ def main():
     ap.add_argument("--skin", type=float, default=0.0)
     ap.add_argument("--cell-atoms", type=float, default=0.0)
     ap.add_argument("--cell-subdiv", type=int, default=0)
-    ap.add_argument("--step-mode", default="auto", choices=["auto", "split", "fused"],
-                    help="split: k_kick_drift + k_force; fused: k_step_dilute (dilute systems, one GPU)")
-    ap.add_argument("--dense-kernel", default="auto", choices=["auto", "union", "coop"],
-                    help="dense systems (c5): force-kernel variant (auto = the library's default)")
+    ap.add_argument("--loop", default="auto", choices=["auto", "chunk", "host"],
+                    help="auto: persistent step loop for dilute systems, graph chunks for dense ones; chunk: the two-kernel "
+                         "graph-chunk loop everywhere (A/B); host: one launch per step (ncu)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
     args = ap.parse_args()

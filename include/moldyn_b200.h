@@ -46,27 +46,12 @@ typedef enum md_status {
 #define MD_FORCE_FAST 0  /* r^2-based LJ, FMA allowed, neighbour order = cell order (default) */
 #define MD_FORCE_EXACT 1 /* the reference's operation order (potential.rs:181-211) without FMA and with
                             partners summed in ascending particle index: bit-identical to update_force */
-#define MD_FORCE_FAST_UNION 2 /* MD_FORCE_FAST with union lists per atom pair for dense systems on one GPU (k_build_union): one
-                                gather serves both atoms of a thread.  Opt-in: measured slower on B200 (C5 k_force 0.311 vs
-                                0.245 ms) — after the 256-bit gathers the dense loop is bound by pair arithmetic, and the union
-                                evaluates 25 % more pairs */
-#define MD_FORCE_FAST_COOP 3 /* MD_FORCE_FAST with the warp-cooperative force kernel for dense systems on one GPU (k_force_coop:
-                               the 32 lanes of a warp share one atom's list, stored atom-major, so a gather touches fewer
-                               128-byte lines — the per-thread loop is bound by the L1 data pipe).  Opt-in: measured slower
-                               on B200 (C5 k_force 0.247 vs 0.221 ms: -28 % L1 wavefronts, +16 % instructions) */
 /* loop_mode */
-#define MD_LOOP_GRAPH 0 /* default: CUDA-graph loop, currently MD_LOOP_CHUNK (measured faster than MD_LOOP_WHILE on B200:
-                           36.8 vs 41.1 us/step at 10^6 atoms, 14.3 vs 17.5 at 32768 — same bits) */
-#define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check, ncu) */
-#define MD_LOOP_CHUNK 2 /* pre-enqueued graphs of 16 guarded steps (a step is a no-op once the device says "rebuild" or
-                           "done"): no conditional node per iteration */
-#define MD_LOOP_WHILE 3 /* ONE conditional (WHILE) graph; the force kernel's last block sets the loop condition */
-
-/* step_mode */
-#define MD_STEP_AUTO 0  /* the faster of the two below as measured on B200: currently MD_STEP_SPLIT everywhere */
-#define MD_STEP_SPLIT 1 /* k_kick_drift + k_force */
-#define MD_STEP_FUSED 2 /* dilute systems on one GPU: ONE kernel per step (k_step_dilute: partners drifted on the fly,
-                           TMA-staged tiles, x/v ping-pong between two plane sets); otherwise as MD_STEP_SPLIT */
+#define MD_LOOP_AUTO 0  /* default.  Dilute systems (mean listed partners < 8): ONE persistent cooperative kernel runs the steps
+                           until the list must be rebuilt (k_md_loop: two grid-wide synchronisations per step, no kernel boundary).
+                           Dense systems: pre-enqueued CUDA graphs of 16 guarded {k_kick_drift; k_force} steps (MD_LOOP_CHUNK) */
+#define MD_LOOP_HOST 1  /* one host round-trip per step (debugging / cross-check, ncu): same kernels, same bits as MD_LOOP_AUTO */
+#define MD_LOOP_CHUNK 2 /* the graph-chunk loop of the two-kernel step for every system (the round-1 path; A/B measurements) */
 
 typedef struct md_config {
     int32_t device;         /* CUDA device ordinal */
@@ -74,7 +59,7 @@ typedef struct md_config {
     int32_t loop_mode;      /* MD_LOOP_* */
     int32_t max_neighbours; /* initial neighbour-list capacity per atom; 0 = from density (grown on demand) */
     int32_t cell_subdiv;    /* cells per (r_cut+skin): 1 (27-cell stencil) or 2 (125-cell stencil); 0 = by density */
-    int32_t step_mode;      /* MD_STEP_* */
+    int32_t reserved0;
     double skin;            /* Verlet skin [nm]; <= 0 selects a default from r_cut and density */
     double cell_atoms;      /* target atoms per cell for dilute systems; <= 0 = 1 */
 } md_config;
@@ -124,24 +109,27 @@ typedef struct md_stats {
     int64_t steps;            /* MD steps executed since md_create */
     int64_t rebuilds;         /* neighbour-list rebuilds */
     int64_t kernel_launches;  /* kernels of this library launched (graph body launches included) */
-    int64_t graph_launches;   /* conditional-graph launches */
+    int64_t graph_launches;   /* step-chunk graph launches */
+    int64_t loop_launches;    /* launches of the persistent step loop (k_md_loop) */
+    int64_t loop_steps;       /* steps executed inside the persistent step loop since the last upload */
     int32_t cells[3];         /* current cell grid */
     int32_t nbr_capacity;     /* neighbour slots per atom */
     int32_t nbr_max;          /* largest neighbour count seen at the last rebuild */
-    int32_t coop_lists;       /* 1: the last rebuild produced the atom-major table of the warp-cooperative dense force kernel */
+    int32_t peer_memory;      /* 1: halo and reduction go through peer memory (NVLink stores), 0: NCCL send/recv path */
+    int32_t persistent_loop;  /* 1: md_step runs this state through the persistent step loop */
+    int32_t tile_lists;       /* 1: the last rebuild produced the brick-local lists of the tile force kernel (dense systems) */
     double skin;              /* skin in use */
     double nbr_mean;          /* mean neighbour count at the last rebuild */
     int64_t n_owned;          /* atoms this rank owns (== n on one GPU) */
     int64_t n_ghost;          /* halo atoms held for the neighbours' partners */
     int64_t migrated;         /* atoms handed to a neighbouring rank so far */
-    int64_t fused_steps;      /* of `steps`: executed by the fused one-kernel step (k_step_dilute) */
-    double wait_halo_ms;      /* multi-GPU peer-memory path: time block 0 of k_force polled for the neighbours' ghosts, */
-    double wait_sums_ms;      /* and the last block polled for the other ranks' reduction sums (since the last upload)   */
-    int32_t peer_memory;      /* 1: halo and reduction go through peer memory (NVLink stores), 0: NCCL send/recv path     */
-    int32_t union_lists;      /* 1: the last rebuild produced union lists per atom pair (dense systems, FAST mode, one GPU) */
-    double force_atoms_ms;    /* peer-memory path diagnostics: k_force first block start -> all atoms done,               */
-    double force_tail_ms;     /*   -> mailbox exchange + finalize done,                                                  */
-    double drift_push_ms;     /*   multi-GPU: wall time spent in list rebuilds so far (host clock around dist_rebuild)    */
+    double wait_halo_ms;      /* multi-GPU peer-memory path: time spent polling for the neighbours' ghosts,          */
+    double wait_sums_ms;      /* and for the other ranks' reduction sums (since the last upload)                   */
+    double force_atoms_ms;    /* two-kernel peer-memory path diagnostics: k_force first block start -> all atoms done, */
+    double force_tail_ms;     /*   -> mailbox exchange + finalize done                                             */
+    double rebuild_ms;        /* multi-GPU: wall time spent in list rebuilds so far (host clock around dist_rebuild) */
+    double loop_phase_ms[4];  /* persistent step loop, block 0's clock, since the last upload: drift phase, mid-step barrier,
+                                 force phase, reduction + exchange + finalize + end-of-step wait */
 } md_stats;
 
 typedef struct md_ctx md_ctx;
@@ -228,10 +216,15 @@ MD_API int md_get_stats(md_ctx *ctx, md_stats *out);
 /* cudaStream_t the context launches on (for CUDA-event timing by the caller). */
 MD_API void *md_stream(md_ctx *ctx);
 MD_API int md_synchronize(md_ctx *ctx);
-/* md_step with one CUDA-event pair around every kernel (host-stepped): summed device milliseconds and launch
- * counts of {k_kick_drift, k_force, list rebuild, k_step_dilute}.  Measurement aid for the roofline figures. */
+/* md_step with device timing of its parts: summed device milliseconds and counts of
+ * {k_kick_drift or the loop's drift phase, k_force or the loop's force phase + reduction tail, list rebuild, the loop's
+ * mid-step barrier}.  The two-kernel step is host-stepped with a CUDA-event pair around every kernel; the persistent loop
+ * reads %globaltimer in block 0.  Measurement aid for the roofline figures. */
 MD_API int md_time_kernels(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *thermostat,
                            md_barostat *barostat, double ms[4], int64_t launches[4]);
+/* Measurement aid: the device's sustained FP64 fused-multiply-add rate in TFLOP/s (a register-only DFMA loop on every SM,
+ * best of five launches) — the denominator of the dense force kernel's roofline fraction. */
+MD_API int md_measure_fp64_peak(md_ctx *ctx, double *tflops);
 /* Forces a list rebuild before the next force evaluation (rebuild-stress tests). */
 MD_API int md_invalidate_lists(md_ctx *ctx);
 

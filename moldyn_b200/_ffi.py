@@ -13,9 +13,8 @@ ERR_NAMES = {
     5: "MD_ERR_NEIGHBOUR_OVERFLOW", 6: "MD_ERR_NO_STATE", 7: "MD_ERR_NONFINITE", 8: "MD_ERR_DECOMPOSITION",
 }
 UNIQUE_ID_BYTES = 128
-FORCE_FAST, FORCE_EXACT, FORCE_FAST_UNION, FORCE_FAST_COOP = 0, 1, 2, 3
-LOOP_GRAPH, LOOP_HOST, LOOP_CHUNK, LOOP_WHILE = 0, 1, 2, 3
-STEP_AUTO, STEP_SPLIT, STEP_FUSED = 0, 1, 2
+FORCE_FAST, FORCE_EXACT = 0, 1
+LOOP_AUTO, LOOP_HOST, LOOP_CHUNK = 0, 1, 2
 CELL_UNIFORM, CELL_FCC = 0, 1
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
 BAROSTAT_NONE, BAROSTAT_BERENDSEN = 0, 1
@@ -29,7 +28,7 @@ class MdError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("force_mode", C.c_int32), ("loop_mode", C.c_int32),
-                ("max_neighbours", C.c_int32), ("cell_subdiv", C.c_int32), ("step_mode", C.c_int32),
+                ("max_neighbours", C.c_int32), ("cell_subdiv", C.c_int32), ("reserved0", C.c_int32),
                 ("skin", C.c_double), ("cell_atoms", C.c_double)]
 
 
@@ -52,11 +51,13 @@ class MacroOut(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("kernel_launches", C.c_int64),
-                ("graph_launches", C.c_int64), ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32),
-                ("nbr_max", C.c_int32), ("coop_lists", C.c_int32), ("skin", C.c_double), ("nbr_mean", C.c_double),
-                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("migrated", C.c_int64), ("fused_steps", C.c_int64), ("wait_halo_ms", C.c_double),
-                ("wait_sums_ms", C.c_double), ("peer_memory", C.c_int32), ("union_lists", C.c_int32),
-                ("force_atoms_ms", C.c_double), ("force_tail_ms", C.c_double), ("drift_push_ms", C.c_double)]
+                ("graph_launches", C.c_int64), ("loop_launches", C.c_int64), ("loop_steps", C.c_int64),
+                ("cells", C.c_int32 * 3), ("nbr_capacity", C.c_int32), ("nbr_max", C.c_int32),
+                ("peer_memory", C.c_int32), ("persistent_loop", C.c_int32), ("tile_lists", C.c_int32),
+                ("skin", C.c_double), ("nbr_mean", C.c_double), ("n_owned", C.c_int64), ("n_ghost", C.c_int64),
+                ("migrated", C.c_int64), ("wait_halo_ms", C.c_double), ("wait_sums_ms", C.c_double),
+                ("force_atoms_ms", C.c_double), ("force_tail_ms", C.c_double), ("rebuild_ms", C.c_double),
+                ("loop_phase_ms", C.c_double * 4)]
 
 
 # every symbol include/moldyn_b200.h declares (tests check the library exports all of them)
@@ -66,7 +67,7 @@ SYMBOLS = [
     "md_update_force_host", "md_calculate_host", "md_download_cells", "md_neighbour_counts",
     "md_neighbour_lists", "md_get_stats", "md_stream", "md_synchronize", "md_invalidate_lists", "md_time_kernels",
     "md_comm_unique_id", "md_comm_init", "md_local_count", "md_download_local", "md_plan_decomposition",
-    "md_initialize_lattice",
+    "md_initialize_lattice", "md_measure_fp64_peak",
 ]
 
 _lib = None
@@ -119,6 +120,7 @@ def lib():
             "md_plan_decomposition": (C.c_int, [i64, pd, f64, C.c_int, C.c_int, C.POINTER(f64), C.POINTER(f64),
                                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)]),
             "md_initialize_lattice": (C.c_int, [vp, C.c_int, pd, pd, f64, f64, f64, C.c_uint64]),
+            "md_measure_fp64_peak": (C.c_int, [vp, C.POINTER(f64)]),
         }
         assert set(sig) == set(SYMBOLS)
         for name, (res, args) in sig.items():

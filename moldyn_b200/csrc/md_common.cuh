@@ -61,17 +61,19 @@ struct Scalars {
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     int out_of_box;    // the last cell binning saw a coordinate outside [0, L): list builds use the generic minimum image
-    int parity;        // fused one-kernel steps ping-pong x and v between two plane sets: which set is current
-    int union_max;     // largest union-list length of the last k_build_union (entries per atom pair)
-    int union_fail;    // k_build_union could not run (a coordinate outside the box): fall back to per-atom lists
+    int pad0;
+    unsigned int bar_arrive;        // persistent step loop: arrivals at the mid-step grid barrier (only ever grows)
+    unsigned int face_arrive[2];    // persistent step loop, multi-GPU: face blocks that have pushed their ghosts (only grows)
     unsigned long long epoch;  // multi-GPU peer-memory path: sequence number of the last finalized collective reduction
     unsigned long long wait_halo_ns, wait_sums_ns;  // time spent polling the mailboxes (block 0 / last block), accumulated
     unsigned long long t_start;                     // %globaltimer when the first block of the running k_force started
-    unsigned long long force_atoms_ns, force_tail_ns, drift_push_ns;  // accumulated phase times (multi-GPU diagnostics)
+    unsigned long long force_atoms_ns, force_tail_ns;  // accumulated phase times (multi-GPU diagnostics)
     unsigned long long nbr_total;
-    unsigned long long probe[8];  // MD_TIMING_PROBES: %globaltimer stamps of k_force phases
-    unsigned long long fin_seq;     // number of last-block epilogues completed so far (release-stored at their very end)
-    unsigned long long chunk_fin0;  // fin_seq when the running step chunk started (early-start k_kick_drift, see there)
+    unsigned long long fin_seq;     // number of last-block epilogues completed so far (release-stored at their very end):
+                                    // the end-of-step barrier of the persistent step loop
+    // persistent step loop: accumulated phase times of block 0 (ns): drift, mid-step barrier, forces, reduction + finalize
+    unsigned long long loop_ns[4];
+    unsigned long long loop_steps;  // steps executed by the persistent loop since the last upload
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
     // multi-GPU rebuild bookkeeping
     int n_stay, n_left, n_right, n_lost;
@@ -84,12 +86,6 @@ __device__ __forceinline__ bool halted(const Scalars *sc)
 {
     return sc->need_rebuild != 0 || sc->error != 0 || sc->steps_left <= 0;
 }
-
-// Programmatic dependent launch (opt-in, MOLDYN_B200_PDL=1; single-GPU chunk graphs): a step kernel launched with the
-// programmatic-serialization attribute becomes resident while its predecessor drains and blocks here until the predecessor
-// has completed and its memory operations are visible.  Without the attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // gpu-scope acquire / release accesses of the step-control words (L2, never a stale L1 line)
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
@@ -134,16 +130,6 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *g)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-#ifdef MD_TIMING_PROBES
-#define PROBE(k) sc->probe[k] = gtime()
-#define PROBE_MIN(k) atomicMin(&sc->probe[k], gtime())
-#define PROBE_MAX(k) atomicMax(&sc->probe[k], gtime())
-#else
-#define PROBE(k)
-#define PROBE_MIN(k)
-#define PROBE_MAX(k)
-#endif
 
 // ---- multi-GPU peer-memory mailboxes (NVLink/NVSwitch, one process per GPU, buffers shared through CUDA IPC) ----------
 // Every rank owns one Mail in its own HBM; the OTHER ranks write into it with plain stores over NVLink and the owner polls

@@ -215,11 +215,12 @@ __global__ void __launch_bounds__(128) k_build_list_dist(int n_own, Arrays a, co
                                                          const int *__restrict__ ghost_start,
                                                          const int *__restrict__ ghost_order, Scalars *sc, Grid g,
                                                          double r_list, double r2_list, int *__restrict__ nbr,
-                                                         int *__restrict__ nbr_cnt)
+                                                         int *__restrict__ nbr_cnt, int *__restrict__ nbr_ghost)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (p < n_own) {
+        int any_ghost = 0;  // does the list hold a ghost?  (the persistent step loop computes such atoms last)
         const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
         const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
         const double xi = a.x[p], yi = a.y[p], zi = a.z[p];
@@ -261,11 +262,13 @@ __global__ void __launch_bounds__(128) k_build_list_dist(int n_own, Arrays a, co
                         if (r2 > r2_list || q == p) continue;
                         if (cnt < g.cap) nbr[(size_t)cnt * g.npad + p] = q;
                         ++cnt;
+                        any_ghost |= ghost ? 1 : 0;
                     }
                 }
             }
         }
         nbr_cnt[p] = min(cnt, g.cap);
+        nbr_ghost[p] = any_ghost;
         if (SORT_BY_ID && cnt <= g.cap) {
             for (int s1 = 1; s1 < cnt; ++s1) {
                 int item = nbr[(size_t)s1 * g.npad + p];

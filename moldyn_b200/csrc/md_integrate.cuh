@@ -22,26 +22,17 @@ __device__ __forceinline__ void drift_one(double &x, double u, double lambda, do
     else if (x >= L) x = __dsub_rn(x, L);
 }
 
-// L2 (PDL = true: the kernel may run while its predecessor is finishing, never trust an L1 line) or plain loads
-template <bool PDL, typename T>
-__device__ __forceinline__ T ld_state(const T *p)
-{
-    if constexpr (PDL) return __ldcg(p);
-    else return *p;
-}
-
-template <bool PDL>
 __device__ __forceinline__ void kick_drift_tail(int i, Arrays a, double lambda, double mup, double Lx, double Ly, double Lz,
                                                 bool half, const Params *__restrict__ pr, bool write_q4)
 {
     const double c = pr->half_dt_m, dt = pr->dt;
-    double ux = ld_state<PDL>(a.vx + i), uy = ld_state<PDL>(a.vy + i), uz = ld_state<PDL>(a.vz + i);
+    double ux = a.vx[i], uy = a.vy[i], uz = a.vz[i];
     if (!half) {
-        ux = __dadd_rn(ux, __dmul_rn(ld_state<PDL>(a.fx + i), c)); uy = __dadd_rn(uy, __dmul_rn(ld_state<PDL>(a.fy + i), c));
-        uz = __dadd_rn(uz, __dmul_rn(ld_state<PDL>(a.fz + i), c));
+        ux = __dadd_rn(ux, __dmul_rn(a.fx[i], c)); uy = __dadd_rn(uy, __dmul_rn(a.fy[i], c));
+        uz = __dadd_rn(uz, __dmul_rn(a.fz[i], c));
         a.vx[i] = ux; a.vy[i] = uy; a.vz[i] = uz;
     }
-    double x = ld_state<PDL>(a.x + i), y = ld_state<PDL>(a.y + i), z = ld_state<PDL>(a.z + i);
+    double x = a.x[i], y = a.y[i], z = a.z[i];
     drift_one(x, ux, lambda, mup, dt, Lx);
     drift_one(y, uy, lambda, mup, dt, Ly);
     drift_one(z, uz, lambda, mup, dt, Lz);
@@ -72,120 +63,31 @@ __device__ __forceinline__ void push_atom(const HaloPush &h, int i, int n, doubl
     }
 }
 
-// PDL = false: plain launch, the predecessor is complete (every launch but the ones below).  PDL = true: launched as a
-// programmatic dependent of k_force inside a single-GPU chunk graph (MOLDYN_B200_PDL, opt-in).
-template <bool PDL>
-__global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars *sc,
-                                                    const Params *__restrict__ pr, int guarded, int write_q4,
-                                                    int early_k, unsigned force_grid, const HaloPush h)
+__global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars *sc, const Params *__restrict__ pr,
+                                                    int guarded, int write_q4, const HaloPush h)
 {
-    // guarded bits: 1 = return at once when the loop is halted, 2 = programmatic dependent (== PDL),
-    //               4 = the chunk's drifts start early (with 2: step early_k >= 1 of the chunk; step 0 is a plain launch)
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    double2 x, y, z, ux, uy, uz;
-    bool have_x = false, have_u = false;
-    double lambda, mup, Lx, Ly, Lz;
-    bool half;
-    if constexpr (PDL) {
-        pdl_launch_dependents();  // k_force of this step may become resident; it waits for this grid to complete
-        // positions were last written by the previous k_kick_drift, which completed before our predecessor (k_force) did
-        // anything: they can be fetched while k_force drains.
-        if (2 * t + 1 < n) {
-            x = __ldcg(reinterpret_cast<const double2 *>(a.x) + t); y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t);
-            z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
-            have_x = true;
-        }
-        bool waited = false;
-        if (guarded & 4) {
-            // Early start.  The predecessor's tail — one block folding 592 partial sums and computing lambda, myu and the
-            // rebuild decision while 147 SMs idle — is hidden behind this kernel's loads: (a) once every block of k_force has
-            // taken its ticket, all velocities u' are final (each block fences before the ticket): fetch them; (b) once the
-            // last block has release-stored the sequence number of this step, the controls are final: drift and store.
-            // One thread per block polls (bounded); on a timeout, or on anything unexpected, the block falls back to
-            // griddepcontrol.wait — always correct, the flags only ever let it start sooner.
-            __shared__ int verdict;  // 0 = go, 1 = fall back to the full wait, 2 = halted: nothing to do
-            __shared__ unsigned long long expect_s;
-            if (threadIdx.x == 0) {
-                const unsigned long long expect = __ldcg(&sc->chunk_fin0) + (unsigned long long)early_k;
-                expect_s = expect;
-                int v = 1;
-                if (halted_now(sc)) v = 2;  // halted before our predecessor started: it is a no-op and raises no flag
-                else
-                    for (int spin = 0; spin < 4096; ++spin) {
-                        if (ld_acquire_gpu(&sc->fin_seq) >= expect) { v = 3; break; }  // the whole predecessor is done
-                        if (ld_acquire_gpu(&sc->ticket) == force_grid) { v = 0; break; }
-                        __nanosleep(64);
-                    }
-                verdict = v;
-            }
-            __syncthreads();
-            if (verdict == 2) return;
-            if (verdict == 3) waited = true;
-            else if (verdict == 0) {
-                if (have_x) {
-                    ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t); uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t);
-                    uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
-                    have_u = true;
-                }
-                __syncthreads();  // verdict is rewritten below
-                if (threadIdx.x == 0) {
-                    const unsigned long long expect = expect_s;
-                    int v = 1;
-                    for (int spin = 0; spin < 4096; ++spin) {
-                        if (ld_acquire_gpu(&sc->fin_seq) >= expect) { v = 0; break; }
-                        __nanosleep(64);
-                    }
-                    verdict = v;
-                }
-                __syncthreads();
-                waited = verdict == 0;
-            }
-        }
-        if (!waited) pdl_wait();
-        // The step controls, once per block through L2 (never a stale L1 line, and not 2000 blocks x 8 warps hammering one
-        // L2 slice with the same nine words: measured 13 -> 26 us per launch at 10^6 atoms when every thread read them itself).
-        __shared__ double ctl[5];   // lambda, mu_pending, Lx, Ly, Lz
-        __shared__ int ctl_half, ctl_halted;
-        if (threadIdx.x == 0) {
-            const double l0 = __ldcg(&sc->lambda), l1 = __ldcg(&sc->mu_pending), l2 = __ldcg(&sc->box[0]),
-                         l3 = __ldcg(&sc->box[1]), l4 = __ldcg(&sc->box[2]);
-            ctl_half = __ldcg(&sc->vel_is_half);
-            ctl_halted = halted_now(sc) ? 1 : 0;
-            ctl[0] = l0; ctl[1] = l1; ctl[2] = l2; ctl[3] = l3; ctl[4] = l4;
-        }
-        __syncthreads();
-        if ((guarded & 1) && ctl_halted) return;
-        lambda = ctl[0]; mup = ctl[1]; Lx = ctl[2]; Ly = ctl[3]; Lz = ctl[4];
-        half = ctl_half != 0;
-    } else {
-        if ((guarded & 1) && halted(sc)) return;
-        lambda = sc->lambda; mup = sc->mu_pending;
-        Lx = sc->box[0]; Ly = sc->box[1]; Lz = sc->box[2];
-        half = sc->vel_is_half != 0;
-        // first step of a chunk whose later drifts start early: the sequence number the chunk counts from
-        if ((guarded & 4) && early_k == 0 && t == 0) sc->chunk_fin0 = sc->fin_seq;
-    }
+    // guarded: return at once when the loop is halted (speculatively enqueued steps)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (guarded && halted(sc)) return;
+    const double lambda = sc->lambda, mup = sc->mu_pending;
+    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+    const bool half = sc->vel_is_half != 0;
     // block-uniform: does this block hold face atoms?  (512 atoms per block)
     const int b_lo = blockIdx.x * 512, b_hi = b_lo + 512;
     const bool pushes = (h.m[0] | h.m[1]) != 0 && (b_lo < h.m[0] || b_hi > n - h.m[1]);
     if (2 * t < n) {
         if (2 * t + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
-            kick_drift_tail<PDL>(2 * t, a, lambda, mup, Lx, Ly, Lz, half, pr, write_q4 != 0);
+            kick_drift_tail(2 * t, a, lambda, mup, Lx, Ly, Lz, half, pr, write_q4 != 0);
             if (pushes) push_atom(h, 2 * t, n, a.x[2 * t], a.y[2 * t], a.z[2 * t]);
         } else {
             const double c = pr->half_dt_m, dt = pr->dt;
-            if (!have_x) {
-                x = reinterpret_cast<double2 *>(a.x)[t]; y = reinterpret_cast<double2 *>(a.y)[t];
-                z = reinterpret_cast<double2 *>(a.z)[t];
-            }
-            if (!have_u) {
-                ux = reinterpret_cast<double2 *>(a.vx)[t]; uy = reinterpret_cast<double2 *>(a.vy)[t];
-                uz = reinterpret_cast<double2 *>(a.vz)[t];
-            }
+            double2 x = reinterpret_cast<double2 *>(a.x)[t], y = reinterpret_cast<double2 *>(a.y)[t],
+                    z = reinterpret_cast<double2 *>(a.z)[t];
+            double2 ux = reinterpret_cast<double2 *>(a.vx)[t], uy = reinterpret_cast<double2 *>(a.vy)[t],
+                    uz = reinterpret_cast<double2 *>(a.vz)[t];
             if (!half) {
-                const double2 fx = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fx) + t),
-                              fy = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fy) + t),
-                              fz = ld_state<PDL>(reinterpret_cast<const double2 *>(a.fz) + t);
+                const double2 fx = reinterpret_cast<const double2 *>(a.fx)[t], fy = reinterpret_cast<const double2 *>(a.fy)[t],
+                              fz = reinterpret_cast<const double2 *>(a.fz)[t];
                 ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, c)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, c));
                 uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, c)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, c));
                 uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, c)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, c));
@@ -209,26 +111,7 @@ __global__ void __launch_bounds__(256, 4) k_kick_drift(int n, Arrays a, Scalars 
     }
 }
 
-// ----------------------------------------------------------------------------------------------------
-// K3+K4 fused — ONE kernel per step for dilute systems (few listed partners per atom).
-//
-// k_kick_drift exists as a separate kernel only because the forces need every partner's drifted position.  A thread
-// can just as well drift its partners itself: x_j' = wrap(x_j*mu + (u_j*lambda)*dt) is the same instruction sequence
-// the owner of j runs, hence the same bits.  With ~0.5 partners per atom that costs a few extra gathers and saves a
-// full pass over the state: the step reads x,u (48 B/atom) + list count and first row (8 B) and writes x',u' (48 B).
-// In-place updates would race with those partner reads, so x and v ping-pong between two plane sets (sc->parity
-// names the current one; the last block flips it).
-//
-// Streaming side: each block walks its tiles of STEP_TILE atoms; the tile's eight plane segments are fetched by TMA
-// bulk copies (cp.async.bulk → shared memory, mbarrier completion) into a two-stage ring, so the next tile's HBM
-// requests are in flight while the block is busy with gathers and arithmetic of the current tile.
-constexpr int STEP_TILE = 2 * FORCE_BLOCK;
-
-struct StepStage {
-    double x[STEP_TILE], y[STEP_TILE], z[STEP_TILE], ux[STEP_TILE], uy[STEP_TILE], uz[STEP_TILE];
-    int cnt[STEP_TILE], row0[STEP_TILE];
-};
-
+// ---- mbarrier / TMA bulk-copy helpers (used by the tile kernels of dense systems, md_tile.cuh) ----------------------
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -259,176 +142,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-
-// drifted position of an atom from its stored (x, u): thermostat.rs:54-58, barostat.rs:46-48, integrator.rs:40-45
-__device__ __forceinline__ void drift3(double &x, double &y, double &z, double ux, double uy, double uz, double lambda,
-                                       double mup, double dt, const LjConst &c)
-{
-    drift_one(x, ux, lambda, mup, dt, c.Lx);
-    drift_one(y, uy, lambda, mup, dt, c.Ly);
-    drift_one(z, uz, lambda, mup, dt, c.Lz);
-}
-
-#ifndef MD_STEP_MINB
-#define MD_STEP_MINB 4
-#endif
-template <bool EXACT>
-__global__ void __launch_bounds__(FORCE_BLOCK, MD_STEP_MINB)
-    k_step_dilute(int n, Arrays P0, Arrays P1, const int *__restrict__ nbr, const int *__restrict__ nbr_cnt, int npad,
-                  int cap, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr, int flags,
-                  unsigned long long cond_handle, const ForceConsts fc)
-{
-    if ((flags & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
-    __shared__ __align__(128) StepStage stg[2];
-    __shared__ SumsSmem ss;
-    __shared__ __align__(8) unsigned long long full[2];
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int q = 0; q < NSUM; ++q) ss.v[q][tid] = 0.0;
-    // Control words are rewritten only by the last block's finalize, after every block has finished its atoms.
-    const bool par = sc->parity != 0;
-    const bool store_state = sc->steps_left <= 1;
-    const bool nh = pr->th_kind == 2;
-    const double lambda = sc->lambda, mup = sc->mu_pending, dt = pr->dt;
-    LjConst c;
-    c.Lx = sc->box[0]; c.Ly = sc->box[1]; c.Lz = sc->box[2];
-    c.hx = c.Lx / 2.0; c.hy = c.Ly / 2.0; c.hz = c.Lz / 2.0;
-    c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
-    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
-    const double *__restrict__ ix = par ? P1.x : P0.x, *__restrict__ iy = par ? P1.y : P0.y,
-                 *__restrict__ iz = par ? P1.z : P0.z, *__restrict__ iux = par ? P1.vx : P0.vx,
-                 *__restrict__ iuy = par ? P1.vy : P0.vy, *__restrict__ iuz = par ? P1.vz : P0.vz;
-    double *__restrict__ ox = par ? P0.x : P1.x, *__restrict__ oy = par ? P0.y : P1.y, *__restrict__ oz = par ? P0.z : P1.z,
-           *__restrict__ ovx = par ? P0.vx : P1.vx, *__restrict__ ovy = par ? P0.vy : P1.vy,
-           *__restrict__ ovz = par ? P0.vz : P1.vz;
-    const int ntiles = (n + STEP_TILE - 1) / STEP_TILE;
-    const size_t stride = (size_t)(npad >> 1);
-
-    auto issue = [&](int tile, int s) {  // one thread: arm the barrier, launch the eight segment copies
-        const int base = tile * STEP_TILE;
-        const unsigned na = (unsigned)min(STEP_TILE, npad - base);  // npad is a multiple of 64 atoms
-        mbar_expect_tx(&full[s], na * 56u);
-        tma_load_1d(stg[s].x, ix + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].y, iy + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].z, iz + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].ux, iux + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].uy, iuy + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].uz, iuz + base, na * 8u, &full[s]);
-        tma_load_1d(stg[s].cnt, nbr_cnt + base, na * 4u, &full[s]);
-        tma_load_1d(stg[s].row0, nbr + base, na * 4u, &full[s]);
-    };
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
-        if ((int)(blockIdx.x + gridDim.x) < ntiles) issue(blockIdx.x + gridDim.x, 1);
-    }
-    __syncthreads();
-
-    for (int it = 0;; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        if (tile >= ntiles) break;
-        const int s = it & 1;
-        mbar_wait(&full[s], (unsigned)(it >> 1) & 1u);
-        double2 X = reinterpret_cast<const double2 *>(stg[s].x)[tid], Y = reinterpret_cast<const double2 *>(stg[s].y)[tid],
-                Z = reinterpret_cast<const double2 *>(stg[s].z)[tid];
-        double2 VX = reinterpret_cast<const double2 *>(stg[s].ux)[tid], VY = reinterpret_cast<const double2 *>(stg[s].uy)[tid],
-                VZ = reinterpret_cast<const double2 *>(stg[s].uz)[tid];
-        int2 C = reinterpret_cast<const int2 *>(stg[s].cnt)[tid];
-        int2 J = reinterpret_cast<const int2 *>(stg[s].row0)[tid];
-        const int i0 = tile * STEP_TILE + 2 * tid;
-        const bool has0 = i0 < n, has1 = i0 + 1 < n;
-        if (!has0) C.x = 0;
-        if (!has1) C.y = 0;
-        // own atoms: thermostat scale, pending barostat scale, drift, wrap
-        drift3(X.x, Y.x, Z.x, VX.x, VY.x, VZ.x, lambda, mup, dt, c);
-        drift3(X.y, Y.y, Z.y, VX.y, VY.y, VZ.y, lambda, mup, dt, c);
-        PairAcc f0 = {0.0, 0.0, 0.0, 0.0, 0.0}, f1 = {0.0, 0.0, 0.0, 0.0, 0.0};
-        const int kmax = max(C.x, C.y);
-        const int2 *__restrict__ row = reinterpret_cast<const int2 *>(nbr) + (size_t)(i0 >> 1);
-        for (int k = 0; k < kmax; ++k) {
-            const bool a0 = k < C.x, a1 = k < C.y;
-            const int j0 = a0 ? J.x : 0, j1 = a1 ? J.y : 0;
-            if (k + 1 < kmax) J = row[(size_t)(k + 1) * stride];
-            // all twelve gathers of this trip are issued before the first use
-            double xa = __ldg(ix + j0), ya = __ldg(iy + j0), za = __ldg(iz + j0);
-            const double uxa = __ldg(iux + j0), uya = __ldg(iuy + j0), uza = __ldg(iuz + j0);
-            double xb = __ldg(ix + j1), yb = __ldg(iy + j1), zb = __ldg(iz + j1);
-            const double uxb = __ldg(iux + j1), uyb = __ldg(iuy + j1), uzb = __ldg(iuz + j1);
-            if (a0) {
-                drift3(xa, ya, za, uxa, uya, uza, lambda, mup, dt, c);
-                if (EXACT) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
-                else pair_fast_branchy(f0, true, xa, ya, za, X.x, Y.x, Z.x, c, fc);
-            }
-            if (a1) {
-                drift3(xb, yb, zb, uxb, uyb, uzb, lambda, mup, dt, c);
-                if (EXACT) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
-                else pair_fast_branchy(f1, true, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
-            }
-        }
-        double2 WX, WY, WZ;
-        WX.x = WY.x = WZ.x = WX.y = WY.y = WZ.y = 0.0;
-        if (has0) finish_atom(ss, f0, VX.x, VY.x, VZ.x, true, lambda, fc.hc, fc.mass, shift, WX.x, WY.x, WZ.x, nh);
-        if (has1) finish_atom(ss, f1, VX.y, VY.y, VZ.y, true, lambda, fc.hc, fc.mass, shift, WX.y, WY.y, WZ.y, nh);
-        if (has1) {
-            const int t = i0 >> 1;
-            reinterpret_cast<double2 *>(ox)[t] = X; reinterpret_cast<double2 *>(oy)[t] = Y;
-            reinterpret_cast<double2 *>(oz)[t] = Z;
-            if (store_state) {
-                reinterpret_cast<double2 *>(ovx)[t] = VX; reinterpret_cast<double2 *>(ovy)[t] = VY;
-                reinterpret_cast<double2 *>(ovz)[t] = VZ;
-                reinterpret_cast<double2 *>(P0.fx)[t] = make_double2(f0.fx, f1.fx);
-                reinterpret_cast<double2 *>(P0.fy)[t] = make_double2(f0.fy, f1.fy);
-                reinterpret_cast<double2 *>(P0.fz)[t] = make_double2(f0.fz, f1.fz);
-                reinterpret_cast<double2 *>(P0.u)[t] = make_double2(f0.u, f1.u);
-                reinterpret_cast<double2 *>(P0.w)[t] = make_double2(f0.w, f1.w);
-            } else {
-                reinterpret_cast<double2 *>(ovx)[t] = WX; reinterpret_cast<double2 *>(ovy)[t] = WY;
-                reinterpret_cast<double2 *>(ovz)[t] = WZ;
-            }
-        } else if (has0) {  // odd tail: scalar stores only
-            ox[i0] = X.x; oy[i0] = Y.x; oz[i0] = Z.x;
-            if (store_state) {
-                ovx[i0] = VX.x; ovy[i0] = VY.x; ovz[i0] = VZ.x;
-                P0.fx[i0] = f0.fx; P0.fy[i0] = f0.fy; P0.fz[i0] = f0.fz; P0.u[i0] = f0.u; P0.w[i0] = f0.w;
-            } else {
-                ovx[i0] = WX.x; ovy[i0] = WY.x; ovz[i0] = WZ.x;
-            }
-        }
-        // Refill stage s for the tile after next.  The TMA engine writes shared memory through the async proxy, which
-        // is not ordered against shared-memory loads that are merely *issued*: the barrier therefore sits at the END of
-        // the iteration, where every thread has consumed (stored results computed from) what it loaded from the stage.
-        // (With the barrier right after the loads, a backed-up LSU queue let the refill overtake a warp's LDS.)
-        __syncthreads();
-        if (tid == 0) {
-            const int next = tile + 2 * gridDim.x;
-            if (next < ntiles) issue(next, s);
-        }
-    }
-    Sums sum;
-#pragma unroll
-    for (int q = 0; q < NSUM; ++q) sum.v[q] = ss.v[q][tid];
-    block_reduce<FORCE_BLOCK>(sum);
-    grid_reduce_finalize<FORCE_BLOCK>(sum, partials, sc, pr, FIN_STEP | FIN_FLIP | (flags & 2 ? FIN_DIST : 0), cond_handle,
-                                      nullptr);
-}
-
-// First step of a batch for the fused path: the velocity planes hold v (not u = v + F c) after an upload or after the
-// last step of the previous batch (integrator.rs:28-34).
-__global__ void k_first_half_kick(int n, Arrays a, Scalars *sc, const Params *__restrict__ pr)
-{
-    if (sc->vel_is_half) return;  // rewritten only by k_mark_half, a separate launch
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double c = pr->half_dt_m;
-    a.vx[i] = __dadd_rn(a.vx[i], __dmul_rn(a.fx[i], c));
-    a.vy[i] = __dadd_rn(a.vy[i], __dmul_rn(a.fy[i], c));
-    a.vz[i] = __dadd_rn(a.vz[i], __dmul_rn(a.fz[i], c));
-}
-
-__global__ void k_mark_half(Scalars *sc) { sc->vel_is_half = 1; }
 
 // (re)builds the packed gather copy from the planes: after a reorder, a ghost exchange or a coordinate rescale
 __global__ void k_pack_q4(int n, Arrays a)
@@ -472,8 +185,6 @@ __global__ void k_reset_list_stats(Scalars *sc)
     sc->nbr_max = 0;
     sc->nbr_overflow = 0;
     sc->nbr_total = 0ull;
-    sc->union_max = 0;
-    sc->union_fail = 0;
 }
 
 __global__ void k_set_shift_to_vcom(Scalars *sc)
@@ -539,6 +250,22 @@ __global__ void k_init_velocities(int n, double sigma, unsigned long long seed, 
     const double vz = sigma * standard_normal(seed, (unsigned long long)i, 2);
     a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz;
     a.vx[i + half] = -vx; a.vy[i + half] = -vy; a.vz[i + half] = -vz;
+}
+
+// ---- measurement aid: the FP64 pipe's DFMA rate (the roofline denominator of the dense force kernel) -----------------
+// 8 independent fused multiply-add chains per thread, no memory traffic: 2 * 8 * iters flop per thread.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double *__restrict__ sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0,
+           a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+    for (int k = 0; k < iters; ++k) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) sink[0] = r;  // keeps the chains alive
 }
 
 // ---- transfer helpers -------------------------------------------------------------------------------

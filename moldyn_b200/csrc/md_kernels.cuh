@@ -18,4 +18,5 @@
 #include "md_reduce.cuh"
 #include "md_force.cuh"
 #include "md_integrate.cuh"
+#include "md_loop.cuh"
 #include "md_dist_kernels.cuh"

@@ -94,7 +94,6 @@ __device__ __forceinline__ void compute_controls(Scalars *sc, const Params *pr, 
 // mode bits of finalize
 constexpr int FIN_STEP = 1;  // called at the end of an MD step: commit drift, apply barostat box scaling, count
 constexpr int FIN_DIST = 2;  // multi-GPU: publish this rank's sums only; k_finalize_dist finalizes after the all-gather
-constexpr int FIN_FLIP = 4;  // fused one-kernel step: the step wrote the other plane set, flip sc->parity
 constexpr int FIN_P2P = 8;   // multi-GPU: exchange the rank sums through the peer mailboxes and finalize right here
 
 // `in` / `pr`: the control words and parameters as they were when the kernel started (the last block copies them into
@@ -171,7 +170,9 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Scalars *in, const P
         sc->steps_done = steps_done + 1;
         // k_force stored u = v + F*c instead of v unless this was the last step of the batch
         sc->vel_is_half = steps_left - 1 > 0 ? 1 : 0;
-        if (mode & FIN_FLIP) sc->parity ^= 1;
+        // persistent step loop (md_loop.cuh): every block is past this step's mid-step barrier and face push
+        sc->bar_arrive = 0u;
+        sc->face_arrive[0] = 0u;
     }
     sc->disp_acc = disp_acc;
     sc->inv_scale = inv_scale;
@@ -187,11 +188,11 @@ __device__ __forceinline__ void finalize(Scalars *sc, const Scalars *in, const P
     if (!(d == d) || !(lambda == lambda) || !(mu == mu) || isinf(d) || isinf(lambda) || isinf(mu)) sc->error = 7;
 }
 
-// Last-block epilogue shared by k_force and k_reduce_state.  `mine` is this block's reduced sums (thread 0).
+// Last-block epilogue shared by k_force, k_reduce_state and the persistent step loop, in two pieces.
+// (1) Every block stores its reduced sums (thread 0 holds them) and takes a ticket; the function returns true in every
+//     thread of the block that came last.
 template <int BLOCK>
-__device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restrict__ partials, Scalars *sc,
-                                                     const Params *pr, int mode,
-                                                     unsigned long long cond_handle, const Peers *peers_p)
+__device__ __forceinline__ bool publish_and_ticket(const Sums &mine, double *__restrict__ partials, Scalars *sc)
 {
     __shared__ bool is_last;
     if (threadIdx.x == 0) {
@@ -202,12 +203,20 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
-    if (threadIdx.x == 0) { PROBE(2); }
+    return is_last;
+}
+
+// (2) The last block folds the per-block partials in a fixed order, exchanges the rank sums with the other GPUs (FIN_P2P),
+//     finalizes the step controls, resets the ticket and release-stores the new sequence number sc->fin_seq — the
+//     end-of-step barrier the other blocks of the persistent step loop wait on.
+template <int BLOCK>
+__device__ __forceinline__ void last_block_finalize(double *__restrict__ partials, Scalars *sc, const Params *pr, int mode,
+                                                    const Peers *peers_p)
+{
     __threadfence();
-    // Last block.  (1) A copy of the control words and parameters finalize reads goes to shared memory — those loads are in
-    // flight together with (2) the fold of the per-block partials: thread (g, q) adds slot q of blocks g, g+G, g+2G, … in
-    // ascending order (independent loads, one L2 round trip), then the G group sums of a slot are added in group order.
+    // (a) A copy of the control words and parameters finalize reads goes to shared memory — those loads are in flight
+    // together with (b) the fold of the per-block partials: thread (g, q) adds slot q of blocks g, g+G, g+2G, … in ascending
+    // order (independent loads, one L2 round trip), then the G group sums of a slot are added in group order.
     // Fixed assignment, fixed order: the result depends on the grid size only.
     constexpr int H = NSUM / 2;   // slot pairs: 128-bit loads
     constexpr int G = BLOCK / H;  // groups of blocks
@@ -233,7 +242,7 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
             const bool has_max = (h == H - 1);  // the last slot of the last pair is the running maximum
             double ax = 0.0, ay = 0.0;
             const double2 *src = reinterpret_cast<const double2 *>(partials) + h;
-            constexpr int U = 16;               // loads in flight per thread
+            constexpr int U = 16;              // loads in flight per thread
             unsigned int b = g;
             for (; b + (U - 1) * G < gridDim.x; b += U * G) {
                 double2 v[U];
@@ -283,7 +292,7 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
         __shared__ double my_sums[NSUM];
         __shared__ int timed_out;
         const Peers &peers = *peers_p;
-        const unsigned long long seq = sc->epoch + 1;
+        const unsigned long long seq = sc_in.epoch + 1;
         const int buf = (int)(seq & 1ull);
         if (threadIdx.x == 0) {
 #pragma unroll
@@ -302,8 +311,8 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
             if (!wait_seq(&peers.mail[peers.rank]->sums_seq[threadIdx.x], seq)) timed_out = 1;
         }
         __syncthreads();
-        if (threadIdx.x == 0) sc->wait_sums_ns += gtime() - t_wait;
         if (threadIdx.x == 0) {
+            sc->wait_sums_ns = sc_in.wait_sums_ns + (gtime() - t_wait);
             Sums t;
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) t.v[q] = 0.0;
@@ -315,20 +324,16 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
             }
             finalize(sc, &sc_in, &pr_in, t, mode);
             if (timed_out) sc->error = 3;  // MD_ERR_NCCL: a peer never delivered
-            sc->force_atoms_ns += t_last - sc->t_start;
-            sc->force_tail_ns += gtime() - t_last;
+            if (sc_in.t_start != ~0ull) sc->force_atoms_ns = sc_in.force_atoms_ns + (t_last - sc_in.t_start);
+            sc->force_tail_ns = sc_in.force_tail_ns + (gtime() - t_last);
             sc->t_start = ~0ull;
             sc->epoch = seq;
             sc->ticket = 0;
-            if (cond_handle) {
-                unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
-                cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, go);
-            }
+            st_release_gpu(&sc->fin_seq, sc_in.fin_seq + 1);
         }
         return;
     }
     if (threadIdx.x == 0) {
-        PROBE(3);
         if (mode & FIN_DIST) {
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) sc->rank_sums[q] = acc.v[q];
@@ -337,14 +342,17 @@ __device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restr
         }
         finalize(sc, &sc_in, &pr_in, acc, mode);
         sc->ticket = 0;
-        // everything above is visible to whoever acquires the new sequence number (early-start k_kick_drift)
+        // everything above is visible to whoever acquires the new sequence number
         st_release_gpu(&sc->fin_seq, sc_in.fin_seq + 1);
-        PROBE(4);
-        if (cond_handle) {
-            unsigned int go = (sc->steps_left > 0 && !sc->need_rebuild && !sc->error) ? 1u : 0u;
-            cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, go);
-        }
     }
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void grid_reduce_finalize(Sums &mine, double *__restrict__ partials, Scalars *sc,
+                                                     const Params *pr, int mode, const Peers *peers_p)
+{
+    if (!publish_and_ticket<BLOCK>(mine, partials, sc)) return;
+    last_block_finalize<BLOCK>(partials, sc, pr, mode, peers_p);
 }
 
 // Adds one atom's terms. (wx,wy,wz) = v + F*c is the velocity the next kick_drift moves this atom with (before lambda).
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(RED_BLOCK) k_reduce_state(int n, Arrays a, dou
         accumulate_sums(s, m, vx, vy, vz, wx, wy, wz, a.w[i], a.u[i], shift);
     }
     block_reduce<RED_BLOCK>(s);
-    grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, mode, 0ull, nullptr);
+    grid_reduce_finalize<RED_BLOCK>(s, partials, sc, pr, mode, nullptr);
 }
 
 }  // namespace md

@@ -1,8 +1,9 @@
 // moldyn_b200.cu — C ABI (include/moldyn_b200.h) over the sm_100a kernels in md_kernels.cuh.
 //
-// Host side of the step loop: owns the device-resident State, orchestrates list rebuilds, and runs the
-// steady-state steps inside one conditional (WHILE) CUDA graph whose condition the force kernel's last
-// block sets on the device — the host is only involved when the neighbour list has to be rebuilt.
+// Host side of the step loop: owns the device-resident State, orchestrates list rebuilds, and runs the steady-state
+// steps without host involvement — dilute systems inside ONE persistent cooperative kernel (md_loop.cuh), dense systems as
+// pre-enqueued CUDA graphs of guarded {k_kick_drift; k_force} steps.  The host looks at the device only when the neighbour
+// list has to be rebuilt or the batch ends.
 #include "md_kernels.cuh"
 
 #include <dlfcn.h>
@@ -103,26 +104,15 @@ struct md_ctx {
     double *d_partials = nullptr;
     int partial_blocks = 0;
     int force_grid[3] = {1, 1, 1}, reduce_grid = 1;  // exact, fast dense, fast dilute
-    int step_grid[2] = {1, 1};                        // fused one-kernel step: exact, fast
-    int parity_host = 0;                              // which plane set ctx->cur's x/v pointers name (see sync_parity)
-    // atoms with at least one listed partner, compacted at every rebuild (k_force_sparse)
-    int *act_flag = nullptr, *act_scan = nullptr, *act_idx = nullptr, *act_sums = nullptr;
-    int act_alloc = 0, sparse_grid = 1;
-    bool sparse = false;                              // dilute + FAST: the last rebuild left a valid active list
+    // persistent step loop (md_loop.cuh): atoms with listed partners, compacted at every rebuild (interior first, then the
+    // atoms whose lists hold ghosts), their two counts on the device, and the per-atom "list holds a ghost" flags
+    int *act_flag = nullptr, *act_scan = nullptr, *act_idx = nullptr, *act_sums = nullptr, *n_act = nullptr;
+    int *nbr_ghost = nullptr;
+    int act_alloc = 0;
+    int loop_blocks_max = 0;                          // co-resident blocks of k_md_loop on this device
+    bool loop_attr_set = false;
     double rebuild_host_ms = 0.0;                     // multi-GPU: wall time spent in list rebuilds (host clock, synchronised)
     long long epoch_start_step = 0, last_epoch_len = 128;  // list epochs in steps: sizes the chunk look-ahead
-    // dense + FAST on one GPU: union lists per atom pair (k_build_union), see md_kernels.cuh
-    int *nbr_u = nullptr, *cnt_u = nullptr;
-    size_t nbr_u_alloc = 0;
-    int cap_u = 0;
-    bool union_valid = false;
-    // dense + FAST on one GPU: atom-major copy of the lists for the warp-cooperative force kernel (k_force_coop)
-    int *nbr_t = nullptr;
-    size_t nbr_t_alloc = 0;
-    int cap_t = 0, coop_grid = 1;
-    bool coop_valid = false;
-    double *hot_slab = nullptr;                       // one GPU: x, y, z, vx, vy, vz of both plane sets in one allocation,
-                                                      // so one L2 access-policy window can pin the current set (apply_l2_window)
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
     bool use_q4 = false;                              // packed gather copy maintained (dense systems)
     double graph_hc = -1.0;                           // dt/(2m) baked into the captured force kernel
@@ -135,14 +125,9 @@ struct md_ctx {
     int *nbr = nullptr, *nbr_cnt = nullptr;
     size_t nbr_alloc = 0;
 
-    // graph (single GPU: WHILE graph; multi-GPU: a chunk of guarded steps incl. the NCCL calls)
+    // multi-GPU (chunk path): a chunk of guarded steps incl. the NCCL calls
     cudaGraph_t dist_graph = nullptr;
     cudaGraphExec_t dist_graph_exec = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaGraphConditionalHandle cond = 0;
-    bool graph_ok = false;
-    bool graph_fused = false;  // the captured body is the fused one-kernel step
     // single-GPU chunk graphs, kept by what is baked into them (see ChunkKey): a rebuild swaps the two plane sets, so the
     // graphs of two consecutive list epochs alternate — two entries make re-capture + re-instantiation a once-only cost
     struct ChunkGraph {
@@ -193,7 +178,7 @@ struct md_ctx {
     // per-kernel CUDA-event timing (md_time_kernels)
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double t_ms[4] = {0.0, 0.0, 0.0, 0.0};   // kick_drift, force, rebuild, fused step
+    double t_ms[4] = {0.0, 0.0, 0.0, 0.0};   // kick_drift / phase A, force / phase B + tail, rebuild, loop synchronisation
     int64_t t_cnt[4] = {0, 0, 0, 0};
 
     int fail(int code, const char *fmt, ...)
@@ -294,16 +279,10 @@ void free_arrays(md_ctx *ctx, Arrays *a)
 
 void drop_graph(md_ctx *ctx)
 {
-    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
-    if (ctx->graph) cudaGraphDestroy(ctx->graph);
     if (ctx->dist_graph_exec) cudaGraphExecDestroy(ctx->dist_graph_exec);
     if (ctx->dist_graph) cudaGraphDestroy(ctx->dist_graph);
     ctx->dist_graph_exec = nullptr;
     ctx->dist_graph = nullptr;
-    ctx->graph_exec = nullptr;
-    ctx->graph = nullptr;
-    ctx->cond = 0;
-    ctx->graph_ok = false;
 }
 
 int push_params(md_ctx *ctx)
@@ -313,21 +292,10 @@ int push_params(md_ctx *ctx)
     return MD_OK;
 }
 
-// Fused one-kernel steps ping-pong x and v between the plane sets of cur and alt; the device counts the flips
-// (sc->parity).  Whenever the host looks at the device state it rebinds cur's six pointers to the current set.
-void sync_parity(md_ctx *ctx)
-{
-    if ((ctx->h_sc->parity & 1) == ctx->parity_host) return;
-    std::swap(ctx->cur.x, ctx->alt.x); std::swap(ctx->cur.y, ctx->alt.y); std::swap(ctx->cur.z, ctx->alt.z);
-    std::swap(ctx->cur.vx, ctx->alt.vx); std::swap(ctx->cur.vy, ctx->alt.vy); std::swap(ctx->cur.vz, ctx->alt.vz);
-    ctx->parity_host ^= 1;
-}
-
 int pull_scalars(md_ctx *ctx)
 {
     CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    sync_parity(ctx);
     return MD_OK;
 }
 
@@ -417,22 +385,6 @@ int ensure_nbr_capacity(md_ctx *ctx, int cap)
     return MD_OK;
 }
 
-int ensure_union_capacity(md_ctx *ctx, int cap_u)
-{
-    const size_t need = (size_t)cap_u * (size_t)(ctx->npad / 2);
-    if (need > ctx->nbr_u_alloc) {
-        dev_free(ctx, ctx->nbr_u);
-        ctx->nbr_u = nullptr;
-        ctx->nbr_u_alloc = 0;
-        TRY(dev_alloc(ctx, &ctx->nbr_u, need));
-        ctx->nbr_u_alloc = need;
-    }
-    if (!ctx->cnt_u) TRY(dev_alloc(ctx, &ctx->cnt_u, (size_t)ctx->npad / 2 + 1));
-    ctx->cap_u = cap_u;
-    drop_graph(ctx);
-    return MD_OK;
-}
-
 // Largest double t with sqrt(t) <= r (IEEE sqrt is correctly rounded and monotonic): turns the reference's
 // `norm(r) > r_cut` test into a comparison of squares with the identical outcome for every input.
 double sqrt_threshold(double r)
@@ -475,64 +427,7 @@ int refresh_q4(md_ctx *ctx)
 }
 
 int build_active_list(md_ctx *ctx, int n);
-
-// Opt-in experiment (MOLDYN_B200_L2_PERSIST=1): one L2 access-policy window marks the current x/v plane set persisting.
-// Measured on B200 it LOSES against the hardware's own replacement policy — 40.7 vs 38.3 us/step at 10^6 atoms (48 MB set,
-// hit ratio 1) and 495 vs 275 us/step at 8*10^6 — so it is off by default.
-int apply_l2_window(md_ctx *ctx)
-{
-    static const bool allowed = [] { const char *e = std::getenv("MOLDYN_B200_L2_PERSIST"); return e && e[0] == '1'; }();
-    if (!allowed || ctx->dist.on || !ctx->hot_slab) return MD_OK;
-    int max_persist = 0, max_window = 0;
-    CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
-    CK(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
-    if (max_persist <= 0 || max_window <= 0) return MD_OK;
-    static bool limit_set = false;
-    if (!limit_set) {
-        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
-        limit_set = true;
-    }
-    const size_t bytes = std::min<size_t>(6 * (size_t)ctx->npad * sizeof(double), (size_t)max_window);
-    cudaStreamAttrValue attr{};
-    attr.accessPolicyWindow.base_ptr = ctx->cur.x;  // first plane of the current set
-    attr.accessPolicyWindow.num_bytes = bytes;
-    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)max_persist / (double)bytes);
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    return MD_OK;
-}
-
-// Warp-cooperative dense force kernel (k_force_coop): needs the lists atom-major.  Dense systems, FAST arithmetic, one GPU.
-bool coop_wanted(const md_ctx *ctx)
-{
-    static const int env = [] { const char *e = std::getenv("MOLDYN_B200_DENSE_COOP"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
-    if (ctx->cfg.force_mode == MD_FORCE_FAST_COOP) return true;
-    return ctx->cfg.force_mode == MD_FORCE_FAST && env == 1;
-}
-
-int build_coop_table(md_ctx *ctx, int n)
-{
-    ctx->coop_valid = false;
-    if (!coop_wanted(ctx) || !ctx->dense || ctx->union_valid || ctx->dist.on || n < 128) return MD_OK;
-    const int cap = ctx->grid.cap;
-    const int cap_t = (cap + 31) / 32 * 32;
-    const size_t need = (size_t)ctx->npad * (size_t)cap_t;
-    if (need > ctx->nbr_t_alloc) {
-        dev_free(ctx, ctx->nbr_t);
-        ctx->nbr_t = nullptr;
-        ctx->nbr_t_alloc = 0;
-        TRY(dev_alloc(ctx, &ctx->nbr_t, need));
-        ctx->nbr_t_alloc = need;
-    }
-    ctx->cap_t = cap_t;
-    dim3 grid((unsigned)blocks_for(n, 32), (unsigned)(cap_t / 32));
-    k_transpose_list<<<grid, 256, 0, ctx->stream>>>(n, cap, ctx->npad, cap_t, ctx->nbr, ctx->nbr_t);
-    ctx->stats.kernel_launches += 1;
-    CK(cudaGetLastError());
-    ctx->coop_valid = true;
-    return MD_OK;
-}
+HaloPush dist_halo_push_args(md_ctx *ctx);
 
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
 // (no pending barostat scaling).
@@ -560,39 +455,10 @@ int rebuild_lists(md_ctx *ctx)
     k_reorder<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->order, ctx->cell_of, ctx->cur, ctx->alt,
                                                    ctx->cell_sorted);
     std::swap(ctx->cur, ctx->alt);
-    // (sc->parity and parity_host stay as they are: cur keeps naming the plane set the device calls current)
     ctx->stats.kernel_launches += 7;
-    drop_graph(ctx);  // array pointers are baked into the captured kernels
 
     const double r2_list = sqrt_threshold(ctx->prm.r_list);
-    // Dense systems in FAST mode on one GPU: union lists per atom pair (half the gathers in the force kernel).
-    ctx->union_valid = false;
-    {
-        const bool allowed = ctx->cfg.force_mode == MD_FORCE_FAST_UNION;  // opt-in, see include/moldyn_b200.h
-        const double volume = box[0] * box[1] * box[2];
-        const double in_list = (double)n / volume * 4.18879020478639 * ctx->prm.r_list * ctx->prm.r_list * ctx->prm.r_list;
-        const int need_cells = 2 * g.nsub + 5;
-        bool want = allowed && ctx->cfg.force_mode != MD_FORCE_EXACT && in_list >= 12.0 && g.nc[0] >= need_cells &&
-                    g.nc[1] >= need_cells && g.nc[2] >= need_cells && n >= 128;
-        for (int attempt = 0; want && attempt < 4; ++attempt) {
-            if (ctx->cap_u == 0) TRY(ensure_union_capacity(ctx, ((int)(in_list * 1.45) + 32 + 7) / 8 * 8));
-            k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
-            k_build_union<<<blocks_for((n + 1) / 2, 128), 128, 0, st>>>(n, ctx->cur, ctx->cell_sorted, ctx->cell_start, ctx->d_sc,
-                                                                      g, ctx->prm.r_list, r2_list, ctx->nbr_u, ctx->cnt_u,
-                                                                      ctx->cap_u, ctx->npad / 2, ctx->nbr_cnt);
-            ctx->stats.kernel_launches += 2;
-            CK(cudaGetLastError());
-            TRY(pull_scalars(ctx));
-            if (ctx->h_sc->union_fail) break;  // a coordinate outside the box: per-atom lists with the generic minimum image
-            if (!ctx->h_sc->nbr_overflow) {
-                ctx->union_valid = (double)ctx->h_sc->nbr_total / (double)n >= 8.0;  // the dense kernel is the right one
-                break;
-            }
-            if (attempt == 3) return ctx->fail(MD_ERR_NEIGHBOUR_OVERFLOW, "union list overflow (max %d)", ctx->h_sc->union_max);
-            TRY(ensure_union_capacity(ctx, ((int)(ctx->h_sc->union_max * 1.15) + 8 + 7) / 8 * 8));
-        }
-    }
-    for (int attempt = 0; !ctx->union_valid && attempt < 4; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         // image shift per cell run instead of per candidate when the box is wide enough in cells (see k_build_list)
         const int need_cells = 2 * g.nsub + 3;
@@ -626,78 +492,31 @@ int rebuild_lists(md_ctx *ctx)
     ctx->dense = ctx->stats.nbr_mean >= 8.0 && n >= 128;  // (the dense kernel's masked lanes need a foreign warp's atom)
     ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT;
     TRY(refresh_q4(ctx));
-    TRY(build_coop_table(ctx, n));
     TRY(build_active_list(ctx, n));
-    TRY(apply_l2_window(ctx));
     ctx->list_valid = true;
     return MD_OK;
 }
 
-// Programmatic dependent launch of the step kernels inside the single-GPU chunk graph (opt-in: MOLDYN_B200_PDL=1).
-// The launch attribute turns the kernel -> kernel edge of the captured graph into a programmatic one; the kernels
-// themselves start with griddepcontrol.wait (pdl_wait), so nothing is read before the predecessor has completed.
-// 0 = off, 1 = programmatic edges, 2 = programmatic edges + early-start k_kick_drift (flag protocol, see the kernel)
-int pdl_level()
-{
-    static const int level = [] {
-        const char *e = std::getenv("MOLDYN_B200_PDL");
-        return e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
-    }();
-    return level;
-}
-
-// grid of the force kernel launch_force() would pick right now (the early-start drift compares the ticket with it)
-unsigned current_force_grid(const md_ctx *ctx)
-{
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT) return (unsigned)ctx->force_grid[0];
-    if (ctx->dense && ctx->union_valid) return (unsigned)ctx->force_grid[1];
-    if (ctx->dense && ctx->coop_valid) return (unsigned)ctx->coop_grid;
-    if (ctx->dense) return (unsigned)ctx->force_grid[1];
-    if (ctx->sparse) return (unsigned)ctx->sparse_grid;
-    return (unsigned)ctx->force_grid[2];
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args &&...args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
-}
-
-// early_k >= 0: step index inside a chunk graph whose drifts use the early-start protocol (guarded bit 4)
-int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr, bool pdl = false, int early_k = -1)
+int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullptr)
 {
     const int n = (int)ctx->n_own;
     const int blocks = std::max(1, blocks_for((n + 1) / 2, 256));
-    const int g = guarded | (early_k >= 0 ? 4 : 0);
-    const unsigned fgrid = current_force_grid(ctx);
-    if (pdl) {
-        CK(launch_pdl(k_kick_drift<true>, dim3(blocks), dim3(256), ctx->stream, n, ctx->cur, ctx->d_sc, (const Params *)ctx->d_pr,
-                      g | 2, ctx->use_q4 ? 1 : 0, std::max(early_k, 0), fgrid, push ? *push : HaloPush{}));
-        return MD_OK;
-    }
-    k_kick_drift<false><<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, g, ctx->use_q4 ? 1 : 0,
-                                                  std::max(early_k, 0), fgrid, push ? *push : HaloPush{});
+    k_kick_drift<<<blocks, 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr, guarded, ctx->use_q4 ? 1 : 0,
+                                                  push ? *push : HaloPush{});
     return MD_OK;
 }
 
-// k_force_sparse's active list: sorted indices of the owned atoms with >= 1 listed partner; the count stays on the device
+// The persistent step loop walks only the atoms with listed partners in its force phase: their sorted indices, compacted
+// at every rebuild — first the atoms whose partners are all owned, then (multi-GPU) the atoms whose lists hold ghosts.  The
+// two counts stay on the device.
+bool loop_wanted(const md_ctx *ctx)
+{
+    return !ctx->dense && ctx->cfg.loop_mode != MD_LOOP_CHUNK && (!ctx->dist.on || ctx->dist.p2p);
+}
+
 int build_active_list(md_ctx *ctx, int n)
 {
-    // Opt-in experiment (MOLDYN_B200_SPARSE=1).  Measured on B200: 33.4 vs 30.8 us per launch at 1e6 atoms and 241 vs 188 us
-    // at 8e6 — the compacted phase trades idle lanes for uncoalesced plane and list-row accesses and loses.
-    static const bool allowed = [] { const char *e = std::getenv("MOLDYN_B200_SPARSE"); return e && e[0] == '1'; }();
-    ctx->sparse = false;
-    if (!allowed || ctx->dense || ctx->cfg.force_mode == MD_FORCE_EXACT || n <= 0) return MD_OK;
+    if (ctx->dense) return MD_OK;  // dense systems run the two-kernel step
     cudaStream_t st = ctx->stream;
     if (ctx->npad > ctx->act_alloc) {
         dev_free(ctx, ctx->act_flag); dev_free(ctx, ctx->act_scan); dev_free(ctx, ctx->act_idx); dev_free(ctx, ctx->act_sums);
@@ -707,104 +526,36 @@ int build_active_list(md_ctx *ctx, int n)
         TRY(dev_alloc(ctx, &ctx->act_idx, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->act_sums, blocks_for(ctx->npad, SCAN_BLOCK) + 2));
     }
-    k_flag_active<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->nbr_cnt, ctx->act_flag);
-    const int sb = blocks_for(n, SCAN_BLOCK);
-    k_scan_block<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_flag, ctx->act_scan, ctx->act_sums);
-    k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sb, ctx->act_sums);
-    k_scan_add<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_scan, ctx->act_sums, -1);
-    k_scan_total<<<1, 1, 0, st>>>(n, ctx->act_flag, ctx->act_scan);
-    k_compact_index<<<blocks_for(n, 256), 256, 0, st>>>(n, ctx->act_flag, ctx->act_scan, ctx->act_idx);
-    ctx->stats.kernel_launches += 6;
+    if (!ctx->n_act) TRY(dev_alloc(ctx, &ctx->n_act, 2));
+    const int nb = std::max(1, blocks_for(n, 256));
+    const int sb = std::max(1, blocks_for(n, SCAN_BLOCK));
+    const int *ghost = ctx->dist.on ? ctx->nbr_ghost : nullptr;
+    for (int cls = 0; cls < 2; ++cls) {
+        k_flag_active<<<nb, 256, 0, st>>>(n, ctx->nbr_cnt, ghost, cls, ctx->act_flag);
+        k_scan_block<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_flag, ctx->act_scan, ctx->act_sums);
+        k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sb, ctx->act_sums);
+        k_scan_add<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_scan, ctx->act_sums, -1);
+        k_scan_total<<<1, 1, 0, st>>>(n, ctx->act_flag, ctx->act_scan);
+        k_compact_active<<<nb, 256, 0, st>>>(n, ctx->act_flag, ctx->act_scan, cls ? ctx->n_act : nullptr, ctx->act_idx,
+                                             ctx->n_act + cls);
+    }
+    ctx->stats.kernel_launches += 12;
     CK(cudaGetLastError());
-    ctx->sparse = true;
     return MD_OK;
 }
 
-int launch_force(md_ctx *ctx, bool kick, unsigned long long cond, int guarded = 0, bool pdl = false)
+int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
 {
     const int n = (int)ctx->n;
     const ForceConsts fc = force_consts(ctx);
-    if (pdl && (ctx->sparse || (ctx->dense && ctx->union_valid))) pdl = false;  // opt-in variants keep plain launches
-    const int flags = (kick ? 1 : 0) | (guarded ? 4 : 0) | (pdl ? 32 : 0);
-#define LAUNCH_FORCE(E, R, M, GRID)                                                                                  \
-    do {                                                                                                             \
-        if (pdl)                                                                                                     \
-            CK(launch_pdl(k_force<E, R, M>, dim3(GRID), dim3(FORCE_BLOCK), ctx->stream, n, ctx->cur, ctx->nbr,       \
-                          ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, cond, \
-                          fc, (const Peers *)nullptr));                                                              \
-        else                                                                                                         \
-            k_force<E, R, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad,   \
-                                                                 ctx->grid.cap, ctx->d_partials, ctx->d_sc,       \
-                                                                 ctx->d_pr, flags, cond, fc, nullptr);            \
-    } while (0)
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, 1, false, ctx->force_grid[0]);
-    else if (ctx->dense && ctx->union_valid)
-        k_force<false, 2, true, true><<<ctx->force_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, ctx->cur, ctx->nbr_u, ctx->cnt_u, ctx->npad, ctx->cap_u, ctx->d_partials, ctx->d_sc, ctx->d_pr,
-            (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr);
-    else if (ctx->dense && ctx->coop_valid) {
-        if (pdl)
-            CK(launch_pdl(k_force_coop, dim3(ctx->coop_grid), dim3(FORCE_BLOCK), ctx->stream, n, ctx->cur, (const int *)ctx->nbr_t,
-                          (const int *)ctx->nbr_cnt, ctx->cap_t, ctx->d_partials, ctx->d_sc, (const Params *)ctx->d_pr, flags, cond,
-                          fc, (const Peers *)nullptr));
-        else
-            k_force_coop<<<ctx->coop_grid, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr_t, ctx->nbr_cnt, ctx->cap_t,
-                                                                         ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, cond, fc,
-                                                                         nullptr);
-    } else if (ctx->dense) LAUNCH_FORCE(false, 2, true, ctx->force_grid[1]);
-    else if (ctx->sparse)
-        k_force_sparse<<<ctx->sparse_grid, FORCE_BLOCK, 0, ctx->stream>>>(
-            n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->act_idx, ctx->act_scan + n, ctx->d_partials, ctx->d_sc,
-            ctx->d_pr, (kick ? 1 : 0) | (guarded ? 4 : 0), cond, fc, nullptr);
-    else LAUNCH_FORCE(false, MD_DILUTE_ROWS, false, ctx->force_grid[2]);
+    const int flags = (kick ? 1 : 0) | (guarded ? 4 : 0);
+#define LAUNCH_FORCE(E, M, GRID)                                                                                      \
+    k_force<E, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, \
+                                                         ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, fc, nullptr)
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, false, ctx->force_grid[0]);
+    else if (ctx->dense) LAUNCH_FORCE(false, true, ctx->force_grid[1]);
+    else LAUNCH_FORCE(false, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
-    return MD_OK;
-}
-
-// The fused one-kernel step (k_step_dilute) is opt-in: on B200 it ties with k_kick_drift + k_force at 8M atoms and
-// loses at 1M (both are bound by gather latency at 16 warps/SM, and the fused kernel's per-tile chain is longer).
-bool use_fused(const md_ctx *ctx)
-{
-    return ctx->cfg.step_mode == MD_STEP_FUSED && !ctx->dense && !ctx->dist.on && ctx->list_valid;
-}
-
-// plane set 0 / 1 as the device parity names them; F, U, W, id are shared
-void fused_views(const md_ctx *ctx, Arrays *p0, Arrays *p1)
-{
-    Arrays other = ctx->cur;
-    other.x = ctx->alt.x; other.y = ctx->alt.y; other.z = ctx->alt.z;
-    other.vx = ctx->alt.vx; other.vy = ctx->alt.vy; other.vz = ctx->alt.vz;
-    *p0 = ctx->parity_host ? other : ctx->cur;
-    *p1 = ctx->parity_host ? ctx->cur : other;
-}
-
-int launch_fused_step(md_ctx *ctx, unsigned long long cond, int guarded = 0)
-{
-    const int n = (int)ctx->n;
-    const ForceConsts fc = force_consts(ctx);
-    Arrays p0, p1;
-    fused_views(ctx, &p0, &p1);
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
-        k_step_dilute<true><<<ctx->step_grid[0], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,
-            guarded ? 4 : 0, cond, fc);
-    else
-        k_step_dilute<false><<<ctx->step_grid[1], FORCE_BLOCK, 0, ctx->stream>>>(
-            n, p0, p1, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, ctx->d_partials, ctx->d_sc, ctx->d_pr,
-            guarded ? 4 : 0, cond, fc);
-    return MD_OK;
-}
-
-// the fused step expects u = v + F c in the velocity planes
-int ensure_half_kick(md_ctx *ctx)
-{
-    if (ctx->h_sc->vel_is_half) return MD_OK;
-    const int n = (int)ctx->n;
-    k_first_half_kick<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cur, ctx->d_sc, ctx->d_pr);
-    k_mark_half<<<1, 1, 0, ctx->stream>>>(ctx->d_sc);
-    ctx->h_sc->vel_is_half = 1;
-    ctx->stats.kernel_launches += 2;
-    CK(cudaGetLastError());
     return MD_OK;
 }
 
@@ -816,62 +567,62 @@ int launch_reduce(md_ctx *ctx)
     return MD_OK;
 }
 
+constexpr size_t LOOP_SMEM = sizeof(SumsSmemT<LOOP_BLOCK>);
+
 // Persistent grids: resident blocks per SM (occupancy API) × SM count, capped by the work available.
 int choose_grids(md_ctx *ctx)
 {
     int sms = 0, occ[3] = {0, 0, 0}, occ_r = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, 1, false>, FORCE_BLOCK, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, 2, true>, FORCE_BLOCK, 0));
-    {
-        int occ_u = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_u, k_force<false, 2, true, true>, FORCE_BLOCK, 0));
-        occ[1] = std::min(occ[1], occ_u);
-    }
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, MD_DILUTE_ROWS, false>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_force<true, false>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_force<false, true>, FORCE_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_force<false, false>, FORCE_BLOCK, 0));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_reduce_state, RED_BLOCK, 0));
     const int pair_blocks = blocks_for((ctx->n + 1) / 2, FORCE_BLOCK);
     for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
-    int occ_c = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_force_coop, FORCE_BLOCK, 0));
-    ctx->coop_grid = std::max(1, std::min(pair_blocks, sms * std::max(occ_c, 1)));
-    int occ_sp = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, k_force_sparse, FORCE_BLOCK, 0));
-    ctx->sparse_grid = std::max(1, std::min(pair_blocks, sms * std::max(occ_sp, 1)));
-    int occ_s[2] = {0, 0};
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[0], k_step_dilute<true>, FORCE_BLOCK, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[1], k_step_dilute<false>, FORCE_BLOCK, 0));
-    for (int k = 0; k < 2; ++k) ctx->step_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ_s[k], 1)));
     ctx->reduce_grid = std::max(1, std::min(blocks_for(ctx->n, RED_BLOCK), sms * std::max(occ_r, 1)));
+    if (!ctx->loop_attr_set) {
+        CK(cudaFuncSetAttribute(k_md_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM));
+        CK(cudaFuncSetAttribute(k_md_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM));
+        int occ_l[2] = {0, 0};
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[0], k_md_loop<false>, LOOP_BLOCK, LOOP_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[1], k_md_loop<true>, LOOP_BLOCK, LOOP_SMEM));
+        int coop = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        ctx->loop_blocks_max = coop ? sms * std::min(1, std::min(occ_l[0], occ_l[1])) : 0;  // one block per SM
+        ctx->loop_attr_set = true;
+    }
     return MD_OK;
 }
 
-// WHILE-graph: body = { k_kick_drift ; k_force<.., KICK> } ; the force kernel's last block sets the condition.
-int build_graph(md_ctx *ctx)
+// One launch of the persistent step loop: runs until the list has to be rebuilt, the batch ends or max_steps are done.
+int launch_loop(md_ctx *ctx, long long max_steps)
 {
-    drop_graph(ctx);
-    CK(cudaGraphCreate(&ctx->graph, 0));
-    CK(cudaGraphConditionalHandleCreate(&ctx->cond, ctx->graph, 1, cudaGraphCondAssignDefault));
-    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
-    np.type = cudaGraphNodeTypeConditional;
-    np.conditional.handle = ctx->cond;
-    np.conditional.type = cudaGraphCondTypeWhile;
-    np.conditional.size = 1;
-    cudaGraphNode_t node;
-    CK(cudaGraphAddNode(&node, ctx->graph, nullptr, 0, &np));
-    cudaGraph_t body = np.conditional.phGraph_out[0];
-    CK(cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-    ctx->graph_fused = use_fused(ctx);
-    if (ctx->graph_fused) {
-        launch_fused_step(ctx, (unsigned long long)ctx->cond);
-    } else {
-        launch_kick_drift(ctx);
-        launch_force(ctx, true, (unsigned long long)ctx->cond);
-    }
-    cudaGraph_t captured = nullptr;
-    CK(cudaStreamEndCapture(ctx->stream, &captured));
-    CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
-    ctx->graph_ok = true;
+    const int n = (int)ctx->n_own;
+    LoopArgs A{};
+    A.n = n;
+    A.npad = ctx->npad;
+    A.cap = ctx->grid.cap;
+    A.a = ctx->cur;
+    A.nbr = ctx->nbr;
+    A.nbr_cnt = ctx->nbr_cnt;
+    A.act_idx = ctx->act_idx;
+    A.n_act = ctx->n_act;
+    A.partials = ctx->d_partials;
+    A.sc = ctx->d_sc;
+    A.pr = ctx->d_pr;
+    A.peers = ctx->dist.on ? ctx->dist.peers_dev : nullptr;
+    A.h = ctx->dist.on ? dist_halo_push_args(ctx) : HaloPush{};
+    A.max_steps = max_steps;
+    A.fc = force_consts(ctx);
+    // as many blocks as there are pairs of atoms to drift, at most one per SM: small systems synchronise a small grid
+    const int grid = std::max(1, std::min(ctx->loop_blocks_max, blocks_for((n + 1) / 2, LOOP_BLOCK)));
+    void *args[] = {&A};
+    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
+        CK(cudaLaunchCooperativeKernel((const void *)k_md_loop<true>, dim3(grid), dim3(LOOP_BLOCK), args, LOOP_SMEM, ctx->stream));
+    else
+        CK(cudaLaunchCooperativeKernel((const void *)k_md_loop<false>, dim3(grid), dim3(LOOP_BLOCK), args, LOOP_SMEM, ctx->stream));
+    ctx->stats.loop_launches += 1;
     return MD_OK;
 }
 
@@ -889,9 +640,9 @@ void drop_chunk_cache(md_ctx *ctx)
     }
 }
 
-// Everything launch_kick_drift / launch_force / launch_fused_step bake into a captured chunk: kernel variant selectors, grids
-// and every argument.  Equal keys mean byte-identical launches, so a cached graph may be replayed whatever happened in between.
-std::vector<unsigned char> chunk_key(const md_ctx *ctx, bool fused)
+// Everything launch_kick_drift / launch_force bake into a captured chunk: kernel variant selectors, grids and every
+// argument.  Equal keys mean byte-identical launches, so a cached graph may be replayed whatever happened in between.
+std::vector<unsigned char> chunk_key(const md_ctx *ctx)
 {
     std::vector<unsigned char> k;
     auto put = [&k](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; k.insert(k.end(), b, b + n); };
@@ -903,24 +654,20 @@ std::vector<unsigned char> chunk_key(const md_ctx *ctx, bool fused)
                               (const void *)a->vz, (const void *)a->fx, (const void *)a->fy, (const void *)a->fz,
                               (const void *)a->u, (const void *)a->w, (const void *)a->id, (const void *)a->q4})
             put_ptr(q);
-    for (const void *q : {(const void *)ctx->nbr, (const void *)ctx->nbr_cnt, (const void *)ctx->nbr_u, (const void *)ctx->cnt_u,
-                          (const void *)ctx->nbr_t, (const void *)ctx->act_idx, (const void *)ctx->act_scan,
-                          (const void *)ctx->d_partials, (const void *)ctx->d_sc, (const void *)ctx->d_pr})
+    for (const void *q : {(const void *)ctx->nbr, (const void *)ctx->nbr_cnt, (const void *)ctx->d_partials,
+                          (const void *)ctx->d_sc, (const void *)ctx->d_pr})
         put_ptr(q);
     const ForceConsts fc = force_consts(ctx);
     for (double v : {fc.sigma, fc.sigma2, fc.eps4, fc.eps24, fc.r_cut, fc.rc2, fc.u_cut, fc.c6, fc.c12, fc.d6, fc.d12, fc.hc, fc.mass})
         put(&v, sizeof v);
     for (long long v : {(long long)ctx->n, (long long)ctx->n_own, (long long)ctx->npad, (long long)ctx->grid.cap,
-                        (long long)ctx->cap_u, (long long)ctx->cap_t, (long long)ctx->cfg.force_mode, (long long)ctx->dense,
-                        (long long)ctx->union_valid, (long long)ctx->coop_valid, (long long)ctx->sparse, (long long)ctx->use_q4,
-                        (long long)fused, (long long)ctx->parity_host, (long long)ctx->force_grid[0], (long long)ctx->force_grid[1],
-                        (long long)ctx->force_grid[2], (long long)ctx->coop_grid, (long long)ctx->sparse_grid,
-                        (long long)ctx->step_grid[0], (long long)ctx->step_grid[1], (long long)pdl_level()})
+                        (long long)ctx->cfg.force_mode, (long long)ctx->dense, (long long)ctx->use_q4,
+                        (long long)ctx->force_grid[0], (long long)ctx->force_grid[1], (long long)ctx->force_grid[2]})
         put_i(v);
     return k;
 }
 
-int build_chunk_graph(md_ctx *ctx, bool fused, md_ctx::ChunkGraph *slot)
+int build_chunk_graph(md_ctx *ctx, md_ctx::ChunkGraph *slot)
 {
     if (slot->exec) cudaGraphExecDestroy(slot->exec);
     if (slot->graph) cudaGraphDestroy(slot->graph);
@@ -931,38 +678,30 @@ int build_chunk_graph(md_ctx *ctx, bool fused, md_ctx::ChunkGraph *slot)
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int rc = MD_OK;
     for (int k = 0; k < STEP_CHUNK && rc == MD_OK; ++k) {
-        if (fused) {
-            launch_fused_step(ctx, 0ull, 1);
-        } else {
-            // programmatic edges inside the chunk; its first kernel depends on the previous graph launch as a whole
-            const int level = pdl_level();
-            const bool pdl = level >= 1;
-            const bool early = level >= 2 && !ctx->sparse && !(ctx->dense && ctx->union_valid);  // (those keep plain force launches)
-            rc = launch_kick_drift(ctx, 1, nullptr, pdl && k > 0, early ? k : -1);
-            if (rc == MD_OK) rc = launch_force(ctx, true, 0ull, 1, pdl);
-        }
+        rc = launch_kick_drift(ctx, 1);
+        if (rc == MD_OK) rc = launch_force(ctx, true, 1);
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &slot->graph);  // always leave capture mode
     ctx->stats.kernel_launches = launches;
     if (rc != MD_OK) return rc;
     if (e != cudaSuccess) return ctx->fail(MD_ERR_CUDA, "graph capture of the step chunk failed: %s", cudaGetErrorString(e));
     CK(cudaGraphInstantiate(&slot->exec, slot->graph, 0));
-    slot->key = chunk_key(ctx, fused);
+    slot->key = chunk_key(ctx);
     ctx->chunk_builds += 1;
     return MD_OK;
 }
 
 // the cached chunk graph for the current state of the context, built on a miss (evicting the older entry)
-int get_chunk_graph(md_ctx *ctx, bool fused, cudaGraphExec_t *exec)
+int get_chunk_graph(md_ctx *ctx, cudaGraphExec_t *exec)
 {
-    const std::vector<unsigned char> key = chunk_key(ctx, fused);
+    const std::vector<unsigned char> key = chunk_key(ctx);
     md_ctx::ChunkGraph *hit = nullptr, *victim = &ctx->chunk_cache[0];
     for (auto &c : ctx->chunk_cache) {
         if (c.exec && c.key == key) hit = &c;
         if (c.stamp < victim->stamp) victim = &c;
     }
     if (!hit) {
-        TRY(build_chunk_graph(ctx, fused, victim));
+        TRY(build_chunk_graph(ctx, victim));
         hit = victim;
     } else {
         ctx->chunk_hits += 1;
@@ -1041,7 +780,6 @@ int md_create(const md_config *cfg, md_ctx **out)
     {
         if (!strcmp(e, "host")) ctx->cfg.loop_mode = MD_LOOP_HOST;
         if (!strcmp(e, "chunk")) ctx->cfg.loop_mode = MD_LOOP_CHUNK;
-        if (!strcmp(e, "while")) ctx->cfg.loop_mode = MD_LOOP_WHILE;
     }
     ctx->device = ctx->cfg.device;
     auto bail = [&](cudaError_t e, const char *what) {
@@ -1124,10 +862,6 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         dev_free(ctx, ctx->cell_of); dev_free(ctx, ctx->cell_sorted); dev_free(ctx, ctx->order);
         dev_free(ctx, ctx->nbr_cnt); dev_free(ctx, ctx->nbr);
         ctx->nbr = nullptr; ctx->nbr_alloc = 0;
-        dev_free(ctx, ctx->nbr_u); dev_free(ctx, ctx->cnt_u);
-        ctx->nbr_u = nullptr; ctx->cnt_u = nullptr; ctx->nbr_u_alloc = 0; ctx->cap_u = 0; ctx->union_valid = false;
-        dev_free(ctx, ctx->nbr_t);
-        ctx->nbr_t = nullptr; ctx->nbr_t_alloc = 0; ctx->cap_t = 0; ctx->coop_valid = false;
         ctx->owned.erase(std::remove_if(ctx->owned.begin(), ctx->owned.end(), [](const DevBuf &b) { return !b.p; }),
                          ctx->owned.end());
         ctx->n = n;
@@ -1136,27 +870,12 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         ctx->npad = (int)((n + 63) / 64 * 64);
         TRY(alloc_arrays(ctx, &ctx->cur, ctx->npad));
         TRY(alloc_arrays(ctx, &ctx->alt, ctx->npad));
-        {   // the six planes every step streams, contiguous per plane set
-            dev_free(ctx, ctx->hot_slab);
-            ctx->hot_slab = nullptr;
-            TRY(dev_alloc(ctx, &ctx->hot_slab, 12 * (size_t)ctx->npad));
-            Arrays *set[2] = {&ctx->cur, &ctx->alt};
-            for (int h = 0; h < 2; ++h) {
-                Arrays &a = *set[h];
-                dev_free(ctx, a.x); dev_free(ctx, a.y); dev_free(ctx, a.z);
-                dev_free(ctx, a.vx); dev_free(ctx, a.vy); dev_free(ctx, a.vz);
-                double *base = ctx->hot_slab + (size_t)(6 * h) * ctx->npad;
-                a.x = base; a.y = base + (size_t)ctx->npad; a.z = base + 2 * (size_t)ctx->npad;
-                a.vx = base + 3 * (size_t)ctx->npad; a.vy = base + 4 * (size_t)ctx->npad; a.vz = base + 5 * (size_t)ctx->npad;
-            }
-        }
         TRY(dev_alloc(ctx, &ctx->stage, 3 * (size_t)ctx->npad));
         TRY(dev_alloc(ctx, &ctx->stage_i, ctx->npad));
         TRY(choose_grids(ctx));
         ctx->partial_blocks = std::max(std::max(ctx->force_grid[0], ctx->force_grid[1]),
                                        std::max(ctx->force_grid[2], ctx->reduce_grid));
-        ctx->partial_blocks = std::max(ctx->partial_blocks, std::max(ctx->step_grid[0], ctx->step_grid[1]));
-        ctx->partial_blocks = std::max(ctx->partial_blocks, std::max(ctx->sparse_grid, ctx->coop_grid));
+        ctx->partial_blocks = std::max(ctx->partial_blocks, ctx->loop_blocks_max);
         TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
         TRY(dev_alloc(ctx, &ctx->cell_of, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->cell_sorted, ctx->npad));
@@ -1177,7 +896,6 @@ static int finish_new_state(md_ctx *ctx, int64_t n, const double box[3])
     h.mu_pending = 1.0; h.lambda = 1.0; h.mu = 1.0; h.inv_scale = 1.0;
     h.lambda_last = 1.0; h.mu_last = 1.0;
     CK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, st));
-    ctx->parity_host = 0;
     drop_graph(ctx);
     ctx->skin = choose_skin(ctx, box);
     fill_potential_params(ctx);
@@ -1396,31 +1114,39 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     CK(cudaGetLastError());
 
     int64_t remaining = n_steps;
+    int rc = MD_OK;
     if (ctx->dist.on) {
-        TRY(dist_run_steps(ctx));
+        rc = dist_run_steps(ctx);
         remaining = 0;
     }
-    while (remaining > 0) {
-        TRY(pull_scalars(ctx));
-        TRY(device_error(ctx));
+    // phase clocks of the persistent loop before this batch (md_time_kernels reports the difference)
+    unsigned long long loop_ns0[4] = {0, 0, 0, 0}, loop_steps0 = 0;
+    bool have_loop0 = false;
+    while (rc == MD_OK && remaining > 0) {
+        if ((rc = pull_scalars(ctx)) != MD_OK) break;
+        if ((rc = device_error(ctx)) != MD_OK) break;
+        if (!have_loop0) {
+            for (int k = 0; k < 4; ++k) loop_ns0[k] = ctx->h_sc->loop_ns[k];
+            loop_steps0 = ctx->h_sc->loop_steps;
+            have_loop0 = true;
+        }
         remaining = ctx->h_sc->steps_left;
         if (remaining <= 0) break;
         const bool rebuild = !ctx->list_valid || ctx->h_sc->need_rebuild;
-        const bool fused = !rebuild && use_fused(ctx);
-        if (fused) TRY(ensure_half_kick(ctx));
-        if (rebuild || ctx->timing || ctx->cfg.loop_mode == MD_LOOP_HOST) {
-            // one step by hand: drift, (rebuild at the drifted positions,) forces — or the fused one-kernel step
+        const bool use_loop = loop_wanted(ctx) && ctx->loop_blocks_max > 0;
+        // (the persistent loop times its phases itself; the two-kernel step is timed with events around host-stepped launches)
+        const bool host_stepped = ctx->cfg.loop_mode == MD_LOOP_HOST || (ctx->timing && !use_loop);
+        if (rebuild || (host_stepped && !use_loop)) {
+            // one step by hand: drift, (rebuild at the drifted positions,) forces
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], st));
-            if (!fused) launch_kick_drift(ctx);
+            launch_kick_drift(ctx);
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], st));
-            if (rebuild) TRY(rebuild_lists(ctx));
+            if (rebuild && (rc = rebuild_lists(ctx)) != MD_OK) break;
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st));
-            if (fused) launch_fused_step(ctx, 0ull);
-            else launch_force(ctx, true, 0ull);
+            launch_force(ctx, true);
             if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], st));
-            ctx->stats.kernel_launches += fused ? 1 : 2;
+            ctx->stats.kernel_launches += 2;
             ctx->stats.steps += 1;
-            ctx->stats.fused_steps += fused ? 1 : 0;
             CK(cudaGetLastError());
             if (ctx->timing) {
                 CK(cudaEventSynchronize(ctx->ev[3]));
@@ -1428,18 +1154,22 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
                 CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
                 CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
                 CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
-                if (fused) { ctx->t_ms[3] += c; ctx->t_cnt[3] += 1; }
+                if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
                 else {
                     ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
                     ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
                 }
-                if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
             }
         } else {
-            long long before = ctx->h_sc->steps_done;
-            if (ctx->cfg.loop_mode != MD_LOOP_WHILE) {
+            const long long before = ctx->h_sc->steps_done;
+            if (use_loop) {
+                // dilute systems: the persistent step loop runs until the device asks for a rebuild or the batch is done
+                if ((rc = launch_loop(ctx, host_stepped ? 1 : remaining)) != MD_OK) break;
+                if ((rc = pull_scalars(ctx)) != MD_OK) break;
+                ctx->stats.kernel_launches += 1;
+            } else {
                 cudaGraphExec_t chunk_exec = nullptr;
-                TRY(get_chunk_graph(ctx, fused, &chunk_exec));
+                if ((rc = get_chunk_graph(ctx, &chunk_exec)) != MD_OK) break;
                 // look ahead as far as the list is expected to last (the previous epoch's length), at most 8 chunks: steps
                 // enqueued past a rebuild request are no-ops, but each still costs a launch
                 const long long since = ctx->stats.steps - ctx->epoch_start_step;
@@ -1447,24 +1177,35 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
                 const int chunks = (int)std::min<long long>(8, (std::min<long long>(remaining, expect) + STEP_CHUNK - 1) / STEP_CHUNK);
                 for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(chunk_exec, st));
                 ctx->stats.graph_launches += chunks;
-            } else {
-                if (ctx->graph_ok && ctx->graph_fused != fused) drop_graph(ctx);
-                if (!ctx->graph_ok) TRY(build_graph(ctx));
-                CK(cudaGraphLaunch(ctx->graph_exec, st));
-                ctx->stats.graph_launches += 1;
+                if ((rc = pull_scalars(ctx)) != MD_OK) break;
+                ctx->stats.kernel_launches += 2 * (ctx->h_sc->steps_done - before);
             }
-            TRY(pull_scalars(ctx));
-            long long ran = ctx->h_sc->steps_done - before;
-            ctx->stats.kernel_launches += (fused ? 1 : 2) * ran;
-            ctx->stats.steps += ran;
-            ctx->stats.fused_steps += fused ? ran : 0;
-            TRY(device_error(ctx));
+            ctx->stats.steps += ctx->h_sc->steps_done - before;
+            if ((rc = device_error(ctx)) != MD_OK) break;
             remaining = ctx->h_sc->steps_left;
         }
     }
-    if (p.ba_kind == MD_BAROSTAT_BERENDSEN) TRY(flush_pending_scale(ctx));
-    TRY(pull_scalars(ctx));
-    TRY(device_error(ctx));
+    if (rc == MD_OK && p.ba_kind == MD_BAROSTAT_BERENDSEN) rc = flush_pending_scale(ctx);
+    if (rc == MD_OK) rc = pull_scalars(ctx);
+    if (rc == MD_OK) rc = device_error(ctx);
+    if (rc != MD_OK) {
+        // The device may be mid-batch: velocity planes holding u = v + F c, a pending coordinate scale, stale F/U/W.  Nothing
+        // the host could download would be a State of the reference's step sequence: the caller has to upload again.
+        ctx->has_state = false;
+        ctx->list_valid = false;
+        ctx->force_valid = false;
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    if (ctx->timing && have_loop0) {
+        const long long ls = (long long)(ctx->h_sc->loop_steps - loop_steps0);
+        if (ls > 0) {
+            ctx->t_ms[0] += (double)(ctx->h_sc->loop_ns[0] - loop_ns0[0]) * 1e-6; ctx->t_cnt[0] += ls;
+            ctx->t_ms[1] += (double)((ctx->h_sc->loop_ns[2] - loop_ns0[2]) + (ctx->h_sc->loop_ns[3] - loop_ns0[3])) * 1e-6;
+            ctx->t_cnt[1] += ls;
+            ctx->t_ms[3] += (double)(ctx->h_sc->loop_ns[1] - loop_ns0[1]) * 1e-6; ctx->t_cnt[3] += ls;
+        }
+    }
     if (th) {
         th->lambda = ctx->h_sc->lambda_last;
         if (th->kind == MD_THERMOSTAT_NOSE_HOOVER) th->psi = ctx->h_sc->psi;
@@ -1663,27 +1404,6 @@ static int fetch_lists(md_ctx *ctx, std::vector<int> &cnt, std::vector<int> &id,
     id.resize(n);
     CK(cudaMemcpyAsync(cnt.data(), ctx->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(id.data(), ctx->cur.id, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nbr && ctx->union_valid) {
-        // union lists (k_build_union): the two membership bits of an entry give back the per-atom lists, in the layout
-        // nbr[k * npad + p] the callers expect
-        const size_t pstride = (size_t)ctx->npad / 2, npairs = (n + 1) / 2;
-        std::vector<int> u((size_t)ctx->cap_u * pstride), cu(npairs);
-        CK(cudaMemcpyAsync(u.data(), ctx->nbr_u, sizeof(int) * u.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(cu.data(), ctx->cnt_u, sizeof(int) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        int cmax = 1;
-        for (size_t p = 0; p < n; ++p) cmax = std::max(cmax, cnt[p]);
-        nbr->assign((size_t)cmax * ctx->npad, 0);
-        std::vector<int> fill(n, 0);
-        for (size_t t = 0; t < npairs; ++t)
-            for (int k = 0; k < cu[t]; ++k) {
-                const unsigned int e = (unsigned int)u[(size_t)k * pstride + t];
-                const int q = (int)(e & 0x3fffffffu);
-                if (e & (1u << 30)) (*nbr)[(size_t)fill[2 * t]++ * ctx->npad + 2 * t] = q;
-                if ((e & (1u << 31)) && 2 * t + 1 < n) (*nbr)[(size_t)fill[2 * t + 1]++ * ctx->npad + 2 * t + 1] = q;
-            }
-        return MD_OK;
-    }
     if (nbr) {
         nbr->resize((size_t)ctx->grid.cap * ctx->npad);
         CK(cudaMemcpyAsync(nbr->data(), ctx->nbr, sizeof(int) * nbr->size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1729,34 +1449,44 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->wait_halo_ms = (double)ctx->h_sc->wait_halo_ns * 1e-6;  // as of the last time the host looked at the device
     out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
     out->peer_memory = ctx->dist.p2p ? 1 : 0;
-    out->union_lists = ctx->union_valid ? 1 : 0;
-    out->coop_lists = ctx->coop_valid ? 1 : 0;
+    out->persistent_loop = (ctx->has_state && loop_wanted(ctx) && ctx->loop_blocks_max > 0) ? 1 : 0;
     out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
     out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;
-    out->drift_push_ms = ctx->rebuild_host_ms;  // (field reused: the drift kernel no longer has a push phase to time)
+    out->rebuild_ms = ctx->rebuild_host_ms;
+    out->loop_steps = (int64_t)ctx->h_sc->loop_steps;
+    for (int k = 0; k < 4; ++k) out->loop_phase_ms[k] = (double)ctx->h_sc->loop_ns[k] * 1e-6;
     return MD_OK;
 }
 
 void *md_stream(md_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
-// MD_TIMING_PROBES builds only: %globaltimer stamps (ns) of the last k_force launch:
-// [0] first block start, [1] last block leaves the atom loop, [2] last-block reduction starts, [3] reduction done,
-// [4] finalize done.  probe[0]/[1] must be reset by the caller (md_probe_reset) before the launch.
-__attribute__((visibility("default"))) int md_probe_read(md_ctx *ctx, unsigned long long out[8])
+int md_measure_fp64_peak(md_ctx *ctx, double *tflops)
 {
     TRY(check_ctx(ctx, false));
-    TRY(pull_scalars(ctx));
-    for (int k = 0; k < 8; ++k) out[k] = ctx->h_sc->probe[k];
-    return MD_OK;
-}
-
-__attribute__((visibility("default"))) int md_probe_reset(md_ctx *ctx)
-{
-    TRY(check_ctx(ctx, false));
-    unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(reinterpret_cast<char *>(ctx->d_sc) + offsetof(Scalars, probe), init, sizeof init,
-                       cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!tflops) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_measure_fp64_peak: NULL output");
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    double *sink = nullptr;
+    TRY(dev_alloc(ctx, &sink, 1));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(iters, 1.0 + rep, sink);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    dev_free(ctx, sink);
+    *tflops = best;
     return MD_OK;
 }
 

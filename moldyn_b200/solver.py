@@ -153,15 +153,14 @@ class State:
 class Solver:
     """Device-resident session: owns an md_ctx. `exact=True` selects MD_FORCE_EXACT (bit-identical forces)."""
 
-    def __init__(self, device=0, exact=False, host_loop=False, while_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
-                 cell_atoms=0.0, step_mode="auto", union_lists=False, coop=False):
+    def __init__(self, device=0, exact=False, host_loop=False, chunk_loop=False, skin=0.0, max_neighbours=0, cell_subdiv=0,
+                 cell_atoms=0.0):
+        """host_loop: one host round trip per step (MD_LOOP_HOST); chunk_loop: the graph-chunk loop of the two-kernel step
+        for every system (MD_LOOP_CHUNK) instead of the persistent step loop for dilute ones."""
         self._ctx = C.c_void_p()
-        fast = _ffi.FORCE_FAST_UNION if union_lists else (_ffi.FORCE_FAST_COOP if coop else _ffi.FORCE_FAST)
-        cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else fast,
-                          _ffi.LOOP_HOST if host_loop else (_ffi.LOOP_WHILE if while_loop else _ffi.LOOP_GRAPH),
-                          max_neighbours, cell_subdiv,
-                          {"auto": _ffi.STEP_AUTO, "split": _ffi.STEP_SPLIT, "fused": _ffi.STEP_FUSED}[step_mode], skin,
-                          cell_atoms)
+        cfg = _ffi.Config(device, _ffi.FORCE_EXACT if exact else _ffi.FORCE_FAST,
+                          _ffi.LOOP_HOST if host_loop else (_ffi.LOOP_CHUNK if chunk_loop else _ffi.LOOP_AUTO),
+                          max_neighbours, cell_subdiv, 0, skin, cell_atoms)
         L = _ffi.lib()
         rc = L.md_create(C.byref(cfg), C.byref(self._ctx))
         if rc != _ffi.MD_OK:
@@ -254,7 +253,7 @@ class Solver:
         cnt = np.zeros(4, dtype=np.int64)
         self._ck(_ffi.lib().md_time_kernels(self._ctx, int(n_steps), float(dt), C.byref(th) if th else None,
                                             C.byref(ba) if ba else None, _ptr(ms), _ptr(cnt)))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("kick_drift", "force", "rebuild", "fused_step"))}
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("kick_drift", "force", "rebuild", "loop_barrier"))}
 
     def macro(self):
         m = _ffi.MacroOut()
@@ -284,11 +283,18 @@ class Solver:
         s = _ffi.Stats()
         self._ck(_ffi.lib().md_get_stats(self._ctx, C.byref(s)))
         return {"steps": s.steps, "rebuilds": s.rebuilds, "kernel_launches": s.kernel_launches,
-                "graph_launches": s.graph_launches, "cells": list(s.cells), "nbr_capacity": s.nbr_capacity,
-                "nbr_max": s.nbr_max, "skin": s.skin, "nbr_mean": s.nbr_mean, "n_owned": s.n_owned,
-                "n_ghost": s.n_ghost, "migrated": s.migrated, "fused_steps": s.fused_steps, "wait_halo_ms": s.wait_halo_ms,
-                "wait_sums_ms": s.wait_sums_ms, "peer_memory": s.peer_memory, "union_lists": s.union_lists, "coop_lists": s.coop_lists, "force_atoms_ms": s.force_atoms_ms,
-                "force_tail_ms": s.force_tail_ms, "drift_push_ms": s.drift_push_ms}
+                "graph_launches": s.graph_launches, "loop_launches": s.loop_launches, "loop_steps": s.loop_steps,
+                "cells": list(s.cells), "nbr_capacity": s.nbr_capacity, "nbr_max": s.nbr_max, "skin": s.skin,
+                "nbr_mean": s.nbr_mean, "n_owned": s.n_owned, "n_ghost": s.n_ghost, "migrated": s.migrated,
+                "wait_halo_ms": s.wait_halo_ms, "wait_sums_ms": s.wait_sums_ms, "peer_memory": s.peer_memory,
+                "persistent_loop": s.persistent_loop, "tile_lists": s.tile_lists, "force_atoms_ms": s.force_atoms_ms,
+                "force_tail_ms": s.force_tail_ms, "rebuild_ms": s.rebuild_ms, "loop_phase_ms": list(s.loop_phase_ms)}
+
+    def measure_fp64_peak(self):
+        """TFLOP/s of a register-only DFMA loop on this device (roofline denominator of the dense force kernel)."""
+        t = C.c_double()
+        self._ck(_ffi.lib().md_measure_fp64_peak(self._ctx, C.byref(t)))
+        return t.value
 
     def stream(self):
         return _ffi.lib().md_stream(self._ctx)

@@ -26,7 +26,7 @@ def mode(request):
 
 
 def make_solver(mode, **kw):
-    return md.Solver(exact=(mode == "exact"), union_lists=(mode == "fast_union"), **kw)
+    return md.Solver(exact=(mode == "exact"), **kw)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -208,80 +208,6 @@ def test_cells_and_neighbour_sets_bit_exact(name, mode):
     assert np.array_equal(partners, wpartners)
 
 
-def test_union_lists_opt_in():
-    """MD_FORCE_FAST_UNION (k_build_union + the union force loop): pair sets — reconstructed from the membership bits —
-    bit-exact, forces within the FAST bar, 100-step NVT trajectory within 1e-8 of the oracle."""
-    o, _ = SYSTEMS["liquid5832"]()
-    olj, plj = lj_pair(md)
-    ref = o.copy()
-    orc.update_force(olj, ref, mode="cells")
-    st = to_gpu_state(md, o)
-    gth, oth = (md.Thermostat.Berendsen(10.0), 120.0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, 120.0)
-    with make_solver("fast_union") as s:
-        s.upload(st, with_forces=False)
-        s.update_force()
-        assert s.stats()["union_lists"] == 1
-        off, partners = s.neighbour_lists()
-        skin = s.stats()["skin"]
-        s.download(st)
-        f0 = st.force.copy()
-        s.step(100, DT, thermostat=gth)
-        s.download(st)
-    woff, wpartners = orc.neighbour_sets(o.pos, o.box, olj.r_cut + skin)
-    assert np.array_equal(off, woff) and np.array_equal(partners, wpartners)
-    scale = force_scale(olj, ref)
-    rms = np.sqrt((ref.force ** 2).sum(axis=1).mean())
-    assert np.all(np.abs(f0 - ref.force) <= 1e-10 * np.maximum(scale, rms)[:, None])
-    run_oracle(olj, o, 100, oth)
-    dx = np.abs(st.position - o.pos)
-    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
-    assert np.abs(st.velocity - o.vel).max() <= 1e-8
-
-
-@pytest.mark.parametrize("name", ["liquid4096_3.5sigma", "liquid5832", "dense_gas3000", "liquid1000", "liquid729"])
-def test_warp_cooperative_dense_kernel(name):
-    """MD_FORCE_FAST_COOP (k_transpose_list + k_force_coop: one warp per atom over an atom-major list): per-atom force,
-    potential and virial within the FAST bar, 100-step NVT and NPT trajectories within 1e-8 of the oracle (forces-only,
-    + virial and + potential instances of the loop all run), run-to-run bit-reproducible."""
-    o, cut = SYSTEMS[name]()
-    olj, plj = lj_pair(md, *(cut or (None, None)))
-    ref = o.copy()
-    orc.update_force(olj, ref, mode="cells")
-    scale = force_scale(olj, ref)
-    rms = np.sqrt((ref.force ** 2).sum(axis=1).mean())
-    T0 = 120.0 if name.startswith("liquid") else 273.15
-    runs = []
-    for ensemble in ("nvt", "npt", "npt"):
-        st = to_gpu_state(md, o)
-        gth, oth = (md.Thermostat.Berendsen(10.0), T0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, T0)
-        gba = oba = None
-        if ensemble == "npt":
-            gba, oba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325), orc.Barostat(1.0, 5.0, 1.01325)
-        with md.Solver(coop=True) as s:
-            s.set_potential(plj)
-            s.upload(st, with_forces=False)
-            s.update_force()
-            assert s.stats()["coop_lists"] == 1 and s.stats()["nbr_mean"] >= 8.0
-            s.download(st)
-            assert np.all(np.abs(st.force - ref.force) <= 1e-10 * np.maximum(scale, rms)[:, None])
-            assert np.all(np.abs(st.potential - ref.pot) <= 1e-10 * (np.abs(ref.pot) + 4 * olj.eps))
-            assert np.all(np.abs(st.temp - ref.vir) <= 1e-10 * (scale * olj.r_cut + 1e-300) + 1e-300)
-            for k in (1, 36, 63):
-                s.step(k, DT, thermostat=gth, barostat=gba)
-            s.download(st)
-            m = s.macro()
-        r = o.copy()
-        run_oracle(olj, r, 100, oth, oba)
-        dx = np.abs(st.position - r.pos)
-        assert np.minimum(dx, np.abs(dx - r.box)).max() <= 1e-8
-        assert np.abs(st.velocity - r.vel).max() <= 1e-8
-        assert np.abs(st.boundary_box - r.box).max() <= 1e-9
-        runs.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.temp.copy(), m["pressure"]))
-    for a, b in zip(runs[1][:4], runs[2][:4]):
-        assert np.array_equal(a, b)
-    assert runs[1][4] == runs[2][4]
-
-
 def run_oracle(olj, o, n_steps, th=None, ba=None):
     orc.update_force(olj, o, mode="cells")
     orc.step(olj, o, DT, thermostat=th, barostat=ba, mode="cells", n_steps=n_steps)
@@ -371,9 +297,9 @@ def test_nose_hoover_trajectory(name, mode):  # thermostat.rs:35-39, 59-65 (SURV
 
 @pytest.mark.parametrize("ensemble", ["nvt", "npt"])
 def test_long_run_statistics_match_oracle(ensemble):
-    """over long thermostat/barostat runs trajectories diverge chaotically, so the gate is statistical —
-    <T>, <P> and their spreads over the second half of a 3000-step run must agree with the oracle's run from the same
-    frame 0 within the sampling error; total momentum must not drift.  (512 atoms keep the CPU oracle's share short.)"""
+    """over long thermostat/barostat runs (>= 10^4 steps) trajectories diverge chaotically, so the gate is
+    statistical — <T>, <P> and their spreads over the second half of a 10 000-step run must agree with the oracle's run from
+    the same frame 0 within the sampling error; total momentum must not drift.  (512 atoms keep the CPU oracle's share short.)"""
     o = liquid(8)
     olj = orc.LennardJones()
     st = to_gpu_state(md, o)
@@ -381,7 +307,7 @@ def test_long_run_statistics_match_oracle(ensemble):
     oba = gba = None
     if ensemble == "npt":
         oba, gba = orc.Barostat(1.0, 5.0, 1.01325), (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
-    n_steps, every = 3000, 20
+    n_steps, every = 10000, 20
     gt, gp, ot, op_ = [], [], [], []
     with md.Solver() as s:
         s.upload(st, with_forces=False)
@@ -399,12 +325,12 @@ def test_long_run_statistics_match_oracle(ensemble):
             m = orc.macro(o)
             ot.append(m["temperature"]); op_.append(m["pressure"])
     gt, gp, ot, op_ = map(np.array, (gt, gp, ot, op_))
-    # 75 samples 20 steps apart: allow the mean to differ by half a standard deviation of the samples (several standard
-    # errors of the mean even for strongly correlated samples), the spreads by a factor 2
-    assert abs(gt.mean() - ot.mean()) <= 0.5 * ot.std() + 1e-9, (gt.mean(), ot.mean(), ot.std())
-    assert abs(gp.mean() - op_.mean()) <= 0.5 * op_.std() + 1e-9, (gp.mean(), op_.mean(), op_.std())
-    assert 0.5 <= gt.std() / ot.std() <= 2.0 and 0.5 <= gp.std() / op_.std() <= 2.0
-    assert abs(gt.mean() - 120.0) < 15.0  # the melting lattice is still being cooled towards the target
+    # 250 samples 20 steps apart: allow the mean to differ by 0.3 standard deviations of the samples (several standard
+    # errors of the mean even for strongly correlated samples), the spreads by a factor 1.5
+    assert abs(gt.mean() - ot.mean()) <= 0.3 * ot.std() + 1e-9, (gt.mean(), ot.mean(), ot.std())
+    assert abs(gp.mean() - op_.mean()) <= 0.3 * op_.std() + 1e-9, (gp.mean(), op_.mean(), op_.std())
+    assert 1 / 1.5 <= gt.std() / ot.std() <= 1.5 and 1 / 1.5 <= gp.std() / op_.std() <= 1.5
+    assert abs(gt.mean() - 120.0) < 5.0  # Berendsen tau = 1 ps: the thermostat has long since reached the target
     assert mom < 1e-9
 
 
@@ -438,52 +364,46 @@ def test_device_side_initializer(cell):
     assert not st.force.any() and not st.potential.any()
 
 
-def test_graph_loop_equals_host_loop(mode):
-    """The three loop drivers — chunked graphs of guarded steps (default), the conditional WHILE graph, and one host round
-    trip per step — run the same kernels on the same data: identical bits."""
-    o = liquid(10)
-    out = []
-    for kw in ({}, {"while_loop": True}, {"host_loop": True}):
-        st = to_gpu_state(md, o)
-        with make_solver(mode, **kw) as s:
-            s.upload(st, with_forces=False)
-            s.update_force()
-            s.step(150, DT, thermostat=(md.Thermostat.Berendsen(10.0), 120.0),
-                   barostat=(md.Barostat.Berendsen(1.0, 5.0), 1.01325))
-            s.download(st)
-            out.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.boundary_box.copy(), s.stats()))
-    for other in out[1:]:
-        for a, b in zip(out[0][:4], other[:4]):
-            assert np.array_equal(a, b)
-        assert out[0][4]["rebuilds"] == other[4]["rebuilds"]
-    assert out[0][4]["graph_launches"] > 0 and out[1][4]["graph_launches"] > 0 and out[2][4]["graph_launches"] == 0
+def _npt_run(o, mode, t0, **kw):
+    st = to_gpu_state(md, o)
+    th, ba = (md.Thermostat.Berendsen(10.0), t0), (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
+    with make_solver(mode, **kw) as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        for k in (7, 1, 30, 63, 200):
+            s.step(k, DT, thermostat=th, barostat=ba)
+        s.download(st)
+        m = s.macro()
+        return (st.position.copy(), st.velocity.copy(), st.force.copy(), st.potential.copy(), st.temp.copy(),
+                st.boundary_box.copy(), np.array([m["temperature"], m["pressure"], th[0].lambda_, ba[0].myu]), s.stats())
 
 
-@pytest.mark.parametrize("host_loop", [False, True])
-def test_fused_step_equals_split_step(mode, host_loop):
-    """Dilute systems step with ONE fused kernel (k_step_dilute: partners are drifted on the fly, x/v ping-pong between
-    two plane sets); it must reproduce the k_kick_drift + k_force path bit for bit, for any batch length/parity."""
-    o = orc.argon_lattice(12, 1.0, 900.0, 7)   # 1728 atoms, ~6 listed partners each, hot: collisions and list rebuilds
-    out = []
-    for step_mode in ("split", "fused"):
-        st = to_gpu_state(md, o)
-        th = (md.Thermostat.Berendsen(10.0), 300.0)
-        ba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325)
-        with make_solver(mode, host_loop=host_loop, step_mode=step_mode, skin=0.3) as s:
-            s.upload(st, with_forces=False)
-            s.update_force()
-            for k in (7, 1, 30, 63, 200):
-                s.step(k, DT, thermostat=th, barostat=ba)
-            s.download(st)
-            m = s.macro()
-            out.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.potential.copy(), st.temp.copy(),
-                        st.boundary_box.copy(), np.array([m["temperature"], m["pressure"], th[0].lambda_, ba[0].myu]),
-                        s.stats()))
-    for a, b in zip(out[0][:7], out[1][:7]):
+def test_loop_drivers_agree(mode):
+    """Dense systems: pre-enqueued graph chunks of the two-kernel step (default) and one host round trip per step run the
+    same kernels on the same data — identical bits.  Dilute systems: the persistent step loop (default) and the same
+    kernel launched once per step (host loop) — identical bits; the two-kernel chunk loop (chunk_loop=True) sums the K5
+    terms in another order, so lambda/myu differ in the last bits and the trajectories agree to 1e-9 only."""
+    dense = [_npt_run(liquid(10), mode, 120.0, **kw) for kw in ({}, {"host_loop": True})]
+    for a, b in zip(dense[0][:7], dense[1][:7]):
         assert np.array_equal(a, b)
-    assert out[0][7]["fused_steps"] == 0 and out[1][7]["fused_steps"] > 250
-    assert out[0][7]["rebuilds"] == out[1][7]["rebuilds"] > 1
-    assert np.abs(out[1][2]).max() > 0.0   # pair terms were exercised
+    assert dense[0][7]["rebuilds"] == dense[1][7]["rebuilds"]
+    assert dense[0][7]["graph_launches"] > 0 and dense[1][7]["graph_launches"] == 0
+    assert dense[0][7]["persistent_loop"] == 0
+
+    # 1728 atoms, ~6 listed partners each, hot: collisions and list rebuilds
+    hot = orc.argon_lattice(12, 1.0, 900.0, 7)
+    dil = [_npt_run(hot, mode, 300.0, skin=0.3, **kw) for kw in ({}, {"host_loop": True}, {"chunk_loop": True})]
+    for a, b in zip(dil[0][:7], dil[1][:7]):
+        assert np.array_equal(a, b)
+    assert dil[0][7]["persistent_loop"] == 1 and dil[0][7]["loop_steps"] > 250 and dil[0][7]["loop_launches"] < 60
+    assert dil[1][7]["loop_launches"] == dil[1][7]["loop_steps"] > 250          # host loop: one launch per step
+    assert dil[2][7]["loop_launches"] == 0 and dil[2][7]["graph_launches"] > 0  # two-kernel chunk loop
+    assert dil[0][7]["rebuilds"] == dil[1][7]["rebuilds"] == dil[2][7]["rebuilds"] > 1
+    assert np.abs(dil[0][2]).max() > 0.0   # pair terms were exercised
+    dx = np.abs(dil[0][0] - dil[2][0])
+    assert np.minimum(dx, np.abs(dx - dil[0][5])).max() <= 1e-9   # (an atom may sit on either side of the wrap)
+    for a, b in zip(dil[0][1:6], dil[2][1:6]):
+        assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(a).max())
 
 
 def test_run_to_run_determinism():
@@ -602,80 +522,201 @@ def test_errors():
 
 
 # ---------------------------------------------------------------------------------------------------
-# full-size properties (BASELINE configs): size-independent checks + sampled rows against the oracle
+# full-size properties (BASELINE configs): size-independent checks + sampled rows against the oracle, in BOTH force
+# modes — MD_FORCE_FAST is the configuration bench.py times
+def _perturbed_gas(n_side, seed=1):
+    """The gas lattice moved off its zero-force symmetry point (uniform displacements of up to 1.45 nm)."""
+    o = gas(n_side)
+    o.pos += np.random.default_rng(seed).uniform(-1.45, 1.45, o.pos.shape)
+    orc.apply_boundary_conditions(o)
+    return o
+
+
+def _row_scale(olj, o, rows):
+    """Σ_j |f_ij| of the given atoms (periodic KD-tree): the scale the 1e-10 force bar is relative to."""
+    from scipy.spatial import cKDTree
+    pos = np.mod(o.pos, o.box)
+    tree = cKDTree(pos, boxsize=o.box)
+    out = np.zeros(len(rows))
+    for k, i in enumerate(rows):
+        js = np.array([j for j in tree.query_ball_point(pos[i], olj.r_cut * (1 + 1e-12)) if j != i], dtype=np.int64)
+        if len(js) == 0:
+            continue
+        d = pos[js] - pos[i]
+        d -= o.box * np.round(d / o.box)
+        r = np.sqrt((d * d).sum(axis=1))
+        r = r[r <= olj.r_cut]
+        s6 = (olj.sigma / r) ** 6
+        out[k] = np.abs(24.0 * olj.eps / r * (s6 - 2.0 * s6 * s6)).sum()
+    return out
+
+
 @pytest.mark.parametrize("n_side,cut", [(100, None), (64, LONG_CUT)])
 def test_full_size_sampled_rows_and_invariants(n_side, cut):
-    if cut is None:
-        o = gas(n_side)
-        # move the lattice off its zero-force symmetry point
-        rng = np.random.default_rng(1)
-        o.pos += rng.uniform(-1.45, 1.45, o.pos.shape)
-        orc.apply_boundary_conditions(o)
+    o = _perturbed_gas(n_side) if cut is None else liquid(n_side, jitter=0.03)
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    starts = (0, o.n // 2 - 128, o.n - 256)
+    rows = np.concatenate([np.arange(i0, i0 + 256) for i0 in starts])
+    for i0 in starts:  # the reference's Θ(N) row scan for the sampled atoms
+        orc.update_force(olj, o, rows=(i0, i0 + 256))
+    scale = _row_scale(olj, o, rows)
+    for exact in (True, False):
+        st = to_gpu_state(md, o)
+        with md.Solver(exact=exact) as s:
+            s.set_potential(plj)
+            s.upload(st, with_forces=False)
+            s.update_force()
+            s.download(st)
+            m0 = s.macro()
+            if exact:  # bit-exact
+                assert np.array_equal(st.force[rows], o.force[rows])
+                assert np.array_equal(st.potential[rows], o.pot[rows])
+                assert np.array_equal(st.temp[rows], o.vir[rows])
+            else:      # |Δ| <= 1e-10 * max(Σ_j|f_ij|, global RMS)
+                rms = np.sqrt((st.force ** 2).sum(axis=1).mean())
+                bar = 1e-10 * np.maximum(scale, rms)
+                assert np.all(np.abs(st.force[rows] - o.force[rows]) <= bar[:, None])
+                assert np.all(np.abs(st.potential[rows] - o.pot[rows]) <= 1e-10 * (np.abs(o.pot[rows]) + 4 * olj.eps))
+                assert np.all(np.abs(st.temp[rows] - o.vir[rows]) <= 1e-10 * (scale * olj.r_cut) + 1e-300)
+            # Newton's third law holds pairwise → net force is rounding noise
+            assert np.abs(st.force.sum(axis=0)).max() <= 1e-9 * np.abs(st.force).sum()
+            s.step(50, DT)
+            m1 = s.macro()
+            stats = s.stats()
+        assert stats["steps"] == 50
+        e0, e1 = m0["kinetic"] + m0["potential"], m1["kinetic"] + m1["potential"]
+        assert abs(e1 - e0) <= 1e-3 * abs(m0["kinetic"])       # NVE energy conservation at dt = 2 fs (oracle: 1.1e-4)
+        assert np.abs(m1["momentum"]).max() <= 1e-9 * o.n       # Σ m v stays ~0
+
+
+@pytest.mark.parametrize("config", ["c2", "c5"])
+def test_config_size_trajectory_100_steps(config):
+    """BASELINE configs C2 (argon gas 32^3, NVT Berendsen) and C5 (liquid 64^3 = 262 144 atoms, 3.5 sigma cutoff, NVT) in the
+    benchmarked setup — MD_FORCE_FAST, default loop driver — against the oracle's Θ(N) cell-list step from the same frame 0,
+    100 steps: |Δx|, |Δv| <= 1e-8, lambda within 1e-12, macro parameters within 1e-9."""
+    if config == "c2":
+        o, cut, t0 = _perturbed_gas(32, seed=2), None, 300.0
     else:
-        o = liquid(n_side, jitter=0.03)
+        o, cut, t0 = liquid(64, jitter=0.03), LONG_CUT, 120.0
     olj, plj = lj_pair(md, *(cut or (None, None)))
     st = to_gpu_state(md, o)
-    with md.Solver(exact=True) as s:
+    gth, oth = (md.Thermostat.Berendsen(10.0), t0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, t0)
+    with md.Solver() as s:
         s.set_potential(plj)
         s.upload(st, with_forces=False)
         s.update_force()
+        s.step(100, DT, thermostat=gth)
         s.download(st)
-        m0 = s.macro()
-        # sampled rows, bit-exact against the reference's Θ(N) row scan
-        for i0 in (0, o.n // 2 - 128, o.n - 256):
-            orc.update_force(olj, o, rows=(i0, i0 + 256))
-            assert np.array_equal(st.force[i0:i0 + 256], o.force[i0:i0 + 256])
-            assert np.array_equal(st.potential[i0:i0 + 256], o.pot[i0:i0 + 256])
-            assert np.array_equal(st.temp[i0:i0 + 256], o.vir[i0:i0 + 256])
-        # Newton's third law holds pairwise → net force is rounding noise
-        assert np.abs(st.force.sum(axis=0)).max() <= 1e-9 * np.abs(st.force).sum()
-        s.step(50, DT)
-        m1 = s.macro()
-    e0, e1 = m0["kinetic"] + m0["potential"], m1["kinetic"] + m1["potential"]
-    assert abs(e1 - e0) <= 1e-3 * abs(m0["kinetic"])       # NVE energy conservation at dt = 2 fs (oracle: 1.1e-4)
-    assert np.abs(m1["momentum"]).max() <= 1e-9 * o.n       # Σ m v stays ~0
+        m = s.macro()
+        stats = s.stats()
+    run_oracle(olj, o, 100, oth)
+    om = orc.macro(o)
+    dx = np.abs(st.position - o.pos)
+    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    assert abs(gth[0].lambda_ / oth.lambda_ - 1.0) <= 1e-12
+    for key in ("kinetic", "thermal", "potential", "temperature", "pressure"):
+        assert abs(m[key] - om[key]) <= 1e-9 * max(1.0, abs(om[key])), key
+    assert stats["steps"] == 100
+    assert stats["persistent_loop"] == (1 if config == "c2" else 0)
+    if config == "c5":
+        assert stats["rebuilds"] >= 2 and stats["nbr_mean"] > 150   # the liquid rebuilds its lists within 100 steps
+
+
+def test_c4_size_npt_rows_and_box():
+    """BASELINE config C4 (argon 216^3 = 10 077 696 atoms, NPT Berendsen thermostat + barostat) on one GPU, MD_FORCE_FAST:
+    sampled force rows within the 1e-10 bar, then 50 NPT steps against the oracle — the box (scaled by myu every step,
+    barostat.rs:39-49) within 1e-12 relative, positions and velocities within 1e-8, lambda and myu within 1e-12."""
+    o = _perturbed_gas(216, seed=3)
+    olj, plj = lj_pair(md)
+    starts = (0, o.n // 2 - 128, o.n - 256)
+    rows = np.concatenate([np.arange(i0, i0 + 256) for i0 in starts])
+    for i0 in starts:
+        orc.update_force(olj, o, rows=(i0, i0 + 256))
+    scale = _row_scale(olj, o, rows)
+    ref_f, ref_u, ref_w = o.force[rows].copy(), o.pot[rows].copy(), o.vir[rows].copy()
+    st = to_gpu_state(md, o)
+    gth, oth = (md.Thermostat.Berendsen(10.0), 300.0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, 300.0)
+    gba, oba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325), orc.Barostat(1.0, 5.0, 1.01325)
+    with md.Solver() as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.download(st)
+        rms = np.sqrt((st.force ** 2).sum(axis=1).mean())
+        assert np.all(np.abs(st.force[rows] - ref_f) <= 1e-10 * np.maximum(scale, rms)[:, None])
+        assert np.all(np.abs(st.potential[rows] - ref_u) <= 1e-10 * (np.abs(ref_u) + 4 * olj.eps))
+        assert np.all(np.abs(st.temp[rows] - ref_w) <= 1e-10 * (scale * olj.r_cut) + 1e-300)
+        s.step(20, DT, thermostat=gth, barostat=gba)
+        s.step(30, DT, thermostat=gth, barostat=gba)
+        s.download(st)
+        m = s.macro()
+    run_oracle(olj, o, 50, oth, oba)
+    assert np.abs(st.boundary_box / o.box - 1.0).max() <= 1e-12
+    assert abs(gba[0].myu / oba.myu - 1.0) <= 1e-12 and abs(gth[0].lambda_ / oth.lambda_ - 1.0) <= 1e-12
+    dx = np.abs(st.position - o.pos)
+    assert np.minimum(dx, np.abs(dx - o.box)).max() <= 1e-8
+    assert np.abs(st.velocity - o.vel).max() <= 1e-8
+    om = orc.macro(o)
+    for key in ("temperature", "pressure"):
+        assert abs(m[key] - om[key]) <= 1e-9 * max(1.0, abs(om[key])), key
 
 
 # ---------------------------------------------------------------------------------------------------
-# programmatic dependent launch of the step kernels (MOLDYN_B200_PDL, read once per process → a child process each)
-_PDL_CHILD = r"""
-import sys, hashlib
-import numpy as np
-sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
-import moldyn_b200 as md
-from helpers import liquid, gas, to_gpu_state
-for name, o, T in (("liquid", liquid(12), 120.0), ("gas", gas(16), 300.0)):
-    for exact in (False, True):
-        st = to_gpu_state(md, o)
-        with md.Solver(exact=exact) as s:
-            s.upload(st, with_forces=False)
-            s.update_force()
-            for k in (1, 37, 200):
-                s.step(k, 0.002, thermostat=(md.Thermostat.Berendsen(10.0), T),
-                       barostat=(md.Barostat.Berendsen(1.0, 5.0), 1.01325))
-            s.download(st)
-            stats = s.stats()
-        h = hashlib.sha256()
-        for a in (st.position, st.velocity, st.force, st.potential, st.temp, st.boundary_box):
-            h.update(np.ascontiguousarray(a).tobytes())
-        print(name, exact, h.hexdigest(), stats["graph_launches"] > 0, stats["rebuilds"])
-"""
+# the reference's two #[ignore]d long-run tests, through the GPU path for the full 100 000 steps
+# The reference's assertions (|T - 273.15| < 1e-5, |P - 0.101325| < 1e-5 after 100 000 steps of 8 gas atoms) hold exactly when
+# no collision falls into the last ~3000 steps (Berendsen relaxes geometrically, 1/250 per step) — with the reference's
+# unseeded velocities that is a coin flip (oracle, seeds 1..12: the thermostat criterion holds for 6, the barostat's for 5),
+# which is why both tests are #[ignore]d there.  Here the 8 atoms get a collision-free draw: the two atoms of every x-row
+# share one velocity along x and the rows (3.34 nm apart, r_cut 0.85) never approach — forces stay exactly zero, nothing is
+# chaotic, and GPU and oracle can also be compared with each other after all 100 000 steps.
+def _eight_atoms(kat):
+    o = orc.argon_lattice(kat["grid"][0], kat["cell"], 273.15, 42)
+    a, b = 0.31, 0.23
+    o.vel[:] = 0.0
+    o.vel[:, 0] = np.array([a, -a, b, -b])[np.arange(o.n) % 4]   # index = x*4 + y*2 + z: atoms i and i+4 form a row
+    return o
 
 
-def test_programmatic_dependent_launch_is_bit_identical():
-    """MOLDYN_B200_PDL=1 turns the kernel → kernel edges of the step graph into programmatic ones (the kernels wait with
-    griddepcontrol.wait before reading anything; k_kick_drift fetches its positions ahead of the wait).  Scheduling only:
-    NPT trajectories through the graph loop must not change by a bit."""
-    import os
-    import subprocess
-    import sys
-    tests = os.path.dirname(os.path.abspath(__file__))
-    code = _PDL_CHILD.format(root=os.path.dirname(tests), tests=tests)
-    outs = []
-    for pdl in ("0", "1", "2"):  # 2 = + early-start k_kick_drift (ticket / sequence-number protocol)
-        env = dict(os.environ, MOLDYN_B200_PDL=pdl)
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(r.stdout.strip().splitlines())
-    assert len(outs[0]) == 4 and outs[0] == outs[1] == outs[2]
-    assert all(line.split()[3] == "True" for line in outs[0])  # the graph loop ran
+def test_reference_berendsen_thermostat_100000_steps(kats):  # solver/src/lib.rs:429-454 (#[ignore] there)
+    k = kats["berendsen_thermostat"]
+    o = _eight_atoms(k)
+    olj = orc.LennardJones()
+    st = to_gpu_state(md, o)
+    gth, oth = (md.Thermostat.Berendsen(k["tau"]), k["target"]), orc.Thermostat(orc.Thermostat.BERENDSEN, k["tau"], k["target"])
+    t_start = orc.macro(o)["temperature"]
+    assert abs(t_start - k["target"]) > 10.0                               # the thermostat has work to do
+    with md.Solver() as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(k["n_steps_reference"], DT, thermostat=gth)
+        s.download(st)
+        m = s.macro()
+        stats = s.stats()
+    assert stats["steps"] == k["n_steps_reference"]
+    assert abs(m["temperature"] - k["target"]) < k["tolerance"]          # the reference's own assertion
+    run_oracle(olj, o, k["n_steps_reference"], oth)
+    assert abs(orc.macro(o)["temperature"] - k["target"]) < k["tolerance"]
+    assert abs(m["temperature"] - orc.macro(o)["temperature"]) < 1e-9
+    assert np.abs(st.velocity - o.vel).max() < 1e-9
+    assert not st.force.any()
+
+
+def test_reference_berendsen_barostat_100000_steps(kats):  # solver/src/lib.rs:456-482 (#[ignore] there)
+    k = kats["berendsen_barostat"]
+    o = _eight_atoms(k)
+    olj = orc.LennardJones()
+    st = to_gpu_state(md, o)
+    gba, oba = (md.Barostat.Berendsen(k["beta"], k["tau"]), k["target"]), orc.Barostat(k["beta"], k["tau"], k["target"])
+    with md.Solver() as s:
+        s.upload(st, with_forces=False)
+        s.update_force()
+        s.step(k["n_steps_reference"], DT, barostat=gba)
+        s.update_force()                                                   # lib.rs:476: forces at the final box
+        m = s.macro()
+    assert abs(m["pressure"] - k["target"]) < k["tolerance"]              # the reference's own assertion
+    run_oracle(olj, o, k["n_steps_reference"], None, oba)
+    orc.update_force(olj, o, mode="cells")
+    assert abs(orc.macro(o)["pressure"] - k["target"]) < k["tolerance"]
+    assert abs(m["pressure"] - orc.macro(o)["pressure"]) < 1e-9
+    assert np.abs(m["box"] / o.box - 1.0).max() < 1e-9
+    assert abs(m["box"][0] / (k["grid"][0] * k["cell"]) - 1.0) > 1e-3     # the box did move
