@@ -31,19 +31,16 @@ GAS_CELL = 3.338339
 LIQUID_CELL = 0.36165
 DT = 0.002
 ALGO_BYTES_STEP = 160       # r+w of x, v, F (144 B) + write U, W (16 B) per atom-step
-ALGO_BYTES_FORCE = 112      # k_force(+kick2): read x, v; write v, F, U, W
-ALGO_BYTES_KICK_DRIFT = 120  # k_kick_drift: read x, v, F; write x, v
-ALGO_BYTES_FUSED_STEP = 104  # k_step_dilute: read x, u (48) + list count and first row (8); write x', u' (48)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/):
-# (workload, kernel) -> (bytes, capture)
-NCU_TRAFFIC = {
-    ("c3", "k_force"): (66.93e6, "profiles/r01_ncu_c3_v7_k_force_k_kick_drift.txt"),
-    ("c3", "k_kick_drift"): (48.03e6, "profiles/r01_ncu_c3_v7_k_force_k_kick_drift.txt"),
-    ("c3", "k_step_dilute"): (73.33e6, "profiles/r01_ncu_c3_v1_k_step_dilute.txt"),
-    ("c5", "k_force"): (235.19e6, "profiles/r01_ncu_c5_v10_k_force.txt"),
+# What the kernels' steady-state contracts move per atom, used for the per-kernel figures:
+CONTRACT_BYTES = {
+    "k_kick_drift": 72,     # read x, u (48); write x (24)
+    "k_force": 80,          # read x, u (48) + list count and first row (8); write u' (24)
+    "k_md_loop": 104,       # drift phase: read x, u (48) + list count (8), write x (24) and u' of the atoms without partners
+                            # (24); the force phase adds ~(48 + 24 + 28 per partner) B for every atom WITH partners
 }
 ALGO_FLOP_PAIR = 42         # flop per directed in-range pair
 ALGO_FLOP_ATOM = 30
+FP64_FALLBACK_TFLOPS = 40.0  # B200 datasheet FP64 (used only if the in-run DFMA measurement fails)
 
 WORKLOADS = {
     # name: side, lattice cell, T_init, (tau, T0), (beta, tau, P0) or None, (r_cut, u_cut) or None
@@ -140,6 +137,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on `workload`, from profiles/ncu_traffic.json —
+    written by scripts/ncu_traffic.py from an `ncu --set full` capture together with the commit it was taken at.  None when no
+    capture of this kernel/workload is recorded: the line then prints traffic: null rather than a number from another build."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(f"{workload}:{kernel}")
+    except (OSError, ValueError):
+        rec = None
+    return rec or {}
+
+
+def in_range_pairs(pos, box, r_cut, sample=4096, seed=0):
+    """Mean number of partners within r_cut per atom (directed pairs / atom), from a random sample of atoms (periodic KD-tree)."""
+    from scipy.spatial import cKDTree
+    pos = np.mod(pos, box)
+    pos = np.minimum(pos, np.nextafter(box, 0.0))
+    tree = cKDTree(pos, boxsize=box)
+    idx = np.random.default_rng(seed).choice(len(pos), size=min(sample, len(pos)), replace=False)
+    cnt = tree.query_ball_point(pos[idx], r_cut, return_length=True)
+    return float(np.mean(cnt) - 1.0)
+
+
 def cpu_reference_rate(w, sample_rows, threads=None):
     """The reference's Θ(N²) update_force (potential.rs:158-216) on the host cores, rows [0, sample_rows) of the
     workload's own positions against ALL N partners → atoms/s of force evaluation ≈ atom-steps/s of the CPU
@@ -192,6 +213,30 @@ def run_reference(args, w):
     print(json.dumps(out))
 
 
+def timed_steps(s, stream, steps, th, ba, dist=None):
+    """K consecutive steps between two CUDA events on the library's stream, barrier + synchronize on both sides; ms (max over
+    ranks)."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record(stream)
+    s.step(steps, DT, thermostat=th, barostat=ba)
+    e1.record(stream)
+    s.synchronize()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
 def run_ours(args, w):
     import torch
 
@@ -213,6 +258,7 @@ def run_ours(args, w):
     th = lambda: (md.Thermostat.Berendsen(w["thermostat"][0]), w["thermostat"][1])  # noqa: E731
     ba = (lambda: (md.Barostat.Berendsen(w["barostat"][0], w["barostat"][1]), w["barostat"][2])) if w["barostat"] \
         else (lambda: None)
+    r_cut = w["cut"][0] if w["cut"] else 0.8545
 
     s = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv,
                   chunk_loop=args.loop == "chunk", host_loop=args.loop == "host")
@@ -228,60 +274,103 @@ def run_ours(args, w):
     s.step(args.warmup, DT, thermostat=t_th, barostat=t_ba)
     st0 = s.stats()
 
+    # ---- the timed region: K consecutive steps, state resident in HBM -----------------------------------------------
     sampler = ClockSampler(local)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-        torch.cuda.synchronize()
     sampler.start()
-    e0.record(stream)
-    s.step(args.steps, DT, thermostat=t_th, barostat=t_ba)
-    e1.record(stream)
-    s.synchronize()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist:
-        dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = timed_steps(s, stream, args.steps, t_th, t_ba, dist)
     clocks = sampler.stop()
     st1 = s.stats()
     value = n * args.steps / (ms * 1e-3)
     macro = s.macro()
+    dense = st1["nbr_mean"] >= 8.0
+    rebuilds = st1["rebuilds"] - st0["rebuilds"]
 
+    # ---- steady state: the driver's short runs start on the perfect gas lattice (no partner in range, no rebuild for the
+    # first ~10^3 steps), so the same metric is taken again after the system has been run into its collisional steady
+    # state, over a region long enough to contain list rebuilds ------------------------------------------------------
+    steady = None
+    if args.steady_steps > 0:
+        s.step(args.steady_warmup, DT, thermostat=t_th, barostat=t_ba)
+        sa = s.stats()
+        ms_s = timed_steps(s, stream, args.steady_steps, t_th, t_ba, dist)
+        sb = s.stats()
+        steady = {"value": n * args.steady_steps / (ms_s * 1e-3), "unit": "atom-steps/s", "steps": args.steady_steps,
+                  "steps_before": args.warmup + args.steps + args.steady_warmup, "us_per_step": ms_s / args.steady_steps * 1e3,
+                  "rebuilds": sb["rebuilds"] - sa["rebuilds"], "nbr_mean": sb["nbr_mean"], "nbr_max": sb["nbr_max"],
+                  "frac_of_step_roofline": ALGO_BYTES_STEP * n * args.steady_steps / (ms_s * 1e-3) / 1e9 / (peaks()[0] * world)}
+
+    # ---- where the time goes: device timing of the parts of a step (md_time_kernels) --------------------------------
     hbm, peak_src = peaks()
-    if world == 1:
-        # --- per-kernel device times (CUDA events on the launching stream, host-stepped) -----------------
-        kt = s.time_kernels(min(args.steps, 400), DT, thermostat=t_th, barostat=t_ba)
-        per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt}
-        f_ms, k_ms, s_ms = per["force"], per["kick_drift"], per["loop_barrier"]
-        if f_ms >= k_ms:
-            dominant, dom_ms, dom_bytes = "k_force", f_ms, ALGO_BYTES_FORCE
-        else:
-            dominant, dom_ms, dom_bytes = "k_kick_drift", k_ms, ALGO_BYTES_KICK_DRIFT
-        achieved = dom_bytes * n / (dom_ms * 1e-3) / 1e9
+    fp64_peak, fp64_src = None, None
+    kt = s.time_kernels(min(max(args.steps, 50), 400), DT, thermostat=t_th, barostat=t_ba) if world == 1 else None
+    st2 = s.stats()
+    per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt} if kt else {}
+    rebuild_ms = per.get("rebuild")
+    if world == 1 and rebuild_ms is None and args.time_rebuild:
+        # no rebuild fell into the timed steps: force one and time it, so the line always carries its cost
+        s.invalidate_lists()
+        kr = s.time_kernels(1, DT, thermostat=t_th, barostat=t_ba)
+        rebuild_ms = kr["rebuild"][0] / kr["rebuild"][1] if kr["rebuild"][1] else None
+    step_us = ms / args.steps * 1e3
+    loop = bool(st1["persistent_loop"])
+    if world == 1 and loop:
+        phases = {"drift_phase_us": per["kick_drift"] * 1e3, "mid_step_barrier_us": per["loop_barrier"] * 1e3,
+                  "force_phase_and_tail_us": per["force"] * 1e3}
+        tr = ncu_traffic(args.workload, "k_md_loop")
         roofline = {
-            "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-            "frac": achieved / hbm, "traffic": NCU_TRAFFIC.get((args.workload, dominant), (None, None))[0],
-            "traffic_source": NCU_TRAFFIC.get((args.workload, dominant), (None, None))[1], "peak_source": peak_src,
-            "algorithmic_bytes_per_atom": dom_bytes, "algorithmic_bytes_per_launch": dom_bytes * n,
-            "avg_launch_ms": dom_ms,
-            "kernels_ms": {"k_step_dilute": s_ms, "k_force": f_ms, "k_kick_drift": k_ms, "rebuild": per["rebuild"]},
-            "launches_timed": {k: kt[k][1] for k in kt},
+            "bound": "hbm", "kernel": "k_md_loop (one launch runs many steps; figures are per step)",
+            "achieved": ALGO_BYTES_STEP * n / (step_us * 1e-6) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": peak_src,
+            "algorithmic_bytes_per_atom": ALGO_BYTES_STEP, "algorithmic_bytes_per_launch": ALGO_BYTES_STEP * n,
+            "avg_launch_ms": step_us * 1e-3, "contract_bytes_per_atom": CONTRACT_BYTES["k_md_loop"],
+            "phases_us": phases, "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+            "traffic_commit": tr.get("commit"),
         }
+        roofline["frac"] = roofline["achieved"] / hbm
+    elif world == 1:
+        f_ms, k_ms = per["force"], per["kick_drift"]
+        roofline = {"kernel": "k_force", "avg_launch_ms": f_ms, "kernels_ms": {"k_force": f_ms, "k_kick_drift": k_ms},
+                    "launches_timed": {k: kt[k][1] for k in kt}}
+        tr = ncu_traffic(args.workload, "k_force")
+        roofline.update({"traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+                         "traffic_commit": tr.get("commit")})
+        if dense:
+            # FP64-bound: 42 flop per directed in-range pair + 30 per atom-step
+            try:
+                fp64_peak, fp64_src = s.measure_fp64_peak(), "measured in this run (register-only DFMA loop, md_measure_fp64_peak)"
+            except Exception as e:  # noqa: BLE001
+                fp64_peak, fp64_src = FP64_FALLBACK_TFLOPS, f"fallback datasheet figure ({e!r})"
+            cur = np.empty(3 * n)
+            s.download_arrays(pos=cur)
+            pairs = in_range_pairs(cur.reshape(-1, 3), np.array(macro["box"]), r_cut)
+            flop = (ALGO_FLOP_PAIR * pairs + ALGO_FLOP_ATOM) * n
+            roofline.update({"bound": "fp64", "achieved": flop / (f_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "peak_source": fp64_src, "pairs_in_range": pairs, "pairs_listed": st1["nbr_mean"],
+                             "algorithmic_flop_per_launch": flop,
+                             "hbm_view": {"contract_bytes_per_atom": CONTRACT_BYTES["k_force"] + 4 * st1["nbr_mean"],
+                                          "achieved_gbs": (CONTRACT_BYTES["k_force"] + 4 * st1["nbr_mean"]) * n / (f_ms * 1e-3) / 1e9,
+                                          "peak_gbs": hbm}})
+            roofline["frac"] = roofline["achieved"] / fp64_peak
+        else:
+            dom, dom_ms = ("k_force", f_ms) if f_ms >= k_ms else ("k_kick_drift", k_ms)
+            roofline.update({"bound": "hbm", "kernel": dom, "avg_launch_ms": dom_ms,
+                             "achieved": CONTRACT_BYTES[dom] * n / (dom_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "peak_source": peak_src, "algorithmic_bytes_per_atom": CONTRACT_BYTES[dom],
+                             "algorithmic_bytes_per_launch": CONTRACT_BYTES[dom] * n})
+            roofline["frac"] = roofline["achieved"] / hbm
     else:
-        roofline = {"bound": "hbm", "kernel": "step (per-kernel timing is single-GPU only)", "achieved": None,
-                    "peak": hbm * world, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-                    "kernels_ms": {"k_step_dilute": None, "k_force": None, "k_kick_drift": None, "rebuild": None}}
+        roofline = {"bound": "hbm", "kernel": "k_md_loop per rank" if loop else "k_kick_drift + k_force per rank",
+                    "achieved": ALGO_BYTES_STEP * value / 1e9, "peak": hbm * world, "unit": "GB/s", "peak_source": peak_src,
+                    "frac": ALGO_BYTES_STEP * value / 1e9 / (hbm * world), "traffic": None,
+                    "algorithmic_bytes_per_atom": ALGO_BYTES_STEP,
+                    "note": "whole job against N x the single-GPU HBM peak; per-rank phase clocks are in per_rank"}
     roofline["step"] = {"algorithmic_bytes_per_atom_step": ALGO_BYTES_STEP, "achieved": ALGO_BYTES_STEP * value / 1e9,
-                        "frac": ALGO_BYTES_STEP * value / 1e9 / (hbm * world)}
-    if w["cut"] is not None or w["cell"] < 1.0:
-        pairs = s.stats()["nbr_mean"]
-        roofline["note"] = (f"dense system: force kernel is FP64/L1 bound; mean listed partners {pairs:.1f}; "
-                            f"algorithmic flop/atom-step ≈ {ALGO_FLOP_PAIR}*<in-range> + {ALGO_FLOP_ATOM}")
+                        "frac": ALGO_BYTES_STEP * value / 1e9 / (hbm * world), "us_per_step": step_us,
+                        "state_mb": 48 * n / 1e6,
+                        "note": "x, v planes the step streams vs the 126 MB L2: below ~2.6e6 atoms part of the traffic is "
+                                "served from L2, so the step can exceed the HBM-only bound; `big` and c4 give the HBM view"}
+    roofline["rebuild"] = {"ms_each": rebuild_ms, "in_timed_region": rebuilds,
+                           "amortised_us_per_step": (rebuild_ms * 1e3 * steady["rebuilds"] / steady["steps"])
+                           if (steady and rebuild_ms is not None) else None}
 
     # --- e2e: reference-facing per-call API, State in pinned host memory in and out every step ------------
     e2e = None
@@ -354,26 +443,34 @@ def run_ours(args, w):
         r, dt_cpu, rows, _, thr = cpu_reference_rate(w, rows)
         cpu = {"value": r, "unit": "atom-steps/s", "cores": thr, "kind": "port",
                "sample": f"oracle update_force rows [0,{rows}) of {n}, each against all {n} partners "
-                         f"({dt_cpu:.1f} s; reference's Θ(N²) scan, potential.rs:158-216)"}
+                         f"({dt_cpu:.1f} s; reference's Θ(N²) scan, potential.rs:158-216); the oracle is a restatement "
+                         f"pinned to the reference's golden values, many-body behaviour self-pinned (no Rust toolchain)"}
 
+    if world == 1:
+        par = "single GPU"
+    elif st1["peer_memory"]:
+        par = (f"{world} x-slabs (spatial decomposition); per step: ghost positions stored into the neighbours' HBM by the "
+               f"{'persistent step loop' if loop else 'drift kernel'}, rank sums exchanged through peer-memory mailboxes inside the "
+               f"{'loop' if loop else 'force kernel'}")
+    else:
+        par = f"{world} x-slabs (spatial decomposition), NCCL halo send/recv + all-gather of 12 sums per step"
     out = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "parallelism": "single GPU" if world == 1 else (f"{world} x-slabs (spatial decomposition); per step: ghost positions stored into the neighbours' HBM by "
-                                                                "the drift kernel, rank sums exchanged through peer-memory mailboxes inside the force kernel"
-                                                                if st1["peer_memory"] else
-                                                                f"{world} x-slabs (spatial decomposition), NCCL halo send/recv + all-gather of 12 sums per step"),
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "parallelism": par, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "atoms": n, "dt": DT, "thermostat": w["thermostat"],
-                   "barostat": w["barostat"], "r_cut": w["cut"][0] if w["cut"] else 0.8545,
-                   "skin": st1["skin"], "cells": st1["cells"],
+                   "barostat": w["barostat"], "r_cut": r_cut, "skin": st1["skin"], "cells": st1["cells"],
+                   "loop": "persistent cooperative kernel (k_md_loop)" if loop else "graph chunks of {k_kick_drift; k_force}",
+                   "list_state": {"nbr_mean": st1["nbr_mean"], "nbr_max": st1["nbr_max"], "rebuilds_in_timed_region": rebuilds,
+                                  "note": "a run started on the perfect gas lattice has no partner within the list radius "
+                                          "for its first ~10^3 steps; see steady_state for the collisional regime"},
                    "l2": "one timed region of K consecutive, dependent MD steps of one trajectory (no input is "
                          "re-run, so there is no L2 flush between steps); per-step state "
-                         f"{(88 * n + 4 * n) / 1e6:.0f} MB vs 126 MB L2 — see roofline for the HBM view"},
+                         f"{48 * n / 1e6:.0f} MB (x, v) vs 126 MB L2 — see roofline.step"},
         "ns_per_day": args.steps / (ms * 1e-3) * 0.1728,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "roofline": roofline, "steady_state": steady, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
-        "rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
+        "rebuilds_in_timed_region": rebuilds,
         "graph_launches_in_timed_region": st1["graph_launches"] - st0["graph_launches"],
         "loop_launches_in_timed_region": st1["loop_launches"] - st0["loop_launches"],
         "state_check": {"temperature": macro["temperature"], "pressure": macro["pressure"],
@@ -381,13 +478,15 @@ def run_ours(args, w):
     }
     if world > 1:
         alls = [None] * world if rank == 0 else None
-        mine = {k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds", "peer_memory")}
+        mine = {k: st1[k] for k in ("n_owned", "n_ghost", "migrated", "rebuilds", "peer_memory", "persistent_loop")}
         mine["wait_halo_us_per_step"] = (st1["wait_halo_ms"] - st0["wait_halo_ms"]) * 1e3 / args.steps
         mine["wait_sums_us_per_step"] = (st1["wait_sums_ms"] - st0["wait_sums_ms"]) * 1e3 / args.steps
         for k in ("force_atoms", "force_tail"):
             mine[k + "_us_per_step"] = (st1[k + "_ms"] - st0[k + "_ms"]) * 1e3 / args.steps
         mine["rebuild_ms_each"] = (st1["rebuild_ms"] - st0["rebuild_ms"]) / max(st1["rebuilds"] - st0["rebuilds"], 1)
-        mine["loop_phase_us_per_step"] = [(a - b) * 1e3 / args.steps for a, b in zip(st1["loop_phase_ms"], st0["loop_phase_ms"])]
+        names = ("drift_phase", "mid_step_barrier", "force_phase", "tail_reduce_exchange_finalize")
+        mine["loop_us_per_step"] = {k: (a - b) * 1e3 / args.steps
+                                    for k, a, b in zip(names, st1["loop_phase_ms"], st0["loop_phase_ms"])}
         dist.gather_object(mine, alls, dst=0)
         out["per_rank"] = alls
     if rank == 0:
@@ -411,6 +510,12 @@ def main():
                     help="auto: persistent step loop for dilute systems, graph chunks for dense ones; chunk: the two-kernel "
                          "graph-chunk loop everywhere (A/B); host: one launch per step (ncu)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--steady-steps", type=int, default=None,
+                    help="steps of the extra steady-state region (0 = skip; default 4000, 1000 above 2e6 atoms, 0 for N > 1 "
+                         "unless given)")
+    ap.add_argument("--steady-warmup", type=int, default=None, help="steps run before the steady-state region")
+    ap.add_argument("--no-time-rebuild", dest="time_rebuild", action="store_false",
+                    help="do not force + time one list rebuild when none fell into the timed steps")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto, -1 = skip)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -425,6 +530,11 @@ def main():
     if args.warmup is None:
         args.warmup = 500 if n <= 2_000_000 else 100
     args.warmup = max(args.warmup, 3)
+    if args.steady_steps is None:
+        args.steady_steps = (4000 if n <= 2_000_000 else 1000) if args.gpus == 1 else 0
+    if args.steady_warmup is None:
+        # a gas atom needs ~5 ps (2500 steps) to meet its first partner; the liquid is in its steady state at once
+        args.steady_warmup = 0 if w["cell"] < 1.0 else (6000 if n <= 2_000_000 else 3000)
     run_ours(args, w)
 
 
