@@ -31,11 +31,13 @@ def up_to_date() -> bool:
     return os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build_library(force: bool = False, verbose: bool = False, out: str | None = None, extra: tuple = ()) -> str:
+    """`out` / `extra`: a variant build of the same sources (measurement aids such as -DMD_LOOP_TRACE) next to the library."""
+    if out is None and not force and up_to_date():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("MD_NVCC_EXTRA", "").split(), "-o", LIB, SRC, "-ldl"]
+    out = out or LIB
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("MD_NVCC_EXTRA", "").split(), *extra, "-o", out, SRC, "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd), file=sys.stderr)
@@ -43,7 +45,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     env.pop("CC", None)  # the image's $CC wrapper is not a usable host compiler for nvcc
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return out
 
 
 HOST_SRC = [os.path.join(HERE, "host", "moldyn.cpp"), os.path.join(HERE, "host", "moldyn_cli.cpp")]

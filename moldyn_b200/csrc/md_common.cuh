@@ -74,6 +74,7 @@ struct Scalars {
     // persistent step loop: accumulated phase times of block 0 (ns): drift, mid-step barrier, forces, reduction + finalize
     unsigned long long loop_ns[4];
     unsigned long long loop_steps;  // steps executed by the persistent loop since the last upload
+    unsigned long long trace[16];   // MD_LOOP_TRACE builds: %globaltimer stamps of the last step's phases (md_debug_trace)
     double rank_sums[NSUM];  // multi-GPU: this rank's K5 sums (input of the all-gather)
     // multi-GPU rebuild bookkeeping
     int n_stay, n_left, n_right, n_lost;
@@ -104,6 +105,21 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned l
 {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Release / acquire on the atomic itself: one L2 round trip orders the thread's earlier writes (and, cumulatively, the
+// writes of the block's other threads that a bar.sync placed before it) — where __threadfence() + atomicAdd() pays for a
+// sequentially consistent fence (MEMBAR.SC.GPU) on top of the atomic.
+__device__ __forceinline__ unsigned atom_add_release_gpu(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned *p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 // halted(), read through L2: for a kernel that runs while its predecessor is still finishing
 __device__ __forceinline__ bool halted_now(const Scalars *sc)
 {
@@ -116,6 +132,11 @@ __device__ __forceinline__ unsigned long long gtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+#ifdef MD_LOOP_TRACE
+#define MD_TRACE(cond, k) do { if (cond) sc->trace[k] = gtime(); } while (0)
+#else
+#define MD_TRACE(cond, k) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // Per-thread asynchronous copies global → shared (LDGSTS): a thread parks the NEXT tile's operands in shared memory while

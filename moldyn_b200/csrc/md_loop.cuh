@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         __syncthreads();
         if (ctl.halted) break;
         unsigned long long tq = tid == 0 ? gtime() : 0ull;
+        MD_TRACE(bid == 0 && tid == 0, 0);
         const double lambda = ctl.lambda, mup = ctl.mup, Lx = ctl.Lx, Ly = ctl.Ly, Lz = ctl.Lz;
         const double *shift = ctl.shift;
         const bool half = ctl.half != 0;
@@ -187,17 +188,19 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         }
         for (int r = bid * LOOP_BLOCK + tid; r < pr0 - pl; r += nb * LOOP_BLOCK) drift_pair(pl + r, false);
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[0] += t - tq; tq = t; }
+        MD_TRACE(bid == 0 && tid == 0, 1);
 
         // ---- mid-step barrier: all drifted positions (and first-step half-kicks) are visible grid-wide ------------------
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
-            atomicAdd(&sc->bar_arrive, 1u);
+            // release: this block's drifted positions (the bar.sync above makes the release cumulative over its threads);
+            // the acquiring loads below also invalidate this SM's L1
+            atom_add_release_gpu(&sc->bar_arrive, 1u);
             while (ld_acquire_gpu(&sc->bar_arrive) < (unsigned int)nb) { }
-            __threadfence();
         }
         __syncthreads();
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[1] += t - tq; tq = t; }
+        MD_TRACE(bid == 0 && tid == 0, 2);
 
         // ---- phase B ----------------------------------------------------------------------------------------------------
         LjConst c;
@@ -208,14 +211,23 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             const double xi = __ldcg(a.x + i), yi = __ldcg(a.y + i), zi = __ldcg(a.z + i);
             double vx = __ldcg(a.vx + i), vy = __ldcg(a.vy + i), vz = __ldcg(a.vz + i);
             const int cnt = A.nbr_cnt[i];
-            int j = A.nbr[i];  // row 0
             PairAcc f = zero;
-            for (int k = 0; k < cnt; ++k) {
-                const int jn = k + 1 < cnt ? A.nbr[(size_t)(k + 1) * A.npad + i] : 0;
-                const double xj = __ldcg(a.x + j), yj = __ldcg(a.y + j), zj = __ldcg(a.z + j);
-                if (EXACT) pair_exact(f, xj, yj, zj, xi, yi, zi, c, fc);
-                else pair_fast_branchy(f, true, xj, yj, zj, xi, yi, zi, c, fc);
-                j = jn;
+            // partners in groups of four: the four indices are fetched together, then the twelve coordinates, then the pair
+            // terms — two dependent memory round trips per group instead of two per partner
+            for (int k0 = 0; k0 < cnt; k0 += 4) {
+                int j[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = k0 + u < cnt ? A.nbr[(size_t)(k0 + u) * A.npad + i] : i;
+                double xj[4], yj[4], zj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { xj[u] = __ldcg(a.x + j[u]); yj[u] = __ldcg(a.y + j[u]); zj[u] = __ldcg(a.z + j[u]); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u < cnt) {
+                        if (EXACT) pair_exact(f, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
+                        else pair_fast_branchy(f, true, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
+                    }
+                }
             }
             double wx, wy, wz;
             finish_atom(ss, f, vx, vy, vz, true, lambda, hc, mass, shift, wx, wy, wz, nh);
@@ -236,7 +248,6 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 const unsigned long long tw = gtime();
                 const unsigned long long seq = ctl.epoch + 1;
                 halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
-                __threadfence();
                 if (bid == 0) sc->wait_halo_ns += gtime() - tw;
             }
             __syncthreads();
@@ -244,22 +255,26 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             for (int k = bid * LOOP_BLOCK + tid; k < n_bnd; k += nb * LOOP_BLOCK) force_atom(A.act_idx[n_int + k]);
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[2] += t - tq; tq = t; }
+        MD_TRACE(bid == 0 && tid == 0, 3);
 
         // ---- tail: block sums, ticket, last block folds + finalizes + releases -------------------------------------------
         Sums s;
 #pragma unroll
         for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][tid];
         block_reduce<LOOP_BLOCK>(s);
-        if (publish_and_ticket<LOOP_BLOCK>(s, A.partials, sc))
+        MD_TRACE(bid == 0 && tid == 0, 4);
+        const bool last = publish_and_ticket<LOOP_BLOCK>(s, A.partials, sc);
+        MD_TRACE(bid == 0 && tid == 0, 5);
+        if (last)
             last_block_finalize<LOOP_BLOCK>(A.partials, sc, pr, FIN_STEP | (multi ? FIN_P2P : 0), A.peers);
         if (tid == 0) {
             const unsigned long long fin_seq0 = ctl.fin_seq;
             while (ld_acquire_gpu(&sc->fin_seq) <= fin_seq0) { }
-            __threadfence();
             t_acc[3] += gtime() - tq;
             t_acc[4] += 1ull;
         }
         __syncthreads();
+        MD_TRACE(bid == 0 && tid == 0, 6);
     }
     if (bid == 0 && tid == 0 && t_acc[4]) {
         // (the last finalize of this launch is complete: nobody else writes these words)

@@ -198,8 +198,9 @@ __device__ __forceinline__ bool publish_and_ticket(const Sums &mine, double *__r
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < NSUM; ++q) __stcg(&partials[(size_t)blockIdx.x * NSUM + q], mine.v[q]);
-        __threadfence();
-        unsigned int t = atomicAdd(&sc->ticket, 1u);
+        // release: the partial sums above and everything this block stored before its last bar.sync; acquire: the block
+        // that comes last sees every other block's
+        const unsigned int t = atom_add_acq_rel_gpu(&sc->ticket, 1u);
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
@@ -213,7 +214,7 @@ template <int BLOCK>
 __device__ __forceinline__ void last_block_finalize(double *__restrict__ partials, Scalars *sc, const Params *pr, int mode,
                                                     const Peers *peers_p)
 {
-    __threadfence();
+    MD_TRACE(threadIdx.x == 0, 8);
     // (a) A copy of the control words and parameters finalize reads goes to shared memory — those loads are in flight
     // together with (b) the fold of the per-block partials: thread (g, q) adds slot q of blocks g, g+G, g+2G, … in ascending
     // order (independent loads, one L2 round trip), then the G group sums of a slot are added in group order.
@@ -284,6 +285,7 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
 #pragma unroll
         for (int q = 0; q < NSUM; ++q) acc.v[q] = folded[q];
     }
+    MD_TRACE(threadIdx.x == 0, 9);
     const unsigned long long t_last = gtime();  // every block has finished its atoms
     if (mode & FIN_P2P) {
         // All-gather of the rank sums through peer memory, fused into this kernel: every rank stores its 12 sums into every
@@ -342,8 +344,10 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
         }
         finalize(sc, &sc_in, &pr_in, acc, mode);
         sc->ticket = 0;
+        MD_TRACE(true, 10);
         // everything above is visible to whoever acquires the new sequence number
         st_release_gpu(&sc->fin_seq, sc_in.fin_seq + 1);
+        MD_TRACE(true, 11);
     }
 }
 

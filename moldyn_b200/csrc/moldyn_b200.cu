@@ -1490,6 +1490,17 @@ int md_measure_fp64_peak(md_ctx *ctx, double *tflops)
     return MD_OK;
 }
 
+// MD_LOOP_TRACE builds: %globaltimer stamps (ns) of the last step the persistent loop ran — block 0: [0] step start,
+// [1] drift done, [2] mid-step barrier passed, [3] forces done, [4] block sums, [5] ticket taken, [6] next step may start;
+// last block: [8] enters the epilogue, [9] partials folded, [10] finalize done, [11] sequence number released.
+__attribute__((visibility("default"))) int md_debug_trace(md_ctx *ctx, unsigned long long out[16])
+{
+    TRY(check_ctx(ctx, false));
+    TRY(pull_scalars(ctx));
+    for (int k = 0; k < 16; ++k) out[k] = ctx->h_sc->trace[k];
+    return MD_OK;
+}
+
 int md_synchronize(md_ctx *ctx)
 {
     TRY(check_ctx(ctx, false));

@@ -70,6 +70,50 @@ def run_case(name, o, exact, n_steps, thermostat=None, barostat=None, rank=0):
     return migrated
 
 
+def perturbed_gas(n_side, seed):
+    o = gas(n_side)
+    o.pos += np.random.default_rng(seed).uniform(-1.45, 1.45, o.pos.shape)
+    orc.apply_boundary_conditions(o)
+    return o
+
+
+def run_c3_rows(rank):
+    """BASELINE config C3 (argon 100^3 = 10^6 atoms) decomposed over the ranks, MD_FORCE_FAST: sampled force rows against the
+    reference's row scan (1e-10 bar relative to max(|F_i|, RMS) — the perturbed gas has no symmetric cancellation), the
+    macro parameters against the oracle, then 30 NVT steps: every atom still owned exactly once, momentum conserved."""
+    o = perturbed_gas(100, 1)
+    lj = orc.LennardJones()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    with md.Solver(device=local) as s:
+        mdd.init_solver_comm(s)
+        s.upload_arrays(o.pos, o.vel, o.mass, o.box)
+        s.update_force()
+        got = mdd.gather_by_id(s.download_local(), o.n)
+        m0 = s.macro()
+        s.step(30, DT, thermostat=(md.Thermostat.Berendsen(10.0), 300.0))
+        got1 = mdd.gather_by_id(s.download_local(), o.n)
+        m1 = s.macro()
+        stats = s.stats()
+    if rank != 0:
+        return
+    starts = (0, o.n // 2 - 128, o.n - 256)
+    rows = np.concatenate([np.arange(i0, i0 + 256) for i0 in starts])
+    for i0 in starts:
+        orc.update_force(lj, o, rows=(i0, i0 + 256))
+    rms = np.sqrt((got["force"] ** 2).sum(axis=1).mean())
+    scale = np.maximum(np.abs(o.force[rows]).max(axis=1), rms)
+    assert np.all(np.abs(got["force"][rows] - o.force[rows]) <= 1e-10 * 100 * scale[:, None]), "c3 rows"
+    assert np.all(np.abs(got["potential"][rows] - o.pot[rows]) <= 1e-10 * (np.abs(o.pot[rows]) + 4 * lj.eps))
+    orc.update_force(lj, o, mode="cells")
+    om = orc.macro(o)
+    for key in ("kinetic", "thermal", "potential", "temperature", "pressure"):
+        assert abs(m0[key] - om[key]) <= 1e-9 * max(1.0, abs(om[key])), ("c3", key, m0[key], om[key])
+    assert np.abs(m1["momentum"]).max() <= 1e-9 * o.n
+    assert stats["persistent_loop"] == 1 or not stats["peer_memory"]
+    print(f"  c3 10^6 atoms fast rows+macro: ok  owned={got1['owned_per_rank']} T {m0['temperature']:.6f} -> {m1['temperature']:.6f}",
+          flush=True)
+
+
 def main():
     dist.init_process_group("gloo")
     rank = dist.get_rank()
@@ -82,11 +126,13 @@ def main():
         ("dense_gas3000 exact NVE", dense_gas(3000), True, 100, None, None),
         ("hot gas1000 exact NVE", hot, True, 200, None, None),
         ("gas1000 fast NPT", gas(10), False, 100, (10.0, 300.0), (1.0, 5.0, 1.01325)),
+        ("gas32768 (C2 size, perturbed) fast NVT", perturbed_gas(32, 2), False, 100, (10.0, 300.0), None),
+        ("gas32768 (C2 size, perturbed) exact NPT", perturbed_gas(32, 4), True, 60, (10.0, 300.0), (1.0, 5.0, 1.01325)),
     ]
     if dist.get_world_size() > 2:
         # the liquid boxes are too small for more than two slabs (slab width >= 2.1 x halo): keep the gases, add a bigger
         # hot one so atoms cross several slab faces
-        cases = [c for c in cases if "gas1000" in c[0]]
+        cases = [c for c in cases if "gas1000" in c[0] or "gas32768" in c[0]]
         cases.append(("hot gas4096 fast NVT", gas(16, temperature=2000.0), False, 150, (10.0, 300.0), None))
     total_migrated = 0
     for name, o, exact, n_steps, th, ba in cases:
@@ -94,6 +140,8 @@ def main():
         if rank == 0:
             total_migrated += mig
         dist.barrier()
+    run_c3_rows(rank)
+    dist.barrier()
     if rank == 0:
         assert total_migrated > 0, "no atom ever changed rank: migration path untested"
         print("DIST_OK", flush=True)

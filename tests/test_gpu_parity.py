@@ -193,7 +193,6 @@ def test_cells_and_neighbour_sets_bit_exact(name, mode):
         cell, dims = s.cells()
         off, partners = s.neighbour_lists()
         skin = s.stats()["skin"]
-        assert s.stats()["union_lists"] == 0
     # cell assignment: c_d = min(nc_d-1, (int)(frac(x_d / L_d) * nc_d)), linear index (cx*ny + cy)*nz + cz
     c = []
     for d in range(3):
