@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "moldyn_b200.cu")
 DEPS = [SRC, os.path.join(ROOT, "include", "moldyn_b200.h")] + [
     os.path.join(HERE, "csrc", f) for f in ("md_kernels.cuh", "md_common.cuh", "md_cells.cuh", "md_lists.cuh", "md_reduce.cuh",
-                                            "md_force.cuh", "md_integrate.cuh", "md_loop.cuh", "md_dist_kernels.cuh", "md_dist.inc")]
+                                            "md_force.cuh", "md_integrate.cuh", "md_loop.cuh", "md_tile.cuh", "md_dist_kernels.cuh", "md_dist.inc")]
 LIB = os.path.join(HERE, "lib", "libmoldyn_b200.so")
 
 NVCC_FLAGS = [

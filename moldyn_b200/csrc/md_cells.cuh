@@ -24,7 +24,7 @@ __global__ void k_cell_count(int n, const double *__restrict__ x, const double *
     int cx = cell_coord(x[i], sc->box[0], g.nc[0]);
     int cy = cell_coord(y[i], sc->box[1], g.nc[1]);
     int cz = cell_coord(z[i], sc->box[2], g.nc[2]);
-    int c = (cx * g.nc[1] + cy) * g.nc[2] + cz;
+    int c = cell_index(g, cx, cy, cz);
     cell_of[i] = c;
     atomicAdd(&cell_cnt[c], 1);
     // (inside md_step the drift kernel keeps every coordinate in [0, L); an uploaded State may hold anything)

@@ -61,6 +61,8 @@ struct Scalars {
     int nbr_overflow;  // some atom exceeded the capacity
     int vel_is_half;   // 1: the velocity planes hold u = v + F*c (next step's first half-kick already applied)
     int out_of_box;    // the last cell binning saw a coordinate outside [0, L): list builds use the generic minimum image
+    int tile_shell_max;  // tile kernels: largest shell (slots) and largest brick (atoms) of the last k_tile_measure
+    int tile_own_max;
     int pad0;
     unsigned int bar_arrive;        // persistent step loop: arrivals at the mid-step grid barrier (only ever grows)
     unsigned int face_arrive[2];    // persistent step loop, multi-GPU: face blocks that have pushed their ghosts (only grows)
@@ -195,10 +197,41 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigne
 struct Grid {
     int nc[3];
     int nsub;   // stencil half-width in cells
-    int ncell;
+    int ncell;  // cells of the table (brick order pads the (x, y) columns of partial bricks: they stay empty)
     int cap;    // neighbour slots per atom
     int npad;   // row stride of the neighbour table
+    // Brick order (dense systems, tile kernels — md_tile.cuh): the (x, y) columns of cells are numbered brick by brick
+    // (4 x 4 columns each), z stays the fastest index.  An (x, y) brick cut into chunks of `bz` z-cells is the unit of work
+    // of a thread block: its atoms and the +-2-cell shell around them are few contiguous runs of the sorted order.
+    int brick;      // 0: column index cx * ncy + cy (canonical), 1: brick-major columns
+    int nbx, nby;   // bricks along x and y
+    int bz, nbz;    // z cells per chunk, chunks along z
 };
+
+__host__ __device__ __forceinline__ int col_index(const Grid &g, int cx, int cy)
+{
+    if (!g.brick) return cx * g.nc[1] + cy;
+    return ((((cx >> 2) * g.nby) + (cy >> 2)) << 4) + ((cx & 3) << 2) + (cy & 3);
+}
+
+__host__ __device__ __forceinline__ int cell_index(const Grid &g, int cx, int cy, int cz)
+{
+    return col_index(g, cx, cy) * g.nc[2] + cz;
+}
+
+__host__ __device__ __forceinline__ void cell_decode(const Grid &g, int c, int &cx, int &cy, int &cz)
+{
+    cz = c % g.nc[2];
+    const int col = c / g.nc[2];
+    if (!g.brick) {
+        cy = col % g.nc[1];
+        cx = col / g.nc[1];
+    } else {
+        const int b = col >> 4, l = col & 15;
+        cx = (b / g.nby) * 4 + (l >> 2);
+        cy = (b % g.nby) * 4 + (l & 3);
+    }
+}
 
 
 // ----------------------------------------------------------------------------------------------------

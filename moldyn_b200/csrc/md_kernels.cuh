@@ -19,4 +19,5 @@
 #include "md_force.cuh"
 #include "md_integrate.cuh"
 #include "md_loop.cuh"
+#include "md_tile.cuh"
 #include "md_dist_kernels.cuh"

@@ -28,10 +28,8 @@ __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *
         const double hx = Lx / 2.0, hy = Ly / 2.0, hz = Lz / 2.0;
         const double xi = a.x[p], yi = a.y[p], zi = a.z[p];
         const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
-        int c = cell_sorted[p];
-        int cz = c % ncz;
-        int cy = (c / ncz) % ncy;
-        int cx = c / (ncz * ncy);
+        int cx, cy, cz;
+        cell_decode(g, cell_sorted[p], cx, cy, cz);
         int w = 2 * g.nsub + 1;
         int lox, loy, nx, ny;
         if (ncx >= w) { lox = cx - g.nsub; nx = w; } else { lox = 0; nx = ncx; }
@@ -57,7 +55,7 @@ __global__ void __launch_bounds__(128) k_build_list(int n, Arrays a, const int *
                 const double sy = qy < 0 ? -Ly : (qy >= ncy ? Ly : 0.0);
                 qy += (qy < 0) ? ncy : 0;
                 qy -= (qy >= ncy) ? ncy : 0;
-                const int base = (qx * ncy + qy) * ncz;
+                const int base = col_index(g, qx, qy) * ncz;
                 // both runs' bounds are fetched before either is walked
                 const int sa = cell_start[base + z0a], ea = cell_start[base + z1a];
                 const int sb = (z1b > z0b) ? cell_start[base + z0b] : 0, eb = (z1b > z0b) ? cell_start[base + z1b] : 0;

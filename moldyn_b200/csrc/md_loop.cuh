@@ -1,41 +1,49 @@
 // md_loop.cuh — the persistent step loop of dilute systems: ONE cooperative kernel runs MD steps until the neighbour list
-// has to be rebuilt (or the batch ends), with two grid-wide synchronisations per step instead of two kernel boundaries.
+// has to be rebuilt (or the batch ends), with two grid-wide synchronisations per step instead of two kernel boundaries and
+// with the velocities resident in shared memory for the whole launch.
 // Part of md_kernels.cuh (included from there, in order; one translation unit).
 #pragma once
 
 namespace md {
 
-// Why.  Round-1 measurements: at 10^6 atoms the two-kernel step spends 21 of its 30 us in a force kernel
-// that is bound by gather latency, not bandwidth — every warp walks the list path although 60-80 % of the atoms of the gas
-// have no listed partner — and below ~10^5 atoms per GPU (the 8-GPU slabs, C1, C2) the step is nothing but fixed latencies:
-// two launches, a 592-slot fold, a mailbox exchange.  This kernel restructures the step (integrator.rs:14-59) as
+// Why.  Round-1 measurements: the two-kernel step moves 152 B per atom and step through L2/HBM (x and u
+// are read by both kernels) and, below ~10^5 atoms per GPU (the 8-GPU slabs, C1, C2), is nothing but fixed latencies — two
+// launches, a 592-slot fold, a mailbox exchange.  A thread of this kernel owns the same pairs of atoms in every phase of every
+// step of the launch, so what only the owner ever touches — the velocity u — never leaves the SM: 24 B/atom in shared memory
+// (10^6 atoms: 162 KB of the 227 KB per SM), loaded once per launch and written back when the loop exits.  A step
+// (integrator.rs:14-59) is then
 //
-//   phase A  (all atoms, two per thread, 128-bit accesses)  first half-kick on the first step of a batch, lambda-scale,
-//            pending barostat scale, drift, wrap — k_kick_drift's arithmetic — and, for the atoms WITHOUT listed partners,
-//            the rest of the step as well: F = 0, so v'' = u' = lambda*u is final, its K5 terms are summed here and its
-//            velocity is stored once.  Multi-GPU: a few "face blocks" handle the atoms the neighbours see as ghosts first,
-//            store them into the neighbours' planes (NVLink), fence, and raise the neighbours' halo flags — while the rest
-//            of the grid is still drifting.
+//   phase A  lambda-scale, pending barostat scale, drift, wrap of the thread's atoms (k_kick_drift's arithmetic): read x,
+//            write x'.  Atoms WITHOUT listed partners (60-80 % of the gas) finish their step here: F = 0, v'' = u' =
+//            lambda*u stays in shared memory, their K5 terms are summed.  Multi-GPU: the blocks that own the pairs the
+//            neighbours see as ghosts take those first, store them into the neighbours' planes (NVLink), fence, and the last
+//            of them raises the neighbours' halo flags while the rest of the grid is still drifting.
 //   barrier  every drifted position is visible to the whole grid.
-//   phase B  only the atoms WITH listed partners, one per lane through the index list compacted at the last rebuild (every
-//            lane has gather work): pair forces, both half-kicks, K5 terms.  Multi-GPU: interior atoms first; the atoms
-//            whose lists hold ghosts wait for the neighbours' flags only when they get there.
+//   phase B  the thread's pairs with listed partners: pair forces (gathers from L2), both half-kicks, K5 terms; u' back to
+//            shared memory.  Multi-GPU: pairs whose lists hold no ghost first; the others wait for the neighbours' flags
+//            only when the block gets there.
 //   tail     block sums -> ticket -> the last block folds, exchanges the rank sums through the peer mailboxes, finalizes
 //            (T, P, lambda, myu, rebuild decision) and release-stores the step's sequence number; the other blocks wait for
 //            it and start the next step.
 //
-// Per-atom arithmetic is the same finish_atom()/drift_one()/pair term as in the two-kernel path.  Everything that another
-// block (or GPU) wrote during the launch is read with ld.global.cg (L2): the L1 is not coherent across SMs.
+// Per step and atom the kernel reads x (24 B), writes x' (24 B) and re-reads x' plus the list head (32 B, L2 hits) —
+// against 152 B of the two-kernel step.  Per-atom arithmetic is the same drift_one() / pair term / half-kick sequence.
+// Everything another block (or GPU) wrote during the launch is read with ld.global.cg (L2): the L1 is not coherent across SMs.
+//
+// (A first version walked a compacted list of the atoms with partners, one atom per lane, in phase B.  Measured on B200
+// (profiles/r02_loop_trace_v1.txt): 20.7 us for 3.5e5 active atoms — every scattered 8-byte access pulls a 32-byte sector,
+// the phase moved 4x the bytes of a coalesced pass.  Same finding as round 1's k_force_sparse.)
 constexpr int LOOP_BLOCK = 512;
-constexpr int LOOP_FACE_BLOCKS = 8;  // blocks that drift and push the face atoms first (multi-GPU)
+constexpr int LOOP_MAX_PAIRS = 9;         // pairs of atoms per thread whose velocities fit in shared memory (9 x 24 KB per block)
+constexpr int LOOP_GHOST_FLAG = 1 << 30;  // in the loop's copy of the list counts: the list holds a ghost atom
 
 struct LoopArgs {
     int n;                  // owned atoms
     int npad, cap;          // row stride and capacity of the neighbour table
+    int pairs_per_thread;   // P: thread (b, l) owns pairs (b*P + p)*LOOP_BLOCK + l, p < P
     Arrays a;
-    const int *nbr, *nbr_cnt;
-    const int *act_idx;     // atoms with >= 1 listed partner: [0, n_act[0]) interior, then n_act[1] whose lists hold ghosts
-    const int *n_act;       // (device) the two counts
+    const int *nbr;
+    const int *cntg;        // list counts (| LOOP_GHOST_FLAG on the multi-GPU path)
     double *partials;
     Scalars *sc;
     const Params *pr;
@@ -52,30 +60,102 @@ struct LoopCtl {
     int halted, half;
 };
 
-template <bool EXACT>
+// finish_atom() with the running sums in registers (same operations, same order per atom)
+__device__ __forceinline__ void finish_atom_r(Sums &s, const PairAcc &f, double &vx, double &vy, double &vz, double lambda,
+                                              double c, double mass, const double *shift, double &wx, double &wy, double &wz,
+                                              bool nh)
+{
+    vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(f.fx, c));  // v'' = lambda*u + F*c
+    vy = __dadd_rn(__dmul_rn(vy, lambda), __dmul_rn(f.fy, c));
+    vz = __dadd_rn(__dmul_rn(vz, lambda), __dmul_rn(f.fz, c));
+    wx = __dadd_rn(vx, __dmul_rn(f.fx, c));                     // u' = v'' + F*c
+    wy = __dadd_rn(vy, __dmul_rn(f.fy, c));
+    wz = __dadd_rn(vz, __dmul_rn(f.fz, c));
+    s.v[0] += mass * vx; s.v[1] += mass * vy; s.v[2] += mass * vz;
+    const double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
+    s.v[S_TH] += mass * (ax * ax + ay * ay + az * az);
+    s.v[S_KE] += mass * (vx * vx + vy * vy + vz * vz);
+    s.v[S_W] += f.w;
+    s.v[S_U] += f.u;
+    if (nh) {
+        s.v[S_MU] += mass * wx; s.v[S_MU + 1] += mass * wy; s.v[S_MU + 2] += mass * wz;
+        const double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
+        s.v[S_THU] += mass * (bx * bx + by * by + bz * bz);
+    }
+    s.v[S_MAX] = fmax(s.v[S_MAX], wx * wx + wy * wy + wz * wz);
+}
+
+// Block sums for a 16-warp block: lane tree, then the first warp folds the 16 warp results with a second lane tree (the
+// serial fold of block_reduce<> costs 1.9 us at 512 threads — measured, profiles/r02_loop_trace_v1.txt).  Result in thread 0.
+__device__ __forceinline__ void block_reduce_loop(Sums &s)
+{
+    static_assert(LOOP_BLOCK == 512, "16 warps");
+    __shared__ double sm[NSUM][16];
+    warp_reduce(s);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; ++q) sm[q][wid] = s.v[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < NSUM; ++q) {
+            double v = lane < 16 ? sm[q][lane] : 0.0;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const double w = __shfl_xor_sync(0xffffffffu, v, o);
+                v = q == NSUM - 1 ? fmax(v, w) : v + w;
+            }
+            s.v[q] = v;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool EXACT, bool USMEM>
 __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
 {
     extern __shared__ __align__(16) unsigned char loop_smem[];
-    SumsSmemT<LOOP_BLOCK> &ss = *reinterpret_cast<SumsSmemT<LOOP_BLOCK> *>(loop_smem);
+    double2 *su = reinterpret_cast<double2 *>(loop_smem);  // [3][P][LOOP_BLOCK]: ux, uy, uz of the thread's pairs
     __shared__ LoopCtl ctl;
+    __shared__ unsigned long long t_acc[5];  // block 0's phase clocks + step count (thread 0)
     const int tid = threadIdx.x, bid = blockIdx.x, nb = gridDim.x;
     Scalars *sc = A.sc;
     const Params *__restrict__ pr = A.pr;
     const Arrays &a = A.a;
     const ForceConsts &fc = A.fc;
-    const int n = A.n;
+    const int n = A.n, P = A.pairs_per_thread;
     const int npairs = (n + 1) >> 1;
     const bool multi = A.peers != nullptr;
     // face pairs: every pair that holds an atom of the prefix [0, m0) or of the suffix [n - m1, n)
     const int pl = multi ? min((A.h.m[0] + 1) >> 1, npairs) : 0;
     const int pr0 = multi ? max(min((n - A.h.m[1]) >> 1, npairs), pl) : npairs;
-    const int nface = pl + (npairs - pr0);
-    const int nfb = min(LOOP_FACE_BLOCKS, nb);
     const bool nh = pr->th_kind == 2;
     const double dt = pr->dt, hc = fc.hc, mass = fc.mass;
     const PairAcc zero = {0.0, 0.0, 0.0, 0.0, 0.0};
-    __shared__ unsigned long long t_acc[5];  // block 0's phase clocks + step count (thread 0)
     if (tid == 0) { t_acc[0] = t_acc[1] = t_acc[2] = t_acc[3] = t_acc[4] = 0ull; }
+    // pair p of this thread, and where its velocity lives
+    auto pair_of = [&](int p) { return (bid * P + p) * LOOP_BLOCK + tid; };
+    auto ld_u = [&](int p, int t, double2 &ux, double2 &uy, double2 &uz) {
+        if (USMEM) {
+            ux = su[(0 * P + p) * LOOP_BLOCK + tid]; uy = su[(1 * P + p) * LOOP_BLOCK + tid]; uz = su[(2 * P + p) * LOOP_BLOCK + tid];
+        } else {
+            ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t); uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t);
+            uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
+        }
+    };
+    auto st_u = [&](int p, int t, bool has1, const double2 &ux, const double2 &uy, const double2 &uz) {
+        if (USMEM) {
+            su[(0 * P + p) * LOOP_BLOCK + tid] = ux; su[(1 * P + p) * LOOP_BLOCK + tid] = uy; su[(2 * P + p) * LOOP_BLOCK + tid] = uz;
+        } else if (has1) {
+            reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
+            reinterpret_cast<double2 *>(a.vz)[t] = uz;
+        } else {  // odd tail: the slot after it may belong to a ghost atom
+            a.vx[2 * t] = ux.x; a.vy[2 * t] = uy.x; a.vz[2 * t] = uz.x;
+        }
+    };
+    bool loaded = false;
 
     for (long long it = 0; it < A.max_steps; ++it) {
         // ---- step controls: written by the last finalize before its release, uniform over the grid ----------------------
@@ -95,71 +175,69 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         MD_TRACE(bid == 0 && tid == 0, 0);
         const double lambda = ctl.lambda, mup = ctl.mup, Lx = ctl.Lx, Ly = ctl.Ly, Lz = ctl.Lz;
         const double *shift = ctl.shift;
-        const bool half = ctl.half != 0;
         const bool store_state = ctl.steps_left <= 1;  // last step of the batch: the resident State must be complete
+        if (!loaded) {
+            // first step of the launch: velocities into shared memory, with the first half-kick of a batch
+            // (integrator.rs:28-34) when the planes hold v and not u = v + F c
+            const bool half = ctl.half != 0;
+            for (int p = 0; p < P; ++p) {
+                const int t = pair_of(p);
+                if (t >= npairs) break;
+                const bool has1 = 2 * t + 1 < n;
+                double2 ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t), uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t),
+                        uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
+                if (!half) {
+                    const double2 fx = __ldcg(reinterpret_cast<const double2 *>(a.fx) + t),
+                                  fy = __ldcg(reinterpret_cast<const double2 *>(a.fy) + t),
+                                  fz = __ldcg(reinterpret_cast<const double2 *>(a.fz) + t);
+                    ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, hc)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, hc));
+                    uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, hc)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, hc));
+                    uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, hc)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, hc));
+                }
+                if (USMEM || !half) st_u(p, t, has1, ux, uy, uz);
+            }
+            loaded = true;
+        }
+        Sums s;
 #pragma unroll
-        for (int q = 0; q < NSUM; ++q) ss.v[q][tid] = 0.0;
+        for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
 
         // ---- phase A ----------------------------------------------------------------------------------------------------
-        auto drift_pair = [&](int t, bool face) {
+        auto drift_pair = [&](int p, int t, bool face) {
             const int i0 = 2 * t;
-            if (i0 + 1 >= n) {  // odd tail: one atom, scalar accesses (the slot after it may belong to a ghost atom)
-                double ux = __ldcg(a.vx + i0), uy = __ldcg(a.vy + i0), uz = __ldcg(a.vz + i0);
-                if (!half) {
-                    ux = __dadd_rn(ux, __dmul_rn(__ldcg(a.fx + i0), hc)); uy = __dadd_rn(uy, __dmul_rn(__ldcg(a.fy + i0), hc));
-                    uz = __dadd_rn(uz, __dmul_rn(__ldcg(a.fz + i0), hc));
-                }
-                double x = __ldcg(a.x + i0), y = __ldcg(a.y + i0), z = __ldcg(a.z + i0);
-                drift_one(x, ux, lambda, mup, dt, Lx); drift_one(y, uy, lambda, mup, dt, Ly); drift_one(z, uz, lambda, mup, dt, Lz);
-                a.x[i0] = x; a.y[i0] = y; a.z[i0] = z;
-                if (face) push_atom(A.h, i0, n, x, y, z);
-                if (A.nbr_cnt[i0] == 0) {
-                    double wx, wy, wz;
-                    finish_atom(ss, zero, ux, uy, uz, true, lambda, hc, mass, shift, wx, wy, wz, nh);
-                    ux = wx; uy = wy; uz = wz;
-                    if (store_state) { a.fx[i0] = 0.0; a.fy[i0] = 0.0; a.fz[i0] = 0.0; a.u[i0] = 0.0; a.w[i0] = 0.0; }
-                }
-                a.vx[i0] = ux; a.vy[i0] = uy; a.vz[i0] = uz;
-                return;
-            }
+            const bool has1 = i0 + 1 < n;
             double2 x = __ldcg(reinterpret_cast<const double2 *>(a.x) + t), y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t),
                     z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
-            double2 ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t), uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t),
-                    uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
-            const int2 C = reinterpret_cast<const int2 *>(A.nbr_cnt)[t];
-            if (!half) {  // integrator.rs:28-34 on the first step of a batch
-                const double2 fx = __ldcg(reinterpret_cast<const double2 *>(a.fx) + t),
-                              fy = __ldcg(reinterpret_cast<const double2 *>(a.fy) + t),
-                              fz = __ldcg(reinterpret_cast<const double2 *>(a.fz) + t);
-                ux.x = __dadd_rn(ux.x, __dmul_rn(fx.x, hc)); ux.y = __dadd_rn(ux.y, __dmul_rn(fx.y, hc));
-                uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, hc)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, hc));
-                uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, hc)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, hc));
-            }
+            int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+            double2 ux, uy, uz;
+            ld_u(p, t, ux, uy, uz);
             drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
             drift_one(y.x, uy.x, lambda, mup, dt, Ly); drift_one(y.y, uy.y, lambda, mup, dt, Ly);
             drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
-            reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
-            reinterpret_cast<double2 *>(a.z)[t] = z;
+            if (has1) {
+                reinterpret_cast<double2 *>(a.x)[t] = x; reinterpret_cast<double2 *>(a.y)[t] = y;
+                reinterpret_cast<double2 *>(a.z)[t] = z;
+            } else {
+                a.x[i0] = x.x; a.y[i0] = y.x; a.z[i0] = z.x;
+                C.y = 1;  // (not an atom: nothing to finish)
+            }
             if (face) {
                 push_atom(A.h, i0, n, x.x, y.x, z.x);
-                push_atom(A.h, i0 + 1, n, x.y, y.y, z.y);
+                if (has1) push_atom(A.h, i0 + 1, n, x.y, y.y, z.y);
             }
             // atoms without listed partners: F = 0, the step ends here (v'' = u' = lambda*u); the others keep u for phase B
             const bool s0 = C.x == 0, s1 = C.y == 0;
             if (s0) {
                 double wx, wy, wz;
-                finish_atom(ss, zero, ux.x, uy.x, uz.x, true, lambda, hc, mass, shift, wx, wy, wz, nh);
+                finish_atom_r(s, zero, ux.x, uy.x, uz.x, lambda, hc, mass, shift, wx, wy, wz, nh);
                 ux.x = wx; uy.x = wy; uz.x = wz;
             }
             if (s1) {
                 double wx, wy, wz;
-                finish_atom(ss, zero, ux.y, uy.y, uz.y, true, lambda, hc, mass, shift, wx, wy, wz, nh);
+                finish_atom_r(s, zero, ux.y, uy.y, uz.y, lambda, hc, mass, shift, wx, wy, wz, nh);
                 ux.y = wx; uy.y = wy; uz.y = wz;
             }
-            if (!half || s0 || s1) {
-                reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
-                reinterpret_cast<double2 *>(a.vz)[t] = uz;
-            }
+            if (s0 || s1) st_u(p, t, has1, ux, uy, uz);
             if (store_state) {
                 if (s0 && s1) {
                     const double2 z2 = make_double2(0.0, 0.0);
@@ -168,33 +246,54 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                     reinterpret_cast<double2 *>(a.w)[t] = z2;
                 } else {
                     if (s0) { a.fx[i0] = 0.0; a.fy[i0] = 0.0; a.fz[i0] = 0.0; a.u[i0] = 0.0; a.w[i0] = 0.0; }
-                    if (s1) { a.fx[i0 + 1] = 0.0; a.fy[i0 + 1] = 0.0; a.fz[i0 + 1] = 0.0; a.u[i0 + 1] = 0.0; a.w[i0 + 1] = 0.0; }
+                    if (s1 && has1) { a.fx[i0 + 1] = 0.0; a.fy[i0 + 1] = 0.0; a.fz[i0 + 1] = 0.0; a.u[i0 + 1] = 0.0; a.w[i0 + 1] = 0.0; }
                 }
             }
         };
-        if (multi && bid < nfb) {
-            // face atoms first; once every face block's stores are fenced system-wide, the last of them raises the flags
-            for (int q = bid * LOOP_BLOCK + tid; q < nface; q += nfb * LOOP_BLOCK) drift_pair(q < pl ? q : pr0 + (q - pl), true);
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence_system();
-                const unsigned int old = atomicAdd(&sc->face_arrive[0], 1u);
-                if (old == (unsigned int)nfb - 1u) {
-                    __threadfence_system();
-                    st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are the left neighbour's right side
-                    st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
+        const auto is_face = [&](int t) { return t < pl || t >= pr0; };
+        if (multi) {
+            // Face pairs first, in every block that owns some (which blocks do follows from the fixed pair -> thread map:
+            // blocks [0, (pl - 1) / (P*512)] and the blocks from pr0 / (P*512) on); they fence their stores system-wide and
+            // count in; the last of them raises the neighbours' flags.
+            const int per_block = P * LOOP_BLOCK;
+            const int b_last = npairs > 0 ? (npairs - 1) / per_block : 0;
+            const int lo_end = pl > 0 ? (pl - 1) / per_block : -1;        // last block with left-face pairs
+            const int hi_begin = pr0 < npairs ? pr0 / per_block : b_last + 1;  // first block with right-face pairs
+            const bool owns_face = bid <= lo_end || (bid >= hi_begin && bid <= b_last);
+            const int n_face_blocks = (lo_end + 1) + (b_last - hi_begin + 1) - max(0, lo_end - hi_begin + 1);
+            if (owns_face) {
+                for (int p = 0; p < P; ++p) {
+                    const int t = pair_of(p);
+                    if (t < npairs && is_face(t)) drift_pair(p, t, true);
                 }
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence_system();
+                    const unsigned int old = atomicAdd(&sc->face_arrive[0], 1u);
+                    if (old == (unsigned int)n_face_blocks - 1u) {
+                        __threadfence_system();
+                        st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
+                        st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
+                    }
+                }
+            } else if (n_face_blocks == 0 && bid == 0 && tid == 0) {
+                // nothing to push this epoch: the neighbours still wait for the flags
+                st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);
+                st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
             }
         }
-        for (int r = bid * LOOP_BLOCK + tid; r < pr0 - pl; r += nb * LOOP_BLOCK) drift_pair(pl + r, false);
+        for (int p = 0; p < P; ++p) {
+            const int t = pair_of(p);
+            if (t < npairs && !is_face(t)) drift_pair(p, t, false);
+        }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[0] += t - tq; tq = t; }
         MD_TRACE(bid == 0 && tid == 0, 1);
 
-        // ---- mid-step barrier: all drifted positions (and first-step half-kicks) are visible grid-wide ------------------
+        // ---- mid-step barrier: all drifted positions are visible grid-wide -------------------------------------------------
         __syncthreads();
-        if (tid == 0) {
+        if (nb > 1 && tid == 0) {
             // release: this block's drifted positions (the bar.sync above makes the release cumulative over its threads);
-            // the acquiring loads below also invalidate this SM's L1
+            // the acquiring loads also invalidate this SM's L1
             atom_add_release_gpu(&sc->bar_arrive, 1u);
             while (ld_acquire_gpu(&sc->bar_arrive) < (unsigned int)nb) { }
         }
@@ -207,66 +306,76 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         c.Lx = Lx; c.Ly = Ly; c.Lz = Lz;
         c.hx = Lx / 2.0; c.hy = Ly / 2.0; c.hz = Lz / 2.0;
         c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
-        auto force_atom = [&](int i) {
-            const double xi = __ldcg(a.x + i), yi = __ldcg(a.y + i), zi = __ldcg(a.z + i);
-            double vx = __ldcg(a.vx + i), vy = __ldcg(a.vy + i), vz = __ldcg(a.vz + i);
-            const int cnt = A.nbr_cnt[i];
-            PairAcc f = zero;
-            // partners in groups of four: the four indices are fetched together, then the twelve coordinates, then the pair
-            // terms — two dependent memory round trips per group instead of two per partner
-            for (int k0 = 0; k0 < cnt; k0 += 4) {
-                int j[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) j[u] = k0 + u < cnt ? A.nbr[(size_t)(k0 + u) * A.npad + i] : i;
-                double xj[4], yj[4], zj[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { xj[u] = __ldcg(a.x + j[u]); yj[u] = __ldcg(a.y + j[u]); zj[u] = __ldcg(a.z + j[u]); }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u < cnt) {
-                        if (EXACT) pair_exact(f, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
-                        else pair_fast_branchy(f, true, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
-                    }
+        const size_t stride = (size_t)A.npad;
+        auto force_pair = [&](int p, int t, int2 C) {
+            const int i0 = 2 * t;
+            const bool has1 = i0 + 1 < n;
+            const double2 X = __ldcg(reinterpret_cast<const double2 *>(a.x) + t), Y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t),
+                          Z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
+            int2 J = reinterpret_cast<const int2 *>(A.nbr)[t];  // row 0
+            double2 ux, uy, uz;
+            ld_u(p, t, ux, uy, uz);
+            PairAcc f0 = zero, f1 = zero;
+            const int kmax = max(C.x, C.y);
+            for (int k = 0; k < kmax; ++k) {
+                const bool a0 = k < C.x, a1 = k < C.y;
+                const int j0 = a0 ? J.x : i0, j1 = a1 ? J.y : i0;
+                if (k + 1 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 1) * stride + i0);
+                const double xa = __ldcg(a.x + j0), ya = __ldcg(a.y + j0), za = __ldcg(a.z + j0);
+                const double xb = __ldcg(a.x + j1), yb = __ldcg(a.y + j1), zb = __ldcg(a.z + j1);
+                if (EXACT) {
+                    if (a0) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+                    if (a1) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                } else {
+                    pair_fast_branchy(f0, a0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+                    pair_fast_branchy(f1, a1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
                 }
             }
-            double wx, wy, wz;
-            finish_atom(ss, f, vx, vy, vz, true, lambda, hc, mass, shift, wx, wy, wz, nh);
+            double2 wx = ux, wy = uy, wz = uz;
+            if (C.x > 0) finish_atom_r(s, f0, ux.x, uy.x, uz.x, lambda, hc, mass, shift, wx.x, wy.x, wz.x, nh);
+            if (C.y > 0) finish_atom_r(s, f1, ux.y, uy.y, uz.y, lambda, hc, mass, shift, wx.y, wy.y, wz.y, nh);
+            // (an atom of the pair without partners was finished in phase A: ux == wx holds its lambda*u already)
             if (store_state) {
-                a.fx[i] = f.fx; a.fy[i] = f.fy; a.fz[i] = f.fz; a.u[i] = f.u; a.w[i] = f.w;
-                a.vx[i] = vx; a.vy[i] = vy; a.vz[i] = vz;
+                if (C.x > 0) { a.fx[i0] = f0.fx; a.fy[i0] = f0.fy; a.fz[i0] = f0.fz; a.u[i0] = f0.u; a.w[i0] = f0.w; }
+                if (C.y > 0) { a.fx[i0 + 1] = f1.fx; a.fy[i0 + 1] = f1.fy; a.fz[i0 + 1] = f1.fz; a.u[i0 + 1] = f1.u; a.w[i0 + 1] = f1.w; }
+                st_u(p, t, has1, ux, uy, uz);   // v''
             } else {
-                a.vx[i] = wx; a.vy[i] = wy; a.vz[i] = wz;
+                st_u(p, t, has1, wx, wy, wz);   // u'
             }
         };
-        const int n_int = A.n_act[0], n_bnd = A.n_act[1];
-        for (int k = bid * LOOP_BLOCK + tid; k < n_int; k += nb * LOOP_BLOCK) force_atom(A.act_idx[k]);
-        if (multi) {
-            // the neighbours' ghosts of this step (their face blocks fenced the stores before raising the flag)
-            __shared__ int halo_late;
-            if (tid == 0) {
-                const Mail *own = A.peers->mail[A.peers->rank];
-                const unsigned long long tw = gtime();
-                const unsigned long long seq = ctl.epoch + 1;
-                halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
-                if (bid == 0) sc->wait_halo_ns += gtime() - tw;
+        for (int pass = 0; pass < (multi ? 2 : 1); ++pass) {
+            if (pass == 1) {
+                // the neighbours' ghosts of this step (their face blocks fenced the stores before raising the flag)
+                __shared__ int halo_late;
+                if (tid == 0) {
+                    const Mail *own = A.peers->mail[A.peers->rank];
+                    const unsigned long long tw = gtime();
+                    const unsigned long long seq = ctl.epoch + 1;
+                    halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
+                    if (bid == 0) sc->wait_halo_ns += gtime() - tw;
+                }
+                __syncthreads();
+                if (halo_late && tid == 0) atomicExch(&sc->error, 3);
             }
-            __syncthreads();
-            if (halo_late && tid == 0) atomicExch(&sc->error, 3);
-            for (int k = bid * LOOP_BLOCK + tid; k < n_bnd; k += nb * LOOP_BLOCK) force_atom(A.act_idx[n_int + k]);
+            for (int p = 0; p < P; ++p) {
+                const int t = pair_of(p);
+                if (t >= npairs) break;
+                int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+                if (2 * t + 1 >= n) C.y = 0;
+                const int ghost = ((C.x | C.y) & LOOP_GHOST_FLAG) ? 1 : 0;
+                C.x &= ~LOOP_GHOST_FLAG; C.y &= ~LOOP_GHOST_FLAG;
+                if ((C.x | C.y) != 0 && ghost == pass) force_pair(p, t, C);
+            }
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[2] += t - tq; tq = t; }
         MD_TRACE(bid == 0 && tid == 0, 3);
 
         // ---- tail: block sums, ticket, last block folds + finalizes + releases -------------------------------------------
-        Sums s;
-#pragma unroll
-        for (int q = 0; q < NSUM; ++q) s.v[q] = ss.v[q][tid];
-        block_reduce<LOOP_BLOCK>(s);
+        block_reduce_loop(s);
         MD_TRACE(bid == 0 && tid == 0, 4);
         const bool last = publish_and_ticket<LOOP_BLOCK>(s, A.partials, sc);
         MD_TRACE(bid == 0 && tid == 0, 5);
-        if (last)
-            last_block_finalize<LOOP_BLOCK>(A.partials, sc, pr, FIN_STEP | (multi ? FIN_P2P : 0), A.peers);
+        if (last) last_block_finalize<LOOP_BLOCK, true>(A.partials, sc, pr, FIN_STEP | (multi ? FIN_P2P : 0), A.peers);
         if (tid == 0) {
             const unsigned long long fin_seq0 = ctl.fin_seq;
             while (ld_acquire_gpu(&sc->fin_seq) <= fin_seq0) { }
@@ -276,6 +385,22 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         __syncthreads();
         MD_TRACE(bid == 0 && tid == 0, 6);
     }
+    if (USMEM && loaded) {
+        // the loop is over (rebuild, end of the batch, error or max_steps): the velocities go back to the planes — u, or v''
+        // after the last step of a batch, exactly what the two-kernel step leaves there
+        for (int p = 0; p < P; ++p) {
+            const int t = pair_of(p);
+            if (t >= npairs) break;
+            const double2 ux = su[(0 * P + p) * LOOP_BLOCK + tid], uy = su[(1 * P + p) * LOOP_BLOCK + tid],
+                          uz = su[(2 * P + p) * LOOP_BLOCK + tid];
+            if (2 * t + 1 < n) {
+                reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
+                reinterpret_cast<double2 *>(a.vz)[t] = uz;
+            } else {
+                a.vx[2 * t] = ux.x; a.vy[2 * t] = uy.x; a.vz[2 * t] = uz.x;
+            }
+        }
+    }
     if (bid == 0 && tid == 0 && t_acc[4]) {
         // (the last finalize of this launch is complete: nobody else writes these words)
 #pragma unroll
@@ -284,24 +409,12 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     }
 }
 
-// flags for the two compacted index lists of the loop: atoms with listed partners, split by "does the list hold a ghost"
-__global__ void k_flag_active(int n, const int *__restrict__ nbr_cnt, const int *__restrict__ has_ghost, int want_ghost,
-                              int *__restrict__ flag)
+// the loop's copy of the list counts on one GPU is nbr_cnt itself; on the multi-GPU path the builder ORs in LOOP_GHOST_FLAG
+__global__ void k_counts_with_ghost_flag(int n, const int *__restrict__ nbr_cnt, const int *__restrict__ has_ghost,
+                                         int *__restrict__ cntg)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int g = has_ghost ? (has_ghost[i] != 0) : 0;
-    flag[i] = (nbr_cnt[i] > 0 && g == want_ghost) ? 1 : 0;
-}
-
-// idx[base[0] + pos[i]] = i for flagged i; the count of this class goes to count_out[0]
-__global__ void k_compact_active(int n, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ base,
-                                 int *__restrict__ idx, int *__restrict__ count_out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = base ? base[0] : 0;
-    if (i < n && flag[i]) idx[b + pos[i]] = i;
-    if (i == 0) count_out[0] = pos[n];
+    if (i < n) cntg[i] = nbr_cnt[i] | ((has_ghost[i] && nbr_cnt[i] > 0) ? LOOP_GHOST_FLAG : 0);
 }
 
 }  // namespace md

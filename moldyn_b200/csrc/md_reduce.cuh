@@ -210,10 +210,14 @@ __device__ __forceinline__ bool publish_and_ticket(const Sums &mine, double *__r
 // (2) The last block folds the per-block partials in a fixed order, exchanges the rank sums with the other GPUs (FIN_P2P),
 //     finalizes the step controls, resets the ticket and release-stores the new sequence number sc->fin_seq — the
 //     end-of-step barrier the other blocks of the persistent step loop wait on.
-template <int BLOCK>
+// WARPFOLD (blocks of >= 12 warps, grids of a few hundred blocks — the persistent step loop): warp q sums slot q, lane l
+// taking blocks l, l + 32, ... in ascending order, then a lane tree — one L2 round trip and five shuffles; the generic fold's
+// serial walk over its BLOCK/6 groups costs 2.4 us at 512 threads (measured, profiles/r02_loop_trace_v1.txt).
+template <int BLOCK, bool WARPFOLD = false>
 __device__ __forceinline__ void last_block_finalize(double *__restrict__ partials, Scalars *sc, const Params *pr, int mode,
                                                     const Peers *peers_p)
 {
+    static_assert(!WARPFOLD || BLOCK >= 32 * NSUM, "one warp per slot");
     MD_TRACE(threadIdx.x == 0, 8);
     // (a) A copy of the control words and parameters finalize reads goes to shared memory — those loads are in flight
     // together with (b) the fold of the per-block partials: thread (g, q) adds slot q of blocks g, g+G, g+2G, … in ascending
@@ -222,7 +226,7 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
     constexpr int H = NSUM / 2;   // slot pairs: 128-bit loads
     constexpr int G = BLOCK / H;  // groups of blocks
     static_assert(NSUM % 2 == 0, "slots are folded in pairs");
-    __shared__ double fold[G][NSUM];
+    __shared__ double fold[WARPFOLD ? 1 : G][NSUM];
     __shared__ double folded[NSUM];
     __shared__ Scalars sc_in;
     __shared__ Params pr_in;
@@ -237,7 +241,22 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
             else sp_[w - WS] = __ldcg(gp + (w - WS));
         }
     }
-    {
+    if (WARPFOLD) {
+        const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+        if (q < NSUM) {
+            double v = 0.0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) {
+                const double w = __ldcg(partials + (size_t)b * NSUM + q);
+                v = q == NSUM - 1 ? fmax(v, w) : v + w;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double w = __shfl_xor_sync(0xffffffffu, v, o);
+                v = q == NSUM - 1 ? fmax(v, w) : v + w;
+            }
+            if (lane == 0) folded[q] = v;
+        }
+    } else {
         const int h = threadIdx.x % H, g = threadIdx.x / H;
         if (g < G) {
             const bool has_max = (h == H - 1);  // the last slot of the last pair is the running maximum
@@ -273,13 +292,13 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
         }
     }
     __syncthreads();
-    if (threadIdx.x < NSUM) {
+    if (!WARPFOLD && threadIdx.x < NSUM) {
         const int q = threadIdx.x;
         double a = fold[0][q];
         for (int g = 1; g < G; ++g) a = (q == NSUM - 1) ? fmax(a, fold[g][q]) : a + fold[g][q];
         folded[q] = a;
     }
-    __syncthreads();
+    if (!WARPFOLD) __syncthreads();
     Sums acc;
     if (threadIdx.x == 0) {
 #pragma unroll

@@ -1,0 +1,443 @@
+// md_tile.cuh — K2 + K3 for dense systems (FAST mode, one GPU): brick tiles staged in shared memory by TMA bulk copies,
+// brick-local 16-bit neighbour lists, warp-cooperative pair loop with shuffle accumulation.
+// Part of md_kernels.cuh (included from there, in order; one translation unit).
+#pragma once
+
+namespace md {
+
+// Why (profiles/r01_ncu_c5_v10_k_force.txt): the per-thread Verlet loop of k_force<.., MASKED> gathers every partner from
+// global memory — one L1 wavefront per lane and partner, l1tex data pipe 74 % busy on average and 89 % on the busiest SM,
+// FP64 pipe a third busy.  Here a thread block owns a BRICK of the cell grid (4 x 4 columns x bz cells, a few hundred atoms)
+// and stages the brick plus the two-cell shell around it — every possible partner of its atoms, ~8 x the brick — in shared
+// memory once: the cell sort numbers the (x, y) columns brick by brick (Grid::brick), so the shell is 64 columns x (one or
+// two) contiguous z-runs of the sorted planes, fetched with cp.async.bulk (UBLKCP) and an mbarrier.  The lists hold
+// 16-bit indices into the shell, stored atom-major; the 32 lanes of a warp walk ONE atom's list together (coalesced index
+// reads, shared-memory gathers of mostly consecutive slots: conflict-free), four independent pair terms per lane in flight,
+// and fold their partial forces with xor-shuffles in a fixed order (deterministic).  Periodic images are resolved when the
+// shell is staged (the wrapped runs get +-L added in shared memory), so the pair loop has no minimum-image step at all.
+// The K2 kernel stages the same shell (same code, same local indices) and evaluates the reference's predicate
+// (potential.rs:181-204 widened by the skin) in the reference's own operation order on the unshifted coordinates.
+constexpr int TILE_BLOCK = 256;
+constexpr int TILE_WARPS = TILE_BLOCK / 32;
+constexpr int TILE_WIN = 8;                          // window columns per dimension: 4 own + 2 on either side
+constexpr int TILE_COLS = TILE_WIN * TILE_WIN;       // 64
+constexpr int TILE_RUNS = 2 * TILE_COLS;             // per column: the unwrapped z-run and the periodically wrapped one
+constexpr int TILE_MIN_CELLS = 8;                    // cells per dimension the brick order needs (a window never meets itself)
+
+struct TileTab {
+    int run_src[TILE_RUNS];   // sorted index of the run's first atom
+    int run_len[TILE_RUNS];
+    int run_loc[TILE_RUNS];   // shell slot of the run's first atom
+    int cp_src[TILE_RUNS];    // bulk copy: first element (even), element count (even), first slot (even)
+    int cp_cnt[TILE_RUNS];
+    int cp_dst[TILE_RUNS];
+    int col_base[TILE_COLS];  // first cell of the window column in the cell table
+    double shx[TILE_COLS], shy[TILE_COLS];  // image shift of the window column (-L, 0, +L)
+    double shz;               // image shift of the wrapped z-runs (odd run index)
+    int own_src[16], own_loc[16], own_pref[17];
+    int n_shell, n_own;
+    int zlo, zhi;             // own z cells [zlo, zhi)
+};
+
+// Brick `id` → its tables.  Block-wide (>= 64 threads); ends with a barrier.  `measure`: sizes only.
+__device__ __forceinline__ void tile_setup(TileTab &T, const Grid &g, const int *__restrict__ cell_start, const Scalars *sc,
+                                           int id)
+{
+    const int t = threadIdx.x;
+    const int ncx = g.nc[0], ncy = g.nc[1], ncz = g.nc[2];
+    const int bzc = id % g.nbz, bxy = id / g.nbz, by = bxy % g.nby, bx = bxy / g.nby;
+    const int zlo = g.bz * bzc, zhi = min(g.bz * (bzc + 1), ncz);
+    const int uz0 = zlo - 2, uz1 = zhi + 2;  // window along z, unwrapped cell coordinates
+    if (t < TILE_COLS) {
+        const int wx = t >> 3, wy = t & 7;
+        const int ux = 4 * bx - 2 + wx, uy = 4 * by - 2 + wy;
+        const int sxc = ux < 0 ? -1 : (ux >= ncx ? 1 : 0), syc = uy < 0 ? -1 : (uy >= ncy ? 1 : 0);
+        const int cx = ux - sxc * ncx, cy = uy - syc * ncy;
+        const int base = col_index(g, cx, cy) * ncz;
+        T.col_base[t] = base;
+        T.shx[t] = sxc < 0 ? -sc->box[0] : (sxc > 0 ? sc->box[0] : 0.0);
+        T.shy[t] = syc < 0 ? -sc->box[1] : (syc > 0 ? sc->box[1] : 0.0);
+        const int zA0 = max(uz0, 0), zA1 = min(uz1, ncz);
+        int zB0 = 0, zB1 = 0;
+        if (uz0 < 0) { zB0 = uz0 + ncz; zB1 = ncz; }
+        else if (uz1 > ncz) { zB0 = 0; zB1 = uz1 - ncz; }
+        const int sA = cell_start[base + zA0], eA = cell_start[base + zA1];
+        const int sB = zB1 > zB0 ? cell_start[base + zB0] : 0, eB = zB1 > zB0 ? cell_start[base + zB1] : 0;
+        T.run_src[2 * t] = sA; T.run_len[2 * t] = eA - sA;
+        T.run_src[2 * t + 1] = sB; T.run_len[2 * t + 1] = eB - sB;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int s = h ? sB : sA, e = h ? eB : eA;
+            // 16-byte granules of the planes: the copy starts at an even element and has an even length
+            T.cp_src[2 * t + h] = s & ~1;
+            T.cp_cnt[2 * t + h] = e > s ? ((e + 1) & ~1) - (s & ~1) : 0;
+        }
+        if (t == 0) {
+            T.shz = uz0 < 0 ? -sc->box[2] : sc->box[2];
+            T.zlo = zlo; T.zhi = zhi;
+        }
+    }
+    __syncthreads();
+    if (t < 32) {  // exclusive scan of the 128 copy lengths: four runs per lane
+        int c[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c[k] = T.cp_cnt[4 * t + k]; sum += c[k]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= o) inc += v;
+        }
+        int off = inc - sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = 4 * t + k;
+            T.cp_dst[r] = off;
+            T.run_loc[r] = off + (T.run_src[r] & 1);
+            off += c[k];
+        }
+        if (t == 31) T.n_shell = inc;
+    }
+    __syncthreads();
+    if (t < 16) {
+        const int lx = t >> 2, ly = t & 3;
+        const bool exists = 4 * bx + lx < ncx && 4 * by + ly < ncy;
+        const int wcol = (lx + 2) * TILE_WIN + (ly + 2), rA = 2 * wcol;
+        const int base = T.col_base[wcol];
+        const int s = exists ? cell_start[base + zlo] : 0, e = exists ? cell_start[base + zhi] : 0;
+        T.own_src[t] = s;
+        T.own_loc[t] = T.run_loc[rA] + (s - T.run_src[rA]);
+        T.own_pref[t + 1] = e - s;  // counts for now
+    }
+    __syncthreads();
+    if (t == 0) {
+        int acc = 0;
+        T.own_pref[0] = 0;
+        for (int k = 0; k < 16; ++k) { acc += T.own_pref[k + 1]; T.own_pref[k + 1] = acc; }
+        T.n_own = acc;
+    }
+    __syncthreads();
+}
+
+// Largest shell and brick of the current sort: sizes the tile kernels' shared memory.
+__global__ void __launch_bounds__(64) k_tile_measure(Grid g, const int *__restrict__ cell_start, Scalars *sc)
+{
+    __shared__ TileTab T;
+    tile_setup(T, g, cell_start, sc, blockIdx.x);
+    if (threadIdx.x == 0) {
+        atomicMax(&sc->tile_shell_max, T.n_shell);
+        atomicMax(&sc->tile_own_max, T.n_own);
+    }
+}
+
+__global__ void k_tile_reset(Scalars *sc)
+{
+    sc->tile_shell_max = 0;
+    sc->tile_own_max = 0;
+}
+
+// Stages the shell: x, y, z planes of every run → sx, sy, sz (sh_cap doubles each), cp.async.bulk + mbarrier.  `shift`:
+// add the periodic image shifts in place afterwards (force kernel); the list builder keeps the stored coordinates.
+__device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, double *sx, double *sy, double *sz,
+                                           unsigned long long *bar, bool shift)
+{
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)T.n_shell * 24u);
+    }
+    __syncthreads();
+    if (t < 32) {
+        for (int r = t; r < TILE_RUNS; r += 32) {
+            const int cnt = T.cp_cnt[r];
+            if (cnt > 0) {
+                const int s = T.cp_src[r], d = T.cp_dst[r];
+                tma_load_1d(sx + d, a.x + s, (unsigned)cnt * 8u, bar);
+                tma_load_1d(sy + d, a.y + s, (unsigned)cnt * 8u, bar);
+                tma_load_1d(sz + d, a.z + s, (unsigned)cnt * 8u, bar);
+            }
+        }
+    }
+    mbar_wait(bar, 0u);
+    if (shift) {
+        __syncthreads();
+        const int w = t >> 5, lane = t & 31;
+        for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
+            const int len = T.run_len[r];
+            if (len == 0) continue;
+            const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
+            if (dx == 0.0 && dy == 0.0 && dz == 0.0) continue;
+            const int loc = T.run_loc[r];
+            for (int e = lane; e < len; e += 32) {
+                sx[loc + e] += dx; sy[loc + e] += dy; sz[loc + e] += dz;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// brick atom a (0 <= a < n_own) → own column, shell slot, sorted index
+__device__ __forceinline__ void tile_locate(const TileTab &T, int a, int &oc, int &slot, int &gi)
+{
+    oc = 0;
+#pragma unroll
+    for (int step = 8; step > 0; step >>= 1)
+        if (a >= T.own_pref[oc + step]) oc += step;
+    const int k = a - T.own_pref[oc];
+    slot = T.own_loc[oc] + k;
+    gi = T.own_src[oc] + k;
+}
+
+// K2, tile form.  One block per brick; a warp takes an atom, its lanes scan the 25 stencil columns' candidates (one
+// contiguous range of shell slots per column and z part), ballot-compact the hits and write the atom's list: 16-bit shell
+// slots, ascending, atom-major (nbrT[i * cap + k]).
+__global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, const int *__restrict__ cell_start,
+                                                           const int *__restrict__ cell_sorted, Scalars *sc, double r_list,
+                                                           double r2_list, unsigned short *__restrict__ nbrT, int cap,
+                                                           int *__restrict__ nbr_cnt, const int *__restrict__ brick_order,
+                                                           int sh_cap)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    double *sx = reinterpret_cast<double *>(tile_smem), *sy = sx + sh_cap, *sz = sy + sh_cap;
+    __shared__ TileTab T;
+    __shared__ __align__(8) unsigned long long bar;
+    tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
+    tile_stage(T, a, sx, sy, sz, &bar, false);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncz = g.nc[2];
+    int wmax = 0;
+    unsigned long long wsum = 0ull;
+    for (int ai = warp; ai < T.n_own; ai += TILE_WARPS) {
+        int oc, slot, gi;
+        tile_locate(T, ai, oc, slot, gi);
+        const double xi = sx[slot], yi = sy[slot], zi = sz[slot];
+        const int cz = cell_sorted[gi] % ncz;
+        const int lx = oc >> 2, ly = oc & 3;
+        // lane l < 25 prepares stencil column l: slot ranges of the unwrapped and of the wrapped z part
+        int sA = 0, eA = 0, sB = 0, eB = 0;
+        double shx = 0.0, shy = 0.0;
+        if (lane < 25) {
+            const int wcol = (lx + lane / 5) * TILE_WIN + (ly + lane % 5);
+            const int base = T.col_base[wcol];
+            const int za = max(cz - 2, 0), zb = min(cz + 3, ncz);
+            const int ca = cell_start[base + za], cb = cell_start[base + zb];
+            sA = T.run_loc[2 * wcol] + (ca - T.run_src[2 * wcol]);
+            eA = sA + (cb - ca);
+            int zc = 0, zd = 0;
+            if (cz - 2 < 0) { zc = cz - 2 + ncz; zd = ncz; }
+            else if (cz + 3 > ncz) { zc = 0; zd = cz + 3 - ncz; }
+            if (zd > zc) {
+                const int cc = cell_start[base + zc], cd = cell_start[base + zd];
+                sB = T.run_loc[2 * wcol + 1] + (cc - T.run_src[2 * wcol + 1]);
+                eB = sB + (cd - cc);
+            }
+            shx = T.shx[wcol]; shy = T.shy[wcol];
+        }
+        int cnt = 0;
+        unsigned short *__restrict__ out = nbrT + (size_t)gi * cap;
+        for (int col = 0; col < 25; ++col) {
+            const double dx = __shfl_sync(0xffffffffu, shx, col), dy = __shfl_sync(0xffffffffu, shy, col);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const int s = __shfl_sync(0xffffffffu, part ? sB : sA, col), e = __shfl_sync(0xffffffffu, part ? eB : eA, col);
+                const double dz = part ? T.shz : 0.0;
+                for (int q0 = s; q0 < e; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool hit = false;
+                    if (q < e) {
+                        // the reference's operations in the reference's order: (x_q - x_i) -+ L, norm² compared against the
+                        // largest double whose square root is <= r_list
+                        const double rx = __dadd_rn(__dsub_rn(sx[q], xi), dx);
+                        const double ry = __dadd_rn(__dsub_rn(sy[q], yi), dy);
+                        const double rz = __dadd_rn(__dsub_rn(sz[q], zi), dz);
+                        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                        hit = r2 <= r2_list && q != slot;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+                        if (pos < cap) out[pos] = (unsigned short)q;
+                    }
+                    cnt += __popc(m);
+                }
+            }
+        }
+        if (lane == 0) nbr_cnt[gi] = min(cnt, cap);
+        wmax = max(wmax, cnt);
+        wsum += (unsigned long long)cnt;
+    }
+    (void)r_list;
+    if (lane == 0 && wsum) {
+        atomicMax(&sc->nbr_max, wmax);
+        atomicAdd(&sc->nbr_total, wsum);
+        if (wmax > cap) atomicExch(&sc->nbr_overflow, 1);
+    }
+}
+
+// Introspection (md_neighbour_lists): the brick-local lists as sorted indices in the k-major table of the other paths.
+__global__ void __launch_bounds__(TILE_BLOCK) k_tile_expand(Grid g, const int *__restrict__ cell_start, const Scalars *sc,
+                                                            const unsigned short *__restrict__ nbrT, int cap,
+                                                            const int *__restrict__ nbr_cnt, int *__restrict__ nbr, int npad,
+                                                            int sh_cap)
+{
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    int *slot_to_sorted = reinterpret_cast<int *>(tile_smem);  // sh_cap ints
+    __shared__ TileTab T;
+    tile_setup(T, g, cell_start, sc, blockIdx.x);
+    for (int r = threadIdx.x >> 5; r < TILE_RUNS; r += TILE_WARPS)
+        for (int e = threadIdx.x & 31; e < T.run_len[r]; e += 32) slot_to_sorted[T.run_loc[r] + e] = T.run_src[r] + e;
+    __syncthreads();
+    for (int ai = threadIdx.x >> 5; ai < T.n_own; ai += TILE_WARPS) {
+        int oc, slot, gi;
+        tile_locate(T, ai, oc, slot, gi);
+        const int cnt = nbr_cnt[gi];
+        for (int k = threadIdx.x & 31; k < cnt; k += 32) nbr[(size_t)k * npad + gi] = slot_to_sorted[nbrT[(size_t)gi * cap + k]];
+    }
+    (void)sh_cap;
+}
+
+// ---- K3, tile form ----------------------------------------------------------------------------------------------------
+// Pair phase: warp w takes brick atoms w, w + 8, ...; lane l evaluates list entries l, l + 32, ... — rows of 32 entries, four
+// rows (four independent pair terms per lane) per trip.  The index rows of the NEXT atom are fetched before the current
+// atom's pair terms (registers), so the table's HBM latency hides behind ~6 rows of arithmetic.
+constexpr int TILE_ROWS_MAX = 8;  // rows of 32 entries kept in registers per atom (cap <= 256)
+
+template <int UW>
+__device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *sx, const double *sy, const double *sz,
+                                                const unsigned short *__restrict__ nbrT, int cap,
+                                                const int *__restrict__ nbr_cnt, const ForceConsts &fc, double *fst)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LjConst c{};  // (no minimum image: the shell holds the images)
+    int cur[TILE_ROWS_MAX], nxt[TILE_ROWS_MAX];
+    int oc, slot, gi, cnt = 0;
+    int n_slot = 0, n_gi = 0, n_cnt = 0;
+    const int n_own = T.n_own, own_cap = T.own_pref[16];
+    (void)own_cap;
+    auto fetch = [&](int ai, int &s_, int &g_, int &c_, int *rows) {
+        int oc_;
+        tile_locate(T, ai, oc_, s_, g_);
+        c_ = nbr_cnt[g_];
+        const unsigned short *lst = nbrT + (size_t)g_ * cap;
+#pragma unroll
+        for (int r = 0; r < TILE_ROWS_MAX; ++r) rows[r] = (r * 32 + lane < c_) ? (int)lst[r * 32 + lane] : 0;
+    };
+    if (warp < n_own) fetch(warp, n_slot, n_gi, n_cnt, nxt);
+    for (int ai = warp; ai < n_own; ai += TILE_WARPS) {
+        slot = n_slot; gi = n_gi; cnt = n_cnt;
+#pragma unroll
+        for (int r = 0; r < TILE_ROWS_MAX; ++r) cur[r] = nxt[r];
+        if (ai + TILE_WARPS < n_own) fetch(ai + TILE_WARPS, n_slot, n_gi, n_cnt, nxt);
+        (void)oc; (void)gi;
+        const double xi = sx[slot], yi = sy[slot], zi = sz[slot];
+        PairAcc acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = PairAcc{0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int r0 = 0; r0 < TILE_ROWS_MAX; r0 += 4) {
+            if (r0 * 32 < cnt) {  // warp-uniform
+                double xj[4], yj[4], zj[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int j = cur[r0 + u]; xj[u] = sx[j]; yj[u] = sy[j]; zj[u] = sz[j]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((r0 + u) * 32 < cnt)  // warp-uniform: rows beyond the list cost nothing
+                        pair_dense<false, UW>(acc[u], (r0 + u) * 32 + lane < cnt, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
+            }
+        }
+        // lists longer than the register rows (cap > 256): straight from the table
+        for (int k = TILE_ROWS_MAX * 32 + lane; k - lane < cnt; k += 32) {
+            const int j = k < cnt ? (int)nbrT[(size_t)gi * cap + k] : 0;
+            pair_dense<false, UW>(acc[0], k < cnt, sx[j], sy[j], sz[j], xi, yi, zi, c, fc);
+        }
+        PairAcc f;
+        f.fx = (acc[0].fx + acc[1].fx) + (acc[2].fx + acc[3].fx);
+        f.fy = (acc[0].fy + acc[1].fy) + (acc[2].fy + acc[3].fy);
+        f.fz = (acc[0].fz + acc[1].fz) + (acc[2].fz + acc[3].fz);
+        f.w = UW >= 1 ? (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w) : 0.0;
+        f.u = UW >= 2 ? (acc[0].u + acc[1].u) + (acc[2].u + acc[3].u) : 0.0;
+        // fixed-order fold over the lanes
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            f.fx += __shfl_xor_sync(0xffffffffu, f.fx, o);
+            f.fy += __shfl_xor_sync(0xffffffffu, f.fy, o);
+            f.fz += __shfl_xor_sync(0xffffffffu, f.fz, o);
+            if (UW >= 1) f.w += __shfl_xor_sync(0xffffffffu, f.w, o);
+            if (UW >= 2) f.u += __shfl_xor_sync(0xffffffffu, f.u, o);
+        }
+        if (lane == 0) {
+            double *o = fst + (size_t)ai * 5;
+            o[0] = f.fx; o[1] = f.fy; o[2] = f.fz; o[3] = f.u; o[4] = f.w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TILE_BLOCK, 2)
+    k_force_tile(Grid g, Arrays a, const int *__restrict__ cell_start, const unsigned short *__restrict__ nbrT, int cap,
+                 const int *__restrict__ nbr_cnt, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr,
+                 int do_step, const ForceConsts fc, const int *__restrict__ brick_order, int sh_cap, int own_cap)
+{
+    // do_step bits: 1 = MD step (both half-kicks fused in), 4 = guarded (see k_force)
+    if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    double *sx = reinterpret_cast<double *>(tile_smem), *sy = sx + sh_cap, *sz = sy + sh_cap;
+    double *fst = sz + sh_cap;  // own_cap x {fx, fy, fz, u, w}
+    __shared__ TileTab T;
+    __shared__ __align__(8) unsigned long long bar;
+    tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
+    tile_stage(T, a, sx, sy, sz, &bar, true);
+    const bool step = (do_step & 1) != 0;
+    const bool store_state = !step || sc->steps_left <= 1;
+    const bool nh = pr->th_kind == 2 || !step;
+    // per-atom potential and virial enter nothing but the stored State and the S_U / S_W sums (see k_force)
+    const bool need_u = store_state, need_w = store_state || pr->ba_kind != 0;
+    if (need_u) tile_pair_phase<2>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
+    else if (need_w) tile_pair_phase<1>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
+    else tile_pair_phase<0>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
+    __syncthreads();
+    // epilogue: one thread per brick atom — both half-kicks, K5 terms, stores (k_force's, same arithmetic)
+    Sums s;
+#pragma unroll
+    for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
+    const double lambda = sc->lambda, c = fc.hc, mass = fc.mass;
+    const double shift[3] = {sc->shift[0], sc->shift[1], sc->shift[2]};
+    for (int ai = threadIdx.x; ai < T.n_own; ai += TILE_BLOCK) {
+        int oc, slot, gi;
+        tile_locate(T, ai, oc, slot, gi);
+        const double *f = fst + (size_t)ai * 5;
+        const double fx = f[0], fy = f[1], fz = f[2], fu = f[3], fw = f[4];
+        double vx = a.vx[gi], vy = a.vy[gi], vz = a.vz[gi];
+        if (step) {
+            vx = __dadd_rn(__dmul_rn(vx, lambda), __dmul_rn(fx, c));  // v'' = lambda*u + F*c
+            vy = __dadd_rn(__dmul_rn(vy, lambda), __dmul_rn(fy, c));
+            vz = __dadd_rn(__dmul_rn(vz, lambda), __dmul_rn(fz, c));
+        }
+        const double wx = __dadd_rn(vx, __dmul_rn(fx, c)), wy = __dadd_rn(vy, __dmul_rn(fy, c)),
+                     wz = __dadd_rn(vz, __dmul_rn(fz, c));  // u' = v'' + F*c
+        s.v[0] += mass * vx; s.v[1] += mass * vy; s.v[2] += mass * vz;
+        const double ax = vx - shift[0], ay = vy - shift[1], az = vz - shift[2];
+        s.v[S_TH] += mass * (ax * ax + ay * ay + az * az);
+        s.v[S_KE] += mass * (vx * vx + vy * vy + vz * vz);
+        s.v[S_W] += fw;
+        s.v[S_U] += fu;
+        if (nh) {
+            s.v[S_MU] += mass * wx; s.v[S_MU + 1] += mass * wy; s.v[S_MU + 2] += mass * wz;
+            const double bx = wx - shift[0], by = wy - shift[1], bz = wz - shift[2];
+            s.v[S_THU] += mass * (bx * bx + by * by + bz * bz);
+        }
+        s.v[S_MAX] = fmax(s.v[S_MAX], wx * wx + wy * wy + wz * wz);
+        if (store_state) {
+            a.fx[gi] = fx; a.fy[gi] = fy; a.fz[gi] = fz; a.u[gi] = fu; a.w[gi] = fw;
+            if (step) { a.vx[gi] = vx; a.vy[gi] = vy; a.vz[gi] = vz; }
+        } else {
+            a.vx[gi] = wx; a.vy[gi] = wy; a.vz[gi] = wz;
+        }
+    }
+    (void)own_cap;
+    block_reduce<TILE_BLOCK>(s);
+    grid_reduce_finalize<TILE_BLOCK>(s, partials, sc, pr, step ? FIN_STEP : 0, nullptr);
+}
+
+}  // namespace md

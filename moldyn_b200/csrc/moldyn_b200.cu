@@ -104,15 +104,22 @@ struct md_ctx {
     double *d_partials = nullptr;
     int partial_blocks = 0;
     int force_grid[3] = {1, 1, 1}, reduce_grid = 1;  // exact, fast dense, fast dilute
-    // persistent step loop (md_loop.cuh): atoms with listed partners, compacted at every rebuild (interior first, then the
-    // atoms whose lists hold ghosts), their two counts on the device, and the per-atom "list holds a ghost" flags
-    int *act_flag = nullptr, *act_scan = nullptr, *act_idx = nullptr, *act_sums = nullptr, *n_act = nullptr;
-    int *nbr_ghost = nullptr;
-    int act_alloc = 0;
+    // persistent step loop (md_loop.cuh)
+    int *nbr_ghost = nullptr;                         // multi-GPU: per-atom "the list holds a ghost" flags (list build)
+    int *cntg = nullptr;                              // multi-GPU: list counts | LOOP_GHOST_FLAG (the loop's copy)
     int loop_blocks_max = 0;                          // co-resident blocks of k_md_loop on this device
     bool loop_attr_set = false;
     double rebuild_host_ms = 0.0;                     // multi-GPU: wall time spent in list rebuilds (host clock, synchronised)
     long long epoch_start_step = 0, last_epoch_len = 128;  // list epochs in steps: sizes the chunk look-ahead
+    // dense + FAST on one GPU: brick tiles (md_tile.cuh) — 16-bit brick-local lists, atom-major
+    unsigned short *nbrT = nullptr;
+    size_t nbrT_alloc = 0;
+    int cap16 = 0;                                    // list slots per atom (multiple of 32)
+    int *brick_order = nullptr;                       // block → brick: full bricks first, the partial ones fill the tail
+    int brick_alloc = 0, nbricks = 0;
+    int sh_cap = 0, own_cap = 0;                      // shell slots / brick atoms the tile kernels' shared memory is sized for
+    bool tile_valid = false;                          // the last rebuild produced tile lists
+    bool tile_disabled = false;                       // this State cannot use them (a coordinate outside the box, shell too large)
     bool dense = false;                               // mean listed partners >= 8 at the last rebuild
     bool use_q4 = false;                              // packed gather copy maintained (dense systems)
     double graph_hc = -1.0;                           // dt/(2m) baked into the captured force kernel
@@ -344,6 +351,20 @@ int choose_grid(md_ctx *ctx, const double box[3])
         g.nc[d] = c;
         ncell *= c;
     }
+    // Dense systems, FAST arithmetic, one GPU: brick order for the tile kernels (md_tile.cuh).  MOLDYN_B200_TILE=0 keeps the
+    // per-thread Verlet path (A/B measurements); MOLDYN_B200_TILE_BZ sets the z cells per brick (default 4).
+    static const int tile_env = [] { const char *e = std::getenv("MOLDYN_B200_TILE"); return e ? atoi(e) : 1; }();
+    static const int bz_env = [] { const char *e = std::getenv("MOLDYN_B200_TILE_BZ"); return e ? atoi(e) : 4; }();
+    g.brick = 0;
+    if (tile_env != 0 && !ctx->tile_disabled && !ctx->dist.on && ctx->cfg.force_mode == MD_FORCE_FAST && nsub == 2 &&
+        g.nc[0] >= TILE_MIN_CELLS && g.nc[1] >= TILE_MIN_CELLS && g.nc[2] >= TILE_MIN_CELLS && ctx->n >= 128) {
+        g.brick = 1;
+        g.nbx = (g.nc[0] + 3) / 4;
+        g.nby = (g.nc[1] + 3) / 4;
+        g.bz = std::max(1, std::min(bz_env, g.nc[2] - 4));
+        g.nbz = (g.nc[2] + g.bz - 1) / g.bz;
+        ncell = (int64_t)g.nbx * g.nby * 16 * g.nc[2];
+    }
     if (ncell > (int64_t)1 << 30) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "cell grid too large");
     g.nsub = nsub;
     g.ncell = (int)ncell;
@@ -356,6 +377,28 @@ int choose_grid(md_ctx *ctx, const double box[3])
         TRY(dev_alloc(ctx, &ctx->cell_cnt, ctx->cell_alloc));
         TRY(dev_alloc(ctx, &ctx->cell_start, ctx->cell_alloc));
         TRY(dev_alloc(ctx, &ctx->block_sums, blocks_for(ctx->cell_alloc, SCAN_BLOCK) + 1));
+    }
+    if (g.brick) {
+        // block → brick: by the number of real cells, descending (stable): the partial bricks at the upper faces are the
+        // cheap ones and fill the tail of the grid
+        ctx->nbricks = g.nbx * g.nby * g.nbz;
+        std::vector<int> order((size_t)ctx->nbricks);
+        std::vector<long long> weight((size_t)ctx->nbricks);
+        for (int id = 0; id < ctx->nbricks; ++id) {
+            const int bzc = id % g.nbz, bxy = id / g.nbz, by = bxy % g.nby, bx = bxy / g.nby;
+            const long long wx = std::min(4, g.nc[0] - 4 * bx), wy = std::min(4, g.nc[1] - 4 * by),
+                            wz = std::min(g.bz, g.nc[2] - g.bz * bzc);
+            order[(size_t)id] = id;
+            weight[(size_t)id] = wx * wy * wz;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int p, int q) { return weight[(size_t)p] > weight[(size_t)q]; });
+        if (ctx->nbricks > ctx->brick_alloc) {
+            dev_free(ctx, ctx->brick_order);
+            ctx->brick_alloc = ctx->nbricks + ctx->nbricks / 8;
+            TRY(dev_alloc(ctx, &ctx->brick_order, ctx->brick_alloc));
+        }
+        CK(cudaMemcpyAsync(ctx->brick_order, order.data(), sizeof(int) * (size_t)ctx->nbricks, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // (order is a local)
     }
     return MD_OK;
 }
@@ -426,8 +469,8 @@ int refresh_q4(md_ctx *ctx)
     return MD_OK;
 }
 
-int build_active_list(md_ctx *ctx, int n);
 HaloPush dist_halo_push_args(md_ctx *ctx);
+int build_tile_lists(md_ctx *ctx, bool *fallback);
 
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
 // (no pending barostat scaling).
@@ -458,7 +501,20 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.kernel_launches += 7;
 
     const double r2_list = sqrt_threshold(ctx->prm.r_list);
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    ctx->tile_valid = false;
+    if (g.brick) {
+        // dense systems: brick-local 16-bit lists for the tile force kernel (md_tile.cuh)
+        bool fallback = false;
+        TRY(build_tile_lists(ctx, &fallback));
+        if (fallback) {
+            // a coordinate outside the box, or a shell that does not fit in shared memory: canonical order, per-thread lists
+            ctx->tile_disabled = true;
+            ctx->list_valid = false;
+            return rebuild_lists(ctx);
+        }
+        ctx->tile_valid = true;
+    }
+    for (int attempt = 0; !g.brick && attempt < 4; ++attempt) {
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         // image shift per cell run instead of per candidate when the box is wide enough in cells (see k_build_list)
         const int need_cells = 2 * g.nsub + 3;
@@ -490,10 +546,65 @@ int rebuild_lists(md_ctx *ctx)
     ctx->stats.nbr_max = ctx->h_sc->nbr_max;
     ctx->stats.nbr_mean = (double)ctx->h_sc->nbr_total / (double)ctx->n;
     ctx->dense = ctx->stats.nbr_mean >= 8.0 && n >= 128;  // (the dense kernel's masked lanes need a foreign warp's atom)
-    ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT;
+    ctx->use_q4 = ctx->dense && ctx->cfg.force_mode != MD_FORCE_EXACT && !ctx->tile_valid;
     TRY(refresh_q4(ctx));
-    TRY(build_active_list(ctx, n));
     ctx->list_valid = true;
+    return MD_OK;
+}
+
+// K2 in tile form: shell sizes first (they size the kernels' shared memory), then the brick-local lists.
+int build_tile_lists(md_ctx *ctx, bool *fallback)
+{
+    cudaStream_t st = ctx->stream;
+    const Grid &g = ctx->grid;
+    *fallback = false;
+    k_tile_reset<<<1, 1, 0, st>>>(ctx->d_sc);
+    k_tile_measure<<<ctx->nbricks, 64, 0, st>>>(g, ctx->cell_start, ctx->d_sc);
+    ctx->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    TRY(pull_scalars(ctx));
+    if (ctx->h_sc->out_of_box) { *fallback = true; return MD_OK; }
+    ctx->sh_cap = (ctx->h_sc->tile_shell_max + 63) / 64 * 64;
+    ctx->own_cap = (ctx->h_sc->tile_own_max + 31) / 32 * 32;
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const size_t smem_force = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
+    const size_t smem_build = (size_t)3 * ctx->sh_cap * sizeof(double);
+    if (ctx->sh_cap > 65535 || smem_force + 16 * 1024 > (size_t)optin) { *fallback = true; return MD_OK; }
+    if (ctx->nbricks > ctx->partial_blocks) {  // one slot of partial sums per brick
+        dev_free(ctx, ctx->d_partials);
+        ctx->partial_blocks = ctx->nbricks + ctx->nbricks / 8;
+        TRY(dev_alloc(ctx, &ctx->d_partials, (size_t)ctx->partial_blocks * NSUM));
+    }
+    CK(cudaFuncSetAttribute(k_force_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_force));
+    CK(cudaFuncSetAttribute(k_build_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_build));
+    CK(cudaFuncSetAttribute(k_tile_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)ctx->sh_cap * sizeof(int))));
+    const double r2_list = sqrt_threshold(ctx->prm.r_list);
+    if (ctx->cap16 == 0) {
+        const double volume = ctx->h_sc->box[0] * ctx->h_sc->box[1] * ctx->h_sc->box[2];
+        const double expect = (double)ctx->n / volume * 4.18879020478639 * ctx->prm.r_list * ctx->prm.r_list * ctx->prm.r_list;
+        ctx->cap16 = ((int)(expect * 1.3) + 16 + 31) / 32 * 32;
+    }
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const size_t need = (size_t)ctx->cap16 * (size_t)ctx->npad;
+        if (need > ctx->nbrT_alloc) {
+            dev_free(ctx, ctx->nbrT);
+            ctx->nbrT = nullptr;
+            ctx->nbrT_alloc = 0;
+            TRY(dev_alloc(ctx, &ctx->nbrT, need));
+            ctx->nbrT_alloc = need;
+        }
+        k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
+        k_build_tile<<<ctx->nbricks, TILE_BLOCK, smem_build, st>>>(g, ctx->cur, ctx->cell_start, ctx->cell_sorted, ctx->d_sc,
+                                                                   ctx->prm.r_list, r2_list, ctx->nbrT, ctx->cap16,
+                                                                   ctx->nbr_cnt, ctx->brick_order, ctx->sh_cap);
+        ctx->stats.kernel_launches += 2;
+        CK(cudaGetLastError());
+        TRY(pull_scalars(ctx));
+        if (!ctx->h_sc->nbr_overflow) break;
+        if (attempt == 3) return ctx->fail(MD_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow (max %d)", ctx->h_sc->nbr_max);
+        ctx->cap16 = ((int)(ctx->h_sc->nbr_max * 1.15) + 8 + 31) / 32 * 32;
+    }
     return MD_OK;
 }
 
@@ -506,42 +617,10 @@ int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullp
     return MD_OK;
 }
 
-// The persistent step loop walks only the atoms with listed partners in its force phase: their sorted indices, compacted
-// at every rebuild — first the atoms whose partners are all owned, then (multi-GPU) the atoms whose lists hold ghosts.  The
-// two counts stay on the device.
+// Dilute systems run their steps inside the persistent loop (md_loop.cuh); dense ones as graph chunks of the two-kernel step.
 bool loop_wanted(const md_ctx *ctx)
 {
     return !ctx->dense && ctx->cfg.loop_mode != MD_LOOP_CHUNK && (!ctx->dist.on || ctx->dist.p2p);
-}
-
-int build_active_list(md_ctx *ctx, int n)
-{
-    if (ctx->dense) return MD_OK;  // dense systems run the two-kernel step
-    cudaStream_t st = ctx->stream;
-    if (ctx->npad > ctx->act_alloc) {
-        dev_free(ctx, ctx->act_flag); dev_free(ctx, ctx->act_scan); dev_free(ctx, ctx->act_idx); dev_free(ctx, ctx->act_sums);
-        ctx->act_alloc = ctx->npad;
-        TRY(dev_alloc(ctx, &ctx->act_flag, ctx->npad));
-        TRY(dev_alloc(ctx, &ctx->act_scan, (size_t)ctx->npad + 1));
-        TRY(dev_alloc(ctx, &ctx->act_idx, ctx->npad));
-        TRY(dev_alloc(ctx, &ctx->act_sums, blocks_for(ctx->npad, SCAN_BLOCK) + 2));
-    }
-    if (!ctx->n_act) TRY(dev_alloc(ctx, &ctx->n_act, 2));
-    const int nb = std::max(1, blocks_for(n, 256));
-    const int sb = std::max(1, blocks_for(n, SCAN_BLOCK));
-    const int *ghost = ctx->dist.on ? ctx->nbr_ghost : nullptr;
-    for (int cls = 0; cls < 2; ++cls) {
-        k_flag_active<<<nb, 256, 0, st>>>(n, ctx->nbr_cnt, ghost, cls, ctx->act_flag);
-        k_scan_block<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_flag, ctx->act_scan, ctx->act_sums);
-        k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sb, ctx->act_sums);
-        k_scan_add<<<sb, SCAN_BLOCK, 0, st>>>(n, ctx->act_scan, ctx->act_sums, -1);
-        k_scan_total<<<1, 1, 0, st>>>(n, ctx->act_flag, ctx->act_scan);
-        k_compact_active<<<nb, 256, 0, st>>>(n, ctx->act_flag, ctx->act_scan, cls ? ctx->n_act : nullptr, ctx->act_idx,
-                                             ctx->n_act + cls);
-    }
-    ctx->stats.kernel_launches += 12;
-    CK(cudaGetLastError());
-    return MD_OK;
 }
 
 int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
@@ -553,7 +632,12 @@ int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
     k_force<E, M><<<GRID, FORCE_BLOCK, 0, ctx->stream>>>(n, ctx->cur, ctx->nbr, ctx->nbr_cnt, ctx->npad, ctx->grid.cap, \
                                                          ctx->d_partials, ctx->d_sc, ctx->d_pr, flags, fc, nullptr)
     if (ctx->cfg.force_mode == MD_FORCE_EXACT) LAUNCH_FORCE(true, false, ctx->force_grid[0]);
-    else if (ctx->dense) LAUNCH_FORCE(false, true, ctx->force_grid[1]);
+    else if (ctx->tile_valid) {
+        const size_t smem = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
+        k_force_tile<<<ctx->nbricks, TILE_BLOCK, smem, ctx->stream>>>(ctx->grid, ctx->cur, ctx->cell_start, ctx->nbrT, ctx->cap16,
+                                                                      ctx->nbr_cnt, ctx->d_partials, ctx->d_sc, ctx->d_pr, flags,
+                                                                      fc, ctx->brick_order, ctx->sh_cap, ctx->own_cap);
+    } else if (ctx->dense) LAUNCH_FORCE(false, true, ctx->force_grid[1]);
     else LAUNCH_FORCE(false, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
     return MD_OK;
@@ -567,7 +651,8 @@ int launch_reduce(md_ctx *ctx)
     return MD_OK;
 }
 
-constexpr size_t LOOP_SMEM = sizeof(SumsSmemT<LOOP_BLOCK>);
+constexpr size_t LOOP_SMEM_PER_PAIR = 3 * LOOP_BLOCK * sizeof(double2);  // ux, uy, uz of one pair per thread
+constexpr size_t LOOP_SMEM_MAX = LOOP_MAX_PAIRS * LOOP_SMEM_PER_PAIR;
 
 // Persistent grids: resident blocks per SM (occupancy API) × SM count, capped by the work available.
 int choose_grids(md_ctx *ctx)
@@ -582,14 +667,17 @@ int choose_grids(md_ctx *ctx)
     for (int k = 0; k < 3; ++k) ctx->force_grid[k] = std::max(1, std::min(pair_blocks, sms * std::max(occ[k], 1)));
     ctx->reduce_grid = std::max(1, std::min(blocks_for(ctx->n, RED_BLOCK), sms * std::max(occ_r, 1)));
     if (!ctx->loop_attr_set) {
-        CK(cudaFuncSetAttribute(k_md_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM));
-        CK(cudaFuncSetAttribute(k_md_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM));
-        int occ_l[2] = {0, 0};
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[0], k_md_loop<false>, LOOP_BLOCK, LOOP_SMEM));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[1], k_md_loop<true>, LOOP_BLOCK, LOOP_SMEM));
+        CK(cudaFuncSetAttribute(k_md_loop<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM_MAX));
+        CK(cudaFuncSetAttribute(k_md_loop<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOOP_SMEM_MAX));
+        int occ_l[4] = {0, 0, 0, 0};
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[0], k_md_loop<false, true>, LOOP_BLOCK, LOOP_SMEM_MAX));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[1], k_md_loop<true, true>, LOOP_BLOCK, LOOP_SMEM_MAX));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[2], k_md_loop<false, false>, LOOP_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l[3], k_md_loop<true, false>, LOOP_BLOCK, 0));
         int coop = 0;
         CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-        ctx->loop_blocks_max = coop ? sms * std::min(1, std::min(occ_l[0], occ_l[1])) : 0;  // one block per SM
+        const int occ_min = std::min(std::min(occ_l[0], occ_l[1]), std::min(occ_l[2], occ_l[3]));
+        ctx->loop_blocks_max = coop ? sms * std::min(1, occ_min) : 0;  // one block per SM
         ctx->loop_attr_set = true;
     }
     return MD_OK;
@@ -599,15 +687,19 @@ int choose_grids(md_ctx *ctx)
 int launch_loop(md_ctx *ctx, long long max_steps)
 {
     const int n = (int)ctx->n_own;
+    const int npairs = (n + 1) / 2;
+    // as many blocks as there are pairs of atoms to drift, at most one per SM: small systems synchronise a small grid
+    const int grid = std::max(1, std::min(ctx->loop_blocks_max, blocks_for(npairs, LOOP_BLOCK)));
+    const int P = std::max(1, blocks_for(npairs, (int64_t)grid * LOOP_BLOCK));
+    const bool usmem = P <= LOOP_MAX_PAIRS;
     LoopArgs A{};
     A.n = n;
     A.npad = ctx->npad;
     A.cap = ctx->grid.cap;
+    A.pairs_per_thread = P;
     A.a = ctx->cur;
     A.nbr = ctx->nbr;
-    A.nbr_cnt = ctx->nbr_cnt;
-    A.act_idx = ctx->act_idx;
-    A.n_act = ctx->n_act;
+    A.cntg = ctx->dist.on ? ctx->cntg : ctx->nbr_cnt;
     A.partials = ctx->d_partials;
     A.sc = ctx->d_sc;
     A.pr = ctx->d_pr;
@@ -615,13 +707,12 @@ int launch_loop(md_ctx *ctx, long long max_steps)
     A.h = ctx->dist.on ? dist_halo_push_args(ctx) : HaloPush{};
     A.max_steps = max_steps;
     A.fc = force_consts(ctx);
-    // as many blocks as there are pairs of atoms to drift, at most one per SM: small systems synchronise a small grid
-    const int grid = std::max(1, std::min(ctx->loop_blocks_max, blocks_for((n + 1) / 2, LOOP_BLOCK)));
     void *args[] = {&A};
-    if (ctx->cfg.force_mode == MD_FORCE_EXACT)
-        CK(cudaLaunchCooperativeKernel((const void *)k_md_loop<true>, dim3(grid), dim3(LOOP_BLOCK), args, LOOP_SMEM, ctx->stream));
-    else
-        CK(cudaLaunchCooperativeKernel((const void *)k_md_loop<false>, dim3(grid), dim3(LOOP_BLOCK), args, LOOP_SMEM, ctx->stream));
+    const size_t smem = usmem ? (size_t)P * LOOP_SMEM_PER_PAIR : 0;
+    const bool exact = ctx->cfg.force_mode == MD_FORCE_EXACT;
+    const void *fn = exact ? (usmem ? (const void *)k_md_loop<true, true> : (const void *)k_md_loop<true, false>)
+                           : (usmem ? (const void *)k_md_loop<false, true> : (const void *)k_md_loop<false, false>);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LOOP_BLOCK), args, smem, ctx->stream));
     ctx->stats.loop_launches += 1;
     return MD_OK;
 }
@@ -655,14 +746,18 @@ std::vector<unsigned char> chunk_key(const md_ctx *ctx)
                               (const void *)a->u, (const void *)a->w, (const void *)a->id, (const void *)a->q4})
             put_ptr(q);
     for (const void *q : {(const void *)ctx->nbr, (const void *)ctx->nbr_cnt, (const void *)ctx->d_partials,
-                          (const void *)ctx->d_sc, (const void *)ctx->d_pr})
+                          (const void *)ctx->d_sc, (const void *)ctx->d_pr, (const void *)ctx->nbrT,
+                          (const void *)ctx->cell_start, (const void *)ctx->brick_order})
         put_ptr(q);
     const ForceConsts fc = force_consts(ctx);
     for (double v : {fc.sigma, fc.sigma2, fc.eps4, fc.eps24, fc.r_cut, fc.rc2, fc.u_cut, fc.c6, fc.c12, fc.d6, fc.d12, fc.hc, fc.mass})
         put(&v, sizeof v);
     for (long long v : {(long long)ctx->n, (long long)ctx->n_own, (long long)ctx->npad, (long long)ctx->grid.cap,
                         (long long)ctx->cfg.force_mode, (long long)ctx->dense, (long long)ctx->use_q4,
-                        (long long)ctx->force_grid[0], (long long)ctx->force_grid[1], (long long)ctx->force_grid[2]})
+                        (long long)ctx->force_grid[0], (long long)ctx->force_grid[1], (long long)ctx->force_grid[2],
+                        (long long)ctx->tile_valid, (long long)ctx->cap16, (long long)ctx->sh_cap, (long long)ctx->own_cap,
+                        (long long)ctx->nbricks, (long long)ctx->grid.nc[0], (long long)ctx->grid.nc[1],
+                        (long long)ctx->grid.nc[2], (long long)ctx->grid.bz})
         put_i(v);
     return k;
 }
@@ -867,7 +962,7 @@ static int alloc_state(md_ctx *ctx, int64_t n)
         ctx->n = n;
         ctx->n_own = n;
         ctx->n_ghost = 0;
-        ctx->npad = (int)((n + 63) / 64 * 64);
+        ctx->npad = (int)((n + 64) / 64 * 64);  // at least one spare slot: the tile kernels' bulk copies end on even indices
         TRY(alloc_arrays(ctx, &ctx->cur, ctx->npad));
         TRY(alloc_arrays(ctx, &ctx->alt, ctx->npad));
         TRY(dev_alloc(ctx, &ctx->stage, 3 * (size_t)ctx->npad));
@@ -897,6 +992,9 @@ static int finish_new_state(md_ctx *ctx, int64_t n, const double box[3])
     h.lambda_last = 1.0; h.mu_last = 1.0;
     CK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(Scalars), cudaMemcpyHostToDevice, st));
     drop_graph(ctx);
+    ctx->tile_disabled = false;
+    ctx->tile_valid = false;
+    ctx->cap16 = 0;
     ctx->skin = choose_skin(ctx, box);
     fill_potential_params(ctx);
     // neighbour capacity from density
@@ -1389,6 +1487,12 @@ int md_download_cells(md_ctx *ctx, int32_t *cell_of_atom, int32_t dims[3])
         k_unsort1i<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(n, ctx->cell_sorted, ctx->cur.id, ctx->stage_i);
         CK(cudaMemcpyAsync(cell_of_atom, ctx->stage_i, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->grid.brick)  // brick-major column numbering → the canonical (cx*ny + cy)*nz + cz
+            for (int i = 0; i < n; ++i) {
+                int cx, cy, cz;
+                cell_decode(ctx->grid, cell_of_atom[i], cx, cy, cz);
+                cell_of_atom[i] = (cx * ctx->grid.nc[1] + cy) * ctx->grid.nc[2] + cz;
+            }
     }
     if (dims) {
         dims[0] = ctx->grid.nc[0]; dims[1] = ctx->grid.nc[1]; dims[2] = ctx->grid.nc[2];
@@ -1404,6 +1508,14 @@ static int fetch_lists(md_ctx *ctx, std::vector<int> &cnt, std::vector<int> &id,
     id.resize(n);
     CK(cudaMemcpyAsync(cnt.data(), ctx->nbr_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(id.data(), ctx->cur.id, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nbr && ctx->tile_valid) {
+        // brick-local 16-bit lists → sorted indices in the k-major table the other paths use (introspection only)
+        if ((size_t)ctx->cap16 * (size_t)ctx->npad > ctx->nbr_alloc || ctx->grid.cap < ctx->cap16)
+            TRY(ensure_nbr_capacity(ctx, ctx->cap16));
+        k_tile_expand<<<ctx->nbricks, TILE_BLOCK, (size_t)ctx->sh_cap * sizeof(int), ctx->stream>>>(
+            ctx->grid, ctx->cell_start, ctx->d_sc, ctx->nbrT, ctx->cap16, ctx->nbr_cnt, ctx->nbr, ctx->npad, ctx->sh_cap);
+        CK(cudaGetLastError());
+    }
     if (nbr) {
         nbr->resize((size_t)ctx->grid.cap * ctx->npad);
         CK(cudaMemcpyAsync(nbr->data(), ctx->nbr, sizeof(int) * nbr->size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1450,6 +1562,7 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
     out->peer_memory = ctx->dist.p2p ? 1 : 0;
     out->persistent_loop = (ctx->has_state && loop_wanted(ctx) && ctx->loop_blocks_max > 0) ? 1 : 0;
+    out->tile_lists = ctx->tile_valid ? 1 : 0;
     out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
     out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;
     out->rebuild_ms = ctx->rebuild_host_ms;

@@ -152,7 +152,7 @@ SYSTEMS = {
     "liquid1000": lambda: (liquid(10), None),
     "liquid4096_3.5sigma": lambda: (liquid(16), LONG_CUT),
     "liquid_small_box": lambda: (liquid(5), None),   # box 1.81 nm: fewer than 3 cells per axis
-    "liquid5832": lambda: (liquid(18), None),        # 13 cells per axis: the dense FAST path uses union lists
+    "liquid5832": lambda: (liquid(18), None),        # 13 cells per axis: the dense FAST path runs the tile kernels
     "liquid729": lambda: (liquid(9), None),          # odd atom count: the last thread owns one atom
 }
 
@@ -205,6 +205,64 @@ def test_cells_and_neighbour_sets_bit_exact(name, mode):
     woff, wpartners = orc.neighbour_sets(o.pos, o.box, olj.r_cut + skin)
     assert np.array_equal(off, woff)
     assert np.array_equal(partners, wpartners)
+
+
+@pytest.mark.parametrize("name", ["liquid4096_3.5sigma", "liquid5832", "liquid13824"])
+def test_tile_kernels_dense(name):
+    """Dense systems in MD_FORCE_FAST on one GPU run the tile kernels (md_tile.cuh: brick order, TMA-staged shells, 16-bit
+    brick-local lists, warp-cooperative pair loop): pair sets bit-exact, per-atom force / potential / virial within the FAST
+    bar, 100-step NVT and NPT trajectories within 1e-8 of the oracle (forces-only, + virial and + potential instances of the
+    loop all run), run-to-run bit-reproducible."""
+    if name == "liquid13824":
+        o, cut = liquid(24), None      # 6 x 6 x 6 bricks, partial ones at the upper faces
+    else:
+        o, cut = SYSTEMS[name]()
+    olj, plj = lj_pair(md, *(cut or (None, None)))
+    ref = o.copy()
+    orc.update_force(olj, ref, mode="cells")
+    scale = force_scale(olj, ref)
+    rms = np.sqrt((ref.force ** 2).sum(axis=1).mean())
+    runs = []
+    for ensemble in ("nvt", "npt", "npt"):
+        st = to_gpu_state(md, o)
+        gth, oth = (md.Thermostat.Berendsen(10.0), 120.0), orc.Thermostat(orc.Thermostat.BERENDSEN, 10.0, 120.0)
+        gba = oba = None
+        if ensemble == "npt":
+            gba, oba = (md.Barostat.Berendsen(1.0, 5.0), 1.01325), orc.Barostat(1.0, 5.0, 1.01325)
+        with md.Solver() as s:
+            s.set_potential(plj)
+            s.upload(st, with_forces=False)
+            s.update_force()
+            stats = s.stats()
+            assert stats["tile_lists"] == 1 and stats["nbr_mean"] >= 8.0, stats
+            if ensemble == "nvt":
+                off, partners = s.neighbour_lists()
+                woff, wpartners = orc.neighbour_sets(o.pos, o.box, olj.r_cut + stats["skin"])
+                assert np.array_equal(off, woff) and np.array_equal(partners, wpartners)
+                cell, dims = s.cells()
+                frac = o.pos / o.box
+                frac -= np.floor(frac)
+                c3 = np.minimum((frac * dims).astype(np.int64), dims - 1)
+                assert np.array_equal(cell, (c3[:, 0] * dims[1] + c3[:, 1]) * dims[2] + c3[:, 2])
+            s.download(st)
+            assert np.all(np.abs(st.force - ref.force) <= 1e-10 * np.maximum(scale, rms)[:, None])
+            assert np.all(np.abs(st.potential - ref.pot) <= 1e-10 * (np.abs(ref.pot) + 4 * olj.eps))
+            assert np.all(np.abs(st.temp - ref.vir) <= 1e-10 * (scale * olj.r_cut + 1e-300) + 1e-300)
+            for k in (1, 36, 63):
+                s.step(k, DT, thermostat=gth, barostat=gba)
+            s.download(st)
+            m = s.macro()
+            assert s.stats()["tile_lists"] == 1
+        r = o.copy()
+        run_oracle(olj, r, 100, oth, oba)
+        dx = np.abs(st.position - r.pos)
+        assert np.minimum(dx, np.abs(dx - r.box)).max() <= 1e-8
+        assert np.abs(st.velocity - r.vel).max() <= 1e-8
+        assert np.abs(st.boundary_box - r.box).max() <= 1e-9
+        runs.append((st.position.copy(), st.velocity.copy(), st.force.copy(), st.temp.copy(), m["pressure"]))
+    for a_, b_ in zip(runs[1][:4], runs[2][:4]):
+        assert np.array_equal(a_, b_)
+    assert runs[1][4] == runs[2][4]
 
 
 def run_oracle(olj, o, n_steps, th=None, ba=None):
