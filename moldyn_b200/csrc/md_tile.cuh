@@ -34,6 +34,7 @@ struct TileTab {
     int col_base[TILE_COLS];  // first cell of the window column in the cell table
     double shx[TILE_COLS], shy[TILE_COLS];  // image shift of the window column (-L, 0, +L)
     double shz;               // image shift of the wrapped z-runs (odd run index)
+    double ctr[3];            // centre of the brick's nominal extent: staged atoms are re-imaged next to it
     int own_src[16], own_loc[16], own_pref[17];
     int n_shell, n_own;
     int zlo, zhi;             // own z cells [zlo, zhi)
@@ -75,6 +76,9 @@ __device__ __forceinline__ void tile_setup(TileTab &T, const Grid &g, const int 
         if (t == 0) {
             T.shz = uz0 < 0 ? -sc->box[2] : sc->box[2];
             T.zlo = zlo; T.zhi = zhi;
+            T.ctr[0] = (4 * bx + 2) * (sc->box[0] / ncx);
+            T.ctr[1] = (4 * by + 2) * (sc->box[1] / ncy);
+            T.ctr[2] = 0.5 * (zlo + zhi) * (sc->box[2] / ncz);
         }
     }
     __syncthreads();
@@ -136,46 +140,70 @@ __global__ void k_tile_reset(Scalars *sc)
     sc->tile_own_max = 0;
 }
 
-// Stages the shell: x, y, z planes of every run → sx, sy, sz (sh_cap doubles each), cp.async.bulk + mbarrier.  `shift`:
-// add the periodic image shifts in place afterwards (force kernel); the list builder keeps the stored coordinates.
-__device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, double *sx, double *sy, double *sz,
-                                           unsigned long long *bar, bool shift)
+// Stages the shell: x, y, z planes of every run → sx, sy, sz (sh_cap doubles each).
+//   image = false (list builder): the stored coordinates as they are — the builder applies the reference's own (x_q - x_i) -+ L.
+//   image = true (force kernel): every atom is placed next to the brick — the run's periodic shift, then one more box length
+//     if the atom has crossed a box face since the lists were built (the drift wraps coordinates into [0, L); relative to the
+//     brick centre the true image is the one within half a box).  The pair loop then needs no minimum-image step at all.
+//   tma = true: cp.async.bulk per run and plane + mbarrier, then the image pass over shared memory; tma = false: the block's
+//     threads copy the runs themselves (coalesced within a run) and apply the image on the way.
+__device__ __forceinline__ double tile_image(double x, double shift, double centre, double L)
 {
-    const int t = threadIdx.x;
-    if (t == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (unsigned)T.n_shell * 24u);
+    x += shift;
+    const double d = x - centre, h = 0.5 * L;
+    return d > h ? x - L : (d < -h ? x + L : x);
+}
+
+__device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, const Scalars *sc, double *sx, double *sy, double *sz,
+                                           unsigned long long *bar, bool image, bool tma)
+{
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
+    if (tma) {
+        if (t == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (unsigned)T.n_shell * 24u);
+        }
+        __syncthreads();
+        if (t < 32) {
+            for (int r = t; r < TILE_RUNS; r += 32) {
+                const int cnt = T.cp_cnt[r];
+                if (cnt > 0) {
+                    const int s = T.cp_src[r], d = T.cp_dst[r];
+                    tma_load_1d(sx + d, a.x + s, (unsigned)cnt * 8u, bar);
+                    tma_load_1d(sy + d, a.y + s, (unsigned)cnt * 8u, bar);
+                    tma_load_1d(sz + d, a.z + s, (unsigned)cnt * 8u, bar);
+                }
+            }
+        }
+        mbar_wait(bar, 0u);
+        if (image) {
+            __syncthreads();
+            for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
+                const int len = T.run_len[r], loc = T.run_loc[r];
+                const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
+                for (int e = lane; e < len; e += 32) {
+                    sx[loc + e] = tile_image(sx[loc + e], dx, T.ctr[0], Lx);
+                    sy[loc + e] = tile_image(sy[loc + e], dy, T.ctr[1], Ly);
+                    sz[loc + e] = tile_image(sz[loc + e], dz, T.ctr[2], Lz);
+                }
+            }
+        }
+    } else {
+        for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
+            const int len = T.run_len[r], loc = T.run_loc[r], src = T.run_src[r];
+            const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
+            for (int e = lane; e < len; e += 32) {
+                const double x = a.x[src + e], y = a.y[src + e], z = a.z[src + e];
+                sx[loc + e] = image ? tile_image(x, dx, T.ctr[0], Lx) : x;
+                sy[loc + e] = image ? tile_image(y, dy, T.ctr[1], Ly) : y;
+                sz[loc + e] = image ? tile_image(z, dz, T.ctr[2], Lz) : z;
+            }
+        }
     }
     __syncthreads();
-    if (t < 32) {
-        for (int r = t; r < TILE_RUNS; r += 32) {
-            const int cnt = T.cp_cnt[r];
-            if (cnt > 0) {
-                const int s = T.cp_src[r], d = T.cp_dst[r];
-                tma_load_1d(sx + d, a.x + s, (unsigned)cnt * 8u, bar);
-                tma_load_1d(sy + d, a.y + s, (unsigned)cnt * 8u, bar);
-                tma_load_1d(sz + d, a.z + s, (unsigned)cnt * 8u, bar);
-            }
-        }
-    }
-    mbar_wait(bar, 0u);
-    if (shift) {
-        __syncthreads();
-        const int w = t >> 5, lane = t & 31;
-        for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
-            const int len = T.run_len[r];
-            if (len == 0) continue;
-            const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
-            if (dx == 0.0 && dy == 0.0 && dz == 0.0) continue;
-            const int loc = T.run_loc[r];
-            for (int e = lane; e < len; e += 32) {
-                sx[loc + e] += dx; sy[loc + e] += dy; sz[loc + e] += dz;
-            }
-        }
-        __syncthreads();
-    }
 }
 
 // brick atom a (0 <= a < n_own) → own column, shell slot, sorted index
@@ -197,14 +225,14 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
                                                            const int *__restrict__ cell_sorted, Scalars *sc, double r_list,
                                                            double r2_list, unsigned short *__restrict__ nbrT, int cap,
                                                            int *__restrict__ nbr_cnt, const int *__restrict__ brick_order,
-                                                           int sh_cap)
+                                                           int sh_cap, int tma)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     double *sx = reinterpret_cast<double *>(tile_smem), *sy = sx + sh_cap, *sz = sy + sh_cap;
     __shared__ TileTab T;
     __shared__ __align__(8) unsigned long long bar;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
-    tile_stage(T, a, sx, sy, sz, &bar, false);
+    tile_stage(T, a, sc, sx, sy, sz, &bar, false, tma != 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncz = g.nc[2];
     int wmax = 0;
@@ -377,7 +405,7 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
 __global__ void __launch_bounds__(TILE_BLOCK, 2)
     k_force_tile(Grid g, Arrays a, const int *__restrict__ cell_start, const unsigned short *__restrict__ nbrT, int cap,
                  const int *__restrict__ nbr_cnt, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr,
-                 int do_step, const ForceConsts fc, const int *__restrict__ brick_order, int sh_cap, int own_cap)
+                 int do_step, const ForceConsts fc, const int *__restrict__ brick_order, int sh_cap, int own_cap, int tma)
 {
     // do_step bits: 1 = MD step (both half-kicks fused in), 4 = guarded (see k_force)
     if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
@@ -387,7 +415,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2)
     __shared__ TileTab T;
     __shared__ __align__(8) unsigned long long bar;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
-    tile_stage(T, a, sx, sy, sz, &bar, true);
+    tile_stage(T, a, sc, sx, sy, sz, &bar, true, tma != 0);
     const bool step = (do_step & 1) != 0;
     const bool store_state = !step || sc->steps_left <= 1;
     const bool nh = pr->th_kind == 2 || !step;

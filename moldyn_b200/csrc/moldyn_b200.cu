@@ -552,6 +552,13 @@ int rebuild_lists(md_ctx *ctx)
     return MD_OK;
 }
 
+// Shell staging of the tile kernels: 1 = cp.async.bulk (TMA) per run and plane, 0 = cooperative loads (MOLDYN_B200_TILE_TMA).
+int tile_tma()
+{
+    static const int v = [] { const char *e = std::getenv("MOLDYN_B200_TILE_TMA"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 // K2 in tile form: shell sizes first (they size the kernels' shared memory), then the brick-local lists.
 int build_tile_lists(md_ctx *ctx, bool *fallback)
 {
@@ -597,7 +604,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         k_build_tile<<<ctx->nbricks, TILE_BLOCK, smem_build, st>>>(g, ctx->cur, ctx->cell_start, ctx->cell_sorted, ctx->d_sc,
                                                                    ctx->prm.r_list, r2_list, ctx->nbrT, ctx->cap16,
-                                                                   ctx->nbr_cnt, ctx->brick_order, ctx->sh_cap);
+                                                                   ctx->nbr_cnt, ctx->brick_order, ctx->sh_cap, tile_tma());
         ctx->stats.kernel_launches += 2;
         CK(cudaGetLastError());
         TRY(pull_scalars(ctx));
@@ -636,7 +643,7 @@ int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
         const size_t smem = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
         k_force_tile<<<ctx->nbricks, TILE_BLOCK, smem, ctx->stream>>>(ctx->grid, ctx->cur, ctx->cell_start, ctx->nbrT, ctx->cap16,
                                                                       ctx->nbr_cnt, ctx->d_partials, ctx->d_sc, ctx->d_pr, flags,
-                                                                      fc, ctx->brick_order, ctx->sh_cap, ctx->own_cap);
+                                                                      fc, ctx->brick_order, ctx->sh_cap, ctx->own_cap, tile_tma());
     } else if (ctx->dense) LAUNCH_FORCE(false, true, ctx->force_grid[1]);
     else LAUNCH_FORCE(false, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
@@ -757,7 +764,7 @@ std::vector<unsigned char> chunk_key(const md_ctx *ctx)
                         (long long)ctx->force_grid[0], (long long)ctx->force_grid[1], (long long)ctx->force_grid[2],
                         (long long)ctx->tile_valid, (long long)ctx->cap16, (long long)ctx->sh_cap, (long long)ctx->own_cap,
                         (long long)ctx->nbricks, (long long)ctx->grid.nc[0], (long long)ctx->grid.nc[1],
-                        (long long)ctx->grid.nc[2], (long long)ctx->grid.bz})
+                        (long long)ctx->grid.nc[2], (long long)ctx->grid.bz, (long long)tile_tma()})
         put_i(v);
     return k;
 }
