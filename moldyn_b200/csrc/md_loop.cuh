@@ -310,8 +310,10 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         auto force_pair = [&](int p, int t, int2 C) {
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
-            const double2 X = __ldcg(reinterpret_cast<const double2 *>(a.x) + t), Y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t),
-                          Z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
+            // (positions are stable throughout the phase and the barrier's acquiring loads invalidated this SM's L1 — CCTL.IVALL
+            // in the SASS — so the gathers may use it: partners shared by neighbouring atoms hit)
+            const double2 X = reinterpret_cast<const double2 *>(a.x)[t], Y = reinterpret_cast<const double2 *>(a.y)[t],
+                          Z = reinterpret_cast<const double2 *>(a.z)[t];
             int2 J = reinterpret_cast<const int2 *>(A.nbr)[t];  // row 0
             double2 ux, uy, uz;
             ld_u(p, t, ux, uy, uz);
@@ -321,8 +323,8 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 const bool a0 = k < C.x, a1 = k < C.y;
                 const int j0 = a0 ? J.x : i0, j1 = a1 ? J.y : i0;
                 if (k + 1 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 1) * stride + i0);
-                const double xa = __ldcg(a.x + j0), ya = __ldcg(a.y + j0), za = __ldcg(a.z + j0);
-                const double xb = __ldcg(a.x + j1), yb = __ldcg(a.y + j1), zb = __ldcg(a.z + j1);
+                const double xa = a.x[j0], ya = a.y[j0], za = a.z[j0];
+                const double xb = a.x[j1], yb = a.y[j1], zb = a.z[j1];
                 if (EXACT) {
                     if (a0) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
                     if (a1) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);

@@ -1370,7 +1370,6 @@ int md_comm_init(md_ctx *ctx, int rank, int nranks, const uint8_t id[MD_UNIQUE_I
     d.right = (rank + 1) % nranks;
     TRY(dev_alloc(ctx, &d.d_cnt, 8));
     CK(cudaMallocHost((void **)&d.h_cnt, 8 * sizeof(int)));
-    ctx->cfg.loop_mode = MD_LOOP_HOST;
     return MD_OK;
 }
 
