@@ -15,13 +15,16 @@ namespace md {
 //
 //   phase A  lambda-scale, pending barostat scale, drift, wrap of the thread's atoms (k_kick_drift's arithmetic): read x,
 //            write x'.  Atoms WITHOUT listed partners (60-80 % of the gas) finish their step here: F = 0, v'' = u' =
-//            lambda*u stays in shared memory, their K5 terms are summed.  Multi-GPU: the blocks that own the pairs the
-//            neighbours see as ghosts take those first, store them into the neighbours' planes (NVLink), fence, and the last
-//            of them raises the neighbours' halo flags while the rest of the grid is still drifting.
-//   barrier  every drifted position is visible to the whole grid.
+//            lambda*u stays in shared memory, their K5 terms are summed.
+//   barrier  every drifted position is visible to the whole grid.  Multi-GPU: block 0 then raises the step's flag in both
+//            neighbours' mailboxes (one release store each over NVLink) — nothing else crosses the link on the sender's side.
 //   phase B  the thread's pairs with listed partners: pair forces (gathers from L2), both half-kicks, K5 terms; u' back to
 //            shared memory.  Multi-GPU: pairs whose lists hold no ghost first; the others wait for the neighbours' flags
-//            only when the block gets there.
+//            only when the block gets there and then read their ghost partners STRAIGHT FROM THE NEIGHBOUR'S PLANES (peer
+//            loads): a ghost is a face atom of the neighbour — a prefix / suffix of its sorted order — so its address is
+//            the list index plus a constant.  (A first version pushed the face atoms into the neighbours' ghost slots from
+//            phase A: the pushing blocks' system-scope fences sat on the critical path, drift + barrier 17.9 us at
+//            5*10^5 atoms per GPU against 12.2 us for 10^6 on one GPU — profiles/r02_bench_c3_2gpu_push.txt.)
 //   tail     block sums -> ticket -> the last block folds, exchanges the rank sums through the peer mailboxes, finalizes
 //            (T, P, lambda, myu, rebuild decision) and release-stores the step's sequence number; the other blocks wait for
 //            it and start the next step.
@@ -48,7 +51,9 @@ struct LoopArgs {
     Scalars *sc;
     const Params *pr;
     const Peers *peers;     // NULL on one GPU
-    HaloPush h;             // where the face atoms land in the neighbours' planes (m = {0, 0} on one GPU)
+    // multi-GPU: ghost j in [n, n_gl) is atom j + off of the LEFT neighbour's planes gl*, ghost j >= n_gl of the right one's
+    int n_gl;
+    const double *glx, *gly, *glz, *grx, *gry, *grz;  // (already offset: index them with the list entry j)
     long long max_steps;    // steps this launch may run (host-stepped loop: 1)
     ForceConsts fc;
 };
@@ -128,9 +133,6 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     const int n = A.n, P = A.pairs_per_thread;
     const int npairs = (n + 1) >> 1;
     const bool multi = A.peers != nullptr;
-    // face pairs: every pair that holds an atom of the prefix [0, m0) or of the suffix [n - m1, n)
-    const int pl = multi ? min((A.h.m[0] + 1) >> 1, npairs) : 0;
-    const int pr0 = multi ? max(min((n - A.h.m[1]) >> 1, npairs), pl) : npairs;
     const bool nh = pr->th_kind == 2;
     const double dt = pr->dt, hc = fc.hc, mass = fc.mass;
     const PairAcc zero = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         for (int q = 0; q < NSUM; ++q) s.v[q] = 0.0;
 
         // ---- phase A ----------------------------------------------------------------------------------------------------
-        auto drift_pair = [&](int p, int t, bool face) {
+        auto drift_pair = [&](int p, int t) {
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
             double2 x = __ldcg(reinterpret_cast<const double2 *>(a.x) + t), y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t),
@@ -220,10 +222,6 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             } else {
                 a.x[i0] = x.x; a.y[i0] = y.x; a.z[i0] = z.x;
                 C.y = 1;  // (not an atom: nothing to finish)
-            }
-            if (face) {
-                push_atom(A.h, i0, n, x.x, y.x, z.x);
-                if (has1) push_atom(A.h, i0 + 1, n, x.y, y.y, z.y);
             }
             // atoms without listed partners: F = 0, the step ends here (v'' = u' = lambda*u); the others keep u for phase B
             const bool s0 = C.x == 0, s1 = C.y == 0;
@@ -250,41 +248,9 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 }
             }
         };
-        const auto is_face = [&](int t) { return t < pl || t >= pr0; };
-        if (multi) {
-            // Face pairs first, in every block that owns some (which blocks do follows from the fixed pair -> thread map:
-            // blocks [0, (pl - 1) / (P*512)] and the blocks from pr0 / (P*512) on); they fence their stores system-wide and
-            // count in; the last of them raises the neighbours' flags.
-            const int per_block = P * LOOP_BLOCK;
-            const int b_last = npairs > 0 ? (npairs - 1) / per_block : 0;
-            const int lo_end = pl > 0 ? (pl - 1) / per_block : -1;        // last block with left-face pairs
-            const int hi_begin = pr0 < npairs ? pr0 / per_block : b_last + 1;  // first block with right-face pairs
-            const bool owns_face = bid <= lo_end || (bid >= hi_begin && bid <= b_last);
-            const int n_face_blocks = (lo_end + 1) + (b_last - hi_begin + 1) - max(0, lo_end - hi_begin + 1);
-            if (owns_face) {
-                for (int p = 0; p < P; ++p) {
-                    const int t = pair_of(p);
-                    if (t < npairs && is_face(t)) drift_pair(p, t, true);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    __threadfence_system();
-                    const unsigned int old = atomicAdd(&sc->face_arrive[0], 1u);
-                    if (old == (unsigned int)n_face_blocks - 1u) {
-                        __threadfence_system();
-                        st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
-                        st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
-                    }
-                }
-            } else if (n_face_blocks == 0 && bid == 0 && tid == 0) {
-                // nothing to push this epoch: the neighbours still wait for the flags
-                st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);
-                st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
-            }
-        }
         for (int p = 0; p < P; ++p) {
             const int t = pair_of(p);
-            if (t < npairs && !is_face(t)) drift_pair(p, t, false);
+            if (t < npairs) drift_pair(p, t);
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[0] += t - tq; tq = t; }
         MD_TRACE(bid == 0 && tid == 0, 1);
@@ -298,6 +264,12 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             while (ld_acquire_gpu(&sc->bar_arrive) < (unsigned int)nb) { }
         }
         __syncthreads();
+        if (multi && bid == 0 && tid == 0) {
+            // every block's drifted positions are in this GPU's L2 (the barrier's releases): the neighbours may read our face
+            // atoms of this step
+            st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
+            st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
+        }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[1] += t - tq; tq = t; }
         MD_TRACE(bid == 0 && tid == 0, 2);
 
@@ -307,7 +279,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         c.hx = Lx / 2.0; c.hy = Ly / 2.0; c.hz = Lz / 2.0;
         c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
         const size_t stride = (size_t)A.npad;
-        auto force_pair = [&](int p, int t, int2 C) {
+        auto force_pair = [&](int p, int t, int2 C, bool ghosts) {
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
             // (positions are stable throughout the phase and the barrier's acquiring loads invalidated this SM's L1 — CCTL.IVALL
@@ -323,8 +295,13 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 const bool a0 = k < C.x, a1 = k < C.y;
                 const int j0 = a0 ? J.x : i0, j1 = a1 ? J.y : i0;
                 if (k + 1 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 1) * stride + i0);
-                const double xa = a.x[j0], ya = a.y[j0], za = a.z[j0];
-                const double xb = a.x[j1], yb = a.y[j1], zb = a.z[j1];
+                const double *bxa = a.x, *bya = a.y, *bza = a.z, *bxb = a.x, *byb = a.y, *bzb = a.z;
+                if (ghosts) {  // (second pass of the multi-GPU path only: a partner at or beyond n lives on a neighbour)
+                    if (j0 >= n) { const bool l = j0 < A.n_gl; bxa = l ? A.glx : A.grx; bya = l ? A.gly : A.gry; bza = l ? A.glz : A.grz; }
+                    if (j1 >= n) { const bool l = j1 < A.n_gl; bxb = l ? A.glx : A.grx; byb = l ? A.gly : A.gry; bzb = l ? A.glz : A.grz; }
+                }
+                const double xa = bxa[j0], ya = bya[j0], za = bza[j0];
+                const double xb = bxb[j1], yb = byb[j1], zb = bzb[j1];
                 if (EXACT) {
                     if (a0) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
                     if (a1) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
@@ -347,7 +324,8 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         };
         for (int pass = 0; pass < (multi ? 2 : 1); ++pass) {
             if (pass == 1) {
-                // the neighbours' ghosts of this step (their face blocks fenced the stores before raising the flag)
+                // the neighbours' drifted positions of this step are in their L2 (the acquiring loads also drop this SM's L1
+                // lines of the previous step's peer reads)
                 __shared__ int halo_late;
                 if (tid == 0) {
                     const Mail *own = A.peers->mail[A.peers->rank];
@@ -366,7 +344,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 if (2 * t + 1 >= n) C.y = 0;
                 const int ghost = ((C.x | C.y) & LOOP_GHOST_FLAG) ? 1 : 0;
                 C.x &= ~LOOP_GHOST_FLAG; C.y &= ~LOOP_GHOST_FLAG;
-                if ((C.x | C.y) != 0 && ghost == pass) force_pair(p, t, C);
+                if ((C.x | C.y) != 0 && ghost == pass) force_pair(p, t, C, pass == 1);
             }
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[2] += t - tq; tq = t; }

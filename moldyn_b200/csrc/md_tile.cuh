@@ -1,5 +1,5 @@
-// md_tile.cuh — K2 + K3 for dense systems (FAST mode, one GPU): brick tiles staged in shared memory by TMA bulk copies,
-// brick-local 16-bit neighbour lists, warp-cooperative pair loop with shuffle accumulation.
+// md_tile.cuh — K2 + K3 for dense systems (FAST mode, one GPU): brick tiles staged in shared memory, brick-local 16-bit
+// neighbour lists, warp-cooperative pair loop with shuffle accumulation.
 // Part of md_kernels.cuh (included from there, in order; one translation unit).
 #pragma once
 
@@ -10,11 +10,10 @@ namespace md {
 // FP64 pipe a third busy.  Here a thread block owns a BRICK of the cell grid (4 x 4 columns x bz cells, a few hundred atoms)
 // and stages the brick plus the two-cell shell around it — every possible partner of its atoms, ~8 x the brick — in shared
 // memory once: the cell sort numbers the (x, y) columns brick by brick (Grid::brick), so the shell is 64 columns x (one or
-// two) contiguous z-runs of the sorted planes, fetched with cp.async.bulk (UBLKCP) and an mbarrier.  The lists hold
-// 16-bit indices into the shell, stored atom-major; the 32 lanes of a warp walk ONE atom's list together (coalesced index
-// reads, shared-memory gathers of mostly consecutive slots: conflict-free), four independent pair terms per lane in flight,
-// and fold their partial forces with xor-shuffles in a fixed order (deterministic).  Periodic images are resolved when the
-// shell is staged (the wrapped runs get +-L added in shared memory), so the pair loop has no minimum-image step at all.
+// two) contiguous z-runs of the sorted planes.  The lists hold 16-bit indices into the shell, stored atom-major; eight
+// lanes of a warp walk ONE atom's list together (shared-memory gathers of mostly consecutive slots: conflict-free), four
+// independent pair terms per lane in flight, and fold their partial forces with xor-shuffles in a fixed order
+// (deterministic).  Periodic images are resolved when the shell is staged, so the pair loop has no minimum-image step.
 // The K2 kernel stages the same shell (same code, same local indices) and evaluates the reference's predicate
 // (potential.rs:181-204 widened by the skin) in the reference's own operation order on the unshifted coordinates.
 constexpr int TILE_BLOCK = 256;
@@ -28,9 +27,6 @@ struct TileTab {
     int run_src[TILE_RUNS];   // sorted index of the run's first atom
     int run_len[TILE_RUNS];
     int run_loc[TILE_RUNS];   // shell slot of the run's first atom
-    int cp_src[TILE_RUNS];    // bulk copy: first element (even), element count (even), first slot (even)
-    int cp_cnt[TILE_RUNS];
-    int cp_dst[TILE_RUNS];
     int col_base[TILE_COLS];  // first cell of the window column in the cell table
     double shx[TILE_COLS], shy[TILE_COLS];  // image shift of the window column (-L, 0, +L)
     double shz;               // image shift of the wrapped z-runs (odd run index)
@@ -66,13 +62,6 @@ __device__ __forceinline__ void tile_setup(TileTab &T, const Grid &g, const int 
         const int sB = zB1 > zB0 ? cell_start[base + zB0] : 0, eB = zB1 > zB0 ? cell_start[base + zB1] : 0;
         T.run_src[2 * t] = sA; T.run_len[2 * t] = eA - sA;
         T.run_src[2 * t + 1] = sB; T.run_len[2 * t + 1] = eB - sB;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int s = h ? sB : sA, e = h ? eB : eA;
-            // 16-byte granules of the planes: the copy starts at an even element and has an even length
-            T.cp_src[2 * t + h] = s & ~1;
-            T.cp_cnt[2 * t + h] = e > s ? ((e + 1) & ~1) - (s & ~1) : 0;
-        }
         if (t == 0) {
             T.shz = uz0 < 0 ? -sc->box[2] : sc->box[2];
             T.zlo = zlo; T.zhi = zhi;
@@ -82,10 +71,10 @@ __device__ __forceinline__ void tile_setup(TileTab &T, const Grid &g, const int 
         }
     }
     __syncthreads();
-    if (t < 32) {  // exclusive scan of the 128 copy lengths: four runs per lane
+    if (t < 32) {  // exclusive scan of the 128 run lengths: four runs per lane
         int c[4], sum = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { c[k] = T.cp_cnt[4 * t + k]; sum += c[k]; }
+        for (int k = 0; k < 4; ++k) { c[k] = T.run_len[4 * t + k]; sum += c[k]; }
         int inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -95,9 +84,7 @@ __device__ __forceinline__ void tile_setup(TileTab &T, const Grid &g, const int 
         int off = inc - sum;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int r = 4 * t + k;
-            T.cp_dst[r] = off;
-            T.run_loc[r] = off + (T.run_src[r] & 1);
+            T.run_loc[4 * t + k] = off;
             off += c[k];
         }
         if (t == 31) T.n_shell = inc;
@@ -140,13 +127,16 @@ __global__ void k_tile_reset(Scalars *sc)
     sc->tile_own_max = 0;
 }
 
-// Stages the shell: x, y, z planes of every run → sx, sy, sz (sh_cap doubles each).
+// Stages the shell: the x, y, z planes of every run → sp[3 * slot + {0, 1, 2}] (array of structures: a partner costs the pair
+// loop ONE address computation and three LDS.64 at immediate offsets; consecutive slots are conflict-free — 24-byte stride).
 //   image = false (list builder): the stored coordinates as they are — the builder applies the reference's own (x_q - x_i) -+ L.
 //   image = true (force kernel): every atom is placed next to the brick — the run's periodic shift, then one more box length
 //     if the atom has crossed a box face since the lists were built (the drift wraps coordinates into [0, L); relative to the
 //     brick centre the true image is the one within half a box).  The pair loop then needs no minimum-image step at all.
-//   tma = true: cp.async.bulk per run and plane + mbarrier, then the image pass over shared memory; tma = false: the block's
-//     threads copy the runs themselves (coalesced within a run) and apply the image on the way.
+// The block's threads copy the runs themselves, coalesced within a run.  (A cp.async.bulk — TMA — copy per run and plane into
+// separate planes was measured first: k_force_tile 263.3 vs 261.0 us on C5, no gain — a shell is ~200 runs of ~200 bytes, too
+// small and too irregular for bulk copies to pay — and the planes cost the pair loop two more address computations per
+// partner.  profiles/r02_bench_c5_tile_v1.txt)
 __device__ __forceinline__ double tile_image(double x, double shift, double centre, double L)
 {
     x += shift;
@@ -154,53 +144,19 @@ __device__ __forceinline__ double tile_image(double x, double shift, double cent
     return d > h ? x - L : (d < -h ? x + L : x);
 }
 
-__device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, const Scalars *sc, double *sx, double *sy, double *sz,
-                                           unsigned long long *bar, bool image, bool tma)
+__device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, const Scalars *sc, double *sp, bool image)
 {
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-    if (tma) {
-        if (t == 0) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)T.n_shell * 24u);
-        }
-        __syncthreads();
-        if (t < 32) {
-            for (int r = t; r < TILE_RUNS; r += 32) {
-                const int cnt = T.cp_cnt[r];
-                if (cnt > 0) {
-                    const int s = T.cp_src[r], d = T.cp_dst[r];
-                    tma_load_1d(sx + d, a.x + s, (unsigned)cnt * 8u, bar);
-                    tma_load_1d(sy + d, a.y + s, (unsigned)cnt * 8u, bar);
-                    tma_load_1d(sz + d, a.z + s, (unsigned)cnt * 8u, bar);
-                }
-            }
-        }
-        mbar_wait(bar, 0u);
-        if (image) {
-            __syncthreads();
-            for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
-                const int len = T.run_len[r], loc = T.run_loc[r];
-                const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
-                for (int e = lane; e < len; e += 32) {
-                    sx[loc + e] = tile_image(sx[loc + e], dx, T.ctr[0], Lx);
-                    sy[loc + e] = tile_image(sy[loc + e], dy, T.ctr[1], Ly);
-                    sz[loc + e] = tile_image(sz[loc + e], dz, T.ctr[2], Lz);
-                }
-            }
-        }
-    } else {
-        for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
-            const int len = T.run_len[r], loc = T.run_loc[r], src = T.run_src[r];
-            const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
-            for (int e = lane; e < len; e += 32) {
-                const double x = a.x[src + e], y = a.y[src + e], z = a.z[src + e];
-                sx[loc + e] = image ? tile_image(x, dx, T.ctr[0], Lx) : x;
-                sy[loc + e] = image ? tile_image(y, dy, T.ctr[1], Ly) : y;
-                sz[loc + e] = image ? tile_image(z, dz, T.ctr[2], Lz) : z;
-            }
+    for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
+        const int len = T.run_len[r], loc = T.run_loc[r], src = T.run_src[r];
+        const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
+        for (int e = lane; e < len; e += 32) {
+            const double x = a.x[src + e], y = a.y[src + e], z = a.z[src + e];
+            double *o = sp + 3 * (loc + e);
+            o[0] = image ? tile_image(x, dx, T.ctr[0], Lx) : x;
+            o[1] = image ? tile_image(y, dy, T.ctr[1], Ly) : y;
+            o[2] = image ? tile_image(z, dz, T.ctr[2], Lz) : z;
         }
     }
     __syncthreads();
@@ -218,21 +174,22 @@ __device__ __forceinline__ void tile_locate(const TileTab &T, int a, int &oc, in
     gi = T.own_src[oc] + k;
 }
 
-// K2, tile form.  One block per brick; a warp takes an atom, its lanes scan the 25 stencil columns' candidates (one
-// contiguous range of shell slots per column and z part), ballot-compact the hits and write the atom's list: 16-bit shell
-// slots, ascending, atom-major (nbrT[i * cap + k]).
+// K2, tile form.  One block per brick, a warp per atom; lane l < 25 owns stencil column l and walks its candidates — one
+// contiguous range of shell slots for the unwrapped z cells, one for the periodically wrapped ones — evaluating the
+// reference's predicate (potential.rs:181-204 widened by the skin) in the reference's own operation order.  Hits are
+// remembered as bits (64 candidates of the unwrapped range, 32 of the wrapped one per word), the lanes' hit counts are
+// scanned, and every lane writes its hits at its offset: the atom's list is ascending in (column, slot) — the same order
+// whatever the scheduling — 16-bit shell slots, atom-major (nbrT[i * cap + k]).
 __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, const int *__restrict__ cell_start,
-                                                           const int *__restrict__ cell_sorted, Scalars *sc, double r_list,
+                                                           const int *__restrict__ cell_sorted, Scalars *sc,
                                                            double r2_list, unsigned short *__restrict__ nbrT, int cap,
-                                                           int *__restrict__ nbr_cnt, const int *__restrict__ brick_order,
-                                                           int sh_cap, int tma)
+                                                           int *__restrict__ nbr_cnt, const int *__restrict__ brick_order)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    double *sx = reinterpret_cast<double *>(tile_smem), *sy = sx + sh_cap, *sz = sy + sh_cap;
+    double *sp = reinterpret_cast<double *>(tile_smem);
     __shared__ TileTab T;
-    __shared__ __align__(8) unsigned long long bar;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
-    tile_stage(T, a, sc, sx, sy, sz, &bar, false, tma != 0);
+    tile_stage(T, a, sc, sp, false);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncz = g.nc[2];
     int wmax = 0;
@@ -240,10 +197,10 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
     for (int ai = warp; ai < T.n_own; ai += TILE_WARPS) {
         int oc, slot, gi;
         tile_locate(T, ai, oc, slot, gi);
-        const double xi = sx[slot], yi = sy[slot], zi = sz[slot];
+        const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
         const int cz = cell_sorted[gi] % ncz;
         const int lx = oc >> 2, ly = oc & 3;
-        // lane l < 25 prepares stencil column l: slot ranges of the unwrapped and of the wrapped z part
+        // this lane's stencil column: slot ranges of the unwrapped (A) and of the wrapped (B) z part
         int sA = 0, eA = 0, sB = 0, eB = 0;
         double shx = 0.0, shy = 0.0;
         if (lane < 25) {
@@ -263,40 +220,62 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
             }
             shx = T.shx[wcol]; shy = T.shy[wcol];
         }
-        int cnt = 0;
-        unsigned short *__restrict__ out = nbrT + (size_t)gi * cap;
-        for (int col = 0; col < 25; ++col) {
-            const double dx = __shfl_sync(0xffffffffu, shx, col), dy = __shfl_sync(0xffffffffu, shy, col);
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                const int s = __shfl_sync(0xffffffffu, part ? sB : sA, col), e = __shfl_sync(0xffffffffu, part ? eB : eA, col);
-                const double dz = part ? T.shz : 0.0;
-                for (int q0 = s; q0 < e; q0 += 32) {
-                    const int q = q0 + lane;
-                    bool hit = false;
-                    if (q < e) {
-                        // the reference's operations in the reference's order: (x_q - x_i) -+ L, norm² compared against the
-                        // largest double whose square root is <= r_list
-                        const double rx = __dadd_rn(__dsub_rn(sx[q], xi), dx);
-                        const double ry = __dadd_rn(__dsub_rn(sy[q], yi), dy);
-                        const double rz = __dadd_rn(__dsub_rn(sz[q], zi), dz);
-                        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                        hit = r2 <= r2_list && q != slot;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-                        if (pos < cap) out[pos] = (unsigned short)q;
-                    }
-                    cnt += __popc(m);
-                }
-            }
+        // the reference's operations in the reference's order: (x_q - x_i) -+ L, norm² compared against the largest double
+        // whose square root is <= r_list (adding 0.0 is exact: unshifted columns skip the add)
+        auto hit = [&](int q, double dz) {
+            const double *pq = sp + 3 * q;
+            const double rx = __dadd_rn(__dsub_rn(pq[0], xi), shx);
+            const double ry = __dadd_rn(__dsub_rn(pq[1], yi), shy);
+            const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+            return r2 <= r2_list && q != slot;
+        };
+        unsigned long long mA = 0ull;
+        unsigned int mB = 0u;
+        int extra = 0;  // hits beyond the bit words (runs longer than 64 / 32 candidates): counted, written by a second scan
+        const int nA = eA - sA, nB = eB - sB;
+        for (int k = 0; k < nA; ++k) {
+            const bool h = hit(sA + k, 0.0);
+            if (k < 64) mA |= (unsigned long long)h << k;
+            else extra += h;
         }
+        const double shz = T.shz;
+        for (int k = 0; k < nB; ++k) {
+            const bool h = hit(sB + k, shz);
+            if (k < 32) mB |= (unsigned int)h << k;
+            else extra += h;
+        }
+        const int mine = __popcll(mA) + __popc(mB) + extra;
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int cnt = __shfl_sync(0xffffffffu, inc, 31);
+        int pos = inc - mine;
+        unsigned short *__restrict__ out = nbrT + (size_t)gi * cap;
+        // A part: bits, then whatever lies beyond the word; then the B part likewise — ascending slots within the column
+        while (mA) {
+            const int k = __ffsll((long long)mA) - 1;
+            mA &= mA - 1;
+            if (pos < cap) out[pos] = (unsigned short)(sA + k);
+            ++pos;
+        }
+        for (int k = 64; k < nA; ++k)
+            if (hit(sA + k, 0.0)) { if (pos < cap) out[pos] = (unsigned short)(sA + k); ++pos; }
+        while (mB) {
+            const int k = __ffs((int)mB) - 1;
+            mB &= mB - 1;
+            if (pos < cap) out[pos] = (unsigned short)(sB + k);
+            ++pos;
+        }
+        for (int k = 32; k < nB; ++k)
+            if (hit(sB + k, shz)) { if (pos < cap) out[pos] = (unsigned short)(sB + k); ++pos; }
         if (lane == 0) nbr_cnt[gi] = min(cnt, cap);
         wmax = max(wmax, cnt);
         wsum += (unsigned long long)cnt;
     }
-    (void)r_list;
     if (lane == 0 && wsum) {
         atomicMax(&sc->nbr_max, wmax);
         atomicAdd(&sc->nbr_total, wsum);
@@ -307,11 +286,10 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
 // Introspection (md_neighbour_lists): the brick-local lists as sorted indices in the k-major table of the other paths.
 __global__ void __launch_bounds__(TILE_BLOCK) k_tile_expand(Grid g, const int *__restrict__ cell_start, const Scalars *sc,
                                                             const unsigned short *__restrict__ nbrT, int cap,
-                                                            const int *__restrict__ nbr_cnt, int *__restrict__ nbr, int npad,
-                                                            int sh_cap)
+                                                            const int *__restrict__ nbr_cnt, int *__restrict__ nbr, int npad)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    int *slot_to_sorted = reinterpret_cast<int *>(tile_smem);  // sh_cap ints
+    int *slot_to_sorted = reinterpret_cast<int *>(tile_smem);  // one int per shell slot
     __shared__ TileTab T;
     tile_setup(T, g, cell_start, sc, blockIdx.x);
     for (int r = threadIdx.x >> 5; r < TILE_RUNS; r += TILE_WARPS)
@@ -323,62 +301,52 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_tile_expand(Grid g, const int *_
         const int cnt = nbr_cnt[gi];
         for (int k = threadIdx.x & 31; k < cnt; k += 32) nbr[(size_t)k * npad + gi] = slot_to_sorted[nbrT[(size_t)gi * cap + k]];
     }
-    (void)sh_cap;
 }
 
 // ---- K3, tile form ----------------------------------------------------------------------------------------------------
-// Pair phase: warp w takes brick atoms w, w + 8, ...; lane l evaluates list entries l, l + 32, ... — rows of 32 entries, four
-// rows (four independent pair terms per lane) per trip.  The index rows of the NEXT atom are fetched before the current
-// atom's pair terms (registers), so the table's HBM latency hides behind ~6 rows of arithmetic.
-constexpr int TILE_ROWS_MAX = 8;  // rows of 32 entries kept in registers per atom (cap <= 256)
-
+// Pair phase: a warp takes FOUR brick atoms at a time, eight lanes each.  Lane (s, l) evaluates entries l, l + 8, l + 16,
+// l + 24 of atom s's list per trip — four independent pair terms in flight, consecutive lanes on consecutive slots
+// (conflict-free LDS.64) — with the next trip's four 16-bit indices fetched before the current trip's arithmetic.  The
+// partial forces of an atom are folded over its eight lanes with three xor-shuffles in a fixed order (deterministic): all
+// the per-atom work — locate, count, fold, hand-over — is paid once per four atoms.
 template <int UW>
-__device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *sx, const double *sy, const double *sz,
+__device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *__restrict__ sp,
                                                 const unsigned short *__restrict__ nbrT, int cap,
                                                 const int *__restrict__ nbr_cnt, const ForceConsts &fc, double *fst)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    LjConst c{};  // (no minimum image: the shell holds the images)
-    int cur[TILE_ROWS_MAX], nxt[TILE_ROWS_MAX];
-    int oc, slot, gi, cnt = 0;
-    int n_slot = 0, n_gi = 0, n_cnt = 0;
-    const int n_own = T.n_own, own_cap = T.own_pref[16];
-    (void)own_cap;
-    auto fetch = [&](int ai, int &s_, int &g_, int &c_, int *rows) {
-        int oc_;
-        tile_locate(T, ai, oc_, s_, g_);
-        c_ = nbr_cnt[g_];
-        const unsigned short *lst = nbrT + (size_t)g_ * cap;
-#pragma unroll
-        for (int r = 0; r < TILE_ROWS_MAX; ++r) rows[r] = (r * 32 + lane < c_) ? (int)lst[r * 32 + lane] : 0;
-    };
-    if (warp < n_own) fetch(warp, n_slot, n_gi, n_cnt, nxt);
-    for (int ai = warp; ai < n_own; ai += TILE_WARPS) {
-        slot = n_slot; gi = n_gi; cnt = n_cnt;
-#pragma unroll
-        for (int r = 0; r < TILE_ROWS_MAX; ++r) cur[r] = nxt[r];
-        if (ai + TILE_WARPS < n_own) fetch(ai + TILE_WARPS, n_slot, n_gi, n_cnt, nxt);
-        (void)oc; (void)gi;
-        const double xi = sx[slot], yi = sy[slot], zi = sz[slot];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+    const LjConst c{};  // (no minimum image: the shell holds the images)
+    const int n_own = T.n_own;
+    for (int g0 = 4 * warp; g0 < n_own; g0 += 4 * TILE_WARPS) {  // warp-uniform
+        const int ai = g0 + sub;
+        int oc, slot = 0, gi = 0, cnt = 0;
+        if (ai < n_own) {
+            tile_locate(T, ai, oc, slot, gi);
+            cnt = nbr_cnt[gi];
+        }
+        const unsigned short *__restrict__ lst = nbrT + (size_t)gi * cap;
+        const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
+        const int kmax = __reduce_max_sync(0xffffffffu, cnt);
         PairAcc acc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[u] = PairAcc{0.0, 0.0, 0.0, 0.0, 0.0};
+        int jn[4];
 #pragma unroll
-        for (int r0 = 0; r0 < TILE_ROWS_MAX; r0 += 4) {
-            if (r0 * 32 < cnt) {  // warp-uniform
-                double xj[4], yj[4], zj[4];
+        for (int u = 0; u < 4; ++u) { const int k = u * 8 + l8; jn[u] = k < cnt ? (int)lst[k] : 0; }
+        for (int k0 = 0; k0 < kmax; k0 += 32) {
+            int j[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int j = cur[r0 + u]; xj[u] = sx[j]; yj[u] = sy[j]; zj[u] = sz[j]; }
+            for (int u = 0; u < 4; ++u) j[u] = jn[u];
+            if (k0 + 32 < kmax) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if ((r0 + u) * 32 < cnt)  // warp-uniform: rows beyond the list cost nothing
-                        pair_dense<false, UW>(acc[u], (r0 + u) * 32 + lane < cnt, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
+                for (int u = 0; u < 4; ++u) { const int k = k0 + 32 + u * 8 + l8; jn[u] = k < cnt ? (int)lst[k] : 0; }
             }
-        }
-        // lists longer than the register rows (cap > 256): straight from the table
-        for (int k = TILE_ROWS_MAX * 32 + lane; k - lane < cnt; k += 32) {
-            const int j = k < cnt ? (int)nbrT[(size_t)gi * cap + k] : 0;
-            pair_dense<false, UW>(acc[0], k < cnt, sx[j], sy[j], sz[j], xi, yi, zi, c, fc);
+            double xj[4], yj[4], zj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const double *pj = sp + 3 * j[u]; xj[u] = pj[0]; yj[u] = pj[1]; zj[u] = pj[2]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                pair_dense<false, UW>(acc[u], k0 + u * 8 + l8 < cnt, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
         }
         PairAcc f;
         f.fx = (acc[0].fx + acc[1].fx) + (acc[2].fx + acc[3].fx);
@@ -386,16 +354,16 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
         f.fz = (acc[0].fz + acc[1].fz) + (acc[2].fz + acc[3].fz);
         f.w = UW >= 1 ? (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w) : 0.0;
         f.u = UW >= 2 ? (acc[0].u + acc[1].u) + (acc[2].u + acc[3].u) : 0.0;
-        // fixed-order fold over the lanes
+        // fixed-order fold over the atom's eight lanes
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 4; o > 0; o >>= 1) {
             f.fx += __shfl_xor_sync(0xffffffffu, f.fx, o);
             f.fy += __shfl_xor_sync(0xffffffffu, f.fy, o);
             f.fz += __shfl_xor_sync(0xffffffffu, f.fz, o);
             if (UW >= 1) f.w += __shfl_xor_sync(0xffffffffu, f.w, o);
             if (UW >= 2) f.u += __shfl_xor_sync(0xffffffffu, f.u, o);
         }
-        if (lane == 0) {
+        if (l8 == 0 && ai < n_own) {
             double *o = fst + (size_t)ai * 5;
             o[0] = f.fx; o[1] = f.fy; o[2] = f.fz; o[3] = f.u; o[4] = f.w;
         }
@@ -405,25 +373,24 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
 __global__ void __launch_bounds__(TILE_BLOCK, 2)
     k_force_tile(Grid g, Arrays a, const int *__restrict__ cell_start, const unsigned short *__restrict__ nbrT, int cap,
                  const int *__restrict__ nbr_cnt, double *__restrict__ partials, Scalars *sc, const Params *__restrict__ pr,
-                 int do_step, const ForceConsts fc, const int *__restrict__ brick_order, int sh_cap, int own_cap, int tma)
+                 int do_step, const ForceConsts fc, const int *__restrict__ brick_order, int sh_cap)
 {
     // do_step bits: 1 = MD step (both half-kicks fused in), 4 = guarded (see k_force)
     if ((do_step & 4) && halted(sc)) return;  // uniform over the grid: nobody takes a ticket
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    double *sx = reinterpret_cast<double *>(tile_smem), *sy = sx + sh_cap, *sz = sy + sh_cap;
-    double *fst = sz + sh_cap;  // own_cap x {fx, fy, fz, u, w}
+    double *sp = reinterpret_cast<double *>(tile_smem);  // 3 doubles per shell slot
+    double *fst = sp + 3 * (size_t)sh_cap;                // per brick atom {fx, fy, fz, u, w}
     __shared__ TileTab T;
-    __shared__ __align__(8) unsigned long long bar;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
-    tile_stage(T, a, sc, sx, sy, sz, &bar, true, tma != 0);
+    tile_stage(T, a, sc, sp, true);
     const bool step = (do_step & 1) != 0;
     const bool store_state = !step || sc->steps_left <= 1;
     const bool nh = pr->th_kind == 2 || !step;
     // per-atom potential and virial enter nothing but the stored State and the S_U / S_W sums (see k_force)
     const bool need_u = store_state, need_w = store_state || pr->ba_kind != 0;
-    if (need_u) tile_pair_phase<2>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
-    else if (need_w) tile_pair_phase<1>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
-    else tile_pair_phase<0>(T, sx, sy, sz, nbrT, cap, nbr_cnt, fc, fst);
+    if (need_u) tile_pair_phase<2>(T, sp, nbrT, cap, nbr_cnt, fc, fst);
+    else if (need_w) tile_pair_phase<1>(T, sp, nbrT, cap, nbr_cnt, fc, fst);
+    else tile_pair_phase<0>(T, sp, nbrT, cap, nbr_cnt, fc, fst);
     __syncthreads();
     // epilogue: one thread per brick atom — both half-kicks, K5 terms, stores (k_force's, same arithmetic)
     Sums s;
@@ -463,7 +430,6 @@ __global__ void __launch_bounds__(TILE_BLOCK, 2)
             a.vx[gi] = wx; a.vy[gi] = wy; a.vz[gi] = wz;
         }
     }
-    (void)own_cap;
     block_reduce<TILE_BLOCK>(s);
     grid_reduce_finalize<TILE_BLOCK>(s, partials, sc, pr, step ? FIN_STEP : 0, nullptr);
 }

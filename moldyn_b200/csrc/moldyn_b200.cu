@@ -174,6 +174,7 @@ struct md_ctx {
         double *peer_slab[2] = {nullptr, nullptr};  // left / right neighbour's slab as mapped here
         int64_t peer_npad[2] = {0, 0};
         int peer_base[2] = {0, 0}, peer_half[2] = {0, 0};  // where our face atoms land in the neighbour's planes
+        int peer_own[2] = {0, 0};                          // the neighbours' owned-atom counts (ghost pulls of the step loop)
         unsigned int *push_ticket = nullptr;
         char *gather_buf = nullptr;   // small persistent device buffer for host-level all-gathers
         char *up_buf = nullptr;       // upload staging arena (kept between uploads)
@@ -470,6 +471,7 @@ int refresh_q4(md_ctx *ctx)
 }
 
 HaloPush dist_halo_push_args(md_ctx *ctx);
+void dist_ghost_pull_args(md_ctx *ctx, LoopArgs *A);
 int build_tile_lists(md_ctx *ctx, bool *fallback);
 
 // K1 + K2, host-orchestrated (rare: every O(10-100) steps).  Positions must be consistent with the box
@@ -552,13 +554,6 @@ int rebuild_lists(md_ctx *ctx)
     return MD_OK;
 }
 
-// Shell staging of the tile kernels: 1 = cp.async.bulk (TMA) per run and plane, 0 = cooperative loads (MOLDYN_B200_TILE_TMA).
-int tile_tma()
-{
-    static const int v = [] { const char *e = std::getenv("MOLDYN_B200_TILE_TMA"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 // K2 in tile form: shell sizes first (they size the kernels' shared memory), then the brick-local lists.
 int build_tile_lists(md_ctx *ctx, bool *fallback)
 {
@@ -603,8 +598,8 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
         }
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         k_build_tile<<<ctx->nbricks, TILE_BLOCK, smem_build, st>>>(g, ctx->cur, ctx->cell_start, ctx->cell_sorted, ctx->d_sc,
-                                                                   ctx->prm.r_list, r2_list, ctx->nbrT, ctx->cap16,
-                                                                   ctx->nbr_cnt, ctx->brick_order, ctx->sh_cap, tile_tma());
+                                                                   r2_list, ctx->nbrT, ctx->cap16, ctx->nbr_cnt,
+                                                                   ctx->brick_order);
         ctx->stats.kernel_launches += 2;
         CK(cudaGetLastError());
         TRY(pull_scalars(ctx));
@@ -627,7 +622,12 @@ int launch_kick_drift(md_ctx *ctx, int guarded = 0, const HaloPush *push = nullp
 // Dilute systems run their steps inside the persistent loop (md_loop.cuh); dense ones as graph chunks of the two-kernel step.
 bool loop_wanted(const md_ctx *ctx)
 {
-    return !ctx->dense && ctx->cfg.loop_mode != MD_LOOP_CHUNK && (!ctx->dist.on || ctx->dist.p2p);
+    if (ctx->dense || ctx->cfg.loop_mode == MD_LOOP_CHUNK) return false;
+    if (ctx->dist.on) return ctx->dist.p2p;
+    // one GPU: with a few partners per atom the two-kernel step's force kernel (two atoms per thread, operands of the next
+    // pair prefetched) walks its lists faster than the loop's force phase — measured on C1's steady state (4.9 listed
+    // partners: 14.5 vs 27 us/step); the loop wins where most atoms have none (C2-C4: 0.55) and on states beyond L2
+    return ctx->stats.nbr_mean < 2.0;
 }
 
 int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
@@ -643,7 +643,7 @@ int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
         const size_t smem = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
         k_force_tile<<<ctx->nbricks, TILE_BLOCK, smem, ctx->stream>>>(ctx->grid, ctx->cur, ctx->cell_start, ctx->nbrT, ctx->cap16,
                                                                       ctx->nbr_cnt, ctx->d_partials, ctx->d_sc, ctx->d_pr, flags,
-                                                                      fc, ctx->brick_order, ctx->sh_cap, ctx->own_cap, tile_tma());
+                                                                      fc, ctx->brick_order, ctx->sh_cap);
     } else if (ctx->dense) LAUNCH_FORCE(false, true, ctx->force_grid[1]);
     else LAUNCH_FORCE(false, false, ctx->force_grid[2]);
 #undef LAUNCH_FORCE
@@ -711,7 +711,7 @@ int launch_loop(md_ctx *ctx, long long max_steps)
     A.sc = ctx->d_sc;
     A.pr = ctx->d_pr;
     A.peers = ctx->dist.on ? ctx->dist.peers_dev : nullptr;
-    A.h = ctx->dist.on ? dist_halo_push_args(ctx) : HaloPush{};
+    if (ctx->dist.on) dist_ghost_pull_args(ctx, &A);
     A.max_steps = max_steps;
     A.fc = force_consts(ctx);
     void *args[] = {&A};
@@ -764,7 +764,7 @@ std::vector<unsigned char> chunk_key(const md_ctx *ctx)
                         (long long)ctx->force_grid[0], (long long)ctx->force_grid[1], (long long)ctx->force_grid[2],
                         (long long)ctx->tile_valid, (long long)ctx->cap16, (long long)ctx->sh_cap, (long long)ctx->own_cap,
                         (long long)ctx->nbricks, (long long)ctx->grid.nc[0], (long long)ctx->grid.nc[1],
-                        (long long)ctx->grid.nc[2], (long long)ctx->grid.bz, (long long)tile_tma()})
+                        (long long)ctx->grid.nc[2], (long long)ctx->grid.bz})
         put_i(v);
     return k;
 }
@@ -1519,7 +1519,7 @@ static int fetch_lists(md_ctx *ctx, std::vector<int> &cnt, std::vector<int> &id,
         if ((size_t)ctx->cap16 * (size_t)ctx->npad > ctx->nbr_alloc || ctx->grid.cap < ctx->cap16)
             TRY(ensure_nbr_capacity(ctx, ctx->cap16));
         k_tile_expand<<<ctx->nbricks, TILE_BLOCK, (size_t)ctx->sh_cap * sizeof(int), ctx->stream>>>(
-            ctx->grid, ctx->cell_start, ctx->d_sc, ctx->nbrT, ctx->cap16, ctx->nbr_cnt, ctx->nbr, ctx->npad, ctx->sh_cap);
+            ctx->grid, ctx->cell_start, ctx->d_sc, ctx->nbrT, ctx->cap16, ctx->nbr_cnt, ctx->nbr, ctx->npad);
         CK(cudaGetLastError());
     }
     if (nbr) {
