@@ -312,7 +312,7 @@ def run_ours(args, w):
         kr = s.time_kernels(1, DT, thermostat=t_th, barostat=t_ba)
         rebuild_ms = kr["rebuild"][0] / kr["rebuild"][1] if kr["rebuild"][1] else None
     step_us = ms / args.steps * 1e3
-    loop = bool(st1["persistent_loop"])
+    loop = bool(st1["persistent_loop"]) and (world > 1 or (per.get("loop_barrier") is not None))
     if world == 1 and loop:
         phases = {"drift_phase_us": per["kick_drift"] * 1e3, "mid_step_barrier_us": per["loop_barrier"] * 1e3,
                   "force_phase_and_tail_us": per["force"] * 1e3}

@@ -160,17 +160,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // a rank may publish reduction s+1 while a non-neighbour is still folding reduction s.
 constexpr int MAX_PEERS = 8;
 struct Mail {
-    double sums[2][MAX_PEERS][12];          // [seq & 1][source rank][K5 slot]
-    unsigned long long sums_seq[MAX_PEERS];  // sums_seq[r] = s: rank r's sums of reduction s have landed
-    unsigned long long halo_seq[2];          // [0] left neighbour's, [1] right neighbour's ghost positions of step s landed
+    // The rank sums travel as 8-byte words that carry their own flag (the low-latency protocol of collective libraries): a
+    // word is {32 bits of payload, the low 32 bits of the reduction's sequence number}; an aligned 8-byte store arrives
+    // whole, so the receiver polls the word itself and neither side needs a fence or a separate flag.  A double is two words.
+    unsigned long long ll[2][MAX_PEERS][2 * NSUM];  // [seq & 1][source rank][2 * K5 slot + half]
+    unsigned long long halo_seq[2];  // [0] left neighbour's, [1] right neighbour's drifted positions of step s are readable
 };
-static_assert(NSUM == 12, "Mail::sums holds NSUM slots per rank");
 struct Peers {      // lives in device memory; kernels get a pointer (NULL on one GPU)
     Mail *mail[MAX_PEERS];  // rank r's Mail as mapped into this process (mail[rank] is the local one)
     int rank, nranks;
     int left, right;        // ring neighbours (slab decomposition along x)
 };
 
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

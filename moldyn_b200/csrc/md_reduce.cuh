@@ -307,29 +307,44 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
     MD_TRACE(threadIdx.x == 0, 9);
     const unsigned long long t_last = gtime();  // every block has finished its atoms
     if (mode & FIN_P2P) {
-        // All-gather of the rank sums through peer memory, fused into this kernel: every rank stores its 12 sums into every
-        // rank's mailbox (NVLink stores), raises its sequence flag there, waits for the flags of all ranks in its own
-        // mailbox and folds the ranks in rank order — identical lambda / myu / rebuild decision everywhere.
+        // All-gather of the rank sums through peer memory, fused into this kernel.  Every rank stores its 12 sums into every
+        // rank's mailbox as 24 self-flagged 8-byte words (Mail::ll) — no fence, no separate flag: one NVLink store latency —
+        // polls its own mailbox until every rank's words carry this reduction's sequence number, and folds the ranks in rank
+        // order: identical lambda / myu / rebuild decision everywhere.
+        constexpr int W = 2 * NSUM;
         __shared__ double my_sums[NSUM];
+        __shared__ unsigned int parts[MAX_PEERS][W];
         __shared__ int timed_out;
         const Peers &peers = *peers_p;
         const unsigned long long seq = sc_in.epoch + 1;
         const int buf = (int)(seq & 1ull);
+        const unsigned long long tag = (seq & 0xffffffffull) << 32;
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) my_sums[q] = acc.v[q];
             timed_out = 0;
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < peers.nranks * NSUM; t += BLOCK) {
-            const int r = t / NSUM, q = t - r * NSUM;
-            *reinterpret_cast<volatile double *>(&peers.mail[r]->sums[buf][peers.rank][q]) = my_sums[q];
-        }
-        __syncthreads();  // the stores above happen-before the release stores below (cumulative over the barrier)
         const unsigned long long t_wait = gtime();
-        if ((int)threadIdx.x < peers.nranks) {
-            st_release_sys(&peers.mail[threadIdx.x]->sums_seq[peers.rank], seq);
-            if (!wait_seq(&peers.mail[peers.rank]->sums_seq[threadIdx.x], seq)) timed_out = 1;
+        for (int t = threadIdx.x; t < peers.nranks * W; t += BLOCK) {
+            const int r = t / W, w = t - r * W;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(my_sums[w >> 1]);
+            const unsigned long long part = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+            st_relaxed_sys(&peers.mail[r]->ll[buf][peers.rank][w], tag | part);
+        }
+        const Mail *own = peers.mail[peers.rank];
+        for (int t = threadIdx.x; t < peers.nranks * W; t += BLOCK) {
+            const int r = t / W, w = t - r * W;
+            unsigned long long v = ld_relaxed_sys(&own->ll[buf][r][w]);
+            if ((v & 0xffffffff00000000ull) != tag) {
+                const unsigned long long t0 = gtime();
+                for (;;) {
+                    v = ld_relaxed_sys(&own->ll[buf][r][w]);
+                    if ((v & 0xffffffff00000000ull) == tag) break;
+                    if (gtime() - t0 > 20000000000ull) { timed_out = 1; break; }  // a peer died or the ranks diverged
+                }
+            }
+            parts[r][w] = (unsigned int)(v & 0xffffffffull);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -337,11 +352,12 @@ __device__ __forceinline__ void last_block_finalize(double *__restrict__ partial
             Sums t;
 #pragma unroll
             for (int q = 0; q < NSUM; ++q) t.v[q] = 0.0;
-            const Mail *own = peers.mail[peers.rank];
             for (int r = 0; r < peers.nranks; ++r) {
 #pragma unroll
-                for (int q = 0; q < NSUM - 1; ++q) t.v[q] += __ldcg(&own->sums[buf][r][q]);
-                t.v[NSUM - 1] = fmax(t.v[NSUM - 1], __ldcg(&own->sums[buf][r][NSUM - 1]));
+                for (int q = 0; q < NSUM; ++q) {
+                    const double v = __longlong_as_double((long long)(((unsigned long long)parts[r][2 * q + 1] << 32) | parts[r][2 * q]));
+                    t.v[q] = q == NSUM - 1 ? fmax(t.v[q], v) : t.v[q] + v;
+                }
             }
             finalize(sc, &sc_in, &pr_in, t, mode);
             if (timed_out) sc->error = 3;  // MD_ERR_NCCL: a peer never delivered

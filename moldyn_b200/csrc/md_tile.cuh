@@ -325,6 +325,20 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
             cnt = nbr_cnt[gi];
         }
         const unsigned short *__restrict__ lst = nbrT + (size_t)gi * cap;
+        // The index table streams from HBM (98 MB per step on C5) and a trip's lead is shorter than the DRAM latency under
+        // load: 40 % of the first version's stall samples sat on the first use of a freshly loaded index
+        // (profiles/r02_ncu_c5_force_tile_v2.txt).  The lists of the warp's NEXT group are therefore pulled into L2 now — a
+        // whole group (~6 trips) ahead — and the register prefetch one trip ahead then hits L2.
+        {
+            const int an = g0 + 4 * TILE_WARPS + sub;
+            if (an < n_own) {
+                int oc2, slot2, gi2;
+                tile_locate(T, an, oc2, slot2, gi2);
+                const char *nl = reinterpret_cast<const char *>(nbrT + (size_t)gi2 * cap);
+                const int bytes = 2 * cap;
+                for (int b = l8 * 128; b < bytes; b += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + b));
+            }
+        }
         const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
         const int kmax = __reduce_max_sync(0xffffffffu, cnt);
         PairAcc acc[4];

@@ -37,3 +37,11 @@ for g in 1 $N; do
 done
 run c4_loop_$N $N "A=1" --workload c4 --steps 300 --warmup 100 --e2e-steps 0 --cpu-rows -1 --steady-steps 0
 run c4_chunk_$N $N "MOLDYN_B200_LOOP=chunk" --workload c4 --steps 300 --warmup 100 --e2e-steps 0 --cpu-rows -1 --steady-steps 0
+if [ "${2:-}" = "extra" ]; then
+  timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "loop_drivers or tile or determinism" > $O/e_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 $O/e_pytest.log
+  run c5_tile_1 1 "A=1" --workload c5 --steps 1000 --warmup 300 --e2e-steps 0 --cpu-rows -1 --steady-steps 0
+  python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/e_c5_tile_1.json") if l.startswith("{")][-1]); print(d["roofline"]["kernels_ms"], d["roofline"]["rebuild"], d["roofline"].get("frac"))
+PY
+fi

@@ -447,8 +447,11 @@ def test_loop_drivers_agree(mode):
     assert dense[0][7]["graph_launches"] > 0 and dense[1][7]["graph_launches"] == 0
     assert dense[0][7]["persistent_loop"] == 0
 
-    # 1728 atoms, ~6 listed partners each, hot: collisions and list rebuilds
-    hot = orc.argon_lattice(12, 1.0, 900.0, 7)
+    # 1728 atoms on a jittered 1.7 nm lattice, hot: ~1.3 listed partners each (below 2 the persistent loop is the default
+    # driver on one GPU), collisions and list rebuilds
+    hot = orc.argon_lattice(12, 1.7, 900.0, 7)
+    hot.pos += np.random.default_rng(5).uniform(-0.6, 0.6, hot.pos.shape)
+    orc.apply_boundary_conditions(hot)
     dil = [_npt_run(hot, mode, 300.0, skin=0.3, **kw) for kw in ({}, {"host_loop": True}, {"chunk_loop": True})]
     for a, b in zip(dil[0][:7], dil[1][:7]):
         assert np.array_equal(a, b)
