@@ -47,6 +47,10 @@ struct LoopArgs {
     Arrays a;
     const int *nbr;
     const int *cntg;        // list counts (| LOOP_GHOST_FLAG on the multi-GPU path)
+    const int *bnd_pairs;   // multi-GPU: the pairs with a ghost partner, compacted at the last rebuild, and (device) their number:
+    const int *n_bnd;       // they are spread over the whole grid in the second pass of the force phase (their velocities stay
+                            // in the planes) — each costs a dependent chain of NVLink reads, and the slab's faces would
+                            // otherwise pile them all onto the first and the last blocks
     double *partials;
     Scalars *sc;
     const Params *pr;
@@ -139,16 +143,16 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     if (tid == 0) { t_acc[0] = t_acc[1] = t_acc[2] = t_acc[3] = t_acc[4] = 0ull; }
     // pair p of this thread, and where its velocity lives
     auto pair_of = [&](int p) { return (bid * P + p) * LOOP_BLOCK + tid; };
-    auto ld_u = [&](int p, int t, double2 &ux, double2 &uy, double2 &uz) {
-        if (USMEM) {
+    auto ld_u = [&](bool in_smem, int p, int t, double2 &ux, double2 &uy, double2 &uz) {
+        if (USMEM && in_smem) {
             ux = su[(0 * P + p) * LOOP_BLOCK + tid]; uy = su[(1 * P + p) * LOOP_BLOCK + tid]; uz = su[(2 * P + p) * LOOP_BLOCK + tid];
         } else {
             ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t); uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t);
             uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
         }
     };
-    auto st_u = [&](int p, int t, bool has1, const double2 &ux, const double2 &uy, const double2 &uz) {
-        if (USMEM) {
+    auto st_u = [&](bool in_smem, int p, int t, bool has1, const double2 &ux, const double2 &uy, const double2 &uz) {
+        if (USMEM && in_smem) {
             su[(0 * P + p) * LOOP_BLOCK + tid] = ux; su[(1 * P + p) * LOOP_BLOCK + tid] = uy; su[(2 * P + p) * LOOP_BLOCK + tid] = uz;
         } else if (has1) {
             reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
@@ -186,6 +190,8 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 const int t = pair_of(p);
                 if (t >= npairs) break;
                 const bool has1 = 2 * t + 1 < n;
+                const int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+                const bool in_smem = (((C.x | (has1 ? C.y : 0)) & LOOP_GHOST_FLAG) == 0);
                 double2 ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t), uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t),
                         uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
                 if (!half) {
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                     uy.x = __dadd_rn(uy.x, __dmul_rn(fy.x, hc)); uy.y = __dadd_rn(uy.y, __dmul_rn(fy.y, hc));
                     uz.x = __dadd_rn(uz.x, __dmul_rn(fz.x, hc)); uz.y = __dadd_rn(uz.y, __dmul_rn(fz.y, hc));
                 }
-                if (USMEM || !half) st_u(p, t, has1, ux, uy, uz);
+                if ((USMEM && in_smem) || !half) st_u(in_smem, p, t, has1, ux, uy, uz);
             }
             loaded = true;
         }
@@ -211,8 +217,10 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             double2 x = __ldcg(reinterpret_cast<const double2 *>(a.x) + t), y = __ldcg(reinterpret_cast<const double2 *>(a.y) + t),
                     z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
             int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+            if (!has1) C.y = 1;  // (not an atom: nothing to finish, no ghost flag)
+            const bool in_smem = ((C.x | C.y) & LOOP_GHOST_FLAG) == 0;
             double2 ux, uy, uz;
-            ld_u(p, t, ux, uy, uz);
+            ld_u(in_smem, p, t, ux, uy, uz);
             drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
             drift_one(y.x, uy.x, lambda, mup, dt, Ly); drift_one(y.y, uy.y, lambda, mup, dt, Ly);
             drift_one(z.x, uz.x, lambda, mup, dt, Lz); drift_one(z.y, uz.y, lambda, mup, dt, Lz);
@@ -221,7 +229,6 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 reinterpret_cast<double2 *>(a.z)[t] = z;
             } else {
                 a.x[i0] = x.x; a.y[i0] = y.x; a.z[i0] = z.x;
-                C.y = 1;  // (not an atom: nothing to finish)
             }
             // atoms without listed partners: F = 0, the step ends here (v'' = u' = lambda*u); the others keep u for phase B
             const bool s0 = C.x == 0, s1 = C.y == 0;
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 finish_atom_r(s, zero, ux.y, uy.y, uz.y, lambda, hc, mass, shift, wx, wy, wz, nh);
                 ux.y = wx; uy.y = wy; uz.y = wz;
             }
-            if (s0 || s1) st_u(p, t, has1, ux, uy, uz);
+            if (s0 || s1) st_u(in_smem, p, t, has1, ux, uy, uz);
             if (store_state) {
                 if (s0 && s1) {
                     const double2 z2 = make_double2(0.0, 0.0);
@@ -264,9 +271,9 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             while (ld_acquire_gpu(&sc->bar_arrive) < (unsigned int)nb) { }
         }
         __syncthreads();
-        if (multi && bid == 0 && tid == 0) {
+        if (multi && bid == nb - 1 && tid == 0) {
             // every block's drifted positions are in this GPU's L2 (the barrier's releases): the neighbours may read our face
-            // atoms of this step
+            // atoms of this step.  (The last block has the least work: the system-scope release stalls its first warp for ~3 us.)
             st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
             st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
         }
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
         const size_t stride = (size_t)A.npad;
         auto force_pair = [&](int p, int t, int2 C, bool ghosts) {
+            const bool in_smem = !ghosts;
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
             // (positions are stable throughout the phase and the barrier's acquiring loads invalidated this SM's L1 — CCTL.IVALL
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                           Z = reinterpret_cast<const double2 *>(a.z)[t];
             int2 J = reinterpret_cast<const int2 *>(A.nbr)[t];  // row 0
             double2 ux, uy, uz;
-            ld_u(p, t, ux, uy, uz);
+            ld_u(in_smem, p, t, ux, uy, uz);
             PairAcc f0 = zero, f1 = zero;
             const int kmax = max(C.x, C.y);
             for (int k = 0; k < kmax; ++k) {
@@ -317,34 +325,38 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             if (store_state) {
                 if (C.x > 0) { a.fx[i0] = f0.fx; a.fy[i0] = f0.fy; a.fz[i0] = f0.fz; a.u[i0] = f0.u; a.w[i0] = f0.w; }
                 if (C.y > 0) { a.fx[i0 + 1] = f1.fx; a.fy[i0 + 1] = f1.fy; a.fz[i0 + 1] = f1.fz; a.u[i0 + 1] = f1.u; a.w[i0 + 1] = f1.w; }
-                st_u(p, t, has1, ux, uy, uz);   // v''
+                st_u(in_smem, p, t, has1, ux, uy, uz);   // v''
             } else {
-                st_u(p, t, has1, wx, wy, wz);   // u'
+                st_u(in_smem, p, t, has1, wx, wy, wz);   // u'
             }
         };
-        for (int pass = 0; pass < (multi ? 2 : 1); ++pass) {
-            if (pass == 1) {
-                // the neighbours' drifted positions of this step are in their L2 (the acquiring loads also drop this SM's L1
-                // lines of the previous step's peer reads)
-                __shared__ int halo_late;
-                if (tid == 0) {
-                    const Mail *own = A.peers->mail[A.peers->rank];
-                    const unsigned long long tw = gtime();
-                    const unsigned long long seq = ctl.epoch + 1;
-                    halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
-                    if (bid == 0) sc->wait_halo_ns += gtime() - tw;
-                }
-                __syncthreads();
-                if (halo_late && tid == 0) atomicExch(&sc->error, 3);
+        for (int p = 0; p < P; ++p) {  // the thread's own pairs whose partners are all owned
+            const int t = pair_of(p);
+            if (t >= npairs) break;
+            int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+            if (2 * t + 1 >= n) C.y = 0;
+            if (((C.x | C.y) & LOOP_GHOST_FLAG) == 0 && (C.x | C.y) != 0) force_pair(p, t, C, false);
+        }
+        if (multi) {
+            // the neighbours' drifted positions of this step are in their L2 (the acquiring loads also drop this SM's L1
+            // lines of the previous step's peer reads)
+            __shared__ int halo_late;
+            if (tid == 0) {
+                const Mail *own = A.peers->mail[A.peers->rank];
+                const unsigned long long tw = gtime();
+                const unsigned long long seq = ctl.epoch + 1;
+                halo_late = !(wait_seq(&own->halo_seq[0], seq) && wait_seq(&own->halo_seq[1], seq));
+                if (bid == 0) sc->wait_halo_ns += gtime() - tw;
             }
-            for (int p = 0; p < P; ++p) {
-                const int t = pair_of(p);
-                if (t >= npairs) break;
+            __syncthreads();
+            if (halo_late && tid == 0) atomicExch(&sc->error, 3);
+            const int n_bnd = A.n_bnd[0];
+            for (int k = bid * LOOP_BLOCK + tid; k < n_bnd; k += nb * LOOP_BLOCK) {
+                const int t = A.bnd_pairs[k];
                 int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
                 if (2 * t + 1 >= n) C.y = 0;
-                const int ghost = ((C.x | C.y) & LOOP_GHOST_FLAG) ? 1 : 0;
                 C.x &= ~LOOP_GHOST_FLAG; C.y &= ~LOOP_GHOST_FLAG;
-                if ((C.x | C.y) != 0 && ghost == pass) force_pair(p, t, C, pass == 1);
+                force_pair(0, t, C, true);
             }
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[2] += t - tq; tq = t; }
@@ -371,6 +383,8 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         for (int p = 0; p < P; ++p) {
             const int t = pair_of(p);
             if (t >= npairs) break;
+            const int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
+            if (((C.x | (2 * t + 1 < n ? C.y : 0)) & LOOP_GHOST_FLAG) != 0) continue;  // lives in the planes
             const double2 ux = su[(0 * P + p) * LOOP_BLOCK + tid], uy = su[(1 * P + p) * LOOP_BLOCK + tid],
                           uz = su[(2 * P + p) * LOOP_BLOCK + tid];
             if (2 * t + 1 < n) {
@@ -387,6 +401,15 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         for (int k = 0; k < 4; ++k) sc->loop_ns[k] += t_acc[k];
         sc->loop_steps += t_acc[4];
     }
+}
+
+// pairs with a ghost partner (second pass of the loop's force phase)
+__global__ void k_flag_bnd_pairs(int npairs, int n, const int *__restrict__ cntg, int *__restrict__ flag)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) return;
+    const int c = cntg[2 * t] | (2 * t + 1 < n ? cntg[2 * t + 1] : 0);
+    flag[t] = (c & LOOP_GHOST_FLAG) ? 1 : 0;
 }
 
 // the loop's copy of the list counts on one GPU is nbr_cnt itself; on the multi-GPU path the builder ORs in LOOP_GHOST_FLAG

@@ -174,109 +174,95 @@ __device__ __forceinline__ void tile_locate(const TileTab &T, int a, int &oc, in
     gi = T.own_src[oc] + k;
 }
 
-// K2, tile form.  One block per brick, a warp per atom; lane l < 25 owns stencil column l and walks its candidates — one
-// contiguous range of shell slots for the unwrapped z cells, one for the periodically wrapped ones — evaluating the
-// reference's predicate (potential.rs:181-204 widened by the skin) in the reference's own operation order.  Hits are
-// remembered as bits (64 candidates of the unwrapped range, 32 of the wrapped one per word), the lanes' hit counts are
-// scanned, and every lane writes its hits at its offset: the atom's list is ascending in (column, slot) — the same order
-// whatever the scheduling — 16-bit shell slots, atom-major (nbrT[i * cap + k]).
+// K2, tile form.  One block per brick, ONE THREAD PER ATOM: the thread walks its atom's 25 stencil columns — per column one
+// contiguous range of shell slots for the unwrapped z cells and one for the periodically wrapped ones — out of shared memory,
+// evaluating the reference's predicate (potential.rs:181-204 widened by the skin) in the reference's own operation order.
+// Hits collect in a 16-entry buffer of the thread (32 bytes of shared memory) that is written to the atom's row as one
+// sector whenever it fills: the list is ascending in (column, slot), 16-bit shell slots, atom-major (nbrT[i * cap + k]).
+// (Two warp-cooperative forms came first — lanes over a column's candidates, then one lane per column with bit masks: 1.36
+// and 0.95 ms on C5, 2800 and 2260 instructions per atom, half the lanes idle; profiles/r02_ncu_c5_build_tile_v2.txt.)
+constexpr int TILE_BUF = 16;
+
 __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, const int *__restrict__ cell_start,
                                                            const int *__restrict__ cell_sorted, Scalars *sc,
                                                            double r2_list, unsigned short *__restrict__ nbrT, int cap,
-                                                           int *__restrict__ nbr_cnt, const int *__restrict__ brick_order)
+                                                           int *__restrict__ nbr_cnt, const int *__restrict__ brick_order,
+                                                           int sh_cap)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     double *sp = reinterpret_cast<double *>(tile_smem);
+    uint4 *bufs = reinterpret_cast<uint4 *>(sp + 3 * (size_t)sh_cap);  // TILE_BLOCK buffers of TILE_BUF 16-bit entries
     __shared__ TileTab T;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
     tile_stage(T, a, sc, sp, false);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncz = g.nc[2];
+    unsigned short *mybuf = reinterpret_cast<unsigned short *>(bufs + 2 * threadIdx.x);
     int wmax = 0;
     unsigned long long wsum = 0ull;
-    for (int ai = warp; ai < T.n_own; ai += TILE_WARPS) {
+    for (int ai = threadIdx.x; ai < T.n_own; ai += TILE_BLOCK) {
         int oc, slot, gi;
         tile_locate(T, ai, oc, slot, gi);
         const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
         const int cz = cell_sorted[gi] % ncz;
         const int lx = oc >> 2, ly = oc & 3;
-        // this lane's stencil column: slot ranges of the unwrapped (A) and of the wrapped (B) z part
-        int sA = 0, eA = 0, sB = 0, eB = 0;
-        double shx = 0.0, shy = 0.0;
-        if (lane < 25) {
-            const int wcol = (lx + lane / 5) * TILE_WIN + (ly + lane % 5);
+        const int za = max(cz - 2, 0), zb = min(cz + 3, ncz);
+        int zc = 0, zd = 0;  // wrapped cells of the stencil
+        if (cz - 2 < 0) { zc = cz - 2 + ncz; zd = ncz; }
+        else if (cz + 3 > ncz) { zc = 0; zd = cz + 3 - ncz; }
+        uint4 *__restrict__ out = reinterpret_cast<uint4 *>(nbrT + (size_t)gi * cap);
+        int cnt = 0;
+        auto scan = [&](int s, int e, double dx, double dy, double dz) {
+            for (int q = s; q < e; ++q) {
+                // the reference's operations in the reference's order: (x_q - x_i) -+ L (adding 0.0 is exact), norm² compared
+                // against the largest double whose square root is <= r_list
+                const double *pq = sp + 3 * q;
+                const double rx = __dadd_rn(__dsub_rn(pq[0], xi), dx);
+                const double ry = __dadd_rn(__dsub_rn(pq[1], yi), dy);
+                const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+                if (r2 <= r2_list && q != slot) {
+                    mybuf[cnt & (TILE_BUF - 1)] = (unsigned short)q;
+                    ++cnt;
+                    if ((cnt & (TILE_BUF - 1)) == 0 && cnt <= cap) {
+                        const int chunk = (cnt >> 4) - 1;
+                        asm volatile("" ::: "memory");  // (the buffer is written as 16-bit words and read back as two 16-byte ones)
+                        out[2 * chunk] = bufs[2 * threadIdx.x];
+                        out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
+                    }
+                }
+            }
+        };
+        for (int col = 0; col < 25; ++col) {
+            const int wcol = (lx + col / 5) * TILE_WIN + (ly + col % 5);
             const int base = T.col_base[wcol];
-            const int za = max(cz - 2, 0), zb = min(cz + 3, ncz);
             const int ca = cell_start[base + za], cb = cell_start[base + zb];
-            sA = T.run_loc[2 * wcol] + (ca - T.run_src[2 * wcol]);
-            eA = sA + (cb - ca);
-            int zc = 0, zd = 0;
-            if (cz - 2 < 0) { zc = cz - 2 + ncz; zd = ncz; }
-            else if (cz + 3 > ncz) { zc = 0; zd = cz + 3 - ncz; }
+            const int sA = T.run_loc[2 * wcol] + (ca - T.run_src[2 * wcol]);
+            const double dx = T.shx[wcol], dy = T.shy[wcol];
+            scan(sA, sA + (cb - ca), dx, dy, 0.0);
             if (zd > zc) {
                 const int cc = cell_start[base + zc], cd = cell_start[base + zd];
-                sB = T.run_loc[2 * wcol + 1] + (cc - T.run_src[2 * wcol + 1]);
-                eB = sB + (cd - cc);
+                const int sB = T.run_loc[2 * wcol + 1] + (cc - T.run_src[2 * wcol + 1]);
+                scan(sB, sB + (cd - cc), dx, dy, T.shz);
             }
-            shx = T.shx[wcol]; shy = T.shy[wcol];
         }
-        // the reference's operations in the reference's order: (x_q - x_i) -+ L, norm² compared against the largest double
-        // whose square root is <= r_list (adding 0.0 is exact: unshifted columns skip the add)
-        auto hit = [&](int q, double dz) {
-            const double *pq = sp + 3 * q;
-            const double rx = __dadd_rn(__dsub_rn(pq[0], xi), shx);
-            const double ry = __dadd_rn(__dsub_rn(pq[1], yi), shy);
-            const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
-            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-            return r2 <= r2_list && q != slot;
-        };
-        unsigned long long mA = 0ull;
-        unsigned int mB = 0u;
-        int extra = 0;  // hits beyond the bit words (runs longer than 64 / 32 candidates): counted, written by a second scan
-        const int nA = eA - sA, nB = eB - sB;
-        for (int k = 0; k < nA; ++k) {
-            const bool h = hit(sA + k, 0.0);
-            if (k < 64) mA |= (unsigned long long)h << k;
-            else extra += h;
+        // the last, partly filled buffer (the row has room for whole 16-entry chunks: cap is a multiple of 32)
+        if ((cnt & (TILE_BUF - 1)) != 0 && cnt <= cap) {
+            const int chunk = cnt >> 4;
+            asm volatile("" ::: "memory");
+            out[2 * chunk] = bufs[2 * threadIdx.x];
+            out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
         }
-        const double shz = T.shz;
-        for (int k = 0; k < nB; ++k) {
-            const bool h = hit(sB + k, shz);
-            if (k < 32) mB |= (unsigned int)h << k;
-            else extra += h;
-        }
-        const int mine = __popcll(mA) + __popc(mB) + extra;
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-        }
-        const int cnt = __shfl_sync(0xffffffffu, inc, 31);
-        int pos = inc - mine;
-        unsigned short *__restrict__ out = nbrT + (size_t)gi * cap;
-        // A part: bits, then whatever lies beyond the word; then the B part likewise — ascending slots within the column
-        while (mA) {
-            const int k = __ffsll((long long)mA) - 1;
-            mA &= mA - 1;
-            if (pos < cap) out[pos] = (unsigned short)(sA + k);
-            ++pos;
-        }
-        for (int k = 64; k < nA; ++k)
-            if (hit(sA + k, 0.0)) { if (pos < cap) out[pos] = (unsigned short)(sA + k); ++pos; }
-        while (mB) {
-            const int k = __ffs((int)mB) - 1;
-            mB &= mB - 1;
-            if (pos < cap) out[pos] = (unsigned short)(sB + k);
-            ++pos;
-        }
-        for (int k = 32; k < nB; ++k)
-            if (hit(sB + k, shz)) { if (pos < cap) out[pos] = (unsigned short)(sB + k); ++pos; }
-        if (lane == 0) nbr_cnt[gi] = min(cnt, cap);
+        nbr_cnt[gi] = min(cnt, cap);
         wmax = max(wmax, cnt);
         wsum += (unsigned long long)cnt;
     }
-    if (lane == 0 && wsum) {
+    // statistics: max / total / overflow (integer atomics — order-independent results)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if ((threadIdx.x & 31) == 0 && wsum) {
         atomicMax(&sc->nbr_max, wmax);
         atomicAdd(&sc->nbr_total, wsum);
         if (wmax > cap) atomicExch(&sc->nbr_overflow, 1);
@@ -317,36 +303,39 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
     const LjConst c{};  // (no minimum image: the shell holds the images)
     const int n_own = T.n_own;
+    // Software pipeline ACROSS groups: while a group's trips run, the next group's atom is located (shared memory only), its
+    // list length and the four indices of its first trip are fetched — so no group starts with the chain
+    // locate -> count -> indices -> positions exposed (each link a trip to L2 or HBM; it was a third of the first version's
+    // time, profiles/r02_ncu_c5_force_tile_v2.txt) — and its whole list is pulled into L2 for the later trips.
+    int n_slot = 0, n_gi = 0, n_cnt = 0, n_first[4] = {0, 0, 0, 0};
+    auto fetch_group = [&](int g0) {
+        const int ai = g0 + sub;
+        int oc;
+        n_slot = 0; n_gi = 0; n_cnt = 0;
+        if (ai < n_own) {
+            tile_locate(T, ai, oc, n_slot, n_gi);
+            n_cnt = nbr_cnt[n_gi];
+        }
+        const unsigned short *__restrict__ lst = nbrT + (size_t)n_gi * cap;  // (row 0 for lanes without an atom: never used)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) n_first[u] = (int)lst[u * 8 + l8];     // unconditional: a row holds cap >= 32 entries
+        const char *nl = reinterpret_cast<const char *>(lst);
+        for (int b = (l8 + 1) * 128; b < 2 * cap; b += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + b));
+    };
+    if (4 * warp < n_own) fetch_group(4 * warp);
     for (int g0 = 4 * warp; g0 < n_own; g0 += 4 * TILE_WARPS) {  // warp-uniform
         const int ai = g0 + sub;
-        int oc, slot = 0, gi = 0, cnt = 0;
-        if (ai < n_own) {
-            tile_locate(T, ai, oc, slot, gi);
-            cnt = nbr_cnt[gi];
-        }
+        const int slot = n_slot, gi = n_gi, cnt = n_cnt;
+        int jn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) jn[u] = u * 8 + l8 < cnt ? n_first[u] : 0;
+        if (g0 + 4 * TILE_WARPS < n_own) fetch_group(g0 + 4 * TILE_WARPS);
         const unsigned short *__restrict__ lst = nbrT + (size_t)gi * cap;
-        // The index table streams from HBM (98 MB per step on C5) and a trip's lead is shorter than the DRAM latency under
-        // load: 40 % of the first version's stall samples sat on the first use of a freshly loaded index
-        // (profiles/r02_ncu_c5_force_tile_v2.txt).  The lists of the warp's NEXT group are therefore pulled into L2 now — a
-        // whole group (~6 trips) ahead — and the register prefetch one trip ahead then hits L2.
-        {
-            const int an = g0 + 4 * TILE_WARPS + sub;
-            if (an < n_own) {
-                int oc2, slot2, gi2;
-                tile_locate(T, an, oc2, slot2, gi2);
-                const char *nl = reinterpret_cast<const char *>(nbrT + (size_t)gi2 * cap);
-                const int bytes = 2 * cap;
-                for (int b = l8 * 128; b < bytes; b += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + b));
-            }
-        }
         const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
         const int kmax = __reduce_max_sync(0xffffffffu, cnt);
         PairAcc acc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[u] = PairAcc{0.0, 0.0, 0.0, 0.0, 0.0};
-        int jn[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { const int k = u * 8 + l8; jn[u] = k < cnt ? (int)lst[k] : 0; }
         for (int k0 = 0; k0 < kmax; k0 += 32) {
             int j[4];
 #pragma unroll

@@ -107,6 +107,7 @@ struct md_ctx {
     // persistent step loop (md_loop.cuh)
     int *nbr_ghost = nullptr;                         // multi-GPU: per-atom "the list holds a ghost" flags (list build)
     int *cntg = nullptr;                              // multi-GPU: list counts | LOOP_GHOST_FLAG (the loop's copy)
+    int *bnd_pairs = nullptr, *n_bnd = nullptr;       // multi-GPU: pairs with a ghost partner, compacted; their number (device)
     int loop_blocks_max = 0;                          // co-resident blocks of k_md_loop on this device
     bool loop_attr_set = false;
     double rebuild_host_ms = 0.0;                     // multi-GPU: wall time spent in list rebuilds (host clock, synchronised)
@@ -571,7 +572,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const size_t smem_force = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
-    const size_t smem_build = (size_t)3 * ctx->sh_cap * sizeof(double);
+    const size_t smem_build = (size_t)3 * ctx->sh_cap * sizeof(double) + (size_t)TILE_BLOCK * TILE_BUF * sizeof(unsigned short);
     if (ctx->sh_cap > 65535 || smem_force + 16 * 1024 > (size_t)optin) { *fallback = true; return MD_OK; }
     if (ctx->nbricks > ctx->partial_blocks) {  // one slot of partial sums per brick
         dev_free(ctx, ctx->d_partials);
@@ -599,7 +600,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
         k_reset_list_stats<<<1, 1, 0, st>>>(ctx->d_sc);
         k_build_tile<<<ctx->nbricks, TILE_BLOCK, smem_build, st>>>(g, ctx->cur, ctx->cell_start, ctx->cell_sorted, ctx->d_sc,
                                                                    r2_list, ctx->nbrT, ctx->cap16, ctx->nbr_cnt,
-                                                                   ctx->brick_order);
+                                                                   ctx->brick_order, ctx->sh_cap);
         ctx->stats.kernel_launches += 2;
         CK(cudaGetLastError());
         TRY(pull_scalars(ctx));
@@ -707,6 +708,8 @@ int launch_loop(md_ctx *ctx, long long max_steps)
     A.a = ctx->cur;
     A.nbr = ctx->nbr;
     A.cntg = ctx->dist.on ? ctx->cntg : ctx->nbr_cnt;
+    A.bnd_pairs = ctx->bnd_pairs;
+    A.n_bnd = ctx->n_bnd;
     A.partials = ctx->d_partials;
     A.sc = ctx->d_sc;
     A.pr = ctx->d_pr;
