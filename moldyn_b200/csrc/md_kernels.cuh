@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "md_common.cuh"
 #include "md_cells.cuh"
 #include "md_lists.cuh"

@@ -274,8 +274,11 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         if (multi && bid == nb - 1 && tid == 0) {
             // every block's drifted positions are in this GPU's L2 (the barrier's releases): the neighbours may read our face
             // atoms of this step.  (The last block has the least work: the system-scope release stalls its first warp for ~3 us.)
-            st_release_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
-            st_release_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
+            // ONE system-scope fence, then the two flags as relaxed stores (a release store each would pay the fence twice:
+            // 7.4 us of halo wait on the neighbour, profiles/r02_bench_c3_2gpu_pull_v1.txt)
+            __threadfence_system();
+            st_relaxed_sys(&A.peers->mail[A.peers->left]->halo_seq[1], ctl.epoch + 1);   // we are its right side
+            st_relaxed_sys(&A.peers->mail[A.peers->right]->halo_seq[0], ctl.epoch + 1);
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[1] += t - tq; tq = t; }
         MD_TRACE(bid == 0 && tid == 0, 2);
@@ -286,7 +289,8 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         c.hx = Lx / 2.0; c.hy = Ly / 2.0; c.hz = Lz / 2.0;
         c.hxi = __double2hiint(c.hx); c.hyi = __double2hiint(c.hy); c.hzi = __double2hiint(c.hz);
         const size_t stride = (size_t)A.npad;
-        auto force_pair = [&](int p, int t, int2 C, bool ghosts) {
+        auto force_pair = [&](int p, int t, int2 C, auto ghosts_tag) {
+            constexpr bool ghosts = decltype(ghosts_tag)::value;  // compile-time: the owned-partner pass keeps plain base pointers
             const bool in_smem = !ghosts;
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
@@ -299,23 +303,38 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             ld_u(in_smem, p, t, ux, uy, uz);
             PairAcc f0 = zero, f1 = zero;
             const int kmax = max(C.x, C.y);
-            for (int k = 0; k < kmax; ++k) {
-                const bool a0 = k < C.x, a1 = k < C.y;
-                const int j0 = a0 ? J.x : i0, j1 = a1 ? J.y : i0;
-                if (k + 1 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 1) * stride + i0);
-                const double *bxa = a.x, *bya = a.y, *bza = a.z, *bxb = a.x, *byb = a.y, *bzb = a.z;
-                if (ghosts) {  // (second pass of the multi-GPU path only: a partner at or beyond n lives on a neighbour)
-                    if (j0 >= n) { const bool l = j0 < A.n_gl; bxa = l ? A.glx : A.grx; bya = l ? A.gly : A.gry; bza = l ? A.glz : A.grz; }
-                    if (j1 >= n) { const bool l = j1 < A.n_gl; bxb = l ? A.glx : A.grx; byb = l ? A.gly : A.gry; bzb = l ? A.glz : A.grz; }
+            // two list rows per trip: both rows' indices, then the four partners' coordinates, then the pair terms — one
+            // dependent memory round trip per two partners (a round trip is an NVLink read in the ghost pass)
+            int2 Jb = kmax > 1 ? *reinterpret_cast<const int2 *>(A.nbr + stride + i0) : J;
+            for (int k = 0; k < kmax; k += 2) {
+                const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+                const int ja0 = a0 ? J.x : i0, ja1 = a1 ? J.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
+                if (k + 2 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 2) * stride + i0);
+                if (k + 3 < kmax) Jb = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 3) * stride + i0);
+                const int jj[4] = {ja0, ja1, jb0, jb1};
+                double xq[4], yq[4], zq[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if constexpr (ghosts) {  // a partner at or beyond n lives on a neighbour: read it there
+                        const int j = jj[u];
+                        const bool own = j < n, l = j < A.n_gl;
+                        xq[u] = (own ? a.x : (l ? A.glx : A.grx))[j];
+                        yq[u] = (own ? a.y : (l ? A.gly : A.gry))[j];
+                        zq[u] = (own ? a.z : (l ? A.glz : A.grz))[j];
+                    } else {
+                        xq[u] = a.x[jj[u]]; yq[u] = a.y[jj[u]]; zq[u] = a.z[jj[u]];
+                    }
                 }
-                const double xa = bxa[j0], ya = bya[j0], za = bza[j0];
-                const double xb = bxb[j1], yb = byb[j1], zb = bzb[j1];
                 if (EXACT) {
-                    if (a0) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
-                    if (a1) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                    if (a0) pair_exact(f0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
+                    if (a1) pair_exact(f1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
+                    if (b0) pair_exact(f0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
+                    if (b1) pair_exact(f1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
                 } else {
-                    pair_fast_branchy(f0, a0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
-                    pair_fast_branchy(f1, a1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                    pair_fast_branchy(f0, a0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
+                    pair_fast_branchy(f1, a1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
+                    pair_fast_branchy(f0, b0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
+                    pair_fast_branchy(f1, b1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
                 }
             }
             double2 wx = ux, wy = uy, wz = uz;
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             if (t >= npairs) break;
             int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
             if (2 * t + 1 >= n) C.y = 0;
-            if (((C.x | C.y) & LOOP_GHOST_FLAG) == 0 && (C.x | C.y) != 0) force_pair(p, t, C, false);
+            if (((C.x | C.y) & LOOP_GHOST_FLAG) == 0 && (C.x | C.y) != 0) force_pair(p, t, C, std::false_type{});
         }
         if (multi) {
             // the neighbours' drifted positions of this step are in their L2 (the acquiring loads also drop this SM's L1
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
                 if (2 * t + 1 >= n) C.y = 0;
                 C.x &= ~LOOP_GHOST_FLAG; C.y &= ~LOOP_GHOST_FLAG;
-                force_pair(0, t, C, true);
+                force_pair(0, t, C, std::true_type{});
             }
         }
         if (tid == 0) { const unsigned long long t = gtime(); t_acc[2] += t - tq; tq = t; }

@@ -307,7 +307,7 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
     // list length and the four indices of its first trip are fetched — so no group starts with the chain
     // locate -> count -> indices -> positions exposed (each link a trip to L2 or HBM; it was a third of the first version's
     // time, profiles/r02_ncu_c5_force_tile_v2.txt) — and its whole list is pulled into L2 for the later trips.
-    int n_slot = 0, n_gi = 0, n_cnt = 0, n_first[4] = {0, 0, 0, 0};
+    int n_slot = 0, n_gi = 0, n_cnt = 0, n_first[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto fetch_group = [&](int g0) {
         const int ai = g0 + sub;
         int oc;
@@ -318,7 +318,7 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
         }
         const unsigned short *__restrict__ lst = nbrT + (size_t)n_gi * cap;  // (row 0 for lanes without an atom: never used)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) n_first[u] = (int)lst[u * 8 + l8];     // unconditional: a row holds cap >= 32 entries
+        for (int u = 0; u < 8; ++u) n_first[u] = (int)lst[u * 8 + l8];     // unconditional: a row holds cap >= 64 entries
         const char *nl = reinterpret_cast<const char *>(lst);
         for (int b = (l8 + 1) * 128; b < 2 * cap; b += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + b));
     };
@@ -326,9 +326,13 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
     for (int g0 = 4 * warp; g0 < n_own; g0 += 4 * TILE_WARPS) {  // warp-uniform
         const int ai = g0 + sub;
         const int slot = n_slot, gi = n_gi, cnt = n_cnt;
-        int jn[4];
+        // index registers two trips deep: a trip is shorter than a round trip to L2
+        int jn[4], jnn[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) jn[u] = u * 8 + l8 < cnt ? n_first[u] : 0;
+        for (int u = 0; u < 4; ++u) {
+            jn[u] = u * 8 + l8 < cnt ? n_first[u] : 0;
+            jnn[u] = 32 + u * 8 + l8 < cnt ? n_first[4 + u] : 0;
+        }
         if (g0 + 4 * TILE_WARPS < n_own) fetch_group(g0 + 4 * TILE_WARPS);
         const unsigned short *__restrict__ lst = nbrT + (size_t)gi * cap;
         const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
@@ -339,10 +343,10 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
         for (int k0 = 0; k0 < kmax; k0 += 32) {
             int j[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) j[u] = jn[u];
-            if (k0 + 32 < kmax) {
+            for (int u = 0; u < 4; ++u) { j[u] = jn[u]; jn[u] = jnn[u]; }
+            if (k0 + 64 < kmax) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int k = k0 + 32 + u * 8 + l8; jn[u] = k < cnt ? (int)lst[k] : 0; }
+                for (int u = 0; u < 4; ++u) { const int k = k0 + 64 + u * 8 + l8; jnn[u] = k < cnt ? (int)lst[k] : 0; }
             }
             double xj[4], yj[4], zj[4];
 #pragma unroll

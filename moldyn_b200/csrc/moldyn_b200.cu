@@ -586,7 +586,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
     if (ctx->cap16 == 0) {
         const double volume = ctx->h_sc->box[0] * ctx->h_sc->box[1] * ctx->h_sc->box[2];
         const double expect = (double)ctx->n / volume * 4.18879020478639 * ctx->prm.r_list * ctx->prm.r_list * ctx->prm.r_list;
-        ctx->cap16 = ((int)(expect * 1.3) + 16 + 31) / 32 * 32;
+        ctx->cap16 = std::max(64, ((int)(expect * 1.3) + 16 + 31) / 32 * 32);  // (>= 64: the pair loop's first two trips)
     }
     for (int attempt = 0; attempt < 4; ++attempt) {
         const size_t need = (size_t)ctx->cap16 * (size_t)ctx->npad;
@@ -606,7 +606,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
         TRY(pull_scalars(ctx));
         if (!ctx->h_sc->nbr_overflow) break;
         if (attempt == 3) return ctx->fail(MD_ERR_NEIGHBOUR_OVERFLOW, "neighbour list overflow (max %d)", ctx->h_sc->nbr_max);
-        ctx->cap16 = ((int)(ctx->h_sc->nbr_max * 1.15) + 8 + 31) / 32 * 32;
+        ctx->cap16 = std::max(64, ((int)(ctx->h_sc->nbr_max * 1.15) + 8 + 31) / 32 * 32);
     }
     return MD_OK;
 }
