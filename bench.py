@@ -375,31 +375,77 @@ def run_ours(args, w):
     # --- e2e: reference-facing per-call API, State in pinned host memory in and out every step ------------
     e2e = None
     if args.e2e_steps > 0 and world == 1:
+        # One session: H2D 72 MB -> step -> D2H 88 MB, strictly in this order (the step needs the whole State, the results
+        # exist only after it): PCIe carries one direction at a time.  The link is full duplex, so a host that has more than
+        # one State to advance (an ensemble; or the next frame's State while the previous one is written out) drives two
+        # sessions from two threads: one session's download overlaps the other's upload.  `value` is that; the single-session
+        # number is beside it.
+        import threading
         L = _ffi.lib()
-        hp = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * n, 3 * n, 3 * n, n, n)]
-        hbox = np.array(box)
-        s.download_arrays(*(t.data_ptr() for t in hp))
-        tc = t_th[0]._c(t_th[1])
-        bc = t_ba[0]._c(t_ba[1]) if t_ba else None
+        n_sessions = max(1, args.e2e_sessions)
+        sessions = [s]
+        for _ in range(n_sessions - 1):
+            s2 = md.Solver(device=local, skin=args.skin, cell_atoms=args.cell_atoms, cell_subdiv=args.cell_subdiv,
+                           chunk_loop=args.loop == "chunk", host_loop=args.loop == "host")
+            if w["cut"]:
+                s2.set_potential(md.Potential(0.3418, 1.712, *w["cut"]))
+            sessions.append(s2)
+        hboxes = [np.array(box) for _ in sessions]
+        host = []
+        for _ in sessions:
+            hp = [torch.empty(sz, dtype=torch.float64, pin_memory=True) for sz in (3 * n, 3 * n, 3 * n, n, n)]
+            s.download_arrays(*(t.data_ptr() for t in hp))
+            host.append(hp)
+        tcs = [t_th[0]._c(t_th[1]) for _ in sessions]
+        bcs = [(t_ba[0]._c(t_ba[1]) if t_ba else None) for _ in sessions]
 
-        def call():
-            rc = L.md_calculate_host(s._ctx, n, hp[0].data_ptr(), hp[1].data_ptr(), hp[2].data_ptr(),
+        def call(k):
+            ss, hp, tc, bc, hbox = sessions[k], host[k], tcs[k], bcs[k], hboxes[k]
+            rc = L.md_calculate_host(ss._ctx, n, hp[0].data_ptr(), hp[1].data_ptr(), hp[2].data_ptr(),
                                      hp[3].data_ptr(), hp[4].data_ptr(), ARGON_MASS,
                                      hbox.ctypes.data_as(C.c_void_p), DT, C.byref(tc), C.byref(bc) if bc else None)
-            _ffi.check(s._ctx, rc)
-        for _ in range(3):
-            call()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            call()
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        e2e = {"value": n * args.e2e_steps / t_e2e, "unit": "atom-steps/s",
+            _ffi.check(ss._ctx, rc)
+
+        def timed(n_thr, steps_each):
+            errs = []
+            gate = threading.Barrier(n_thr + 1)
+
+            def work(k):
+                try:
+                    gate.wait()
+                    for _ in range(steps_each):
+                        call(k)
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+            thr = [threading.Thread(target=work, args=(k,)) for k in range(n_thr)]
+            for t in thr:
+                t.start()
+            torch.cuda.synchronize()
+            gate.wait()
+            t0 = time.perf_counter()
+            for t in thr:
+                t.join()
+            torch.cuda.synchronize()
+            dt_ = time.perf_counter() - t0
+            if errs:
+                raise errs[0]
+            return dt_
+
+        for k in range(n_sessions):
+            for _ in range(3):
+                call(k)
+        t_one = timed(1, args.e2e_steps)
+        t_e2e = timed(n_sessions, args.e2e_steps) if n_sessions > 1 else t_one
+        total = n_sessions * args.e2e_steps
+        e2e = {"value": n * total / t_e2e, "unit": "atom-steps/s",
                "h2d_bytes_per_step": (80 if t_ba else 72) * n + 24, "d2h_bytes_per_step": 88 * n + 24,
-               "ms_per_step": t_e2e / args.e2e_steps * 1e3, "steps": args.e2e_steps,
+               "ms_per_step": t_e2e / total * 1e3, "steps": total, "sessions": n_sessions,
+               "single_session": {"value": n * args.e2e_steps / t_one, "ms_per_step": t_one / args.e2e_steps * 1e3,
+                                  "steps": args.e2e_steps},
                "api": "md_calculate_host (≡ Integrator::calculate on a host State: upload x,v,F → 1 step → "
-                      "download x,v,F,U,W; the incoming U — and W without a barostat — are dead and not uploaded), pinned host buffers"}
+                      "download x,v,F,U,W; the incoming U — and W without a barostat — are dead and not uploaded), pinned host "
+                      f"buffers; {n_sessions} independent sessions (States) driven from {n_sessions} host threads so one's "
+                      "download overlaps the other's upload on the duplex link; single_session = one State, strictly serial"}
     elif args.e2e_steps > 0:
         # decomposed form of the same call: every rank uploads the (pinned) host State, one collective step, every
         # rank downloads its own slab
@@ -510,6 +556,8 @@ def main():
                     help="auto: persistent step loop for dilute systems, graph chunks for dense ones; chunk: the two-kernel "
                          "graph-chunk loop everywhere (A/B); host: one launch per step (ncu)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-sessions", type=int, default=2,
+                    help="independent States advanced concurrently through md_calculate_host in the e2e leg (1 GPU)")
     ap.add_argument("--steady-steps", type=int, default=None,
                     help="steps of the extra steady-state region (0 = skip; default 4000, 1000 above 2e6 atoms, 0 for N > 1 "
                          "unless given)")

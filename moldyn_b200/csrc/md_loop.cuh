@@ -303,38 +303,52 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             ld_u(in_smem, p, t, ux, uy, uz);
             PairAcc f0 = zero, f1 = zero;
             const int kmax = max(C.x, C.y);
-            // two list rows per trip: both rows' indices, then the four partners' coordinates, then the pair terms — one
-            // dependent memory round trip per two partners (a round trip is an NVLink read in the ghost pass)
-            int2 Jb = kmax > 1 ? *reinterpret_cast<const int2 *>(A.nbr + stride + i0) : J;
-            for (int k = 0; k < kmax; k += 2) {
-                const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
-                const int ja0 = a0 ? J.x : i0, ja1 = a1 ? J.y : i0, jb0 = b0 ? Jb.x : i0, jb1 = b1 ? Jb.y : i0;
-                if (k + 2 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 2) * stride + i0);
-                if (k + 3 < kmax) Jb = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 3) * stride + i0);
-                const int jj[4] = {ja0, ja1, jb0, jb1};
-                double xq[4], yq[4], zq[4];
+            if constexpr (!ghosts) {
+                // owned partners: one list row per trip, the next row's indices fetched while the current gathers fly
+                for (int k = 0; k < kmax; ++k) {
+                    const bool a0 = k < C.x, a1 = k < C.y;
+                    const int j0 = a0 ? J.x : i0, j1 = a1 ? J.y : i0;
+                    if (k + 1 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 1) * stride + i0);
+                    const double xa = a.x[j0], ya = a.y[j0], za = a.z[j0];
+                    const double xb = a.x[j1], yb = a.y[j1], zb = a.z[j1];
+                    if (EXACT) {
+                        if (a0) pair_exact(f0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+                        if (a1) pair_exact(f1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                    } else {
+                        pair_fast_branchy(f0, a0, xa, ya, za, X.x, Y.x, Z.x, c, fc);
+                        pair_fast_branchy(f1, a1, xb, yb, zb, X.y, Y.y, Z.y, c, fc);
+                    }
+                }
+            } else {
+                // pairs with ghost partners: TWO list rows per trip — both rows' indices, then the four partners' coordinates,
+                // then the pair terms: a dependent round trip here is an NVLink read (~2.5 us), and most of these atoms have
+                // at most two partners.  A partner at or beyond n lives on a neighbour and is read there.
+                int2 Jb = kmax > 1 ? *reinterpret_cast<const int2 *>(A.nbr + stride + i0) : J;
+                for (int k = 0; k < kmax; k += 2) {
+                    const bool a0 = k < C.x, a1 = k < C.y, b0 = k + 1 < C.x, b1 = k + 1 < C.y;
+                    const int jj[4] = {a0 ? J.x : i0, a1 ? J.y : i0, b0 ? Jb.x : i0, b1 ? Jb.y : i0};
+                    if (k + 2 < kmax) J = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 2) * stride + i0);
+                    if (k + 3 < kmax) Jb = *reinterpret_cast<const int2 *>(A.nbr + (size_t)(k + 3) * stride + i0);
+                    double xq[4], yq[4], zq[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if constexpr (ghosts) {  // a partner at or beyond n lives on a neighbour: read it there
+                    for (int u = 0; u < 4; ++u) {
                         const int j = jj[u];
                         const bool own = j < n, l = j < A.n_gl;
                         xq[u] = (own ? a.x : (l ? A.glx : A.grx))[j];
                         yq[u] = (own ? a.y : (l ? A.gly : A.gry))[j];
                         zq[u] = (own ? a.z : (l ? A.glz : A.grz))[j];
-                    } else {
-                        xq[u] = a.x[jj[u]]; yq[u] = a.y[jj[u]]; zq[u] = a.z[jj[u]];
                     }
-                }
-                if (EXACT) {
-                    if (a0) pair_exact(f0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
-                    if (a1) pair_exact(f1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
-                    if (b0) pair_exact(f0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
-                    if (b1) pair_exact(f1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
-                } else {
-                    pair_fast_branchy(f0, a0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
-                    pair_fast_branchy(f1, a1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
-                    pair_fast_branchy(f0, b0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
-                    pair_fast_branchy(f1, b1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
+                    if (EXACT) {
+                        if (a0) pair_exact(f0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
+                        if (a1) pair_exact(f1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
+                        if (b0) pair_exact(f0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
+                        if (b1) pair_exact(f1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
+                    } else {
+                        pair_fast_branchy(f0, a0, xq[0], yq[0], zq[0], X.x, Y.x, Z.x, c, fc);
+                        pair_fast_branchy(f1, a1, xq[1], yq[1], zq[1], X.y, Y.y, Z.y, c, fc);
+                        pair_fast_branchy(f0, b0, xq[2], yq[2], zq[2], X.x, Y.x, Z.x, c, fc);
+                        pair_fast_branchy(f1, b1, xq[3], yq[3], zq[3], X.y, Y.y, Z.y, c, fc);
+                    }
                 }
             }
             double2 wx = ux, wy = uy, wz = uz;
@@ -356,9 +370,12 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             if (2 * t + 1 >= n) C.y = 0;
             if (((C.x | C.y) & LOOP_GHOST_FLAG) == 0 && (C.x | C.y) != 0) force_pair(p, t, C, std::false_type{});
         }
-        if (multi) {
-            // the neighbours' drifted positions of this step are in their L2 (the acquiring loads also drop this SM's L1
-            // lines of the previous step's peer reads)
+        const int n_bnd = multi ? A.n_bnd[0] : 0;
+        if (bid * LOOP_BLOCK < n_bnd) {
+            // Only blocks with pairs to do here wait for the neighbours' flags: their drifted positions of this step are in
+            // their L2 (the acquiring loads also drop this SM's L1 lines of the previous step's peer reads).  A rank without
+            // such pairs does not wait at all; what keeps a neighbour from overwriting positions this rank is still reading
+            // is the sum exchange of the tail — no rank leaves step k before every rank has finished its force phase.
             __shared__ int halo_late;
             if (tid == 0) {
                 const Mail *own = A.peers->mail[A.peers->rank];
@@ -369,7 +386,6 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
             }
             __syncthreads();
             if (halo_late && tid == 0) atomicExch(&sc->error, 3);
-            const int n_bnd = A.n_bnd[0];
             for (int k = bid * LOOP_BLOCK + tid; k < n_bnd; k += nb * LOOP_BLOCK) {
                 const int t = A.bnd_pairs[k];
                 int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];

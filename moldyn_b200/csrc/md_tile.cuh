@@ -146,17 +146,37 @@ __device__ __forceinline__ double tile_image(double x, double shift, double cent
 
 __device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, const Scalars *sc, double *sp, bool image)
 {
-    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    // One shell slot per thread and trip, four trips in flight: the slot's run is found by bisection over the runs' first
+    // slots (shared memory), so all of a thread's global loads are independent of each other.  (Walking the runs one after
+    // the other cost a global-load latency per run, 16 per warp: ~15 % of the first versions' kernel time sat in the
+    // prologue, profiles/r02_ncu_c5_force_tile_v3.txt.)
     const double Lx = sc->box[0], Ly = sc->box[1], Lz = sc->box[2];
-    for (int r = w; r < TILE_RUNS; r += TILE_WARPS) {
-        const int len = T.run_len[r], loc = T.run_loc[r], src = T.run_src[r];
-        const double dx = T.shx[r >> 1], dy = T.shy[r >> 1], dz = (r & 1) ? T.shz : 0.0;
-        for (int e = lane; e < len; e += 32) {
-            const double x = a.x[src + e], y = a.y[src + e], z = a.z[src + e];
-            double *o = sp + 3 * (loc + e);
-            o[0] = image ? tile_image(x, dx, T.ctr[0], Lx) : x;
-            o[1] = image ? tile_image(y, dy, T.ctr[1], Ly) : y;
-            o[2] = image ? tile_image(z, dz, T.ctr[2], Lz) : z;
+    const int n_shell = T.n_shell;
+    for (int s0 = threadIdx.x; s0 < n_shell; s0 += 4 * TILE_BLOCK) {
+        int r[4], g[4];
+        double x[4], y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * TILE_BLOCK;
+            int lo = 0;  // last run whose first slot is <= s (empty runs share their successor's first slot: skipped by >=)
+#pragma unroll
+            for (int step = TILE_RUNS / 2; step > 0; step >>= 1)
+                if (lo + step < TILE_RUNS && T.run_loc[lo + step] <= s) lo += step;
+            r[u] = lo;
+            g[u] = s < n_shell ? T.run_src[lo] + (s - T.run_loc[lo]) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = a.x[g[u]]; y[u] = a.y[g[u]]; z[u] = a.z[g[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * TILE_BLOCK;
+            if (s < n_shell) {
+                const double dx = T.shx[r[u] >> 1], dy = T.shy[r[u] >> 1], dz = (r[u] & 1) ? T.shz : 0.0;
+                double *o = sp + 3 * s;
+                o[0] = image ? tile_image(x[u], dx, T.ctr[0], Lx) : x[u];
+                o[1] = image ? tile_image(y[u], dy, T.ctr[1], Ly) : y[u];
+                o[2] = image ? tile_image(z[u], dz, T.ctr[2], Lz) : z[u];
+            }
         }
     }
     __syncthreads();
@@ -211,26 +231,39 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
         else if (cz + 3 > ncz) { zc = 0; zd = cz + 3 - ncz; }
         uint4 *__restrict__ out = reinterpret_cast<uint4 *>(nbrT + (size_t)gi * cap);
         int cnt = 0;
-        auto scan = [&](int s, int e, double dx, double dy, double dz) {
-            for (int q = s; q < e; ++q) {
-                // the reference's operations in the reference's order: (x_q - x_i) -+ L (adding 0.0 is exact), norm² compared
-                // against the largest double whose square root is <= r_list
-                const double *pq = sp + 3 * q;
-                const double rx = __dadd_rn(__dsub_rn(pq[0], xi), dx);
-                const double ry = __dadd_rn(__dsub_rn(pq[1], yi), dy);
-                const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
-                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
-                if (r2 <= r2_list && q != slot) {
-                    mybuf[cnt & (TILE_BUF - 1)] = (unsigned short)q;
-                    ++cnt;
-                    if ((cnt & (TILE_BUF - 1)) == 0 && cnt <= cap) {
-                        const int chunk = (cnt >> 4) - 1;
-                        asm volatile("" ::: "memory");  // (the buffer is written as 16-bit words and read back as two 16-byte ones)
-                        out[2 * chunk] = bufs[2 * threadIdx.x];
-                        out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
-                    }
-                }
+        auto r2_of = [&](int q, double dx, double dy, double dz) {
+            // the reference's operations in the reference's order: (x_q - x_i) -+ L (adding 0.0 is exact), then norm²
+            const double *pq = sp + 3 * q;
+            const double rx = __dadd_rn(__dsub_rn(pq[0], xi), dx);
+            const double ry = __dadd_rn(__dsub_rn(pq[1], yi), dy);
+            const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
+            return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+        };
+        auto take = [&](int q) {
+            mybuf[cnt & (TILE_BUF - 1)] = (unsigned short)q;
+            ++cnt;
+            if ((cnt & (TILE_BUF - 1)) == 0 && cnt <= cap) {
+                const int chunk = (cnt >> 4) - 1;
+                asm volatile("" ::: "memory");  // (the buffer is written as 16-bit words and read back as two 16-byte ones)
+                out[2 * chunk] = bufs[2 * threadIdx.x];
+                out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
             }
+        };
+        auto scan = [&](int s, int e, double dx, double dy, double dz) {
+            // four candidates per trip: their distance chains are independent (a thread's scan is otherwise one long
+            // dependency chain — 'wait' was the first version's dominant stall); hits are taken in slot order.  r2_list is
+            // the largest double whose square root is <= r_list: r2 <= r2_list IS the reference's norm(r) <= r_list.
+            int q = s;
+            for (; q + 4 <= e; q += 4) {
+                const double r0 = r2_of(q, dx, dy, dz), r1 = r2_of(q + 1, dx, dy, dz), r2 = r2_of(q + 2, dx, dy, dz),
+                             r3 = r2_of(q + 3, dx, dy, dz);
+                if (r0 <= r2_list && q != slot) take(q);
+                if (r1 <= r2_list && q + 1 != slot) take(q + 1);
+                if (r2 <= r2_list && q + 2 != slot) take(q + 2);
+                if (r3 <= r2_list && q + 3 != slot) take(q + 3);
+            }
+            for (; q < e; ++q)
+                if (r2_of(q, dx, dy, dz) <= r2_list && q != slot) take(q);
         };
         for (int col = 0; col < 25; ++col) {
             const int wcol = (lx + col / 5) * TILE_WIN + (ly + col % 5);

@@ -354,16 +354,32 @@ int choose_grid(md_ctx *ctx, const double box[3])
         ncell *= c;
     }
     // Dense systems, FAST arithmetic, one GPU: brick order for the tile kernels (md_tile.cuh).  MOLDYN_B200_TILE=0 keeps the
-    // per-thread Verlet path (A/B measurements); MOLDYN_B200_TILE_BZ sets the z cells per brick (default 4).
+    // per-thread Verlet path (A/B measurements); MOLDYN_B200_TILE_BZ fixes the z cells per brick (default: chosen below).
     static const int tile_env = [] { const char *e = std::getenv("MOLDYN_B200_TILE"); return e ? atoi(e) : 1; }();
-    static const int bz_env = [] { const char *e = std::getenv("MOLDYN_B200_TILE_BZ"); return e ? atoi(e) : 4; }();
+    static const int bz_env = [] { const char *e = std::getenv("MOLDYN_B200_TILE_BZ"); return e ? atoi(e) : 0; }();
     g.brick = 0;
     if (tile_env != 0 && !ctx->tile_disabled && !ctx->dist.on && ctx->cfg.force_mode == MD_FORCE_FAST && nsub == 2 &&
         g.nc[0] >= TILE_MIN_CELLS && g.nc[1] >= TILE_MIN_CELLS && g.nc[2] >= TILE_MIN_CELLS && ctx->n >= 128) {
         g.brick = 1;
         g.nbx = (g.nc[0] + 3) / 4;
         g.nby = (g.nc[1] + 3) / 4;
-        g.bz = std::max(1, std::min(bz_env, g.nc[2] - 4));
+        // z cells per brick: the force kernel runs two blocks per SM and every brick costs about the same, so the kernel
+        // takes ceil(bricks / (2 SMs)) rounds of one brick each.  A brick costs its own cells' pair work plus the staging of
+        // its (bz + 4) x 8 x 8 shell plus a fixed part (weights from C5 on B200: 0.92 us per own cell of 16 columns, 0.01 us
+        // per staged cell, 2 us fixed); shorter bricks stage more per atom but can fill the last round.
+        int bz = bz_env;
+        if (bz <= 0) {
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            double best = 0.0;
+            for (int cand = 4; cand >= 2; --cand) {
+                const long long bricks = (long long)g.nbx * g.nby * ((g.nc[2] + cand - 1) / cand);
+                const double rounds = (double)((bricks + 2 * sms - 1) / (2 * sms));
+                const double cost = rounds * (0.92 * 16.0 * cand + 0.01 * 64.0 * (cand + 4) + 2.0);
+                if (bz <= 0 || cost < best * 0.97) { bz = cand; best = cost; }
+            }
+        }
+        g.bz = std::max(1, std::min(bz, g.nc[2] - 4));
         g.nbz = (g.nc[2] + g.bz - 1) / g.bz;
         ncell = (int64_t)g.nbx * g.nby * 16 * g.nc[2];
     }
@@ -1221,81 +1237,106 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     ctx->stats.kernel_launches += 1;
     CK(cudaGetLastError());
 
-    int64_t remaining = n_steps;
+    // The step loop.  The device knows whether it may step — list still valid, no error, steps left — and every step kernel
+    // checks that itself (a launch that may not step is a no-op).  So the host does not ask first: while its picture of the
+    // device is stale it enqueues steps speculatively and looks afterwards; only a rebuild step, which the host runs by hand,
+    // needs the picture to be fresh.  One host round trip per md_step call or list epoch instead of three.
     int rc = MD_OK;
-    if (ctx->dist.on) {
-        rc = dist_run_steps(ctx);
-        remaining = 0;
-    }
-    // phase clocks of the persistent loop before this batch (md_time_kernels reports the difference)
-    unsigned long long loop_ns0[4] = {0, 0, 0, 0}, loop_steps0 = 0;
+    bool fresh = false;               // h_sc mirrors the device's controls
+    long long bound = n_steps;        // upper bound of the steps left on the device
+    long long seen_done = 0;          // steps_done at the last look (k_prepare reset it)
+    unsigned long long loop_ns0[4] = {0, 0, 0, 0}, loop_steps0 = 0;  // the persistent loop's phase clocks before this batch
     bool have_loop0 = false;
-    while (rc == MD_OK && remaining > 0) {
-        if ((rc = pull_scalars(ctx)) != MD_OK) break;
-        if ((rc = device_error(ctx)) != MD_OK) break;
-        if (!have_loop0) {
+    auto look = [&]() -> int {
+        TRY(pull_scalars(ctx));
+        fresh = true;
+        const long long ran = ctx->h_sc->steps_done - seen_done;
+        seen_done = ctx->h_sc->steps_done;
+        ctx->stats.steps += ran;
+        return device_error(ctx);
+    };
+    if (ctx->timing || !ctx->list_valid) {
+        rc = look();
+        if (rc == MD_OK) {
             for (int k = 0; k < 4; ++k) loop_ns0[k] = ctx->h_sc->loop_ns[k];
             loop_steps0 = ctx->h_sc->loop_steps;
             have_loop0 = true;
         }
-        remaining = ctx->h_sc->steps_left;
-        if (remaining <= 0) break;
-        const bool rebuild = !ctx->list_valid || ctx->h_sc->need_rebuild;
+    }
+    while (rc == MD_OK) {
         const bool use_loop = loop_wanted(ctx) && ctx->loop_blocks_max > 0;
         // (the persistent loop times its phases itself; the two-kernel step is timed with events around host-stepped launches)
         const bool host_stepped = ctx->cfg.loop_mode == MD_LOOP_HOST || (ctx->timing && !use_loop);
-        if (rebuild || (host_stepped && !use_loop)) {
-            // one step by hand: drift, (rebuild at the drifted positions,) forces
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], st));
-            launch_kick_drift(ctx);
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], st));
-            if (rebuild && (rc = rebuild_lists(ctx)) != MD_OK) break;
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st));
-            launch_force(ctx, true);
-            if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], st));
-            ctx->stats.kernel_launches += 2;
-            ctx->stats.steps += 1;
-            CK(cudaGetLastError());
-            if (ctx->timing) {
-                CK(cudaEventSynchronize(ctx->ev[3]));
-                float a = 0.f, b = 0.f, c = 0.f;
-                CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
-                CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
-                CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
-                if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
-                else {
-                    ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
-                    ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
+        const bool by_hand = host_stepped && !use_loop && !ctx->dist.on;
+        if (fresh) {
+            bound = ctx->h_sc->steps_left;
+            if (bound <= 0) break;
+            const bool rebuild = !ctx->list_valid || ctx->h_sc->need_rebuild;
+            if (rebuild || by_hand) {
+                // one step by hand: drift, (rebuild at the drifted positions,) forces
+                if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], st));
+                launch_kick_drift(ctx);
+                if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], st));
+                if (rebuild && (rc = ctx->dist.on ? dist_rebuild(ctx) : rebuild_lists(ctx)) != MD_OK) break;
+                if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], st));
+                if (ctx->dist.on) {
+                    if ((rc = dist_launch_force(ctx, true)) != MD_OK) break;
+                } else {
+                    launch_force(ctx, true);
                 }
+                if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], st));
+                ctx->stats.kernel_launches += 2;
+                CK(cudaGetLastError());
+                if (ctx->timing) {
+                    CK(cudaEventSynchronize(ctx->ev[3]));
+                    float a = 0.f, b = 0.f, c = 0.f;
+                    CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]));
+                    CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+                    CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]));
+                    if (rebuild) { ctx->t_ms[2] += b; ctx->t_cnt[2] += 1; }
+                    else {
+                        ctx->t_ms[0] += a; ctx->t_cnt[0] += 1;
+                        ctx->t_ms[1] += c; ctx->t_cnt[1] += 1;
+                    }
+                }
+                fresh = false;
+                bound -= 1;
+                if (bound <= 0 || by_hand) rc = look();
+                continue;
             }
+        }
+        // list valid as far as the host knows: enqueue, then look
+        if (use_loop) {
+            // dilute systems: the persistent step loop runs until the device asks for a rebuild or the batch is done (on
+            // several GPUs every rank launches its loop; the loops leave at the same step: globally agreed controls)
+            if ((rc = launch_loop(ctx, host_stepped ? 1 : bound)) != MD_OK) break;
+            ctx->stats.kernel_launches += 1;
+            rc = look();
+        } else if (ctx->dist.on) {
+            const long long before = seen_done;
+            if ((rc = dist_enqueue_chunks(ctx, bound)) != MD_OK) break;
+            if ((rc = look()) != MD_OK) break;
+            ctx->stats.kernel_launches += (seen_done - before) * (ctx->dist.p2p ? 2 : 7);  // kick_drift, force, pack x2, unpack x2, finalize
         } else {
-            const long long before = ctx->h_sc->steps_done;
-            if (use_loop) {
-                // dilute systems: the persistent step loop runs until the device asks for a rebuild or the batch is done
-                if ((rc = launch_loop(ctx, host_stepped ? 1 : remaining)) != MD_OK) break;
-                if ((rc = pull_scalars(ctx)) != MD_OK) break;
-                ctx->stats.kernel_launches += 1;
-            } else {
-                cudaGraphExec_t chunk_exec = nullptr;
-                if ((rc = get_chunk_graph(ctx, &chunk_exec)) != MD_OK) break;
-                // look ahead as far as the list is expected to last (the previous epoch's length), at most 8 chunks: steps
-                // enqueued past a rebuild request are no-ops, but each still costs a launch
-                const long long since = ctx->stats.steps - ctx->epoch_start_step;
-                const long long expect = std::max<long long>(STEP_CHUNK, ctx->last_epoch_len - since);
-                const int chunks = (int)std::min<long long>(8, (std::min<long long>(remaining, expect) + STEP_CHUNK - 1) / STEP_CHUNK);
-                for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(chunk_exec, st));
-                ctx->stats.graph_launches += chunks;
-                if ((rc = pull_scalars(ctx)) != MD_OK) break;
-                ctx->stats.kernel_launches += 2 * (ctx->h_sc->steps_done - before);
-            }
-            ctx->stats.steps += ctx->h_sc->steps_done - before;
-            if ((rc = device_error(ctx)) != MD_OK) break;
-            remaining = ctx->h_sc->steps_left;
+            cudaGraphExec_t chunk_exec = nullptr;
+            if ((rc = get_chunk_graph(ctx, &chunk_exec)) != MD_OK) break;
+            // look ahead as far as the list is expected to last (the previous epoch's length), at most 8 chunks: steps
+            // enqueued past a rebuild request are no-ops, but each still costs a launch
+            const long long since = ctx->stats.steps - ctx->epoch_start_step;
+            const long long expect = std::max<long long>(STEP_CHUNK, ctx->last_epoch_len - since);
+            const int chunks = (int)std::min<long long>(8, (std::min<long long>(bound, expect) + STEP_CHUNK - 1) / STEP_CHUNK);
+            for (int c = 0; c < chunks; ++c) CK(cudaGraphLaunch(chunk_exec, st));
+            ctx->stats.graph_launches += chunks;
+            const long long before = seen_done;
+            if ((rc = look()) != MD_OK) break;
+            ctx->stats.kernel_launches += 2 * (seen_done - before);
         }
     }
-    if (rc == MD_OK && p.ba_kind == MD_BAROSTAT_BERENDSEN) rc = flush_pending_scale(ctx);
-    if (rc == MD_OK) rc = pull_scalars(ctx);
-    if (rc == MD_OK) rc = device_error(ctx);
+    if (rc == MD_OK && p.ba_kind == MD_BAROSTAT_BERENDSEN) {
+        rc = flush_pending_scale(ctx);
+        fresh = false;
+    }
+    if (rc == MD_OK && !fresh) rc = look();
     if (rc != MD_OK) {
         // The device may be mid-batch: velocity planes holding u = v + F c, a pending coordinate scale, stale F/U/W.  Nothing
         // the host could download would be a State of the reference's step sequence: the caller has to upload again.
