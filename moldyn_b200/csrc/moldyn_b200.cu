@@ -1305,6 +1305,10 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
                 continue;
             }
         }
+        if (by_hand) {  // (one host round trip per step is what this mode is for)
+            rc = look();
+            continue;
+        }
         // list valid as far as the host knows: enqueue, then look
         if (use_loop) {
             // dilute systems: the persistent step loop runs until the device asks for a rebuild or the batch is done (on
