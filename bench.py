@@ -556,7 +556,7 @@ def main():
                     help="auto: persistent step loop for dilute systems, graph chunks for dense ones; chunk: the two-kernel "
                          "graph-chunk loop everywhere (A/B); host: one launch per step (ncu)")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-sessions", type=int, default=2,
+    ap.add_argument("--e2e-sessions", type=int, default=3,
                     help="independent States advanced concurrently through md_calculate_host in the e2e leg (1 GPU)")
     ap.add_argument("--steady-steps", type=int, default=None,
                     help="steps of the extra steady-state region (0 = skip; default 4000, 1000 above 2e6 atoms, 0 for N > 1 "
