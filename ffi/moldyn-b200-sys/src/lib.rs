@@ -26,6 +26,9 @@ pub const MD_BAROSTAT_BERENDSEN: i32 = 1;
 pub const MD_CELL_UNIFORM: c_int = 0;
 pub const MD_CELL_FCC: c_int = 1;
 pub const MD_UNIQUE_ID_BYTES: usize = 128;
+pub const MD_MAX_TYPES: usize = 8;
+pub const MD_CROSS_REFERENCE: i32 = 0;
+pub const MD_CROSS_SYMMETRIC: i32 = 1;
 
 #[repr(C)]
 pub struct md_ctx {
@@ -119,12 +122,16 @@ extern "C" {
     pub fn md_lj_new(sigma: f64, eps: f64, r_cut: *mut f64, u_cut: *mut f64) -> c_int;
     pub fn md_lj_potential_and_force(sigma: f64, eps: f64, r_cut: f64, u_cut: f64, r: f64, potential: *mut f64, force: *mut f64) -> c_int;
     pub fn md_set_potential_lj(ctx: *mut md_ctx, sigma: f64, eps: f64, r_cut: f64, u_cut: f64) -> c_int;
+    pub fn md_set_potential_pair(ctx: *mut md_ctx, id0: i32, id1: i32, sigma: f64, eps: f64, r_cut: f64, u_cut: f64) -> c_int;
+    pub fn md_set_cross_type_mode(ctx: *mut md_ctx, mode: i32) -> c_int;
+    pub fn md_upload_state_typed(ctx: *mut md_ctx, n: i64, pos: *const f64, vel: *const f64, force: *const f64, potential: *const f64, virial: *const f64, n_types: i32, type_counts: *const i64, type_mass: *const f64, box_: *const f64) -> c_int;
     pub fn md_upload_state(ctx: *mut md_ctx, n: i64, pos: *const f64, vel: *const f64, force: *const f64, potential: *const f64, virial: *const f64, mass: f64, box_: *const f64) -> c_int;
     pub fn md_download_state(ctx: *mut md_ctx, pos: *mut f64, vel: *mut f64, force: *mut f64, potential: *mut f64, virial: *mut f64, box_: *mut f64) -> c_int;
     pub fn md_initialize_lattice(ctx: *mut md_ctx, cell_type: c_int, size: *const i32, start: *const f64, unit_cell: f64, mass: f64, temperature: f64, seed: u64) -> c_int;
     pub fn md_update_force(ctx: *mut md_ctx) -> c_int;
     pub fn md_step(ctx: *mut md_ctx, n_steps: i64, dt: f64, thermostat: *mut md_thermostat, barostat: *mut md_barostat) -> c_int;
     pub fn md_macro(ctx: *mut md_ctx, out: *mut md_macro_out) -> c_int;
+    pub fn md_macro_type(ctx: *mut md_ctx, type_id: i32, out: *mut md_macro_out) -> c_int;
     pub fn md_update_force_host(ctx: *mut md_ctx, n: i64, pos: *const f64, mass: f64, box_: *const f64, force: *mut f64, potential: *mut f64, virial: *mut f64) -> c_int;
     pub fn md_calculate_host(ctx: *mut md_ctx, n: i64, pos: *mut f64, vel: *mut f64, force: *mut f64, potential: *mut f64, virial: *mut f64, mass: f64, box_: *mut f64, dt: f64, thermostat: *mut md_thermostat, barostat: *mut md_barostat) -> c_int;
     pub fn md_comm_unique_id(id: *mut u8) -> c_int;

@@ -7,7 +7,7 @@
 //!                                                              (cli/src/commands.rs:102,185)
 //!
 //! `State` is array-of-structs (`Vec<Vec<Particle>>`, core/src/particle.rs:6-32); the C ABI takes one particle type as
-//! flat xyz-interleaved arrays, so `upload`/`download` marshal `state.particles[0]` field by field.
+//! flat xyz-interleaved arrays, so `upload`/`download` marshal `state.particles` (type by type) field by field.
 use moldyn_b200_sys as sys;
 use moldyn_core::{Particle, State};
 use nalgebra::Vector3;
@@ -57,38 +57,51 @@ impl GpuSession {
     /// State → device (core/src/particle.rs:6-32).  `with_forces = false` is the State right after loading a frame
     /// (save_data.rs:86-98: force, potential and temp are zero).
     pub fn upload(&mut self, state: &State, with_forces: bool) {
-        assert!(state.particles.len() == 1, "one particle type (the reference's cross-type sum is asymmetric, potential.rs:171-176)");
-        let ps: &Vec<Particle> = &state.particles[0];
-        let n = ps.len();
+        // State.particles is indexed by type id: the device takes the types one after the other (md_upload_state_typed); one
+        // type is the plain md_upload_state.  A type without atoms panics in the reference (particle_type[0], integrator.rs:29).
+        assert!(!state.particles.is_empty() && state.particles.iter().all(|t| !t.is_empty()), "every particle type needs an atom");
+        let n: usize = state.particles.iter().map(|t| t.len()).sum();
         self.pos.clear();
         self.vel.clear();
         self.force.clear();
         self.pot.clear();
         self.vir.clear();
-        for p in ps {
+        for p in state.particles.iter().flatten() {
             self.pos.extend_from_slice(&[p.position.x, p.position.y, p.position.z]);
             self.vel.extend_from_slice(&[p.velocity.x, p.velocity.y, p.velocity.z]);
             self.force.extend_from_slice(&[p.force.x, p.force.y, p.force.z]);
             self.pot.push(p.potential);
             self.vir.push(p.temp);
         }
+        let counts: Vec<i64> = state.particles.iter().map(|t| t.len() as i64).collect();
+        let masses: Vec<f64> = state.particles.iter().map(|t| t[0].mass).collect(); // integrator.rs:30
         let bb = [state.boundary_box.x, state.boundary_box.y, state.boundary_box.z];
         let null = std::ptr::null::<f64>();
         check(self.ctx, unsafe {
-            sys::md_upload_state(
+            sys::md_upload_state_typed(
                 self.ctx, n as i64, self.pos.as_ptr(), self.vel.as_ptr(),
                 if with_forces { self.force.as_ptr() } else { null },
                 if with_forces { self.pot.as_ptr() } else { null },
                 if with_forces { self.vir.as_ptr() } else { null },
-                ps[0].mass, // integrator.rs:30: the mass of the type's first particle
-                bb.as_ptr(),
+                counts.len() as i32, counts.as_ptr(), masses.as_ptr(), bb.as_ptr(),
             )
         });
     }
 
+    /// PotentialsDatabase::set_potential(id0, id1, ..) for every entry of the database (potential.rs:141-144).
+    pub fn set_potential_pair(&mut self, id0: u16, id1: u16, sigma: f64, eps: f64, r_cut: f64, u_cut: f64) {
+        check(self.ctx, unsafe { sys::md_set_potential_pair(self.ctx, id0 as i32, id1 as i32, sigma, eps, r_cut, u_cut) });
+    }
+
+    /// false (default): the reference's one-sided cross-type accumulation (potential.rs:168-176); true: symmetric table.
+    pub fn set_symmetric_cross_type_forces(&mut self, symmetric: bool) {
+        let mode = if symmetric { sys::MD_CROSS_SYMMETRIC } else { sys::MD_CROSS_REFERENCE };
+        check(self.ctx, unsafe { sys::md_set_cross_type_mode(self.ctx, mode) });
+    }
+
     /// device → State: positions, velocities, forces, potential, temp (= Σ F·r) and boundary_box, in upload order.
     pub fn download(&mut self, state: &mut State) {
-        let n = state.particles[0].len();
+        let n: usize = state.particles.iter().map(|t| t.len()).sum();
         self.pos.resize(3 * n, 0.0);
         self.vel.resize(3 * n, 0.0);
         self.force.resize(3 * n, 0.0);
@@ -99,7 +112,7 @@ impl GpuSession {
             sys::md_download_state(self.ctx, self.pos.as_mut_ptr(), self.vel.as_mut_ptr(), self.force.as_mut_ptr(),
                                    self.pot.as_mut_ptr(), self.vir.as_mut_ptr(), bb.as_mut_ptr())
         });
-        for (i, p) in state.particles[0].iter_mut().enumerate() {
+        for (i, p) in state.particles.iter_mut().flatten().enumerate() {
             p.position = Vector3::new(self.pos[3 * i], self.pos[3 * i + 1], self.pos[3 * i + 2]);
             p.velocity = Vector3::new(self.vel[3 * i], self.vel[3 * i + 1], self.vel[3 * i + 2]);
             p.force = Vector3::new(self.force[3 * i], self.force[3 * i + 1], self.force[3 * i + 2]);

@@ -35,7 +35,7 @@ typedef enum md_status {
     MD_ERR_INVALID_ARGUMENT = 1,
     MD_ERR_CUDA = 2,
     MD_ERR_NCCL = 3,
-    MD_ERR_UNSUPPORTED = 4,        /* Custom variants (todo!() in the reference), multi-type states */
+    MD_ERR_UNSUPPORTED = 4,        /* Custom variants (todo!() in the reference), multi-type states on several GPUs */
     MD_ERR_NEIGHBOUR_OVERFLOW = 5, /* neighbour list could not be grown */
     MD_ERR_NO_STATE = 6,           /* step/download before md_upload_state */
     MD_ERR_NONFINITE = 7,          /* NaN/inf reached the step controls (e.g. Berendsen lambda at T = 0) */
@@ -150,11 +150,34 @@ MD_API int md_lj_potential_and_force(double sigma, double eps, double r_cut, dou
  * Default after md_create: PotentialsDatabase::new() → argon sigma=0.3418 eps=1.712 (potential.rs:95-101). */
 MD_API int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, double u_cut);
 
+/* PotentialsDatabase::set_potential(id0, id1, LennardJones{..}) (potential.rs:141-144): the entry keyed (min, max).  Pairs
+ * never set fall back to the default potential, argon (potential.rs:147-155).  (0, 0) is md_set_potential_lj. */
+#define MD_MAX_TYPES 8
+MD_API int md_set_potential_pair(md_ctx *ctx, int32_t id0, int32_t id1, double sigma, double eps, double r_cut,
+                                 double u_cut);
+/* What update_force does between particle types.  MD_CROSS_REFERENCE (default) is the reference, literally
+ * (potential.rs:168-176, `for particle_type2 in particle_type1..`): atoms of type t1 accumulate their partners of types
+ * t2 >= t1 only — a type never feels a type with a smaller id.  MD_CROSS_SYMMETRIC lets every atom accumulate its partners
+ * of every type: the symmetric type-pair table.  Everything else the reference does with several types is kept in both
+ * modes: myu and lambda of the LAST type are applied to all (integrator.rs:18-27), kicks use the type's mass
+ * (integrator.rs:29-30), the box is scaled once per type (integrator.rs:54-58). */
+#define MD_CROSS_REFERENCE 0
+#define MD_CROSS_SYMMETRIC 1
+MD_API int md_set_cross_type_mode(md_ctx *ctx, int32_t mode);
+
 /* ---- State transfer (core/src/particle.rs:6-32, core/src/save_data.rs:129-151) ------------ */
 /* pos, vel: 3n doubles.  force (3n), potential (n), virial (n = Particle.temp) may be NULL → zero, as after
  * StateToSave → State (save_data.rs:86-98).  mass: ParticleDatabase mass of the type. box: boundary_box. */
 MD_API int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
                            const double *potential, const double *virial, double mass, const double box[3]);
+/* State with several particle types: State.particles (Vec<Vec<Particle>>, indexed by type id, core/src/particle.rs:24-32)
+ * flattened type by type — type t owns type_counts[t] consecutive atoms, type_mass[t] is their Particle.mass.  Every type
+ * needs at least one atom (the reference indexes particle_type[0], integrator.rs:29).  md_update_force, md_step (thermostat
+ * None / Berendsen, barostat None / Berendsen), md_download_state and md_macro_type then follow the reference's multi-type
+ * behaviour (see md_set_cross_type_mode); one GPU; the step is host-stepped (a correctness path, not the tuned one). */
+MD_API int md_upload_state_typed(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
+                                 const double *potential, const double *virial, int32_t n_types,
+                                 const int64_t *type_counts, const double *type_mass, const double box[3]);
 /* Any output pointer may be NULL. Particles come back in the order they were uploaded. */
 MD_API int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, double *potential,
                              double *virial, double box[3]);
@@ -177,6 +200,8 @@ MD_API int md_update_force(md_ctx *ctx);
 MD_API int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *thermostat, md_barostat *barostat);
 /* macro parameters of the resident state. */
 MD_API int md_macro(md_ctx *ctx, md_macro_out *out);
+/* The same for one particle type of a multi-type State — every macro_parameters function takes a particle_type_id. */
+MD_API int md_macro_type(md_ctx *ctx, int32_t type_id, md_macro_out *out);
 
 /* One-shot host-buffer forms with the reference's per-call semantics (all arrays in/out, caller-owned):
  * md_update_force_host ≡ update_force; md_calculate_host ≡ Integrator::calculate (one step). */

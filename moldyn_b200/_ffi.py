@@ -16,6 +16,8 @@ UNIQUE_ID_BYTES = 128
 FORCE_FAST, FORCE_EXACT = 0, 1
 LOOP_AUTO, LOOP_HOST, LOOP_CHUNK = 0, 1, 2
 CELL_UNIFORM, CELL_FCC = 0, 1
+CROSS_REFERENCE, CROSS_SYMMETRIC = 0, 1  # md_set_cross_type_mode
+MAX_TYPES = 8
 THERMOSTAT_NONE, THERMOSTAT_BERENDSEN, THERMOSTAT_NOSE_HOOVER = 0, 1, 2
 BAROSTAT_NONE, BAROSTAT_BERENDSEN = 0, 1
 
@@ -67,7 +69,8 @@ SYMBOLS = [
     "md_update_force_host", "md_calculate_host", "md_download_cells", "md_neighbour_counts",
     "md_neighbour_lists", "md_get_stats", "md_stream", "md_synchronize", "md_invalidate_lists", "md_time_kernels",
     "md_comm_unique_id", "md_comm_init", "md_local_count", "md_download_local", "md_plan_decomposition",
-    "md_initialize_lattice", "md_measure_fp64_peak",
+    "md_initialize_lattice", "md_measure_fp64_peak", "md_set_potential_pair", "md_set_cross_type_mode",
+    "md_upload_state_typed", "md_macro_type",
 ]
 
 _lib = None
@@ -102,6 +105,10 @@ def lib():
             "md_update_force": (C.c_int, [vp]),
             "md_step": (C.c_int, [vp, i64, f64, C.POINTER(ThermostatC), C.POINTER(BarostatC)]),
             "md_macro": (C.c_int, [vp, C.POINTER(MacroOut)]),
+            "md_macro_type": (C.c_int, [vp, C.c_int32, C.POINTER(MacroOut)]),
+            "md_set_potential_pair": (C.c_int, [vp, C.c_int32, C.c_int32, f64, f64, f64, f64]),
+            "md_set_cross_type_mode": (C.c_int, [vp, C.c_int32]),
+            "md_upload_state_typed": (C.c_int, [vp, i64, pd, pd, pd, pd, pd, C.c_int32, pd, pd, pd]),
             "md_update_force_host": (C.c_int, [vp, i64, pd, f64, pd, pd, pd, pd]),
             "md_calculate_host": (C.c_int, [vp, i64, pd, pd, pd, pd, pd, f64, pd, f64, C.POINTER(ThermostatC),
                                             C.POINTER(BarostatC)]),

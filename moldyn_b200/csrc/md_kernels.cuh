@@ -23,3 +23,4 @@
 #include "md_loop.cuh"
 #include "md_tile.cuh"
 #include "md_dist_kernels.cuh"
+#include "md_multi.cuh"

@@ -10,6 +10,7 @@
 #include <nccl.h>  // types only: the library is dlopen()ed on first multi-GPU use (see nccl_api below)
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -17,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -87,6 +89,21 @@ struct md_ctx {
     int npad = 0;
     double mass = 0.0;
     bool has_state = false;
+    // several particle types (md_multi.cuh / md_multi.inc): State.particles flattened type by type
+    struct Multi {
+        bool on = false;
+        int T = 1;
+        int mode = MD_CROSS_REFERENCE;
+        int64_t start[MULTI_MAX_TYPES + 1] = {0};
+        double mass[MULTI_MAX_TYPES] = {0};
+        std::map<std::pair<int, int>, std::array<double, 4>> pairs;  // PotentialsDatabase entries other than (0, 0)
+        double rc_max = 0.0;  // largest r_cut of the T x T table: the list radius
+        double disp = 0.0;    // bound of any atom's displacement since the list build
+        MultiTable *d_tab = nullptr, *h_tab = nullptr;  // h_*: pinned
+        MultiWork *d_work = nullptr, *h_work = nullptr;
+        double *d_partials = nullptr;
+        int nblocks = 0;
+    } multi;
     bool list_valid = false;
     bool force_valid = false;
     double sums_c = -1.0;  // half_dt_m the stored reduction was computed with
@@ -308,13 +325,16 @@ int pull_scalars(md_ctx *ctx)
     return MD_OK;
 }
 
+// radius the Verlet lists and the cell grid are built for (+ skin): the potential's r_cut, or the largest one of the table
+double list_cut(const md_ctx *ctx) { return ctx->multi.on ? ctx->multi.rc_max : ctx->r_cut; }
+
 void fill_potential_params(md_ctx *ctx)
 {
     ctx->prm.sigma = ctx->sigma;
     ctx->prm.eps = ctx->eps;
     ctx->prm.r_cut = ctx->r_cut;
     ctx->prm.u_cut = ctx->u_cut;
-    ctx->prm.r_list = ctx->r_cut + ctx->skin;
+    ctx->prm.r_list = list_cut(ctx) + ctx->skin;
     ctx->prm.mass = ctx->mass;
     ctx->prm.n = ctx->n;
 }
@@ -326,19 +346,20 @@ double choose_skin(const md_ctx *ctx, const double box[3])
     if (ctx->cfg.skin > 0.0) return ctx->cfg.skin;
     double volume = box[0] * box[1] * box[2];
     double rho = (double)ctx->n / volume;
-    double in_cut = rho * 4.18879020478639 * ctx->r_cut * ctx->r_cut * ctx->r_cut;
+    const double r_cut = list_cut(ctx);
+    double in_cut = rho * 4.18879020478639 * r_cut * r_cut * r_cut;
     // dense: 0.075 r_cut — measured flat between 0.067 and 0.084 r_cut on C5 now that a rebuild costs 0.75 ms (was 0.1 r_cut)
-    double skin = in_cut > 8.0 ? 0.075 * ctx->r_cut : ctx->r_cut;
+    double skin = in_cut > 8.0 ? 0.075 * r_cut : r_cut;
     double min_box = std::min(box[0], std::min(box[1], box[2]));
     // keep r_list below half the smallest box edge when that is possible (single-image list semantics)
-    if (ctx->r_cut + skin > 0.5 * min_box) skin = std::max(0.0, 0.5 * min_box - ctx->r_cut) * 0.5;
+    if (r_cut + skin > 0.5 * min_box) skin = std::max(0.0, 0.5 * min_box - r_cut) * 0.5;
     return skin;
 }
 
 int choose_grid(md_ctx *ctx, const double box[3])
 {
     Grid g{};
-    double r_list = ctx->r_cut + ctx->skin;
+    double r_list = list_cut(ctx) + ctx->skin;
     double volume = box[0] * box[1] * box[2];
     // dense systems: half-size cells and a 5x5x5 stencil (fewer candidates per list build, tighter sorted order)
     const double in_list = (double)ctx->n / volume * 4.18879020478639 * r_list * r_list * r_list;
@@ -423,7 +444,7 @@ int choose_grid(md_ctx *ctx, const double box[3])
 
 bool grid_still_valid(const md_ctx *ctx, const double box[3])
 {
-    double r_list = ctx->r_cut + ctx->skin;
+    double r_list = list_cut(ctx) + ctx->skin;
     for (int d = 0; d < 3; ++d) {
         int w = 2 * ctx->grid.nsub + 1;
         if (ctx->grid.nc[d] >= w && box[d] / ctx->grid.nc[d] * ctx->grid.nsub < r_list) return false;
@@ -863,6 +884,7 @@ int device_error(md_ctx *ctx)
 }
 
 #include "md_dist.inc"
+#include "md_multi.inc"
 
 }  // namespace
 
@@ -951,6 +973,8 @@ void md_destroy(md_ctx *ctx)
     if (ctx->d_pr) cudaFree(ctx->d_pr);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->h_pr) cudaFreeHost(ctx->h_pr);
+    if (ctx->multi.h_tab) cudaFreeHost(ctx->multi.h_tab);
+    if (ctx->multi.h_work) cudaFreeHost(ctx->multi.h_work);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -968,6 +992,38 @@ int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, dou
         ctx->skin = choose_skin(ctx, ctx->h_sc->box);
     }
     fill_potential_params(ctx);
+    return MD_OK;
+}
+
+int md_set_potential_pair(md_ctx *ctx, int32_t id0, int32_t id1, double sigma, double eps, double r_cut, double u_cut)
+{
+    TRY(check_ctx(ctx, false));
+    if (id0 < 0 || id1 < 0 || id0 >= MULTI_MAX_TYPES || id1 >= MULTI_MAX_TYPES)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_set_potential_pair: type ids must be in [0, %d)", MULTI_MAX_TYPES);
+    if (id0 == 0 && id1 == 0) return md_set_potential_lj(ctx, sigma, eps, r_cut, u_cut);
+    if (!(sigma > 0.0) || !(r_cut > 0.0) || !std::isfinite(eps) || !std::isfinite(u_cut))
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "bad Lennard-Jones parameters");
+    ctx->multi.pairs[{std::min(id0, id1), std::max(id0, id1)}] = {sigma, eps, r_cut, u_cut};  // potential.rs:141-144
+    ctx->list_valid = false;
+    ctx->force_valid = false;
+    if (ctx->multi.on) {
+        ctx->multi.rc_max = multi_rc_max(ctx);
+        if (ctx->has_state) {
+            TRY(pull_scalars(ctx));
+            ctx->skin = choose_skin(ctx, ctx->h_sc->box);
+        }
+        fill_potential_params(ctx);
+    }
+    return MD_OK;
+}
+
+int md_set_cross_type_mode(md_ctx *ctx, int32_t mode)
+{
+    TRY(check_ctx(ctx, false));
+    if (mode != MD_CROSS_REFERENCE && mode != MD_CROSS_SYMMETRIC)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_set_cross_type_mode: MD_CROSS_REFERENCE or MD_CROSS_SYMMETRIC");
+    ctx->multi.mode = mode;
+    ctx->force_valid = false;
     return MD_OK;
 }
 
@@ -1026,7 +1082,7 @@ static int finish_new_state(md_ctx *ctx, int64_t n, const double box[3])
     // neighbour capacity from density
     {
         double volume = box[0] * box[1] * box[2];
-        double r_list = ctx->r_cut + ctx->skin;
+        double r_list = list_cut(ctx) + ctx->skin;
         double expect = (double)n / volume * 4.18879020478639 * r_list * r_list * r_list;
         int cap = ctx->cfg.max_neighbours > 0 ? ctx->cfg.max_neighbours : (int)(expect * 1.5) + 16;
         cap = std::min<int64_t>((cap + 7) / 8 * 8, std::max<int64_t>(8, (n - 1 + 7) / 8 * 8));
@@ -1054,6 +1110,7 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
         return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state: mass and box must be positive");
     if (ctx->dist.on) return dist_upload(ctx, n, pos, vel, force, potential, virial, mass, box);
     cudaStream_t st = ctx->stream;
+    ctx->multi.on = false;
     TRY(alloc_state(ctx, n));
     ctx->mass = mass;
     ctx->has_state = true;
@@ -1087,6 +1144,62 @@ int md_upload_state(md_ctx *ctx, int64_t n, const double *pos, const double *vel
 }
 
 
+int md_upload_state_typed(md_ctx *ctx, int64_t n, const double *pos, const double *vel, const double *force,
+                          const double *potential, const double *virial, int32_t n_types, const int64_t *type_counts,
+                          const double *type_mass, const double box[3])
+{
+    TRY(check_ctx(ctx, false));
+    if (n_types < 1 || n_types > MULTI_MAX_TYPES || !type_counts || !type_mass)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state_typed: 1..%d particle types with counts and masses", MULTI_MAX_TYPES);
+    int64_t total = 0;
+    for (int t = 0; t < n_types; ++t) {
+        // an empty type makes the reference panic (particle_type[0], integrator.rs:29)
+        if (type_counts[t] <= 0 || !(type_mass[t] > 0.0))
+            return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state_typed: type %d needs at least one atom and a positive mass", t);
+        total += type_counts[t];
+    }
+    if (total != n) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_upload_state_typed: the type counts do not add up to n");
+    if (ctx->dist.on) return ctx->fail(MD_ERR_UNSUPPORTED, "several particle types on a decomposed context");
+    if (n_types == 1) return md_upload_state(ctx, n, pos, vel, force, potential, virial, type_mass[0], box);
+    // the single-type upload lays out the planes; then the type table takes over (list radius, skin, capacity)
+    TRY(md_upload_state(ctx, n, pos, vel, force, potential, virial, type_mass[0], box));
+    auto &m = ctx->multi;
+    m.T = n_types;
+    m.start[0] = 0;
+    for (int t = 0; t < n_types; ++t) {
+        m.start[t + 1] = m.start[t] + type_counts[t];
+        m.mass[t] = type_mass[t];
+    }
+    if (!m.d_tab) {
+        TRY(dev_alloc(ctx, &m.d_tab, 1));
+        TRY(dev_alloc(ctx, &m.d_work, 1));
+        CK(cudaHostAlloc((void **)&m.h_tab, sizeof(MultiTable), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void **)&m.h_work, sizeof(MultiWork), cudaHostAllocDefault));
+    }
+    const int nblocks = std::max(1, std::min(blocks_for(n, MULTI_BLOCK), 296));
+    if (nblocks > m.nblocks) {
+        dev_free(ctx, m.d_partials);
+        TRY(dev_alloc(ctx, &m.d_partials, (size_t)MULTI_MAX_TYPES * nblocks * MULTI_NA));
+    }
+    m.nblocks = nblocks;
+    m.on = true;
+    m.disp = 0.0;
+    m.rc_max = multi_rc_max(ctx);
+    ctx->skin = choose_skin(ctx, box);
+    fill_potential_params(ctx);
+    {
+        const double volume = box[0] * box[1] * box[2], r_list = m.rc_max + ctx->skin;
+        const double expect = (double)n / volume * 4.18879020478639 * r_list * r_list * r_list;
+        int cap = ctx->cfg.max_neighbours > 0 ? ctx->cfg.max_neighbours : (int)(expect * 1.5) + 16;
+        cap = (int)std::min<int64_t>((cap + 7) / 8 * 8, std::max<int64_t>(8, (n - 1 + 7) / 8 * 8));
+        TRY(ensure_nbr_capacity(ctx, cap));
+    }
+    ctx->tile_disabled = true;  // (the brick kernels are single-type)
+    ctx->list_valid = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
 int md_initialize_lattice(md_ctx *ctx, int cell_type, const int32_t size[3], const double start[3], double unit_cell,
                           double mass, double temperature, uint64_t seed)
 {
@@ -1102,6 +1215,7 @@ int md_initialize_lattice(md_ctx *ctx, int cell_type, const int32_t size[3], con
     const double box[3] = {unit_cell * (double)size[0], unit_cell * (double)size[1], unit_cell * (double)size[2]};
     const double s0[3] = {start ? start[0] : 0.0, start ? start[1] : 0.0, start ? start[2] : 0.0};
     cudaStream_t st = ctx->stream;
+    ctx->multi.on = false;
     TRY(alloc_state(ctx, n));
     ctx->mass = mass;
     ctx->has_state = true;
@@ -1164,6 +1278,7 @@ int md_download_state(md_ctx *ctx, double *pos, double *vel, double *force, doub
 int md_update_force(md_ctx *ctx)
 {
     TRY(check_ctx(ctx, true));
+    if (ctx->multi.on) return multi_update_force(ctx);
     fill_potential_params(ctx);
     TRY(push_params(ctx));
     if (ctx->dist.on) {
@@ -1207,6 +1322,7 @@ int md_step(md_ctx *ctx, int64_t n_steps, double dt, md_thermostat *th, md_baros
     if (ba && ba->kind != MD_BAROSTAT_NONE && ba->kind != MD_BAROSTAT_BERENDSEN)
         return ctx->fail(MD_ERR_UNSUPPORTED, "Barostat::Custom is todo!() in the reference");
     if (n_steps == 0) return MD_OK;
+    if (ctx->multi.on) return multi_step(ctx, n_steps, dt, th, ba);
     cudaStream_t st = ctx->stream;
 
     fill_potential_params(ctx);
@@ -1488,6 +1604,9 @@ int md_macro(md_ctx *ctx, md_macro_out *out)
 {
     TRY(check_ctx(ctx, true));
     if (!out) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro: out is NULL");
+    if (ctx->multi.on)
+        return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro: the State has several particle types — the reference's macro "
+                                                  "parameters are per type: md_macro_type");
     TRY(pull_scalars(ctx));
     const Scalars &h = *ctx->h_sc;
     out->kinetic_energy = h.kinetic;
@@ -1503,6 +1622,37 @@ int md_macro(md_ctx *ctx, md_macro_out *out)
     out->lambda = h.lambda_last;
     out->myu = h.mu_last;
     out->n = ctx->n;
+    return MD_OK;
+}
+
+int md_macro_type(md_ctx *ctx, int32_t type_id, md_macro_out *out)
+{
+    TRY(check_ctx(ctx, true));
+    if (!out) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro_type: out is NULL");
+    if (!ctx->multi.on) {
+        if (type_id != 0) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro_type: the State has one particle type");
+        return md_macro(ctx, out);
+    }
+    auto &m = ctx->multi;
+    if (type_id < 0 || type_id >= m.T) return ctx->fail(MD_ERR_INVALID_ARGUMENT, "md_macro_type: no such particle type");
+    TRY(multi_push_table(ctx, ctx->prm.dt));
+    TRY(multi_reduce(ctx, 0));
+    CK(cudaMemcpyAsync(m.h_work, m.d_work, sizeof(MultiWork), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(pull_scalars(ctx));
+    const MultiTypeSums &ts = m.h_work->type[type_id];
+    out->kinetic_energy = ts.kinetic;
+    out->thermal_energy = ts.thermal;
+    out->potential_energy = ts.potential;
+    out->temperature = ts.temperature;
+    out->pressure = ts.pressure;
+    for (int d = 0; d < 3; ++d) {
+        out->vcom[d] = ts.vcom[d];
+        out->momentum[d] = ts.a[d] * m.mass[type_id];  // get_momentum_of_system mod.rs:28-34
+        out->box[d] = ctx->h_sc->box[d];
+    }
+    out->lambda = ctx->h_sc->lambda_last;
+    out->myu = ctx->h_sc->mu_last;
+    out->n = m.start[type_id + 1] - m.start[type_id];
     return MD_OK;
 }
 

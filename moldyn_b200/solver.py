@@ -126,8 +126,7 @@ class Barostat:
 
 class State:
     """core::State for ONE particle type (particle.rs:25-32): `particles[0]` as flat f64 arrays plus
-    `boundary_box`. Multi-type states are outside the path (the reference's cross-type accumulation is
-    asymmetric, potential.rs:171-176) and are rejected with MD_ERR_UNSUPPORTED by from_particles()."""
+    `boundary_box`.  States with several types: MultiState."""
 
     def __init__(self, position, velocity, mass, boundary_box, radius=0.1, particle_id=0):
         self.position = _f64(position).reshape(-1, 3).copy()
@@ -145,8 +144,39 @@ class State:
     @staticmethod
     def from_particles(ids, position, velocity, masses, boundary_box):
         if len(set(int(i) for i in ids)) != 1:
-            raise MdError(4, "only single-type states are supported on the device path")
+            return MultiState.from_particles(ids, position, velocity, masses, boundary_box)
         return State(position, velocity, masses[int(ids[0])], boundary_box, particle_id=int(ids[0]))
+
+
+class MultiState:
+    """core::State with several particle types (particle.rs:24-32): `particles[t]` for t = 0..T-1 stored one after the
+    other (`counts[t]` atoms of mass `masses[t]`), as Solver.upload_typed takes them."""
+
+    def __init__(self, position, velocity, counts, masses, boundary_box):
+        self.position = _f64(position).reshape(-1, 3).copy()
+        self.velocity = _f64(velocity).reshape(-1, 3).copy()
+        self.counts = np.asarray(counts, dtype=np.int64).copy()
+        self.masses = _f64(masses).copy()
+        self.n = self.position.shape[0]
+        if self.position.shape != self.velocity.shape or self.counts.sum() != self.n or (self.counts <= 0).any() \
+                or self.masses.shape != self.counts.shape:
+            # the reference indexes particle_type[0] and panics on an empty type (integrator.rs:29)
+            raise MdError(1, "MultiState: every type needs at least one atom; counts must add up to the atom count")
+        self.boundary_box = _f64(boundary_box).reshape(3).copy()
+        self.force = np.zeros_like(self.position)
+        self.potential = np.zeros(self.n)
+        self.temp = np.zeros(self.n)
+
+    @staticmethod
+    def from_particles(ids, position, velocity, masses, boundary_box):
+        """Particles in any order with their type ids → grouped by type id, order kept inside a type (save_data.rs:129-151
+        buckets loaded particles the same way)."""
+        ids = np.asarray(ids, dtype=np.int64)
+        T = int(ids.max()) + 1
+        order = np.argsort(ids, kind="stable")
+        counts = np.bincount(ids, minlength=T)
+        return MultiState(_f64(position).reshape(-1, 3)[order], _f64(velocity).reshape(-1, 3)[order], counts,
+                          [masses[t] for t in range(T)], boundary_box)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -188,6 +218,35 @@ class Solver:
     # -- potential / state -------------------------------------------------------------------------
     def set_potential(self, p: Potential):
         self._ck(_ffi.lib().md_set_potential_lj(self._ctx, p.sigma, p.eps, p.r_cut, p.u_cut))
+
+    def set_potential_pair(self, id0, id1, p: Potential):
+        """PotentialsDatabase::set_potential(id0, id1, p) (potential.rs:141-144)."""
+        self._ck(_ffi.lib().md_set_potential_pair(self._ctx, int(id0), int(id1), p.sigma, p.eps, p.r_cut, p.u_cut))
+
+    def set_cross_type_mode(self, symmetric: bool):
+        """False (default): the reference's update_force — a type only accumulates partners of types with the same or a
+        larger id (potential.rs:168-176).  True: every pair acts on both atoms."""
+        self._ck(_ffi.lib().md_set_cross_type_mode(self._ctx, _ffi.CROSS_SYMMETRIC if symmetric else _ffi.CROSS_REFERENCE))
+
+    def upload_typed(self, state: "MultiState", with_forces=True):
+        f = _ptr(state.force) if with_forces else None
+        u = _ptr(state.potential) if with_forces else None
+        w = _ptr(state.temp) if with_forces else None
+        counts = np.ascontiguousarray(state.counts, dtype=np.int64)
+        masses = _f64(state.masses)
+        box = _f64(state.boundary_box)
+        self._ck(_ffi.lib().md_upload_state_typed(self._ctx, state.n, _ptr(state.position), _ptr(state.velocity), f, u, w,
+                                                  len(counts), _ptr(counts), _ptr(masses), _ptr(box)))
+        self.n = state.n
+
+    def macro_type(self, type_id):
+        """The reference's macro parameters of one particle type (macro_parameters/*.rs take a particle_type_id)."""
+        m = _ffi.MacroOut()
+        self._ck(_ffi.lib().md_macro_type(self._ctx, int(type_id), C.byref(m)))
+        return {"kinetic": m.kinetic_energy, "thermal": m.thermal_energy, "potential": m.potential_energy,
+                "temperature": m.temperature, "pressure": m.pressure, "vcom": np.array(m.vcom[:]),
+                "momentum": np.array(m.momentum[:]), "box": np.array(m.box[:]), "lambda": m.lambda_,
+                "myu": m.myu, "n": m.n}
 
     def upload(self, state: State, with_forces=True):
         f = state.force if with_forces else None

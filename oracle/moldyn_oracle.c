@@ -17,9 +17,9 @@
  *   (no FMA contraction and no reassociation: Rust never contracts or
  *    reassociates f64 arithmetic).
  *
- * Data model: one particle type (the reference's cross-type force accumulation is
- * asymmetric, potential.rs:171-176, so only single-type systems are in scope).
- * Arrays are xyz-interleaved: pos[3*i+{0,1,2}] like Vec<Vector3<f64>>.
+ * Data model: arrays are xyz-interleaved: pos[3*i+{0,1,2}] like Vec<Vector3<f64>>.  The orc_* functions of the first part
+ * take one particle type; the orc_*_multi functions at the end take State.particles flattened type by type
+ * (start[t] .. start[t+1]) and restate what the reference does with several types, quirks included (see there).
  */
 #include <math.h>
 #include <stdint.h>
@@ -447,6 +447,127 @@ ORC_API void orc_step(const orc_lj *p, orc_state *s, double dt, orc_thermostat *
         s->bb[0] *= ba->myu; s->bb[1] *= ba->myu; s->bb[2] *= ba->myu;
         for (int64_t k = 0; k < 3 * n; ++k) s->pos[k] *= ba->myu;
     }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Several particle types.  State.particles is Vec<Vec<Particle>> indexed by type id (core/src/particle.rs:24-32); here it is
+ * flattened type by type: type t owns atoms [start[t], start[t+1]), mass[t] is Particle.mass of that type, and table[t1*T+t2]
+ * is PotentialsDatabase::get_potential(t1, t2) = the entry keyed (min, max) (potential.rs:147-155), so table is symmetric.
+ *
+ * What the reference does with T > 1, restated literally:
+ *   update_force (potential.rs:158-216): `for t1 in 0..T { for t2 in t1..T {` — atoms of type t1 accumulate the terms of
+ *     their type-t2 partners, j ascending, on top of what the earlier t2 left in particle.force/potential/temp; atoms of type
+ *     t2 > t1 receive NOTHING from type t1 (no second pass, no Newton's third law).  `symmetric` = 1 lets t2 run over 0..T
+ *     instead (every atom accumulates from every type in ascending flattened order): the physically meaningful variant.
+ *   Integrator::calculate (integrator.rs:14-59): calculate_myu and calculate_lambda are called once per type and overwrite the
+ *     same myu / lambda (Nose-Hoover: psi accumulates), so the coefficients of the LAST type are the ones applied — to every
+ *     type; the kicks use the type's own mass (particle_type[0].mass); barostat.update runs once per type and scales the
+ *     box every time: box *= myu^T while every position is scaled once.
+ * A type without atoms makes the reference panic (index 0 of an empty Vec, integrator.rs:29): callers must not pass one. */
+ORC_API void orc_update_force_multi(int T, const int64_t *start, const orc_lj *table, const double *pos, const double *bb,
+                                    int symmetric, double *force, double *pot, double *vir)
+{
+    for (int t1 = 0; t1 < T; ++t1) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t i = start[t1]; i < start[t1 + 1]; ++i) {
+            double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0, w = 0.0;
+            const double *pi = pos + 3 * i;
+            for (int t2 = symmetric ? 0 : t1; t2 < T; ++t2) {
+                const orc_lj *p = &table[t1 * T + t2];
+                for (int64_t j = start[t2]; j < start[t2 + 1]; ++j) {
+                    if (i == j) continue; /* potential.rs:178-180 (same type, same index) */
+                    double vx, vy, vz, pu, pt;
+                    if (!pair_term(p, pi, pos + 3 * j, bb, &vx, &vy, &vz, &pu, &pt)) continue;
+                    fx += vx; fy += vy; fz += vz; u += pu; w += pt;
+                }
+            }
+            force[3 * i] = fx; force[3 * i + 1] = fy; force[3 * i + 2] = fz;
+            pot[i] = u; vir[i] = w;
+        }
+    }
+}
+
+typedef struct {
+    int T;
+    const int64_t *start;  /* T + 1 offsets */
+    const double *mass;    /* T */
+    double *pos, *vel, *force, *pot, *vir; /* caller-owned, start[T] atoms */
+    double bb[3];
+} orc_state_multi;
+
+static double type_temperature(const orc_state_multi *s, int t)
+{
+    int64_t a = s->start[t], n = s->start[t + 1] - a;
+    double mv[3];
+    orc_center_of_mass_velocity(n, s->vel + 3 * a, s->mass[t], mv);
+    return orc_temperature(orc_thermal_energy(n, s->vel + 3 * a, s->mass[t], mv), n);
+}
+
+/* per-type macro parameters (the reference's functions all take a particle_type_id) */
+ORC_API void orc_macro_type(const orc_state_multi *s, int t, double *out /* ke, thermal, pe, T, P, vcom[3] */)
+{
+    int64_t a = s->start[t], n = s->start[t + 1] - a;
+    double mv[3];
+    orc_center_of_mass_velocity(n, s->vel + 3 * a, s->mass[t], mv);
+    out[0] = orc_kinetic_energy(n, s->vel + 3 * a, s->mass[t]);
+    out[1] = orc_thermal_energy(n, s->vel + 3 * a, s->mass[t], mv);
+    out[2] = orc_potential_energy(n, s->pot + a);
+    out[3] = orc_temperature(out[1], n);
+    out[4] = orc_pressure(n, s->vel + 3 * a, s->vir + a, s->mass[t], s->bb, mv);
+    out[5] = mv[0]; out[6] = mv[1]; out[7] = mv[2];
+}
+
+ORC_API void orc_step_multi(const orc_lj *table, orc_state_multi *s, double dt, orc_thermostat *th, orc_barostat *ba,
+                            int symmetric)
+{
+    const int T = s->T;
+    const int64_t n = s->start[T];
+    if (ba && ba->kind == 1) /* integrator.rs:18-22: once per type, the last one stays */
+        for (int t = 0; t < T; ++t) {
+            int64_t a = s->start[t], nt = s->start[t + 1] - a;
+            double mv[3];
+            orc_center_of_mass_velocity(nt, s->vel + 3 * a, s->mass[t], mv);
+            double pressure = orc_pressure(nt, s->vel + 3 * a, s->vir + a, s->mass[t], s->bb, mv);
+            double myu_cubed = 1.0 + dt * ba->beta / ba->tau * (pressure - ba->target);
+            ba->myu = cbrt(myu_cubed);
+        }
+    if (th && th->kind) /* integrator.rs:23-27 */
+        for (int t = 0; t < T; ++t) {
+            double temperature = type_temperature(s, t);
+            if (th->kind == 1) {
+                double lambda_squared = 1.0 + dt / th->tau * (th->target / temperature - 1.0);
+                th->lambda = sqrt(lambda_squared);
+            } else {
+                double psi_dot = -((th->target / temperature) - 1.0) / th->tau;
+                th->psi += psi_dot * (dt / 2.0);
+                th->lambda = exp(-th->psi * dt / 2.0);
+            }
+        }
+    for (int t = 0; t < T; ++t) { /* integrator.rs:28-34 */
+        double temp = dt / (2.0 * s->mass[t]);
+        for (int64_t k = 3 * s->start[t]; k < 3 * s->start[t + 1]; ++k) s->vel[k] = s->vel[k] + s->force[k] * temp;
+    }
+    if (th && th->kind) /* integrator.rs:35-39 → thermostat.rs:47-73, type by type */
+        for (int t = 0; t < T; ++t) {
+            double temperature = type_temperature(s, t);
+            for (int64_t k = 3 * s->start[t]; k < 3 * s->start[t + 1]; ++k) s->vel[k] *= th->lambda;
+            if (th->kind == 2) {
+                double psi_dot = -((th->target / temperature) - 1.0) / th->tau;
+                th->psi += psi_dot * (dt / 2.0);
+            }
+        }
+    for (int64_t k = 0; k < 3 * n; ++k) s->pos[k] += s->vel[k] * dt;
+    orc_apply_boundary_conditions(n, s->pos, s->bb);
+    orc_update_force_multi(T, s->start, table, s->pos, s->bb, symmetric, s->force, s->pot, s->vir);
+    for (int t = 0; t < T; ++t) { /* integrator.rs:47-53 */
+        double temp = dt / (2.0 * s->mass[t]);
+        for (int64_t k = 3 * s->start[t]; k < 3 * s->start[t + 1]; ++k) s->vel[k] += s->force[k] * temp;
+    }
+    if (ba && ba->kind == 1) /* integrator.rs:54-58 → barostat.rs:39-49: the box is scaled once PER TYPE */
+        for (int t = 0; t < T; ++t) {
+            s->bb[0] *= ba->myu; s->bb[1] *= ba->myu; s->bb[2] *= ba->myu;
+            for (int64_t k = 3 * s->start[t]; k < 3 * s->start[t + 1]; ++k) s->pos[k] *= ba->myu;
+        }
 }
 
 /* ------------------------------------------------------------------------- */

@@ -267,6 +267,107 @@ def neighbour_sets(pos, box, r_list):
     return offsets, nbr[: int(offsets[-1])]
 
 
+# --- several particle types (State.particles indexed by type id, flattened type by type) ----------------------------
+
+class _StateMulti(C.Structure):
+    _fields_ = [("T", C.c_int), ("start", C.c_void_p), ("mass", C.c_void_p),
+                ("pos", C.c_void_p), ("vel", C.c_void_p), ("force", C.c_void_p),
+                ("pot", C.c_void_p), ("vir", C.c_void_p), ("bb", C.c_double * 3)]
+
+
+class MultiState:
+    """core::State with several particle types (core/src/particle.rs:24-32): `counts[t]` atoms of type t, stored type by
+    type; `masses[t]` is Particle.mass of the type."""
+
+    def __init__(self, pos, vel, counts, masses, box):
+        self.pos = _f64(pos).reshape(-1, 3).copy()
+        self.vel = _f64(vel).reshape(-1, 3).copy()
+        self.n = self.pos.shape[0]
+        self.counts = np.asarray(counts, dtype=np.int64).copy()
+        assert self.counts.sum() == self.n and (self.counts > 0).all()
+        self.start = np.zeros(len(self.counts) + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.start[1:])
+        self.masses = _f64(masses).copy()
+        assert self.masses.shape == self.counts.shape
+        self.box = _f64(box).reshape(3).copy()
+        self.force = np.zeros_like(self.pos)
+        self.pot = np.zeros(self.n)
+        self.vir = np.zeros(self.n)
+
+    T = property(lambda s: len(s.counts))
+
+    def types(self):
+        """type id of every atom (uint16 like Particle.id)"""
+        return np.repeat(np.arange(self.T, dtype=np.uint16), self.counts)
+
+    def copy(self):
+        s = MultiState(self.pos, self.vel, self.counts, self.masses, self.box)
+        s.force[:] = self.force
+        s.pot[:] = self.pot
+        s.vir[:] = self.vir
+        return s
+
+    def _c(self):
+        st = _StateMulti()
+        st.T = self.T
+        st.start, st.mass = _p(self.start), _p(self.masses)
+        st.pos, st.vel, st.force = _p(self.pos), _p(self.vel), _p(self.force)
+        st.pot, st.vir = _p(self.pot), _p(self.vir)
+        st.bb[:] = list(self.box)
+        return st
+
+
+class PotentialTable:
+    """PotentialsDatabase (potential.rs:89-155): entries keyed (min id, max id), everything else the default potential."""
+
+    def __init__(self, n_types, default=None):
+        self.T = n_types
+        self.default = default or LennardJones()
+        self.entries = {}
+
+    def set_potential(self, id0, id1, lj):  # potential.rs:141-144
+        self.entries[(min(id0, id1), max(id0, id1))] = lj
+
+    def get_potential(self, id0, id1):  # potential.rs:147-155
+        return self.entries.get((min(id0, id1), max(id0, id1)), self.default)
+
+    def _c(self):
+        arr = (_LJ * (self.T * self.T))()
+        for a in range(self.T):
+            for b in range(self.T):
+                lj = self.get_potential(a, b)._s
+                arr[a * self.T + b] = _LJ(lj.sigma, lj.eps, lj.r_cut, lj.u_cut)
+        return arr
+
+
+def update_force_multi(table: PotentialTable, st: MultiState, symmetric=False):
+    """update_force with several types (potential.rs:158-216).  symmetric=False is the reference: atoms of type t1 only
+    accumulate partners of types t2 >= t1."""
+    lib().orc_update_force_multi(C.c_int(st.T), _p(st.start), table._c(), _p(st.pos), _p(_f64(st.box)),
+                                 C.c_int(1 if symmetric else 0), _p(st.force), _p(st.pot), _p(st.vir))
+
+
+def step_multi(table: PotentialTable, st: MultiState, dt, thermostat: Thermostat | None = None,
+               barostat: Barostat | None = None, symmetric=False, n_steps=1):
+    """Integrator::VerletMethod.calculate with several types (integrator.rs:14-59): per-type calculate_myu /
+    calculate_lambda (the last type's coefficient is applied to all), per-type masses, box scaled once per type."""
+    cs = st._c()
+    tab = table._c()
+    th = C.byref(thermostat._s) if thermostat is not None else None
+    ba = C.byref(barostat._s) if barostat is not None else None
+    for _ in range(n_steps):
+        lib().orc_step_multi(tab, C.byref(cs), C.c_double(dt), th, ba, C.c_int(1 if symmetric else 0))
+    st.box[:] = list(cs.bb)
+
+
+def macro_type(st: MultiState, t):
+    """The reference's per-type macro parameters (macro_parameters/*.rs all take particle_type_id)."""
+    out = np.zeros(8)
+    lib().orc_macro_type(C.byref(st._c()), C.c_int(t), _p(out))
+    return {"kinetic": out[0], "thermal": out[1], "potential": out[2], "temperature": out[3], "pressure": out[4],
+            "vcom": out[5:8].copy()}
+
+
 def num_threads():
     return lib().orc_num_threads()
 
