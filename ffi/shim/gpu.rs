@@ -88,9 +88,20 @@ impl GpuSession {
         });
     }
 
-    /// PotentialsDatabase::set_potential(id0, id1, ..) for every entry of the database (potential.rs:141-144).
-    pub fn set_potential_pair(&mut self, id0: u16, id1: u16, sigma: f64, eps: f64, r_cut: f64, u_cut: f64) {
-        check(self.ctx, unsafe { sys::md_set_potential_pair(self.ctx, id0 as i32, id1 as i32, sigma, eps, r_cut, u_cut) });
+    /// Every potential the State's particle types can meet: get_potential(a, b) for a <= b < T (the (min, max) key or the
+    /// default, potential.rs:147-155).  One type: its own pair only.
+    pub fn set_potentials(&mut self, potentials_database: &PotentialsDatabase, state: &State) {
+        let n_types = state.particles.len() as u16;
+        for a in 0..n_types {
+            for b in a..n_types {
+                match potentials_database.get_potential(a, b) {
+                    Potential::LennardJones { sigma, eps, r_cut, u_cut } => check(self.ctx, unsafe {
+                        sys::md_set_potential_pair(self.ctx, a as i32, b as i32, *sigma, *eps, *r_cut, *u_cut)
+                    }),
+                    Potential::Custom { .. } => todo!(), // potential.rs:71-73
+                }
+            }
+        }
     }
 
     /// false (default): the reference's one-sided cross-type accumulation (potential.rs:168-176); true: symmetric table.
@@ -184,7 +195,7 @@ fn with_session<R>(f: impl FnOnce(&mut GpuSession) -> R) -> R {
 /// Drop-in for `solver::update_force` (potential.rs:158-216): per-call semantics, State in, State out.
 pub fn update_force(potentials_database: &PotentialsDatabase, state: &mut State) {
     with_session(|s| {
-        s.set_potential(potentials_database.get_potential(0, 0));
+        s.set_potentials(potentials_database, state);
         s.upload(state, false);
         s.update_force();
         s.download(state);
@@ -197,7 +208,7 @@ pub fn calculate_gpu(integrator: &Integrator, potentials_database: &PotentialsDa
                      barostat: &mut Option<(&mut Barostat, f64)>, thermostat: &mut Option<(&mut Thermostat, f64)>) {
     let Integrator::VerletMethod = integrator else { todo!() }; // integrator.rs:60-62
     with_session(|s| {
-        s.set_potential(potentials_database.get_potential(0, 0));
+        s.set_potentials(potentials_database, state);
         s.upload(state, true);
         s.step(1, delta_time, barostat, thermostat);
         s.download(state);

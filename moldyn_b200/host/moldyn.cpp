@@ -499,18 +499,19 @@ void PotentialsDatabase::load_potentials_from_file(const std::string &dir)
 
 // ---- Session -----------------------------------------------------------------------------------------------------
 namespace {
-const std::vector<Particle> &single_type(const State &state, uint16_t *type_id)
+// The particle types of a State that have atoms.  One such type (any id) is the single-type device path; several must be the
+// ids 0..T-1 without a gap: the reference indexes particle_type[0] of every entry of State.particles and panics on an empty one
+// (integrator.rs:29).
+std::vector<uint16_t> types_of(const State &state)
 {
-    const std::vector<Particle> *only = nullptr;
-    for (size_t t = 0; t < state.particles.size(); ++t) {
-        if (state.particles[t].empty()) continue;
-        if (only) throw Error(MD_ERR_UNSUPPORTED, "multi-type states are outside the device path (the reference's "
-                                                  "cross-type accumulation is asymmetric, potential.rs:171-176)");
-        only = &state.particles[t];
-        *type_id = (uint16_t)t;
-    }
-    if (!only) throw Error(MD_ERR_INVALID_ARGUMENT, "empty State (the reference panics on particle_type[0])");
-    return *only;
+    std::vector<uint16_t> t;
+    for (size_t k = 0; k < state.particles.size(); ++k)
+        if (!state.particles[k].empty()) t.push_back((uint16_t)k);
+    if (t.empty()) throw Error(MD_ERR_INVALID_ARGUMENT, "empty State (the reference panics on particle_type[0])");
+    if (t.size() > 1 && t.size() != state.particles.size())
+        throw Error(MD_ERR_INVALID_ARGUMENT, "a particle type without atoms between the others (the reference panics on "
+                                             "particle_type[0], integrator.rs:29)");
+    return t;
 }
 }  // namespace
 
@@ -533,44 +534,75 @@ void Session::check(int rc)
 
 void Session::set_potential(const Potential &p) { check(md_set_potential_lj(ctx_, p.sigma, p.eps, p.r_cut, p.u_cut)); }
 
+void Session::set_potentials(const PotentialsDatabase &db, const State &state)
+{
+    const auto types = types_of(state);
+    if (types.size() == 1) {
+        set_potential(db.get_potential(types[0], types[0]));
+        return;
+    }
+    for (uint16_t a : types)
+        for (uint16_t b : types)
+            if (a <= b) {
+                const Potential &p = db.get_potential(a, b);  // (min, max) key or the default (potential.rs:147-155)
+                check(md_set_potential_pair(ctx_, a, b, p.sigma, p.eps, p.r_cut, p.u_cut));
+            }
+}
+
+void Session::set_symmetric_cross_type_forces(bool symmetric)
+{
+    check(md_set_cross_type_mode(ctx_, symmetric ? MD_CROSS_SYMMETRIC : MD_CROSS_REFERENCE));
+}
+
 void Session::upload(const State &state, bool with_forces)
 {
-    uint16_t type_id = 0;
-    const auto &ps = single_type(state, &type_id);
-    const size_t n = ps.size();
+    types_ = types_of(state);
+    size_t n = 0;
+    for (uint16_t t : types_) n += state.particles[t].size();
     pos_.resize(3 * n); vel_.resize(3 * n); force_.resize(3 * n); pot_.resize(n); vir_.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-        for (int d = 0; d < 3; ++d) {
-            pos_[3 * i + d] = ps[i].position[d];
-            vel_[3 * i + d] = ps[i].velocity[d];
-            force_[3 * i + d] = ps[i].force[d];
+    std::vector<int64_t> counts;
+    std::vector<double> masses;
+    size_t i = 0;
+    for (uint16_t t : types_) {  // State.particles flattened type by type
+        const auto &ps = state.particles[t];
+        counts.push_back((int64_t)ps.size());
+        masses.push_back(ps[0].mass);  // integrator.rs:30: the mass of the type's first particle
+        for (const Particle &q : ps) {
+            for (int d = 0; d < 3; ++d) {
+                pos_[3 * i + d] = q.position[d];
+                vel_[3 * i + d] = q.velocity[d];
+                force_[3 * i + d] = q.force[d];
+            }
+            pot_[i] = q.potential;
+            vir_[i] = q.temp;
+            ++i;
         }
-        pot_[i] = ps[i].potential;
-        vir_[i] = ps[i].temp;
     }
-    check(md_upload_state(ctx_, (int64_t)n, pos_.data(), vel_.data(), with_forces ? force_.data() : nullptr,
-                          with_forces ? pot_.data() : nullptr, with_forces ? vir_.data() : nullptr, ps[0].mass,
-                          state.boundary_box.data()));
+    check(md_upload_state_typed(ctx_, (int64_t)n, pos_.data(), vel_.data(), with_forces ? force_.data() : nullptr,
+                                with_forces ? pot_.data() : nullptr, with_forces ? vir_.data() : nullptr,
+                                (int32_t)counts.size(), counts.data(), masses.data(), state.boundary_box.data()));
 }
 
 void Session::download(State &state)
 {
-    uint16_t type_id = 0;
-    single_type(state, &type_id);
-    auto &ps = state.particles[type_id];
-    const size_t n = ps.size();
+    if (types_ != types_of(state)) throw Error(MD_ERR_INVALID_ARGUMENT, "download into a State of another shape than the uploaded one");
+    size_t n = 0;
+    for (uint16_t t : types_) n += state.particles[t].size();
     pos_.resize(3 * n); vel_.resize(3 * n); force_.resize(3 * n); pot_.resize(n); vir_.resize(n);
     check(md_download_state(ctx_, pos_.data(), vel_.data(), force_.data(), pot_.data(), vir_.data(),
                             state.boundary_box.data()));
-    for (size_t i = 0; i < n; ++i) {
-        for (int d = 0; d < 3; ++d) {
-            ps[i].position[d] = pos_[3 * i + d];
-            ps[i].velocity[d] = vel_[3 * i + d];
-            ps[i].force[d] = force_[3 * i + d];
+    size_t i = 0;
+    for (uint16_t t : types_)
+        for (Particle &q : state.particles[t]) {
+            for (int d = 0; d < 3; ++d) {
+                q.position[d] = pos_[3 * i + d];
+                q.velocity[d] = vel_[3 * i + d];
+                q.force[d] = force_[3 * i + d];
+            }
+            q.potential = pot_[i];
+            q.temp = vir_[i];
+            ++i;
         }
-        ps[i].potential = pot_[i];
-        ps[i].temp = vir_[i];
-    }
 }
 
 void Session::update_force() { check(md_update_force(ctx_)); }
@@ -608,6 +640,14 @@ md_macro_out Session::macro()
     return m;
 }
 
+md_macro_out Session::macro(uint16_t particle_type_id)
+{
+    md_macro_out m{};
+    if (types_.size() <= 1) check(md_macro(ctx_, &m));  // (the one type that has atoms, whatever its id)
+    else check(md_macro_type(ctx_, particle_type_id, &m));
+    return m;
+}
+
 md_stats Session::stats()
 {
     md_stats s{};
@@ -622,19 +662,12 @@ Session &shared_session()
     static Session s(0, std::getenv("MOLDYN_B200_EXACT") != nullptr);
     return s;
 }
-uint16_t type_of(const State &state)
-{
-    uint16_t t = 0;
-    single_type(state, &t);
-    return t;
-}
 }  // namespace
 
 void update_force(const PotentialsDatabase &db, State &state)
 {
     Session &s = shared_session();
-    uint16_t t = type_of(state);
-    s.set_potential(db.get_potential(t, t));
+    s.set_potentials(db, state);
     s.upload(state, false);
     s.update_force();
     s.download(state);
@@ -646,8 +679,7 @@ void Integrator::calculate(const PotentialsDatabase &db, State &state, double de
 {
     if (kind != VerletMethod) throw Error(MD_ERR_UNSUPPORTED, "Integrator::Custom is todo!() in the reference");
     Session &s = shared_session();
-    uint16_t t = type_of(state);
-    s.set_potential(db.get_potential(t, t));
+    s.set_potentials(db, state);
     s.upload(state, true);
     s.step(1, delta_time, barostat ? &*barostat : nullptr, thermostat ? &*thermostat : nullptr);
     s.download(state);
@@ -655,32 +687,32 @@ void Integrator::calculate(const PotentialsDatabase &db, State &state, double de
 
 namespace macro_parameters {
 namespace {
-md_macro_out macro_of(const State &state)
+md_macro_out macro_of(const State &state, uint16_t particle_type_id)
 {
     Session &s = shared_session();
     s.upload(state, true);
-    return s.macro();
+    return s.macro(particle_type_id);
 }
 }  // namespace
-Vector3 get_center_of_mass_velocity(const State &state, uint16_t)
+Vector3 get_center_of_mass_velocity(const State &state, uint16_t t)
 {
-    auto m = macro_of(state);
+    auto m = macro_of(state, t);
     return {m.vcom[0], m.vcom[1], m.vcom[2]};
 }
-Vector3 get_momentum_of_system(const State &state, uint16_t)
+Vector3 get_momentum_of_system(const State &state, uint16_t t)
 {
-    auto m = macro_of(state);
+    auto m = macro_of(state, t);
     return {m.momentum[0], m.momentum[1], m.momentum[2]};
 }
-double get_kinetic_energy(const State &state, uint16_t) { return macro_of(state).kinetic_energy; }
-double get_thermal_energy(const State &state, uint16_t, const Vector3 &) { return macro_of(state).thermal_energy; }
-double get_potential_energy(const State &state, uint16_t) { return macro_of(state).potential_energy; }
+double get_kinetic_energy(const State &state, uint16_t t) { return macro_of(state, t).kinetic_energy; }
+double get_thermal_energy(const State &state, uint16_t t, const Vector3 &) { return macro_of(state, t).thermal_energy; }
+double get_potential_energy(const State &state, uint16_t t) { return macro_of(state, t).potential_energy; }
 double get_temperature(double thermal_energy, size_t number_particles)
 {
     double t = (2.0 * thermal_energy) / (3.0 * (double)number_particles * K_B);
     return t * 100.0;
 }
-double get_pressure(const State &state, uint16_t, const Vector3 &) { return macro_of(state).pressure; }
+double get_pressure(const State &state, uint16_t t, const Vector3 &) { return macro_of(state, t).pressure; }
 }  // namespace macro_parameters
 
 // ---- initializer (input generator) ----------------------------------------------------------------------------------------

@@ -144,12 +144,18 @@ public:
     Session &operator=(const Session &) = delete;
 
     void set_potential(const Potential &p);
+    // every PotentialsDatabase entry the State's particle types can meet (one type: its own pair)
+    void set_potentials(const PotentialsDatabase &db, const State &state);
+    // false (default): the reference's one-sided cross-type accumulation (potential.rs:168-176); true: symmetric table
+    void set_symmetric_cross_type_forces(bool symmetric);
+    // State.particles type by type (one type: md_upload_state; several: md_upload_state_typed)
     void upload(const State &state, bool with_forces);
     void download(State &state);
     void update_force();
     void step(int64_t n_steps, double dt, std::pair<Barostat *, double> *barostat,
               std::pair<Thermostat *, double> *thermostat);
     md_macro_out macro();
+    md_macro_out macro(uint16_t particle_type_id);
     md_stats stats();
     md_ctx *raw() { return ctx_; }
 
@@ -157,6 +163,7 @@ private:
     void check(int rc);
     md_ctx *ctx_ = nullptr;
     std::vector<double> pos_, vel_, force_, pot_, vir_;
+    std::vector<uint16_t> types_;  // type ids of the uploaded State, in upload order
 };
 
 // solver/src/solver/potential.rs:158 — per-call semantics (upload → forces → download) on a shared session

@@ -171,11 +171,8 @@ void cmd_solve(const std::string &dir, Args &a, size_t frames_per_save)
         bap.second = pressure;
     }
 
-    uint16_t type_id = 0;
-    for (size_t t = 0; t < state.particles.size(); ++t)
-        if (!state.particles[t].empty()) type_id = (uint16_t)t;
     Session s(0, exact);
-    s.set_potential(db.get_potential(type_id, type_id));
+    s.set_potentials(db, state);
     s.upload(state, false);
     s.update_force();  // commands.rs:102
     if (frames_per_save == 0) frames_per_save = 1;
@@ -222,13 +219,13 @@ void cmd_solve_macro(const std::string &dir, Args &a)
     f << "iteration,kinetic_energy,potential_energy,thermal_energy,unit_kinetic_energy,unit_potential_energy,"
          "unit_thermal_energy,temperature,pressure,custom\n";
     Session s(0, false);
-    s.set_potential(db.get_potential(0, 0));
     for (size_t i = 0; i <= end; ++i) {
         State state = StateToSave::load_from_file(dir, i).into_state();
         double n = (double)state.count();
+        s.set_potentials(db, state);
         s.upload(state, false);
         s.update_force();  // forces are not stored in frames (commands.rs:234)
-        md_macro_out m = s.macro();
+        md_macro_out m = s.macro(0);  // commands.rs:237-264: particle type 0
         double ke = k ? m.kinetic_energy : 0.0, pe = p ? m.potential_energy : 0.0;
         double te = (t || T) ? m.thermal_energy : 0.0;
         f << i << ',' << format_f64(ke) << ',' << format_f64(pe) << ',' << format_f64(te) << ',' << format_f64(ke / n)

@@ -176,3 +176,51 @@ def test_solve_nvt_npt_frames_match_oracle(cli, tmp_path):
                      ("temperature", "temperature"), ("pressure", "pressure")):
         assert abs(float(rows[4][col]) - m[key]) <= 1e-10 * max(1.0, abs(m[key])), key
     assert abs(float(rows[4]["unit_kinetic_energy"]) - m["kinetic"] / last.n) <= 1e-12
+
+
+@pytest.mark.gpu
+def test_solve_two_particle_types(cli, tmp_path):
+    """A State with two particle types through `moldyn_cli solve` (typed upload, the type-pair potentials of potentials.json,
+    the reference's one-sided cross-type forces and last-type thermostat) against the oracle's multi-type step; then
+    solve-macro-parameters, which the reference evaluates for particle type 0 (cli/src/commands.rs:237-264)."""
+    from oracle import oracle as orc
+    from test_multi_type_cpu import mixture
+    o = mixture(n_side=6, cell=0.45, counts=(120, 96), masses=(66.335, 20.18), temperature=150.0, seed=4)
+    d = str(tmp_path / "run")
+    os.makedirs(os.path.join(d, "data"))
+    with open(os.path.join(d, "data", "0.csv"), "w") as f:
+        f.write("id,position_x,position_y,position_z,velocity_x,velocity_y,velocity_z\n")
+        for t, p, v in zip(o.types(), o.pos, o.vel):
+            f.write(f"{t}," + ",".join(repr(float(x)) for x in (*p, *v)) + "\n")
+    with open(os.path.join(d, "bb.csv"), "w") as f:
+        f.write("x,y,z\n" + ",".join(repr(float(x)) for x in o.box) + "\n")
+    with open(os.path.join(d, "db.csv"), "w") as f:
+        f.write("id,name,mass,radius\n0,Argon,66.335,0.071\n1,Neon,20.18,0.038\n")
+    tab = orc.PotentialTable(2)
+    tab.set_potential(0, 1, orc.LennardJones(0.31, 1.1))
+    cross = tab.get_potential(0, 1)
+    dflt = orc.LennardJones()
+    with open(os.path.join(d, "potentials.json"), "w") as f:
+        json.dump({"0,0": {"LennardJones": {"sigma": dflt.sigma, "eps": dflt.eps, "r_cut": dflt.r_cut, "u_cut": dflt.u_cut}},
+                   "0,1": {"LennardJones": {"sigma": cross.sigma, "eps": cross.eps, "r_cut": cross.r_cut,
+                                            "u_cut": cross.u_cut}}}, f)
+    run(cli, "-f", d, "--frames-per-save", "10", "solve", "-s", "0", "-c", "20", "-t", "0.002", "-i", "verlet-method",
+        "--thermostat", "berendsen", "--thermostat-params", "0.5", "-T", "200", "-p")
+    orc.update_force_multi(tab, o)
+    th = orc.Thermostat(orc.Thermostat.BERENDSEN, 0.5, 200.0)
+    for frame in (1, 2):
+        orc.step_multi(tab, o, 0.002, th, n_steps=10)
+        pos, vel, box, ids = read_frame(d, frame)
+        assert ids == list(o.types())
+        assert np.abs(vel - o.vel).max() < 1e-9
+        dx = np.abs(pos - o.pos)
+        assert np.minimum(dx, np.abs(dx - o.box)).max() < 1e-9
+    run(cli, "-f", d, "solve-macro-parameters", "-A", "--use-potentials")
+    rows = list(csv.DictReader(open(os.path.join(d, "macro.csv"))))
+    pos, vel, box, _ = read_frame(d, 2)
+    last = orc.MultiState(pos, vel, o.counts, o.masses, box)
+    orc.update_force_multi(tab, last)
+    m = orc.macro_type(last, 0)
+    for key, col in (("kinetic", "kinetic_energy"), ("thermal", "thermal_energy"), ("potential", "potential_energy"),
+                     ("temperature", "temperature"), ("pressure", "pressure")):
+        assert abs(float(rows[2][col]) - m[key]) <= 1e-9 * max(1.0, abs(m[key])), key

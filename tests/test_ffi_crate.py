@@ -83,6 +83,6 @@ def test_shim_forwards_the_reference_signatures():
     shim = open(os.path.join(ROOT, "ffi", "shim", "gpu.rs")).read()
     for needle in ("pub fn update_force(potentials_database: &PotentialsDatabase, state: &mut State)",
                    "barostat: &mut Option<(&mut Barostat, f64)>, thermostat: &mut Option<(&mut Thermostat, f64)>",
-                   "sys::md_upload_state(", "sys::md_download_state(", "sys::md_step(", "p.temp = self.vir[i]"):
+                   "sys::md_upload_state_typed(", "sys::md_set_potential_pair(", "sys::md_download_state(", "sys::md_step(", "p.temp = self.vir[i]"):
         assert needle in shim, needle
     assert "/* " not in shim.split("impl GpuSession")[1].split("impl Drop")[0]  # upload/download have real bodies
