@@ -44,6 +44,7 @@ struct LoopArgs {
     int n;                  // owned atoms
     int npad, cap;          // row stride and capacity of the neighbour table
     int pairs_per_thread;   // P: thread (b, l) owns pairs (b*P + p)*LOOP_BLOCK + l, p < P
+    int pairs_in_smem;      // PS <= P: the velocities of pairs p < PS live in shared memory, the others in the planes
     Arrays a;
     const int *nbr;
     const int *cntg;        // list counts (| LOOP_GHOST_FLAG on the multi-GPU path)
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     const Params *__restrict__ pr = A.pr;
     const Arrays &a = A.a;
     const ForceConsts &fc = A.fc;
-    const int n = A.n, P = A.pairs_per_thread;
+    const int n = A.n, P = A.pairs_per_thread, PS = USMEM ? A.pairs_in_smem : 0;
     const int npairs = (n + 1) >> 1;
     const bool multi = A.peers != nullptr;
     const bool nh = pr->th_kind == 2;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     auto pair_of = [&](int p) { return (bid * P + p) * LOOP_BLOCK + tid; };
     auto ld_u = [&](bool in_smem, int p, int t, double2 &ux, double2 &uy, double2 &uz) {
         if (USMEM && in_smem) {
-            ux = su[(0 * P + p) * LOOP_BLOCK + tid]; uy = su[(1 * P + p) * LOOP_BLOCK + tid]; uz = su[(2 * P + p) * LOOP_BLOCK + tid];
+            ux = su[(0 * PS + p) * LOOP_BLOCK + tid]; uy = su[(1 * PS + p) * LOOP_BLOCK + tid]; uz = su[(2 * PS + p) * LOOP_BLOCK + tid];
         } else {
             ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t); uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t);
             uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     };
     auto st_u = [&](bool in_smem, int p, int t, bool has1, const double2 &ux, const double2 &uy, const double2 &uz) {
         if (USMEM && in_smem) {
-            su[(0 * P + p) * LOOP_BLOCK + tid] = ux; su[(1 * P + p) * LOOP_BLOCK + tid] = uy; su[(2 * P + p) * LOOP_BLOCK + tid] = uz;
+            su[(0 * PS + p) * LOOP_BLOCK + tid] = ux; su[(1 * PS + p) * LOOP_BLOCK + tid] = uy; su[(2 * PS + p) * LOOP_BLOCK + tid] = uz;
         } else if (has1) {
             reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
             reinterpret_cast<double2 *>(a.vz)[t] = uz;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                 if (t >= npairs) break;
                 const bool has1 = 2 * t + 1 < n;
                 const int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
-                const bool in_smem = (((C.x | (has1 ? C.y : 0)) & LOOP_GHOST_FLAG) == 0);
+                const bool in_smem = p < PS && (((C.x | (has1 ? C.y : 0)) & LOOP_GHOST_FLAG) == 0);
                 double2 ux = __ldcg(reinterpret_cast<const double2 *>(a.vx) + t), uy = __ldcg(reinterpret_cast<const double2 *>(a.vy) + t),
                         uz = __ldcg(reinterpret_cast<const double2 *>(a.vz) + t);
                 if (!half) {
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
                     z = __ldcg(reinterpret_cast<const double2 *>(a.z) + t);
             int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
             if (!has1) C.y = 1;  // (not an atom: nothing to finish, no ghost flag)
-            const bool in_smem = ((C.x | C.y) & LOOP_GHOST_FLAG) == 0;
+            const bool in_smem = p < PS && ((C.x | C.y) & LOOP_GHOST_FLAG) == 0;
             double2 ux, uy, uz;
             ld_u(in_smem, p, t, ux, uy, uz);
             drift_one(x.x, ux.x, lambda, mup, dt, Lx); drift_one(x.y, ux.y, lambda, mup, dt, Lx);
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         const size_t stride = (size_t)A.npad;
         auto force_pair = [&](int p, int t, int2 C, auto ghosts_tag) {
             constexpr bool ghosts = decltype(ghosts_tag)::value;  // compile-time: the owned-partner pass keeps plain base pointers
-            const bool in_smem = !ghosts;
+            const bool in_smem = !ghosts && p < PS;
             const int i0 = 2 * t;
             const bool has1 = i0 + 1 < n;
             // (positions are stable throughout the phase and the barrier's acquiring loads invalidated this SM's L1 — CCTL.IVALL
@@ -415,13 +416,13 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
     if (USMEM && loaded) {
         // the loop is over (rebuild, end of the batch, error or max_steps): the velocities go back to the planes — u, or v''
         // after the last step of a batch, exactly what the two-kernel step leaves there
-        for (int p = 0; p < P; ++p) {
+        for (int p = 0; p < PS; ++p) {
             const int t = pair_of(p);
             if (t >= npairs) break;
             const int2 C = reinterpret_cast<const int2 *>(A.cntg)[t];
             if (((C.x | (2 * t + 1 < n ? C.y : 0)) & LOOP_GHOST_FLAG) != 0) continue;  // lives in the planes
-            const double2 ux = su[(0 * P + p) * LOOP_BLOCK + tid], uy = su[(1 * P + p) * LOOP_BLOCK + tid],
-                          uz = su[(2 * P + p) * LOOP_BLOCK + tid];
+            const double2 ux = su[(0 * PS + p) * LOOP_BLOCK + tid], uy = su[(1 * PS + p) * LOOP_BLOCK + tid],
+                          uz = su[(2 * PS + p) * LOOP_BLOCK + tid];
             if (2 * t + 1 < n) {
                 reinterpret_cast<double2 *>(a.vx)[t] = ux; reinterpret_cast<double2 *>(a.vy)[t] = uy;
                 reinterpret_cast<double2 *>(a.vz)[t] = uz;

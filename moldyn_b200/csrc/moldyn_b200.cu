@@ -736,12 +736,18 @@ int launch_loop(md_ctx *ctx, long long max_steps)
     // as many blocks as there are pairs of atoms to drift, at most one per SM: small systems synchronise a small grid
     const int grid = std::max(1, std::min(ctx->loop_blocks_max, blocks_for(npairs, LOOP_BLOCK)));
     const int P = std::max(1, blocks_for(npairs, (int64_t)grid * LOOP_BLOCK));
-    const bool usmem = P <= LOOP_MAX_PAIRS;
+    // how many of a thread's pairs keep their velocities in shared memory: all of them when they fit (P <= LOOP_MAX_PAIRS),
+    // else none.  MOLDYN_B200_LOOP_PSMEM=k keeps the first min(P, k) instead (A/B: shared memory against L1 capacity for
+    // the gathers; larger systems partly resident).
+    static const int ps_env = [] { const char *e = std::getenv("MOLDYN_B200_LOOP_PSMEM"); return e ? atoi(e) : -1; }();
+    const int PS = ps_env >= 0 ? std::min(P, std::min(ps_env, LOOP_MAX_PAIRS)) : (P <= LOOP_MAX_PAIRS ? P : 0);
+    const bool usmem = PS > 0;
     LoopArgs A{};
     A.n = n;
     A.npad = ctx->npad;
     A.cap = ctx->grid.cap;
     A.pairs_per_thread = P;
+    A.pairs_in_smem = PS;
     A.a = ctx->cur;
     A.nbr = ctx->nbr;
     A.cntg = ctx->dist.on ? ctx->cntg : ctx->nbr_cnt;
@@ -755,7 +761,7 @@ int launch_loop(md_ctx *ctx, long long max_steps)
     A.max_steps = max_steps;
     A.fc = force_consts(ctx);
     void *args[] = {&A};
-    const size_t smem = usmem ? (size_t)P * LOOP_SMEM_PER_PAIR : 0;
+    const size_t smem = (size_t)PS * LOOP_SMEM_PER_PAIR;
     const bool exact = ctx->cfg.force_mode == MD_FORCE_EXACT;
     const void *fn = exact ? (usmem ? (const void *)k_md_loop<true, true> : (const void *)k_md_loop<true, false>)
                            : (usmem ? (const void *)k_md_loop<false, true> : (const void *)k_md_loop<false, false>);
