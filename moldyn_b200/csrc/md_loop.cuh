@@ -97,20 +97,30 @@ __device__ __forceinline__ void finish_atom_r(Sums &s, const PairAcc &f, double 
 
 // Block sums for a 16-warp block: lane tree, then the first warp folds the 16 warp results with a second lane tree (the
 // serial fold of block_reduce<> costs 1.9 us at 512 threads — measured, profiles/r02_loop_trace_v1.txt).  Result in thread 0.
-__device__ __forceinline__ void block_reduce_loop(Sums &s)
+// The trees are shuffle-bound (12 sums x 5 levels x 2 words per warp, 16 warps per SM), so only the sums something reads this
+// step go through them (`mask`, grid-uniform): momentum, thermal energy and the largest speed always; the virial when a
+// barostat runs; kinetic and potential energy only on a step that leaves the State behind; the u sums for Nose-Hoover.
+__device__ __forceinline__ void block_reduce_loop(Sums &s, unsigned int mask)
 {
     static_assert(LOOP_BLOCK == 512, "16 warps");
     __shared__ double sm[NSUM][16];
-    warp_reduce(s);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < NSUM; ++q) sm[q][wid] = s.v[q];
+    for (int q = 0; q < NSUM; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        double v = s.v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = q == NSUM - 1 ? fmax(v, w) : v + w;
+        }
+        if (lane == 0) sm[q][wid] = v;
     }
     __syncthreads();
     if (wid == 0) {
 #pragma unroll
         for (int q = 0; q < NSUM; ++q) {
+            if (!((mask >> q) & 1u)) continue;
             double v = lane < 16 ? sm[q][lane] : 0.0;
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) {
@@ -399,7 +409,13 @@ __global__ void __launch_bounds__(LOOP_BLOCK, 1) k_md_loop(const LoopArgs A)
         MD_TRACE(bid == 0 && tid == 0, 3);
 
         // ---- tail: block sums, ticket, last block folds + finalizes + releases -------------------------------------------
-        block_reduce_loop(s);
+        {
+            unsigned int mask = 0xfu | (1u << S_MAX);                        // S_MV x3, S_TH, S_MAX
+            if (store_state) mask |= (1u << S_KE) | (1u << S_U) | (1u << S_W);
+            if (pr->ba_kind == 1) mask |= 1u << S_W;
+            if (nh) mask |= (7u << S_MU) | (1u << S_THU);
+            block_reduce_loop(s, mask);
+        }
         MD_TRACE(bid == 0 && tid == 0, 4);
         const bool last = publish_and_ticket<LOOP_BLOCK>(s, A.partials, sc);
         MD_TRACE(bid == 0 && tid == 0, 5);

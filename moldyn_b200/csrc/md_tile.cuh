@@ -20,6 +20,7 @@ constexpr int TILE_BLOCK = 256;
 constexpr int TILE_WARPS = TILE_BLOCK / 32;
 constexpr int TILE_WIN = 8;                          // window columns per dimension: 4 own + 2 on either side
 constexpr int TILE_COLS = TILE_WIN * TILE_WIN;       // 64
+constexpr double TILE_FAR = 1.0e7;                   // coordinate of the padding slot [nm]
 constexpr int TILE_RUNS = 2 * TILE_COLS;             // per column: the unwrapped z-run and the periodically wrapped one
 constexpr int TILE_MIN_CELLS = 8;                    // cells per dimension the brick order needs (a window never meets itself)
 
@@ -179,6 +180,9 @@ __device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, co
             }
         }
     }
+    // Slot n_shell is nobody: far outside every cutoff.  The builder pads each list to a multiple of 32 entries with it, so the
+    // pair loop needs no per-entry "is this entry real" test — a padding entry fails the range test like any distant partner.
+    if (threadIdx.x == 0) { sp[3 * n_shell] = TILE_FAR; sp[3 * n_shell + 1] = TILE_FAR; sp[3 * n_shell + 2] = TILE_FAR; }
     __syncthreads();
 }
 
@@ -197,11 +201,17 @@ __device__ __forceinline__ void tile_locate(const TileTab &T, int a, int &oc, in
 // K2, tile form.  One block per brick, ONE THREAD PER ATOM: the thread walks its atom's 25 stencil columns — per column one
 // contiguous range of shell slots for the unwrapped z cells and one for the periodically wrapped ones — out of shared memory,
 // evaluating the reference's predicate (potential.rs:181-204 widened by the skin) in the reference's own operation order.
-// Hits collect in a 16-entry buffer of the thread (32 bytes of shared memory) that is written to the atom's row as one
-// sector whenever it fills: the list is ascending in (column, slot), 16-bit shell slots, atom-major (nbrT[i * cap + k]).
+// Hits collect in a 32-entry buffer of the thread (64 bytes of shared memory) that is written to the atom's row as two
+// sectors whenever it fills: the list is ascending in (column, slot), 16-bit shell slots, atom-major (nbrT[i * cap + ..]),
+// each 32-entry chunk stored in the order the pair loop's lanes read it (tile_chunk_pos) and the last one padded.
 // (Two warp-cooperative forms came first — lanes over a column's candidates, then one lane per column with bit masks: 1.36
 // and 0.95 ms on C5, 2800 and 2260 instructions per atom, half the lanes idle; profiles/r02_ncu_c5_build_tile_v2.txt.)
-constexpr int TILE_BUF = 16;
+constexpr int TILE_BUF = 32;
+// Position of hit h (0..31) of a 32-entry chunk in memory: lane l8 of the pair loop reads positions 4*l8 .. 4*l8+3 as one 8-byte
+// word and wants hits l8, l8+8, l8+16, l8+24 there — at a fixed u the eight lanes of an atom then touch CONSECUTIVE hits, i.e.
+// neighbouring shell slots (few bank conflicts; with hits 4*l8+u instead the kernel lost what the shorter loop gained,
+// profiles/r02_ncu_c5_force_tile_v5.txt: short_scoreboard 1.1 -> 1.95).
+__host__ __device__ constexpr int tile_chunk_pos(int h) { return ((h & 7) << 2) | (h >> 3); }
 
 __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, const int *__restrict__ cell_start,
                                                            const int *__restrict__ cell_sorted, Scalars *sc,
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
     tile_stage(T, a, sc, sp, false);
     const int ncz = g.nc[2];
-    unsigned short *mybuf = reinterpret_cast<unsigned short *>(bufs + 2 * threadIdx.x);
+    unsigned short *mybuf = reinterpret_cast<unsigned short *>(bufs + 4 * threadIdx.x);
     int wmax = 0;
     unsigned long long wsum = 0ull;
     for (int ai = threadIdx.x; ai < T.n_own; ai += TILE_BLOCK) {
@@ -240,13 +250,13 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
             return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
         };
         auto take = [&](int q) {
-            mybuf[cnt & (TILE_BUF - 1)] = (unsigned short)q;
+            mybuf[tile_chunk_pos(cnt & (TILE_BUF - 1))] = (unsigned short)q;
             ++cnt;
             if ((cnt & (TILE_BUF - 1)) == 0 && cnt <= cap) {
-                const int chunk = (cnt >> 4) - 1;
-                asm volatile("" ::: "memory");  // (the buffer is written as 16-bit words and read back as two 16-byte ones)
-                out[2 * chunk] = bufs[2 * threadIdx.x];
-                out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
+                const int chunk = (cnt >> 5) - 1;
+                asm volatile("" ::: "memory");  // (the buffer is written as 16-bit words and read back as four 16-byte ones)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) out[4 * chunk + v] = bufs[4 * threadIdx.x + v];
             }
         };
         auto scan = [&](int s, int e, double dx, double dy, double dz) {
@@ -278,13 +288,12 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
                 scan(sB, sB + (cd - cc), dx, dy, T.shz);
             }
         }
-        // the last, partly filled buffer (the row has room for whole 16-entry chunks: cap is a multiple of 32)
-        if ((cnt & (TILE_BUF - 1)) != 0 && cnt <= cap) {
-            const int chunk = cnt >> 4;
-            asm volatile("" ::: "memory");
-            out[2 * chunk] = bufs[2 * threadIdx.x];
-            out[2 * chunk + 1] = bufs[2 * threadIdx.x + 1];
-        }
+        // pad to a multiple of 32 entries with the nobody slot (cap is a multiple of 32: the row has room), which also
+        // flushes the last, partly filled buffer
+        const int real = cnt;
+        if (real <= cap)
+            while (cnt & 31) take(T.n_shell);
+        cnt = real;
         nbr_cnt[gi] = min(cnt, cap);
         wmax = max(wmax, cnt);
         wsum += (unsigned long long)cnt;
@@ -318,14 +327,15 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_tile_expand(Grid g, const int *_
         int oc, slot, gi;
         tile_locate(T, ai, oc, slot, gi);
         const int cnt = nbr_cnt[gi];
-        for (int k = threadIdx.x & 31; k < cnt; k += 32) nbr[(size_t)k * npad + gi] = slot_to_sorted[nbrT[(size_t)gi * cap + k]];
+        for (int k = threadIdx.x & 31; k < cnt; k += 32)
+            nbr[(size_t)k * npad + gi] = slot_to_sorted[nbrT[(size_t)gi * cap + (k & ~31) + tile_chunk_pos(k & 31)]];
     }
 }
 
 // ---- K3, tile form ----------------------------------------------------------------------------------------------------
-// Pair phase: a warp takes FOUR brick atoms at a time, eight lanes each.  Lane (s, l) evaluates entries l, l + 8, l + 16,
-// l + 24 of atom s's list per trip — four independent pair terms in flight, consecutive lanes on consecutive slots
-// (conflict-free LDS.64) — with the next trip's four 16-bit indices fetched before the current trip's arithmetic.  The
+// Pair phase: a warp takes FOUR brick atoms at a time, eight lanes each.  Lane (s, l) evaluates hits l, l + 8, l + 16, l + 24 of
+// every 32-entry chunk of atom s's list per trip — four independent pair terms in flight, consecutive lanes on neighbouring
+// slots — with the four 16-bit indices of the trip after next fetched as one 8-byte word before the current trip's arithmetic.  The
 // partial forces of an atom are folded over its eight lanes with three xor-shuffles in a fixed order (deterministic): all
 // the per-atom work — locate, count, fold, hand-over — is paid once per four atoms.
 template <int UW>
@@ -340,7 +350,13 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
     // list length and the four indices of its first trip are fetched — so no group starts with the chain
     // locate -> count -> indices -> positions exposed (each link a trip to L2 or HBM; it was a third of the first version's
     // time, profiles/r02_ncu_c5_force_tile_v2.txt) — and its whole list is pulled into L2 for the later trips.
-    int n_slot = 0, n_gi = 0, n_cnt = 0, n_first[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // Lane l8 of an atom takes hits l8, l8+8, l8+16, l8+24 of every 32-entry chunk of the atom's list — stored next to each other
+    // (tile_chunk_pos): ONE 8-byte load per lane and trip.  Lists are padded to whole chunks with the nobody slot
+    // (k_build_tile), chunks beyond an atom's list read as nobody.
+    const unsigned int nobody2 = (unsigned int)T.n_shell * 0x10001u;
+    const uint2 nobody = make_uint2(nobody2, nobody2);
+    int n_slot = 0, n_gi = 0, n_cnt = 0;
+    uint2 n_first[2] = {nobody, nobody};
     auto fetch_group = [&](int g0) {
         const int ai = g0 + sub;
         int oc;
@@ -349,9 +365,9 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
             tile_locate(T, ai, oc, n_slot, n_gi);
             n_cnt = nbr_cnt[n_gi];
         }
-        const unsigned short *__restrict__ lst = nbrT + (size_t)n_gi * cap;  // (row 0 for lanes without an atom: never used)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) n_first[u] = (int)lst[u * 8 + l8];     // unconditional: a row holds cap >= 64 entries
+        const uint2 *__restrict__ lst = reinterpret_cast<const uint2 *>(nbrT + (size_t)n_gi * cap);  // (row 0 for lanes without an atom: never used)
+        n_first[0] = lst[l8];      // unconditional: a row holds cap >= 64 entries
+        n_first[1] = lst[8 + l8];
         const char *nl = reinterpret_cast<const char *>(lst);
         for (int b = (l8 + 1) * 128; b < 2 * cap; b += 8 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nl + b));
     };
@@ -359,34 +375,26 @@ __device__ __forceinline__ void tile_pair_phase(const TileTab &T, const double *
     for (int g0 = 4 * warp; g0 < n_own; g0 += 4 * TILE_WARPS) {  // warp-uniform
         const int ai = g0 + sub;
         const int slot = n_slot, gi = n_gi, cnt = n_cnt;
+        const int cntr = (cnt + 31) & ~31;
         // index registers two trips deep: a trip is shorter than a round trip to L2
-        int jn[4], jnn[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            jn[u] = u * 8 + l8 < cnt ? n_first[u] : 0;
-            jnn[u] = 32 + u * 8 + l8 < cnt ? n_first[4 + u] : 0;
-        }
+        uint2 jn = 0 < cntr ? n_first[0] : nobody, jnn = 32 < cntr ? n_first[1] : nobody;
         if (g0 + 4 * TILE_WARPS < n_own) fetch_group(g0 + 4 * TILE_WARPS);
-        const unsigned short *__restrict__ lst = nbrT + (size_t)gi * cap;
+        const uint2 *__restrict__ lst = reinterpret_cast<const uint2 *>(nbrT + (size_t)gi * cap) + l8;
         const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
         const int kmax = __reduce_max_sync(0xffffffffu, cnt);
         PairAcc acc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[u] = PairAcc{0.0, 0.0, 0.0, 0.0, 0.0};
         for (int k0 = 0; k0 < kmax; k0 += 32) {
-            int j[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { j[u] = jn[u]; jn[u] = jnn[u]; }
-            if (k0 + 64 < kmax) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int k = k0 + 64 + u * 8 + l8; jnn[u] = k < cnt ? (int)lst[k] : 0; }
-            }
+            const uint2 jw = jn;
+            jn = jnn;
+            if (k0 + 64 < kmax) jnn = k0 + 64 < cntr ? lst[(k0 + 64) >> 2] : nobody;
+            const int j[4] = {(int)(jw.x & 0xffffu), (int)(jw.x >> 16), (int)(jw.y & 0xffffu), (int)(jw.y >> 16)};
             double xj[4], yj[4], zj[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) { const double *pj = sp + 3 * j[u]; xj[u] = pj[0]; yj[u] = pj[1]; zj[u] = pj[2]; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                pair_dense<false, UW>(acc[u], k0 + u * 8 + l8 < cnt, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
+            for (int u = 0; u < 4; ++u) pair_dense<false, UW>(acc[u], true, xj[u], yj[u], zj[u], xi, yi, zi, c, fc);
         }
         PairAcc f;
         f.fx = (acc[0].fx + acc[1].fx) + (acc[2].fx + acc[3].fx);

@@ -604,7 +604,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
     CK(cudaGetLastError());
     TRY(pull_scalars(ctx));
     if (ctx->h_sc->out_of_box) { *fallback = true; return MD_OK; }
-    ctx->sh_cap = (ctx->h_sc->tile_shell_max + 63) / 64 * 64;
+    ctx->sh_cap = (ctx->h_sc->tile_shell_max + 1 + 63) / 64 * 64;  // (+1: the padding slot, md_tile.cuh)
     ctx->own_cap = (ctx->h_sc->tile_own_max + 31) / 32 * 32;
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
