@@ -290,10 +290,13 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
         }
         // pad to a multiple of 32 entries with the nobody slot (cap is a multiple of 32: the row has room), which also
         // flushes the last, partly filled buffer
-        const int real = cnt;
-        if (real <= cap)
-            while (cnt & 31) take(T.n_shell);
-        cnt = real;
+        if (cnt <= cap && (cnt & (TILE_BUF - 1)) != 0) {
+            for (int h = cnt & (TILE_BUF - 1); h < TILE_BUF; ++h) mybuf[tile_chunk_pos(h)] = (unsigned short)T.n_shell;
+            const int chunk = cnt >> 5;
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int v = 0; v < 4; ++v) out[4 * chunk + v] = bufs[4 * threadIdx.x + v];
+        }
         nbr_cnt[gi] = min(cnt, cap);
         wmax = max(wmax, cnt);
         wsum += (unsigned long long)cnt;
