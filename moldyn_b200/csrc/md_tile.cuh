@@ -186,6 +186,43 @@ __device__ __forceinline__ void tile_stage(const TileTab &T, const Arrays &a, co
     __syncthreads();
 }
 
+// The builder's view of the shell: single-precision coordinates relative to the brick centre, the run's periodic shift folded
+// in, one 16-byte record per slot (ONE LDS.128 per candidate).  They only PRE-FILTER: a candidate whose single-precision
+// distance² is not within TILE_BAND of the list radius² is decided there (coordinates within ~4 nm of the centre: each is
+// off by < 2.4e-7 nm, distance² by < 3e-6 nm² — TILE_BAND is 30 times that); the few inside the band are decided by the
+// reference's own double-precision operations on the stored coordinates.
+constexpr float TILE_BAND = 1.0e-4f;
+__device__ __forceinline__ void tile_stage_f32(const TileTab &T, const Arrays &a, float4 *sf)
+{
+    const int n_shell = T.n_shell;
+    for (int s0 = threadIdx.x; s0 < n_shell; s0 += 4 * TILE_BLOCK) {
+        int r[4], g[4];
+        double x[4], y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * TILE_BLOCK;
+            int lo = 0;
+#pragma unroll
+            for (int step = TILE_RUNS / 2; step > 0; step >>= 1)
+                if (lo + step < TILE_RUNS && T.run_loc[lo + step] <= s) lo += step;
+            r[u] = lo;
+            g[u] = s < n_shell ? T.run_src[lo] + (s - T.run_loc[lo]) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = a.x[g[u]]; y[u] = a.y[g[u]]; z[u] = a.z[g[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + u * TILE_BLOCK;
+            if (s < n_shell) {
+                const double dx = T.shx[r[u] >> 1], dy = T.shy[r[u] >> 1], dz = (r[u] & 1) ? T.shz : 0.0;
+                sf[s] = make_float4((float)((x[u] + dx) - T.ctr[0]), (float)((y[u] + dy) - T.ctr[1]),
+                                    (float)((z[u] + dz) - T.ctr[2]), 0.f);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // brick atom a (0 <= a < n_own) → own column, shell slot, sorted index
 __device__ __forceinline__ void tile_locate(const TileTab &T, int a, int &oc, int &slot, int &gi)
 {
@@ -220,19 +257,21 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
                                                            int sh_cap)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    double *sp = reinterpret_cast<double *>(tile_smem);
-    uint4 *bufs = reinterpret_cast<uint4 *>(sp + 3 * (size_t)sh_cap);  // TILE_BLOCK buffers of TILE_BUF 16-bit entries
+    float4 *sf = reinterpret_cast<float4 *>(tile_smem);
+    uint4 *bufs = reinterpret_cast<uint4 *>(sf + (size_t)sh_cap);  // TILE_BLOCK buffers of TILE_BUF 16-bit entries
     __shared__ TileTab T;
     tile_setup(T, g, cell_start, sc, brick_order[blockIdx.x]);
-    tile_stage(T, a, sc, sp, false);
+    tile_stage_f32(T, a, sf);
     const int ncz = g.nc[2];
     unsigned short *mybuf = reinterpret_cast<unsigned short *>(bufs + 4 * threadIdx.x);
+    const float r2_lo = (float)r2_list - TILE_BAND, r2_hi = (float)r2_list + TILE_BAND;
     int wmax = 0;
     unsigned long long wsum = 0ull;
     for (int ai = threadIdx.x; ai < T.n_own; ai += TILE_BLOCK) {
         int oc, slot, gi;
         tile_locate(T, ai, oc, slot, gi);
-        const double xi = sp[3 * slot], yi = sp[3 * slot + 1], zi = sp[3 * slot + 2];
+        const double xi = a.x[gi], yi = a.y[gi], zi = a.z[gi];
+        const float4 fi = sf[slot];
         const int cz = cell_sorted[gi] % ncz;
         const int lx = oc >> 2, ly = oc & 3;
         const int za = max(cz - 2, 0), zb = min(cz + 3, ncz);
@@ -241,13 +280,10 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
         else if (cz + 3 > ncz) { zc = 0; zd = cz + 3 - ncz; }
         uint4 *__restrict__ out = reinterpret_cast<uint4 *>(nbrT + (size_t)gi * cap);
         int cnt = 0;
-        auto r2_of = [&](int q, double dx, double dy, double dz) {
-            // the reference's operations in the reference's order: (x_q - x_i) -+ L (adding 0.0 is exact), then norm²
-            const double *pq = sp + 3 * q;
-            const double rx = __dadd_rn(__dsub_rn(pq[0], xi), dx);
-            const double ry = __dadd_rn(__dsub_rn(pq[1], yi), dy);
-            const double rz = __dadd_rn(__dsub_rn(pq[2], zi), dz);
-            return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz));
+        auto d2_of = [&](int q) {
+            const float4 f = sf[q];
+            const float rx = f.x - fi.x, ry = f.y - fi.y, rz = f.z - fi.z;
+            return fmaf(rz, rz, fmaf(ry, ry, rx * rx));
         };
         auto take = [&](int q) {
             mybuf[tile_chunk_pos(cnt & (TILE_BUF - 1))] = (unsigned short)q;
@@ -259,21 +295,28 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
                 for (int v = 0; v < 4; ++v) out[4 * chunk + v] = bufs[4 * threadIdx.x + v];
             }
         };
-        auto scan = [&](int s, int e, double dx, double dy, double dz) {
+        // slot q of a run whose slot s is atom gs of the sorted order: the reference's operations in the reference's order on
+        // the stored coordinates — (x_q - x_i) -+ L (adding 0.0 is exact), then norm².  r2_list is the largest double whose
+        // square root is <= r_list: r2 <= r2_list IS the reference's norm(r) <= r_list.
+        auto exact_hit = [&](int q, int s, int gs, double dx, double dy, double dz) {
+            const int gq = gs + (q - s);
+            const double rx = __dadd_rn(__dsub_rn(a.x[gq], xi), dx);
+            const double ry = __dadd_rn(__dsub_rn(a.y[gq], yi), dy);
+            const double rz = __dadd_rn(__dsub_rn(a.z[gq], zi), dz);
+            return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)) <= r2_list;
+        };
+        auto scan = [&](int s, int e, int gs, double dx, double dy, double dz) {
             // four candidates per trip: their distance chains are independent (a thread's scan is otherwise one long
-            // dependency chain — 'wait' was the first version's dominant stall); hits are taken in slot order.  r2_list is
-            // the largest double whose square root is <= r_list: r2 <= r2_list IS the reference's norm(r) <= r_list.
+            // dependency chain — 'wait' was the first version's dominant stall); hits are taken in slot order
+            auto decide = [&](int q, float d2) {
+                if (d2 < r2_hi && q != slot && (d2 <= r2_lo || exact_hit(q, s, gs, dx, dy, dz))) take(q);
+            };
             int q = s;
             for (; q + 4 <= e; q += 4) {
-                const double r0 = r2_of(q, dx, dy, dz), r1 = r2_of(q + 1, dx, dy, dz), r2 = r2_of(q + 2, dx, dy, dz),
-                             r3 = r2_of(q + 3, dx, dy, dz);
-                if (r0 <= r2_list && q != slot) take(q);
-                if (r1 <= r2_list && q + 1 != slot) take(q + 1);
-                if (r2 <= r2_list && q + 2 != slot) take(q + 2);
-                if (r3 <= r2_list && q + 3 != slot) take(q + 3);
+                const float d0 = d2_of(q), d1 = d2_of(q + 1), d2 = d2_of(q + 2), d3 = d2_of(q + 3);
+                decide(q, d0); decide(q + 1, d1); decide(q + 2, d2); decide(q + 3, d3);
             }
-            for (; q < e; ++q)
-                if (r2_of(q, dx, dy, dz) <= r2_list && q != slot) take(q);
+            for (; q < e; ++q) decide(q, d2_of(q));
         };
         for (int col = 0; col < 25; ++col) {
             const int wcol = (lx + col / 5) * TILE_WIN + (ly + col % 5);
@@ -281,11 +324,11 @@ __global__ void __launch_bounds__(TILE_BLOCK) k_build_tile(Grid g, Arrays a, con
             const int ca = cell_start[base + za], cb = cell_start[base + zb];
             const int sA = T.run_loc[2 * wcol] + (ca - T.run_src[2 * wcol]);
             const double dx = T.shx[wcol], dy = T.shy[wcol];
-            scan(sA, sA + (cb - ca), dx, dy, 0.0);
+            scan(sA, sA + (cb - ca), ca, dx, dy, 0.0);
             if (zd > zc) {
                 const int cc = cell_start[base + zc], cd = cell_start[base + zd];
                 const int sB = T.run_loc[2 * wcol + 1] + (cc - T.run_src[2 * wcol + 1]);
-                scan(sB, sB + (cd - cc), dx, dy, T.shz);
+                scan(sB, sB + (cd - cc), cc, dx, dy, T.shz);
             }
         }
         // pad to a multiple of 32 entries with the nobody slot (cap is a multiple of 32: the row has room), which also

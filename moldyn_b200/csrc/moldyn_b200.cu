@@ -609,7 +609,7 @@ int build_tile_lists(md_ctx *ctx, bool *fallback)
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const size_t smem_force = ((size_t)3 * ctx->sh_cap + (size_t)5 * ctx->own_cap) * sizeof(double);
-    const size_t smem_build = (size_t)3 * ctx->sh_cap * sizeof(double) + (size_t)TILE_BLOCK * TILE_BUF * sizeof(unsigned short);
+    const size_t smem_build = (size_t)ctx->sh_cap * sizeof(float4) + (size_t)TILE_BLOCK * TILE_BUF * sizeof(unsigned short);
     if (ctx->sh_cap > 65535 || smem_force + 16 * 1024 > (size_t)optin) { *fallback = true; return MD_OK; }
     if (ctx->nbricks > ctx->partial_blocks) {  // one slot of partial sums per brick
         dev_free(ctx, ctx->d_partials);
