@@ -664,8 +664,12 @@ bool loop_wanted(const md_ctx *ctx)
     if (ctx->dist.on) return ctx->dist.p2p;
     // one GPU: with a few partners per atom the two-kernel step's force kernel (two atoms per thread, operands of the next
     // pair prefetched) walks its lists faster than the loop's force phase — measured on C1's steady state (4.9 listed
-    // partners: 14.5 vs 27 us/step); the loop wins where most atoms have none (C2-C4: 0.55) and on states beyond L2
-    return ctx->stats.nbr_mean < 2.0;
+    // partners: 14.5 vs 27 us/step).  The loop wins where fixed latencies dominate: small systems (C2: a tie at 0.55
+    // partners), nearly empty lists (C3 from the lattice: 22.2 vs 28-30 us/step) and states beyond L2 (8*10^6 atoms: 174 vs
+    // 197).  For 10^5..2.6*10^6 atoms with populated lists (C3's collisional steady state, 0.55 partners) the two-kernel
+    // step is 5-10 % ahead on three different boxes (35 vs 37-39 us/step, profiles/r02_call_{i,o,r}_*.txt).
+    const bool mid_size = ctx->n >= 131072 && ctx->n <= 2600000;
+    return ctx->stats.nbr_mean < (mid_size ? 0.25 : 2.0);
 }
 
 int launch_force(md_ctx *ctx, bool kick, int guarded = 0)
