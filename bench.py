@@ -299,6 +299,12 @@ def run_ours(args, w):
     dense = st1["nbr_mean"] >= 8.0
     rebuilds = st1["rebuilds"] - st0["rebuilds"]
 
+    # ---- where the time goes: device timing of the parts of a step (md_time_kernels), taken right after the timed region —
+    # the same list state and the same step driver as the steps that were timed ----------------------------------------
+    kt = s.time_kernels(min(max(args.steps, 50), 400), DT, thermostat=t_th, barostat=t_ba) if world == 1 else None
+    st2 = s.stats()
+    per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt} if kt else {}
+
     # ---- steady state: the driver's short runs start on the perfect gas lattice (no partner in range, no rebuild for the
     # first ~10^3 steps), so the same metric is taken again after the system has been run into its collisional steady
     # state, over a region long enough to contain list rebuilds ------------------------------------------------------
@@ -311,14 +317,12 @@ def run_ours(args, w):
         steady = {"value": n * args.steady_steps / (ms_s * 1e-3), "unit": "atom-steps/s", "steps": args.steady_steps,
                   "steps_before": args.warmup + args.steps + args.steady_warmup, "us_per_step": ms_s / args.steady_steps * 1e3,
                   "rebuilds": sb["rebuilds"] - sa["rebuilds"], "nbr_mean": sb["nbr_mean"], "nbr_max": sb["nbr_max"],
+                  "step_driver": "persistent loop (k_md_loop)" if sb["persistent_loop"] else
+                                 ("tile kernels in graph chunks" if sb["tile_lists"] else "two-kernel step in graph chunks"),
                   "frac_of_step_roofline": ALGO_BYTES_STEP * n * args.steady_steps / (ms_s * 1e-3) / 1e9 / (peaks()[0] * world)}
 
-    # ---- where the time goes: device timing of the parts of a step (md_time_kernels) --------------------------------
     hbm, peak_src = peaks()
     fp64_peak, fp64_src = None, None
-    kt = s.time_kernels(min(max(args.steps, 50), 400), DT, thermostat=t_th, barostat=t_ba) if world == 1 else None
-    st2 = s.stats()
-    per = {k: (kt[k][0] / kt[k][1] if kt[k][1] else None) for k in kt} if kt else {}
     rebuild_ms = per.get("rebuild")
     if world == 1 and rebuild_ms is None and args.time_rebuild:
         # no rebuild fell into the timed steps: force one and time it, so the line always carries its cost
