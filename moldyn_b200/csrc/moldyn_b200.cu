@@ -997,6 +997,7 @@ int md_set_potential_lj(md_ctx *ctx, double sigma, double eps, double r_cut, dou
     ctx->sigma = sigma; ctx->eps = eps; ctx->r_cut = r_cut; ctx->u_cut = u_cut;
     ctx->list_valid = false;
     ctx->force_valid = false;
+    if (ctx->multi.on) ctx->multi.rc_max = multi_rc_max(ctx);  // pair (0, 0) of the type table: the list radius may change
     if (ctx->has_state) {
         TRY(pull_scalars(ctx));
         ctx->skin = choose_skin(ctx, ctx->h_sc->box);
@@ -1775,7 +1776,7 @@ int md_get_stats(md_ctx *ctx, md_stats *out)
     out->wait_halo_ms = (double)ctx->h_sc->wait_halo_ns * 1e-6;  // as of the last time the host looked at the device
     out->wait_sums_ms = (double)ctx->h_sc->wait_sums_ns * 1e-6;
     out->peer_memory = ctx->dist.p2p ? 1 : 0;
-    out->persistent_loop = (ctx->has_state && loop_wanted(ctx) && ctx->loop_blocks_max > 0) ? 1 : 0;
+    out->persistent_loop = (ctx->has_state && !ctx->multi.on && loop_wanted(ctx) && ctx->loop_blocks_max > 0) ? 1 : 0;
     out->tile_lists = ctx->tile_valid ? 1 : 0;
     out->force_atoms_ms = (double)ctx->h_sc->force_atoms_ns * 1e-6;
     out->force_tail_ms = (double)ctx->h_sc->force_tail_ns * 1e-6;

@@ -160,3 +160,22 @@ def test_boundaries_of_the_multi_type_path():
         s.download(g1)
         assert s.macro()["n"] == one.n
     assert np.array_equal(g1.force, one.force)
+
+
+def test_changing_pair_00_after_upload_changes_the_list_radius():
+    """md_set_potential_lj is pair (0, 0) of the type table: a longer cutoff set after the upload must widen the lists."""
+    tab = table3()
+    st = big_mixture(seed=13)
+    g = to_md(st)
+    long00 = orc.LennardJones(0.3418, 1.712, r_cut=1.2)
+    with md.Solver(exact=True) as s:
+        set_table(s, tab)
+        s.upload_typed(g, with_forces=False)
+        s.update_force()
+        s.set_potential(md.Potential(long00.sigma, long00.eps, long00.r_cut, long00.u_cut))
+        s.update_force()
+        s.download(g)
+        assert s.stats()["persistent_loop"] == 0
+    tab.set_potential(0, 0, long00)
+    orc.update_force_multi(tab, st)
+    assert np.array_equal(g.force, st.force) and np.array_equal(g.potential, st.pot)
